@@ -1,0 +1,185 @@
+/*
+ * blp.h — C ABI of the batched node-LP bound step (libblp.so, sm_100a).
+ *
+ * The reference (spkelle2/simple_mip_solver) has no FFI: its LP arithmetic is reached through the
+ * CyClpSimplex object held in node.lp. Each entry point below names the reference call it replaces
+ * (paths relative to the reference root). INTEGRATION.md shows the ctypes binding a maintainer
+ * would add on the reference side.
+ *
+ * Problem solved for every node k of a batch (the reference's canonical form, base_node.py:34,111):
+ *
+ *     min c.x   s.t.   A x >= row_lb  (rows >= m_base are cut rows, enabled per node by row_mask)
+ *                      lb_k <= x <= ub_k
+ *
+ * Conventions
+ *   - plain C types only; no C++ exceptions cross the boundary.
+ *   - return value 0 = ok, negative = blp_status error; text via blp_last_error() (thread local).
+ *   - per-node solver outcomes are DATA (status[]), not errors. CLP codes are kept
+ *     (base_node.py:274-275, pseudo_cost.py:86): 0 optimal, 1 primal infeasible,
+ *     2 dual infeasible (unbounded), 3 iteration limit.
+ *   - "device" pointers are CUDA device pointers owned by the caller (torch tensors in the Python
+ *     host layer) and borrowed for the duration of the call. Batched vectors are stored
+ *     node-fastest: element (j, k) of an [rows][ld] array lives at j*ld + k, ld = blp_ld(B).
+ *   - a handle is bound to one GPU and one CUDA stream and is not thread safe.
+ *   - infinite bounds: any |v| >= 1e30 (CLP's getCoinInfinity() is DBL_MAX) or IEEE inf.
+ */
+#ifndef BLP_H
+#define BLP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct blp_handle_s* blp_handle;
+
+enum blp_status {
+    BLP_OK = 0,
+    BLP_ERR_ARG = -1,      /* bad argument */
+    BLP_ERR_CUDA = -2,     /* CUDA runtime error (message has the CUDA string) */
+    BLP_ERR_NOMEM = -3,    /* workspace too small / allocation failed */
+    BLP_ERR_STATE = -4     /* call not valid in this handle state */
+};
+
+typedef struct blp_opts {
+    double eps_rel;        /* relative KKT tolerance (primal, dual, gap); default 1e-8 */
+    double eps_infeas;     /* relative size a Farkas certificate must reach; default 1e-9 */
+    int max_iters;         /* PDHG iteration cap per call (the analogue of lp.maxNumIteration,
+                              base_node.py:645); nodes still running get status 3. default 400000 */
+    int eval_every;        /* iterations between KKT / restart evaluations; default 64 */
+    int use_graph;         /* 1: replay each evaluation period as one CUDA graph; default 1 */
+    int compact;           /* 1: retire finished nodes by compacting the batch; default 1 */
+    int verbose;           /* 1: print one line per evaluation to stderr */
+    int profile;           /* 1: no graphs; time every k_primal / k_dual launch with CUDA events
+                              (blp_stats.primal_kernel_ms / dual_kernel_ms). default 0 */
+} blp_opts;
+
+typedef struct blp_stats {
+    int iterations;            /* PDHG iterations executed by the call (max over nodes) */
+    int evaluations;           /* KKT evaluations */
+    int kernel_launches;       /* kernels of this library launched by the call */
+    int compactions;
+    double step_kernel_ms;     /* device time spent in the two step kernels (CUDA events) */
+    double total_ms;           /* device time of the whole call (CUDA events) */
+    double node_iterations;    /* sum over iterations of the number of node columns swept */
+    double primal_kernel_ms;   /* profile mode: device time of all k_primal launches */
+    double dual_kernel_ms;     /* profile mode: device time of all k_dual launches */
+} blp_stats;
+
+/* default options */
+void blp_default_opts(blp_opts* o);
+
+/* leading dimension (in elements) of every [rows][ld] batched array for a batch of B nodes */
+int blp_ld(int B);
+
+/* bytes of device workspace blp_solve_batch needs for B nodes (depends on m incl. appended rows) */
+size_t blp_workspace_bytes(blp_handle h, int B);
+
+/*
+ * Build the shared part of all node LPs on GPU `device`: CSR of A (m x n), its transpose, the
+ * diagonal scaling and the step size. Host pointers, copied.
+ * Replaces: model construction for the solver — MILPInstance(...).lp handed to
+ * Node(lp=model.lp, ...) (algorithms/base_algorithm.py:18-29) and the per-child rebuild in
+ * BaseNode._base_branch (nodes/base_node.py:592-608), which here is paid once per instance.
+ */
+int blp_create(int device, int m, int n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+               const double* val, const double* c, const double* row_lb, blp_handle* out);
+
+/*
+ * Append k cut rows (CSR, host pointers) "row . x >= rhs" to the shared pool; they become rows
+ * m .. m+k-1 and are enabled per node through row_mask. Returns the id of the first new row.
+ * Replaces: lp.addConstraint(pi * x >= pi0, name) in BaseNode._select_cuts (base_node.py:459-460).
+ */
+int blp_append_rows(blp_handle h, int k, const int32_t* rowptr, const int32_t* colidx,
+                    const double* val, const double* rhs, int* first_row_id);
+
+/* Drop every appended row with id >= m_keep (m_keep >= m_base).
+ * Replaces: lp.removeConstraint(name) in BaseNode._remove_slack_cuts (base_node.py:337-338). */
+int blp_truncate_rows(blp_handle h, int m_keep);
+
+/* current row counts */
+int blp_num_rows(blp_handle h);
+int blp_num_base_rows(blp_handle h);
+int blp_num_cols(blp_handle h);
+
+/*
+ * Solve B node LPs that share the handle's matrix. All array arguments are DEVICE pointers in the
+ * node-fastest layout with ld = blp_ld(B); optional ones may be NULL.
+ *   lb, ub      [n][ld]        per-node variable bounds (the only thing _base_branch changes,
+ *                               base_node.py:595-600)
+ *   row_mask    [m-m_base][ld] uint8, 1 = cut row present in node k's LP; NULL = all present
+ *   x0, y0      [n][ld],[m][ld] warm start (parent's primal / row duals), NULL = cold
+ *   int_idx     [n_int]        int32 integer column ids in ascending order (for frac_idx), or NULL
+ *   workspace   blp_workspace_bytes(h, B) bytes
+ * outputs (each may be NULL):
+ *   obj         [ld]  primal objective c.x at termination (+inf where status == 1)
+ *   lower_bound [ld]  Lagrangian bound b.y + sum_j min((c-A'y)_j l_j, (c-A'y)_j u_j)
+ *   status      [ld]  CLP code per node
+ *   iters       [ld]  PDHG iterations the node ran
+ *   x, y        [n][ld], [m][ld]  primal solution and row duals (y >= 0 for rows "a.x >= b")
+ *   frac_idx    [ld]  most fractional integer column (first wins ties, distance > 1e-4), -1 if
+ *                     the node is integral or not solved  (BaseNode._most_fractional_index,
+ *                     base_node.py:544-562; the integrality test of _bound_lp :281-283)
+ * Replaces: self.lp.dual() + getStatusCode/objectiveValue/primalVariableSolution/
+ * dualConstraintSolution in BaseNode._bound_lp (base_node.py:273-283), and n.lp.dual() for every
+ * strong-branching child in BaseNode._strong_branch (base_node.py:644-646), for a whole batch.
+ */
+int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
+                    const uint8_t* row_mask, const double* x0, const double* y0,
+                    const int32_t* int_idx, int n_int, const blp_opts* opts,
+                    void* workspace, size_t workspace_bytes,
+                    double* obj, double* lower_bound, int32_t* status, int32_t* iters,
+                    double* x, double* y, int32_t* frac_idx, blp_stats* stats);
+
+/*
+ * Host-buffer form of the same call: the form the reference's Python would bind. Inputs are HOST
+ * arrays in node-major order (one contiguous bound vector per node, as each node.lp holds them):
+ *   lb, ub [B][n]; row_mask [B][m-m_base] or NULL; x0 [B][n], y0 [B][m] or NULL.
+ * Outputs are HOST arrays: obj/lower_bound/status/iters/frac_idx [B]; x [B][n], y [B][m] or NULL.
+ * The library stages through its own device memory (grown on demand, released by blp_destroy);
+ * host<->device copies are part of the call.
+ */
+int blp_solve_batch_host(blp_handle h, int B, const double* lb, const double* ub,
+                         const uint8_t* row_mask, const double* x0, const double* y0,
+                         const int32_t* int_idx, int n_int, const blp_opts* opts,
+                         double* obj, double* lower_bound, int32_t* status, int32_t* iters,
+                         double* x, double* y, int32_t* frac_idx, blp_stats* stats);
+
+/*
+ * Children-of-one-parent form (the strong-branching batch, pseudo_cost.py:57-62): node k has the
+ * parent's bounds parent_lb/parent_ub [n] (host) except for delta entries
+ * delta_ptr[k] .. delta_ptr[k+1]-1, each (delta_var, delta_lb, delta_ub). Host inputs/outputs as
+ * in blp_solve_batch_host; x0/y0 are ONE parent vector ([n], [m], host) broadcast to all nodes.
+ */
+int blp_solve_children_host(blp_handle h, int B, const double* parent_lb, const double* parent_ub,
+                            const int32_t* delta_ptr, const int32_t* delta_var,
+                            const double* delta_lb, const double* delta_ub,
+                            const uint8_t* row_mask, const double* x0, const double* y0,
+                            const int32_t* int_idx, int n_int, const blp_opts* opts,
+                            double* obj, double* lower_bound, int32_t* status, int32_t* iters,
+                            double* x, double* y, int32_t* frac_idx, blp_stats* stats);
+
+/* Batched SpMV on the handle's (unscaled) matrix, device pointers, node-fastest layout:
+ * transpose == 0: Y[m][ld] = A X[n][ld];  transpose == 1: Y[n][ld] = A' X[m][ld].
+ * Exposed for parity tests and for the SpMV roofline measurement. */
+int blp_spmv(blp_handle h, int B, int transpose, const double* X, double* Y);
+
+/* cudaStream_t (as void*) the handle launches on; for CUDA-event timing by the caller. */
+void* blp_stream(blp_handle h);
+
+/* Block until everything queued on the handle's stream has finished (blp_spmv is asynchronous). */
+int blp_stream_sync(blp_handle h);
+
+int blp_destroy(blp_handle h);
+
+const char* blp_last_error(void);
+
+/* library / build identification, e.g. "blp 0.1 sm_100a" */
+const char* blp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLP_H */

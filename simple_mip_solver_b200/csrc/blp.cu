@@ -1,0 +1,859 @@
+// libblp.so — host side of the batched node-LP bound step and its C ABI (include/blp.h).
+//
+// One handle = one GPU + one CUDA stream + the shared LP data (A, A', c, b, scaling, step size).
+// blp_solve_batch runs restarted Halpern PDHG for a whole batch of node LPs:
+//   set-up kernels -> [ period graph: K x (k_primal, k_dual) | evaluation graph: k_tick,
+//   k_eval_cols, k_eval_rows, k_decide, k_apply_restart ] repeated until every node has a
+//   status -> output kernels.  The host only reads one int per period (nodes still running).
+#include "../../include/blp.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "blp_kernels.cuh"
+#include "blp_prep.hpp"
+
+using namespace blp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(BLP_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                        cudaGetErrorString(e_));                                           \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+template <class T>
+cudaError_t upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+struct Plan {
+    int NT, tiles, chunks, rows_per_cta;
+};
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+int pick_nt(int B) {
+    int nt = 1;
+    while (nt < 32 && nt < B) nt <<= 1;
+    return nt;
+}
+
+// Step kernels: many small CTAs in tile-major order, so the CTAs resident at one moment work on
+// one or two node tiles and the gathered vector of those tiles stays in L2 (blp_kernels.cuh).
+Plan plan_rows(int rows, int B, int rows_per_warp, int max_chunks) {
+    Plan p;
+    p.NT = pick_nt(B);
+    p.tiles = (B + p.NT - 1) / p.NT;
+    const int pass = kWarps * (32 / p.NT);
+    int rpc = pass * std::max(rows_per_warp, 1);
+    if (max_chunks > 0) {
+        const int need = (rows + max_chunks - 1) / max_chunks;
+        rpc = std::max(rpc, ((need + pass - 1) / pass) * pass);
+    }
+    p.rows_per_cta = rpc;
+    p.chunks = std::max(1, (rows + rpc - 1) / rpc);
+    return p;
+}
+
+constexpr int kEvalChunks = 48;
+
+struct GraphKey {
+    DevProb P;
+    DevState S;
+    DecideArgs D;
+    int K, rpw;
+};
+
+}  // namespace
+
+struct blp_handle_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int m_base = 0, n = 0;
+    HostCsr A0;                        // unscaled rows (base + appended cuts)
+    std::vector<double> c0, b0;
+    std::vector<double> dr, dc;
+    // device copies
+    DevBuf rowptr, colidx, val, cptr, ridx, cval, c, b, rowscale, colscale, d_dr, d_dc;
+    DevBuf uval, ucval;                // unscaled values, same patterns (blp_spmv)
+    DevProb P{};
+    // staging of the host-buffer entry points
+    DevBuf s_lb, s_ub, s_x0, s_y0, s_mask, s_x, s_y, s_tmp, s_ws, s_node, s_int, s_delta, s_par;
+    int32_t* h_counters = nullptr;     // pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> prof_ev;
+    // cached period graphs
+    bool graph_valid = false;
+    GraphKey gkey{};
+    cudaGraphExec_t g_steps = nullptr, g_eval = nullptr;
+
+    void drop_graphs() {
+        if (g_steps) cudaGraphExecDestroy(g_steps);
+        if (g_eval) cudaGraphExecDestroy(g_eval);
+        g_steps = g_eval = nullptr;
+        graph_valid = false;
+    }
+};
+
+namespace {
+
+// (re)build scaling, transpose, step size and the device copies of the shared LP data
+int prepare(blp_handle h) {
+    const int m = h->A0.rows, n = h->n;
+    HostCsr As = h->A0;
+    h->dr.assign(m, 1.0);
+    h->dc.assign(n, 1.0);
+    ruiz_pc(As, h->dr, h->dc, 10, 0);
+    std::vector<double> bs(m), cs(n), rowscale(m), colscale(n);
+    for (int i = 0; i < m; ++i) bs[i] = h->b0[i] * h->dr[i];
+    for (int j = 0; j < n; ++j) cs[j] = h->c0[j] * h->dc[j];
+    const double sb = 1.0 / (norm2(bs) + 1.0), sc = 1.0 / (norm2(cs) + 1.0);
+    double cinf = 0.0;
+    for (int i = 0; i < m; ++i) bs[i] *= sb;
+    for (int j = 0; j < n; ++j) {
+        cs[j] *= sc;
+        cinf = std::max(cinf, std::fabs(cs[j]));
+    }
+    for (int i = 0; i < m; ++i) rowscale[i] = 1.0 / (h->dr[i] * sb);
+    for (int j = 0; j < n; ++j) colscale[j] = 1.0 / (h->dc[j] * sc);
+    HostCsr At = transpose(As);
+    HostCsr A0t = transpose(h->A0);
+    const double eta = 0.998 / sigma_max(As, At);
+    const double nb = norm2(bs), nc = norm2(cs);
+
+    cudaStream_t s = h->stream;
+    CK(upload(h->rowptr, As.ptr, s));
+    CK(upload(h->colidx, As.idx, s));
+    CK(upload(h->val, As.val, s));
+    CK(upload(h->cptr, At.ptr, s));
+    CK(upload(h->ridx, At.idx, s));
+    CK(upload(h->cval, At.val, s));
+    CK(upload(h->uval, h->A0.val, s));
+    CK(upload(h->ucval, A0t.val, s));
+    CK(upload(h->c, cs, s));
+    CK(upload(h->b, bs, s));
+    CK(upload(h->rowscale, rowscale, s));
+    CK(upload(h->colscale, colscale, s));
+    CK(upload(h->d_dr, h->dr, s));
+    CK(upload(h->d_dc, h->dc, s));
+    CK(cudaStreamSynchronize(s));      // host vectors go out of scope
+
+    DevProb& P = h->P;
+    P.m = m;
+    P.m_base = h->m_base;
+    P.n = n;
+    P.rowptr = h->rowptr.as<int32_t>();
+    P.colidx = h->colidx.as<int32_t>();
+    P.val = h->val.as<double>();
+    P.cptr = h->cptr.as<int32_t>();
+    P.ridx = h->ridx.as<int32_t>();
+    P.cval = h->cval.as<double>();
+    P.c = h->c.as<double>();
+    P.b = h->b.as<double>();
+    P.rowscale = h->rowscale.as<double>();
+    P.colscale = h->colscale.as<double>();
+    P.dr = h->d_dr.as<double>();
+    P.dc = h->d_dc.as<double>();
+    P.eta = eta;
+    P.sb = sb;
+    P.sc = sc;
+    P.objscale = 1.0 / (sb * sc);
+    P.bnorm0 = norm2(h->b0);
+    P.cnorm0 = norm2(h->c0);
+    P.cinf_s = cinf;
+    P.omega0 = (nb > 1e-12 && nc > 1e-12) ? nc / nb : 1.0;
+    h->drop_graphs();
+    return BLP_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carve {
+    char* base;
+    size_t off = 0;
+    template <class T> T* take(size_t count) {
+        off = align_up(off, 256);
+        T* p = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
+    const int ld = blp_ld(B);
+    const size_t n = h->n, m = h->A0.rows;
+    Carve cv{reinterpret_cast<char*>(ws)};
+    DevState s{};
+    s.B = B;
+    s.ld = ld;
+    s.xbar = cv.take<double>(n * ld);
+    s.xa = cv.take<double>(n * ld);
+    s.l = cv.take<double>(n * ld);
+    s.u = cv.take<double>(n * ld);
+    s.X1 = cv.take<double>(n * ld);
+    s.DX = cv.take<double>(n * ld);
+    s.G = cv.take<double>(n * ld);
+    s.y = cv.take<double>(m * ld);
+    s.ya = cv.take<double>(m * ld);
+    s.Y1 = cv.take<double>(m * ld);
+    s.DY = cv.take<double>(m * ld);
+    s.omega = cv.take<double>(ld);
+    s.fpe0 = cv.take<double>(ld);
+    s.fpe_prev = cv.take<double>(ld);
+    s.pobj = cv.take<double>(ld);
+    s.dobj = cv.take<double>(ld);
+    s.sbase = cv.take<int32_t>(ld);
+    s.fin = cv.take<int32_t>(ld);
+    s.status = cv.take<int32_t>(ld);
+    s.iters = cv.take<int32_t>(ld);
+    s.restart = cv.take<int32_t>(ld);
+    s.partC = cv.take<double>((size_t)kEvalChunks * C_N * ld);
+    s.partR = cv.take<double>((size_t)kEvalChunks * R_N * ld);
+    s.counters = cv.take<int32_t>(8);
+    if (S) *S = s;
+    return align_up(cv.off, 256);
+}
+
+template <int NT>
+void launch_steps_nt(const DevProb& P, const DevState& S, const Plan& pc, const Plan& pr, int it,
+                     bool major, cudaStream_t st, int which) {
+    const dim3 gc(pc.chunks, pc.tiles), gr(pr.chunks, pr.tiles);
+    if (which != 1) {
+        if (major) k_primal<NT, true><<<gc, kCtaThreads, 0, st>>>(P, S, it, pc.rows_per_cta);
+        else k_primal<NT, false><<<gc, kCtaThreads, 0, st>>>(P, S, it, pc.rows_per_cta);
+    }
+    if (which != 0) {
+        if (major) k_dual<NT, true><<<gr, kCtaThreads, 0, st>>>(P, S, it, pr.rows_per_cta);
+        else k_dual<NT, false><<<gr, kCtaThreads, 0, st>>>(P, S, it, pr.rows_per_cta);
+    }
+}
+
+// which: 0 primal only, 1 dual only, 2 both
+void launch_steps(const DevProb& P, const DevState& S, const Plan& pc, const Plan& pr, int it,
+                  bool major, cudaStream_t st, int which = 2) {
+    switch (pc.NT) {
+        case 1: launch_steps_nt<1>(P, S, pc, pr, it, major, st, which); break;
+        case 2: launch_steps_nt<2>(P, S, pc, pr, it, major, st, which); break;
+        case 4: launch_steps_nt<4>(P, S, pc, pr, it, major, st, which); break;
+        case 8: launch_steps_nt<8>(P, S, pc, pr, it, major, st, which); break;
+        case 16: launch_steps_nt<16>(P, S, pc, pr, it, major, st, which); break;
+        default: launch_steps_nt<32>(P, S, pc, pr, it, major, st, which); break;
+    }
+}
+
+template <int NT>
+void launch_eval_nt(const DevProb& P, const DevState& S, const Plan& ec, const Plan& er,
+                    cudaStream_t st) {
+    k_eval_cols<NT><<<dim3(ec.chunks, ec.tiles), kCtaThreads, 0, st>>>(P, S, ec.rows_per_cta);
+    k_eval_rows<NT><<<dim3(er.chunks, er.tiles), kCtaThreads, 0, st>>>(P, S, er.rows_per_cta);
+}
+
+void launch_eval(const DevProb& P, const DevState& S, const Plan& ec, const Plan& er,
+                 const DecideArgs& D, int K, cudaStream_t st) {
+    k_tick<<<1, 1, 0, st>>>(S, K);
+    switch (ec.NT) {
+        case 1: launch_eval_nt<1>(P, S, ec, er, st); break;
+        case 2: launch_eval_nt<2>(P, S, ec, er, st); break;
+        case 4: launch_eval_nt<4>(P, S, ec, er, st); break;
+        case 8: launch_eval_nt<8>(P, S, ec, er, st); break;
+        case 16: launch_eval_nt<16>(P, S, ec, er, st); break;
+        default: launch_eval_nt<32>(P, S, ec, er, st); break;
+    }
+    k_decide<<<(S.B + 127) / 128, 128, 0, st>>>(P, S, D);
+    const int rchunks = std::min(64, std::max(1, (std::max(P.n, P.m) + 63) / 64));
+    k_apply_restart<<<dim3(rchunks, (S.ld + 31) / 32), kCtaThreads, 0, st>>>(P, S);
+}
+
+void launch_check_rows(const DevProb& P, const DevState& S, const Plan& er, cudaStream_t st) {
+    const dim3 g(er.chunks, er.tiles);
+    switch (er.NT) {
+        case 1: k_check_rows<1><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
+        case 2: k_check_rows<2><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
+        case 4: k_check_rows<4><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
+        case 8: k_check_rows<8><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
+        case 16: k_check_rows<16><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
+        default: k_check_rows<32><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
+    }
+}
+
+int elementwise_grid(size_t total) {
+    size_t g = (total + kCtaThreads - 1) / kCtaThreads;
+    return (int)std::min<size_t>(std::max<size_t>(g, 1), 148 * 16);
+}
+
+int check_opts(const blp_opts* in, blp_opts* o) {
+    blp_default_opts(o);
+    if (in) *o = *in;
+    if (!(o->eps_rel > 0.0) || !(o->eps_infeas > 0.0) || o->max_iters < 1 || o->eval_every < 1)
+        return fail(BLP_ERR_ARG, "blp_opts: eps_rel/eps_infeas must be > 0, max_iters/eval_every >= 1");
+    return BLP_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+void blp_default_opts(blp_opts* o) {
+    if (!o) return;
+    o->eps_rel = 1e-8;
+    o->eps_infeas = 1e-9;
+    o->max_iters = 400000;
+    o->eval_every = 64;
+    o->use_graph = 1;
+    o->compact = 1;
+    o->verbose = 0;
+    o->profile = 0;
+}
+
+int blp_ld(int B) { return B <= 0 ? 0 : (B + 31) / 32 * 32; }
+
+const char* blp_last_error(void) { return g_err.c_str(); }
+
+const char* blp_version(void) { return "blp 0.1 sm_100a"; }
+
+int blp_create(int device, int m, int n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
+               const double* val, const double* c, const double* row_lb, blp_handle* out) {
+    if (!out) return fail(BLP_ERR_ARG, "blp_create: out is NULL");
+    *out = nullptr;
+    if (m < 1 || n < 1 || nnz < 0 || !rowptr || !c || !row_lb || (nnz > 0 && (!colidx || !val)))
+        return fail(BLP_ERR_ARG, "blp_create: need m >= 1, n >= 1, nnz >= 0 and non-NULL arrays");
+    if (rowptr[0] != 0 || rowptr[m] != nnz)
+        return fail(BLP_ERR_ARG, "blp_create: rowptr[0] must be 0 and rowptr[m] must equal nnz");
+    for (int i = 0; i < m; ++i) {
+        if (rowptr[i + 1] < rowptr[i]) return fail(BLP_ERR_ARG, "blp_create: rowptr not monotone at row %d", i);
+        if (!(std::fabs(row_lb[i]) < 1e30))
+            return fail(BLP_ERR_ARG, "blp_create: row_lb[%d] is not finite (rows are 'a.x >= b')", i);
+    }
+    for (int64_t p = 0; p < nnz; ++p)
+        if (colidx[p] < 0 || colidx[p] >= n || !std::isfinite(val[p]))
+            return fail(BLP_ERR_ARG, "blp_create: entry %lld has column %d / non-finite value", (long long)p, colidx[p]);
+    for (int j = 0; j < n; ++j)
+        if (!std::isfinite(c[j])) return fail(BLP_ERR_ARG, "blp_create: c[%d] is not finite", j);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev)
+        return fail(BLP_ERR_ARG, "blp_create: device %d out of range (%d visible)", device, ndev);
+    CK(cudaSetDevice(device));
+    blp_handle h = new (std::nothrow) blp_handle_s;
+    if (!h) return fail(BLP_ERR_NOMEM, "blp_create: out of host memory");
+    h->device = device;
+    h->m_base = m;
+    h->n = n;
+    h->A0.rows = m;
+    h->A0.cols = n;
+    h->A0.ptr.assign(rowptr, rowptr + m + 1);
+    h->A0.idx.assign(colidx, colidx + nnz);
+    h->A0.val.assign(val, val + nnz);
+    h->c0.assign(c, c + n);
+    h->b0.assign(row_lb, row_lb + m);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_counters, 8 * sizeof(int32_t));
+    for (int q = 0; q < 4 && e == cudaSuccess; ++q) e = cudaEventCreate(&h->ev[q]);
+    if (e != cudaSuccess) {
+        blp_destroy(h);
+        return fail(BLP_ERR_CUDA, "blp_create: %s", cudaGetErrorString(e));
+    }
+    int rc = prepare(h);
+    if (rc != BLP_OK) {
+        blp_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return BLP_OK;
+}
+
+int blp_append_rows(blp_handle h, int k, const int32_t* rowptr, const int32_t* colidx,
+                    const double* val, const double* rhs, int* first_row_id) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_append_rows: NULL handle");
+    if (k < 1 || !rowptr || !rhs) return fail(BLP_ERR_ARG, "blp_append_rows: need k >= 1 rows");
+    if (rowptr[0] != 0) return fail(BLP_ERR_ARG, "blp_append_rows: rowptr[0] must be 0");
+    const int64_t nnz = rowptr[k];
+    for (int i = 0; i < k; ++i) {
+        if (rowptr[i + 1] < rowptr[i]) return fail(BLP_ERR_ARG, "blp_append_rows: rowptr not monotone");
+        if (!(std::fabs(rhs[i]) < 1e30)) return fail(BLP_ERR_ARG, "blp_append_rows: rhs[%d] not finite", i);
+    }
+    for (int64_t p = 0; p < nnz; ++p)
+        if (colidx[p] < 0 || colidx[p] >= h->n || !std::isfinite(val[p]))
+            return fail(BLP_ERR_ARG, "blp_append_rows: bad entry %lld", (long long)p);
+    CK(cudaSetDevice(h->device));
+    const int first = h->A0.rows;
+    const int32_t base = h->A0.ptr.back();
+    for (int i = 0; i < k; ++i) h->A0.ptr.push_back(base + rowptr[i + 1]);
+    h->A0.idx.insert(h->A0.idx.end(), colidx, colidx + nnz);
+    h->A0.val.insert(h->A0.val.end(), val, val + nnz);
+    h->b0.insert(h->b0.end(), rhs, rhs + k);
+    h->A0.rows += k;
+    if (first_row_id) *first_row_id = first;
+    return prepare(h);
+}
+
+int blp_truncate_rows(blp_handle h, int m_keep) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_truncate_rows: NULL handle");
+    if (m_keep < h->m_base || m_keep > h->A0.rows)
+        return fail(BLP_ERR_ARG, "blp_truncate_rows: m_keep %d outside [%d, %d]", m_keep, h->m_base, h->A0.rows);
+    if (m_keep == h->A0.rows) return BLP_OK;
+    CK(cudaSetDevice(h->device));
+    h->A0.rows = m_keep;
+    h->A0.ptr.resize(m_keep + 1);
+    h->A0.idx.resize(h->A0.ptr.back());
+    h->A0.val.resize(h->A0.ptr.back());
+    h->b0.resize(m_keep);
+    return prepare(h);
+}
+
+int blp_num_rows(blp_handle h) { return h ? h->A0.rows : 0; }
+int blp_num_base_rows(blp_handle h) { return h ? h->m_base : 0; }
+int blp_num_cols(blp_handle h) { return h ? h->n : 0; }
+void* blp_stream(blp_handle h) { return h ? (void*)h->stream : nullptr; }
+
+size_t blp_workspace_bytes(blp_handle h, int B) {
+    if (!h || B < 1) return 0;
+    return carve_state(h, B, nullptr, nullptr) + 256;
+}
+
+int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
+                    const uint8_t* row_mask, const double* x0, const double* y0,
+                    const int32_t* int_idx, int n_int, const blp_opts* opts_in,
+                    void* workspace, size_t workspace_bytes,
+                    double* obj, double* lower_bound, int32_t* status, int32_t* iters,
+                    double* x, double* y, int32_t* frac_idx, blp_stats* stats) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_solve_batch: NULL handle");
+    if (B < 1 || !lb || !ub) return fail(BLP_ERR_ARG, "blp_solve_batch: need B >= 1 and lb/ub");
+    if (!workspace || workspace_bytes < blp_workspace_bytes(h, B))
+        return fail(BLP_ERR_NOMEM, "blp_solve_batch: workspace of %zu bytes, need %zu", workspace_bytes,
+                    blp_workspace_bytes(h, B));
+    if (frac_idx && int_idx == nullptr && n_int > 0)
+        return fail(BLP_ERR_ARG, "blp_solve_batch: n_int > 0 with int_idx NULL");
+    blp_opts o;
+    int rc = check_opts(opts_in, &o);
+    if (rc != BLP_OK) return rc;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const DevProb& P = h->P;
+
+    void* ws = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+    DevState S;
+    carve_state(h, B, ws, &S);
+    S.rowmask = (P.m > P.m_base) ? row_mask : nullptr;
+
+    const int K = std::min(o.eval_every, o.max_iters);
+    const int rpw = env_int("BLP_ROWS_PER_WARP", 4);
+    const Plan pc = plan_rows(P.n, B, rpw, 0), pr = plan_rows(P.m, B, rpw, 0);
+    const Plan ec = plan_rows(P.n, B, 1, kEvalChunks), er = plan_rows(P.m, B, 1, kEvalChunks);
+    DecideArgs D{ec.chunks, er.chunks, K, o.max_iters, o.eps_rel, o.eps_infeas};
+    int launches = 0;
+
+    CK(cudaEventRecord(h->ev[0], st));
+    CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(int32_t), st));
+    k_init_nodes<<<(S.ld + 127) / 128, 128, 0, st>>>(P, S);
+    k_init_cols<<<elementwise_grid((size_t)P.n * S.ld), kCtaThreads, 0, st>>>(P, S, lb, ub, x0);
+    k_init_rows<<<elementwise_grid((size_t)P.m * S.ld), kCtaThreads, 0, st>>>(P, S, y0);
+    launch_check_rows(P, S, er, st);
+    k_count_active<<<(B + 127) / 128, 128, 0, st>>>(S);
+    launches += 5;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_counters, S.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int active = h->h_counters[0];
+
+    // ---- period graphs (cached on the exact parameter set) ----
+    const bool profile = o.profile == 1;
+    const bool use_graph = o.use_graph && !profile;
+    if (use_graph && active > 0) {
+        GraphKey key;
+        memset(&key, 0, sizeof key);
+        key.P = P;
+        key.S = S;
+        key.D = D;
+        key.K = K;
+        key.rpw = rpw;
+        if (!h->graph_valid || memcmp(&key, &h->gkey, sizeof key) != 0) {
+            h->drop_graphs();
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, st);
+            CK(cudaStreamEndCapture(st, &g));
+            cudaError_t e = cudaGraphInstantiate(&h->g_steps, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(BLP_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            launch_eval(P, S, ec, er, D, K, st);
+            CK(cudaStreamEndCapture(st, &g));
+            e = cudaGraphInstantiate(&h->g_eval, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(BLP_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+            h->gkey = key;
+            h->graph_valid = true;
+        }
+    }
+    if (profile && (int)h->prof_ev.size() < 2 * K + 1) {
+        while ((int)h->prof_ev.size() < 2 * K + 1) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->prof_ev.push_back(e);
+        }
+    }
+
+    int total = 0, evals = 0;
+    double step_ms = 0.0, primal_ms = 0.0, dual_ms = 0.0, node_iters = 0.0;
+    while (active > 0 && total < o.max_iters) {
+        CK(cudaEventRecord(h->ev[2], st));
+        if (use_graph) {
+            CK(cudaGraphLaunch(h->g_steps, st));
+        } else if (profile) {
+            CK(cudaEventRecord(h->prof_ev[0], st));
+            for (int it = 0; it < K; ++it) {
+                launch_steps(P, S, pc, pr, it, it == K - 1, st, 0);
+                CK(cudaEventRecord(h->prof_ev[2 * it + 1], st));
+                launch_steps(P, S, pc, pr, it, it == K - 1, st, 1);
+                CK(cudaEventRecord(h->prof_ev[2 * it + 2], st));
+            }
+        } else {
+            for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, st);
+        }
+        CK(cudaEventRecord(h->ev[3], st));
+        if (use_graph) {
+            CK(cudaGraphLaunch(h->g_eval, st));
+        } else {
+            launch_eval(P, S, ec, er, D, K, st);
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_counters, S.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+        step_ms += ms;
+        if (profile)
+            for (int it = 0; it < K; ++it) {
+                CK(cudaEventElapsedTime(&ms, h->prof_ev[2 * it], h->prof_ev[2 * it + 1]));
+                primal_ms += ms;
+                CK(cudaEventElapsedTime(&ms, h->prof_ev[2 * it + 1], h->prof_ev[2 * it + 2]));
+                dual_ms += ms;
+            }
+        node_iters += (double)active * K;
+        total += K;
+        evals += 1;
+        launches += 2 * K + 5;
+        active = h->h_counters[0];
+        if (o.verbose)
+            fprintf(stderr, "[blp] iters %d  running %d  restarting %d\n", total, active, h->h_counters[1]);
+    }
+
+    // ---- outputs ----
+    if (x) {
+        k_out_vec<<<elementwise_grid((size_t)P.n * S.ld), kCtaThreads, 0, st>>>(
+            S.X1, P.dc, 1.0 / P.sb, P.n, S.ld, B, x);
+        ++launches;
+    }
+    if (y) {
+        k_out_vec<<<elementwise_grid((size_t)P.m * S.ld), kCtaThreads, 0, st>>>(
+            S.Y1, P.dr, 1.0 / P.sc, P.m, S.ld, B, y);
+        ++launches;
+    }
+    k_out_nodes<<<(S.ld + 127) / 128, 128, 0, st>>>(P, S, int_idx, int_idx ? n_int : 0, 1e-4, obj,
+                                                   lower_bound, status, iters, frac_idx);
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        stats->iterations = total;
+        stats->evaluations = evals;
+        stats->kernel_launches = launches;
+        stats->compactions = 0;
+        stats->step_kernel_ms = step_ms;
+        stats->total_ms = ms;
+        stats->node_iterations = node_iters;
+        stats->primal_kernel_ms = primal_ms;
+        stats->dual_kernel_ms = dual_ms;
+    }
+    return BLP_OK;
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------------
+namespace {
+
+int stage_in(blp_handle h, DevBuf& dst, const double* src, int B, int rows, int ld) {
+    cudaStream_t st = h->stream;
+    CK(dst.ensure((size_t)rows * ld * sizeof(double)));
+    CK(h->s_tmp.ensure((size_t)rows * B * sizeof(double)));
+    CK(cudaMemcpyAsync(h->s_tmp.p, src, (size_t)rows * B * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_transpose_in<<<dim3((rows + 31) / 32, (ld + 31) / 32), dim3(32, 8), 0, st>>>(
+        h->s_tmp.as<double>(), B, rows, ld, dst.as<double>());
+    CK(cudaGetLastError());
+    // s_tmp is reused by the next stage_in on the same stream: ordering is by the stream
+    return BLP_OK;
+}
+
+int stage_out(blp_handle h, const DevBuf& src, double* dst, int B, int rows, int ld) {
+    cudaStream_t st = h->stream;
+    CK(h->s_tmp.ensure((size_t)rows * B * sizeof(double)));
+    k_transpose_out<<<dim3((rows + 31) / 32, (ld + 31) / 32), dim3(32, 8), 0, st>>>(
+        src.as<double>(), B, rows, ld, h->s_tmp.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, h->s_tmp.p, (size_t)rows * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return BLP_OK;
+}
+
+struct NodeOut {
+    double *obj, *lower;
+    int32_t *status, *iters, *frac;
+};
+
+NodeOut node_out(blp_handle h, int ld) {
+    char* p = h->s_node.as<char>();
+    NodeOut o;
+    o.obj = reinterpret_cast<double*>(p);
+    o.lower = o.obj + ld;
+    o.status = reinterpret_cast<int32_t*>(o.lower + ld);
+    o.iters = o.status + ld;
+    o.frac = o.iters + ld;
+    return o;
+}
+
+int finish_host(blp_handle h, int B, int ld, const NodeOut& no, bool want_x, bool want_y,
+                double* obj, double* lower_bound, int32_t* status, int32_t* iters, double* x,
+                double* y, int32_t* frac_idx) {
+    cudaStream_t st = h->stream;
+    if (want_x) { int rc = stage_out(h, h->s_x, x, B, h->n, ld); if (rc) return rc; }
+    if (want_y) { int rc = stage_out(h, h->s_y, y, B, h->A0.rows, ld); if (rc) return rc; }
+    if (obj) CK(cudaMemcpyAsync(obj, no.obj, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (lower_bound) CK(cudaMemcpyAsync(lower_bound, no.lower, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, no.status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (iters) CK(cudaMemcpyAsync(iters, no.iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (frac_idx) CK(cudaMemcpyAsync(frac_idx, no.frac, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BLP_OK;
+}
+
+int stage_common(blp_handle h, int B, int ld, const uint8_t* row_mask, const int32_t* int_idx,
+                 int n_int, bool want_x, bool want_y, const uint8_t** d_mask,
+                 const int32_t** d_int) {
+    cudaStream_t st = h->stream;
+    const int m = h->A0.rows, n = h->n, mc = m - h->m_base;
+    *d_mask = nullptr;
+    *d_int = nullptr;
+    if (row_mask && mc > 0) {
+        CK(h->s_mask.ensure((size_t)mc * ld + (size_t)mc * B));
+        uint8_t* raw = h->s_mask.as<uint8_t>() + (size_t)mc * ld;
+        CK(cudaMemcpyAsync(raw, row_mask, (size_t)mc * B, cudaMemcpyHostToDevice, st));
+        k_transpose_in_u8<<<elementwise_grid((size_t)mc * ld), kCtaThreads, 0, st>>>(
+            raw, B, mc, ld, h->s_mask.as<uint8_t>());
+        *d_mask = h->s_mask.as<uint8_t>();
+    }
+    if (int_idx && n_int > 0) {
+        CK(h->s_int.ensure((size_t)n_int * sizeof(int32_t)));
+        CK(cudaMemcpyAsync(h->s_int.p, int_idx, (size_t)n_int * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        *d_int = h->s_int.as<int32_t>();
+    }
+    if (want_x) CK(h->s_x.ensure((size_t)n * ld * sizeof(double)));
+    if (want_y) CK(h->s_y.ensure((size_t)m * ld * sizeof(double)));
+    CK(h->s_node.ensure((size_t)ld * (2 * sizeof(double) + 3 * sizeof(int32_t))));
+    CK(h->s_ws.ensure(blp_workspace_bytes(h, B)));
+    CK(cudaGetLastError());
+    return BLP_OK;
+}
+
+}  // namespace
+
+int blp_solve_batch_host(blp_handle h, int B, const double* lb, const double* ub,
+                         const uint8_t* row_mask, const double* x0, const double* y0,
+                         const int32_t* int_idx, int n_int, const blp_opts* opts,
+                         double* obj, double* lower_bound, int32_t* status, int32_t* iters,
+                         double* x, double* y, int32_t* frac_idx, blp_stats* stats) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_solve_batch_host: NULL handle");
+    if (B < 1 || !lb || !ub) return fail(BLP_ERR_ARG, "blp_solve_batch_host: need B >= 1 and lb/ub");
+    CK(cudaSetDevice(h->device));
+    const int ld = blp_ld(B), n = h->n, m = h->A0.rows;
+    int rc;
+    if ((rc = stage_in(h, h->s_lb, lb, B, n, ld))) return rc;
+    if ((rc = stage_in(h, h->s_ub, ub, B, n, ld))) return rc;
+    if (x0 && (rc = stage_in(h, h->s_x0, x0, B, n, ld))) return rc;
+    if (y0 && (rc = stage_in(h, h->s_y0, y0, B, m, ld))) return rc;
+    const uint8_t* d_mask;
+    const int32_t* d_int;
+    if ((rc = stage_common(h, B, ld, row_mask, int_idx, n_int, x != nullptr, y != nullptr, &d_mask, &d_int)))
+        return rc;
+    NodeOut no = node_out(h, ld);
+    rc = blp_solve_batch(h, B, h->s_lb.as<double>(), h->s_ub.as<double>(), d_mask,
+                         x0 ? h->s_x0.as<double>() : nullptr, y0 ? h->s_y0.as<double>() : nullptr,
+                         d_int, n_int, opts, h->s_ws.p, h->s_ws.cap, no.obj, no.lower, no.status,
+                         no.iters, x ? h->s_x.as<double>() : nullptr,
+                         y ? h->s_y.as<double>() : nullptr, no.frac, stats);
+    if (rc) return rc;
+    return finish_host(h, B, ld, no, x != nullptr, y != nullptr, obj, lower_bound, status, iters, x, y, frac_idx);
+}
+
+int blp_solve_children_host(blp_handle h, int B, const double* parent_lb, const double* parent_ub,
+                            const int32_t* delta_ptr, const int32_t* delta_var,
+                            const double* delta_lb, const double* delta_ub,
+                            const uint8_t* row_mask, const double* x0, const double* y0,
+                            const int32_t* int_idx, int n_int, const blp_opts* opts,
+                            double* obj, double* lower_bound, int32_t* status, int32_t* iters,
+                            double* x, double* y, int32_t* frac_idx, blp_stats* stats) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_solve_children_host: NULL handle");
+    if (B < 1 || !parent_lb || !parent_ub || !delta_ptr)
+        return fail(BLP_ERR_ARG, "blp_solve_children_host: need B >= 1, parent bounds and delta_ptr");
+    const int nd = delta_ptr[B];
+    if (delta_ptr[0] != 0 || nd < 0 || (nd > 0 && (!delta_var || !delta_lb || !delta_ub)))
+        return fail(BLP_ERR_ARG, "blp_solve_children_host: bad delta arrays");
+    for (int k = 0; k < B; ++k)
+        if (delta_ptr[k + 1] < delta_ptr[k]) return fail(BLP_ERR_ARG, "blp_solve_children_host: delta_ptr not monotone");
+    for (int p = 0; p < nd; ++p)
+        if (delta_var[p] < 0 || delta_var[p] >= h->n)
+            return fail(BLP_ERR_ARG, "blp_solve_children_host: delta_var[%d] = %d out of range", p, delta_var[p]);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int ld = blp_ld(B), n = h->n, m = h->A0.rows;
+    // parent vectors: [lb | ub | x0 | y0]
+    CK(h->s_par.ensure((size_t)(3 * n + m) * sizeof(double)));
+    double* par = h->s_par.as<double>();
+    CK(cudaMemcpyAsync(par, parent_lb, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(par + n, parent_ub, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (x0) CK(cudaMemcpyAsync(par + 2 * n, x0, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (y0) CK(cudaMemcpyAsync(par + 3 * n, y0, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(h->s_lb.ensure((size_t)n * ld * sizeof(double)));
+    CK(h->s_ub.ensure((size_t)n * ld * sizeof(double)));
+    const int gcol = elementwise_grid((size_t)n * ld), grow = elementwise_grid((size_t)m * ld);
+    k_broadcast_rows<<<gcol, kCtaThreads, 0, st>>>(par, n, ld, h->s_lb.as<double>());
+    k_broadcast_rows<<<gcol, kCtaThreads, 0, st>>>(par + n, n, ld, h->s_ub.as<double>());
+    if (x0) {
+        CK(h->s_x0.ensure((size_t)n * ld * sizeof(double)));
+        k_broadcast_rows<<<gcol, kCtaThreads, 0, st>>>(par + 2 * n, n, ld, h->s_x0.as<double>());
+    }
+    if (y0) {
+        CK(h->s_y0.ensure((size_t)m * ld * sizeof(double)));
+        k_broadcast_rows<<<grow, kCtaThreads, 0, st>>>(par + 3 * n, m, ld, h->s_y0.as<double>());
+    }
+    if (nd > 0) {
+        const size_t ip = align_up((size_t)(B + 1) * sizeof(int32_t), 8);
+        const size_t iv = align_up((size_t)nd * sizeof(int32_t), 8);
+        CK(h->s_delta.ensure(ip + iv + 2 * (size_t)nd * sizeof(double)));
+        char* d = h->s_delta.as<char>();
+        CK(cudaMemcpyAsync(d, delta_ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + ip, delta_var, nd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + ip + iv, delta_lb, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + ip + iv + nd * sizeof(double), delta_ub, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_patch_bounds<<<(B + 127) / 128, 128, 0, st>>>(
+            B, ld, reinterpret_cast<int32_t*>(d), reinterpret_cast<int32_t*>(d + ip),
+            reinterpret_cast<double*>(d + ip + iv),
+            reinterpret_cast<double*>(d + ip + iv + nd * sizeof(double)), h->s_lb.as<double>(),
+            h->s_ub.as<double>());
+    }
+    CK(cudaGetLastError());
+    const uint8_t* d_mask;
+    const int32_t* d_int;
+    int rc;
+    if ((rc = stage_common(h, B, ld, row_mask, int_idx, n_int, x != nullptr, y != nullptr, &d_mask, &d_int)))
+        return rc;
+    NodeOut no = node_out(h, ld);
+    rc = blp_solve_batch(h, B, h->s_lb.as<double>(), h->s_ub.as<double>(), d_mask,
+                         x0 ? h->s_x0.as<double>() : nullptr, y0 ? h->s_y0.as<double>() : nullptr,
+                         d_int, n_int, opts, h->s_ws.p, h->s_ws.cap, no.obj, no.lower, no.status,
+                         no.iters, x ? h->s_x.as<double>() : nullptr,
+                         y ? h->s_y.as<double>() : nullptr, no.frac, stats);
+    if (rc) return rc;
+    return finish_host(h, B, ld, no, x != nullptr, y != nullptr, obj, lower_bound, status, iters, x, y, frac_idx);
+}
+
+int blp_spmv(blp_handle h, int B, int transpose, const double* X, double* Y) {
+    if (!h || B < 1 || !X || !Y) return fail(BLP_ERR_ARG, "blp_spmv: bad arguments");
+    CK(cudaSetDevice(h->device));
+    const int ld = blp_ld(B);
+    const int rows = transpose ? h->n : h->A0.rows;
+    const int32_t* ptr = transpose ? h->P.cptr : h->P.rowptr;
+    const int32_t* idx = transpose ? h->P.ridx : h->P.colidx;
+    const double* val = transpose ? h->ucval.as<double>() : h->uval.as<double>();
+    const Plan p = plan_rows(rows, B, env_int("BLP_ROWS_PER_WARP", 4), 0);
+    const dim3 g(p.chunks, p.tiles);
+    cudaStream_t st = h->stream;
+    switch (p.NT) {
+        case 1: k_spmv<1><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 2: k_spmv<2><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 4: k_spmv<4><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 8: k_spmv<8><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 16: k_spmv<16><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
+        default: k_spmv<32><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
+    }
+    CK(cudaGetLastError());
+    return BLP_OK;
+}
+
+int blp_stream_sync(blp_handle h) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_stream_sync: NULL handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return BLP_OK;
+}
+
+int blp_destroy(blp_handle h) {
+    if (!h) return BLP_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->drop_graphs();
+    DevBuf* bufs[] = {&h->rowptr, &h->colidx, &h->val, &h->cptr, &h->ridx, &h->cval, &h->c, &h->b,
+                      &h->rowscale, &h->colscale, &h->d_dr, &h->d_dc, &h->uval, &h->ucval, &h->s_lb,
+                      &h->s_ub, &h->s_x0, &h->s_y0, &h->s_mask, &h->s_x, &h->s_y, &h->s_tmp,
+                      &h->s_ws, &h->s_node, &h->s_int, &h->s_delta, &h->s_par};
+    for (DevBuf* b : bufs) b->release();
+    for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    if (h->h_counters) cudaFreeHost(h->h_counters);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return BLP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,346 @@
+"""ctypes binding of libblp.so (include/blp.h): the batched node-LP bound step on one B200.
+
+This is the thin layer between the Python branch-and-bound control flow and the CUDA kernels.
+PyTorch is used for device-buffer ownership only. There is no CPU fallback: if the shared
+library is missing or the call fails, an exception is raised.
+
+Replaces, for a whole batch of nodes at once, what the reference does one node at a time through
+CyClpSimplex: ``self.lp.dual()`` and the status/objective/solution reads of
+``BaseNode._bound_lp`` (simple_mip_solver/nodes/base_node.py:259-286) and the per-child
+``n.lp.dual()`` of ``BaseNode._strong_branch`` (base_node.py:629-647).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+
+_LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libblp.so'
+_lib = None
+
+INF = 1e30   # |bound| >= INF means "no bound" on the device side
+
+
+class BlpError(RuntimeError):
+    pass
+
+
+class BlpOpts(C.Structure):
+    _fields_ = [('eps_rel', C.c_double), ('eps_infeas', C.c_double), ('max_iters', C.c_int),
+                ('eval_every', C.c_int), ('use_graph', C.c_int), ('compact', C.c_int),
+                ('verbose', C.c_int), ('profile', C.c_int)]
+
+
+class BlpStats(C.Structure):
+    _fields_ = [('iterations', C.c_int), ('evaluations', C.c_int), ('kernel_launches', C.c_int),
+                ('compactions', C.c_int), ('step_kernel_ms', C.c_double), ('total_ms', C.c_double),
+                ('node_iterations', C.c_double), ('primal_kernel_ms', C.c_double),
+                ('dual_kernel_ms', C.c_double)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    'blp_default_opts': (None, [C.POINTER(BlpOpts)]),
+    'blp_ld': (C.c_int, [C.c_int]),
+    'blp_workspace_bytes': (C.c_size_t, [_P, C.c_int]),
+    'blp_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    'blp_append_rows': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_int)]),
+    'blp_truncate_rows': (C.c_int, [_P, C.c_int]),
+    'blp_num_rows': (C.c_int, [_P]),
+    'blp_num_base_rows': (C.c_int, [_P]),
+    'blp_num_cols': (C.c_int, [_P]),
+    'blp_solve_batch': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.POINTER(BlpOpts),
+                                  _P, C.c_size_t, _P, _P, _P, _P, _P, _P, _P, C.POINTER(BlpStats)]),
+    'blp_solve_batch_host': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int,
+                                       C.POINTER(BlpOpts), _P, _P, _P, _P, _P, _P, _P,
+                                       C.POINTER(BlpStats)]),
+    'blp_solve_children_host': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                          C.c_int, C.POINTER(BlpOpts), _P, _P, _P, _P, _P, _P, _P,
+                                          C.POINTER(BlpStats)]),
+    'blp_spmv': (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    'blp_stream': (_P, [_P]),
+    'blp_stream_sync': (C.c_int, [_P]),
+    'blp_destroy': (C.c_int, [_P]),
+    'blp_last_error': (C.c_char_p, []),
+    'blp_version': (C.c_char_p, []),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load_library():
+    """Load libblp.so. Raises BlpError when it has not been built — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise BlpError(f'{_LIB_PATH} is missing: build it with `python -m simple_mip_solver_b200._build` '
+                       '(nvcc, sm_100a). The bound step has no CPU fallback.')
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise BlpError(f'{what} failed ({rc}): {load_library().blp_last_error().decode()}')
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f'expected array of shape {shape}, got {a.shape}')
+    return a
+
+
+def default_opts(**kw) -> BlpOpts:
+    o = BlpOpts()
+    load_library().blp_default_opts(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise TypeError(f'unknown solver option {k!r}')
+        setattr(o, k, v)
+    return o
+
+
+def leading_dim(B: int) -> int:
+    return (B + 31) // 32 * 32
+
+
+@dataclass
+class BatchResult:
+    """Per-node results of one batched bound call (host arrays)."""
+    objective: np.ndarray         # [B] c.x (inf where infeasible)
+    lower_bound: np.ndarray       # [B] dual objective (a valid lower bound at optimality)
+    status: np.ndarray            # [B] CLP codes: 0 optimal, 1 infeasible, 2 unbounded, 3 iteration limit
+    iterations: np.ndarray        # [B]
+    frac_idx: np.ndarray          # [B] most fractional integer column or -1
+    x: Optional[np.ndarray]       # [B, n]
+    y: Optional[np.ndarray]       # [B, m] row duals (>= 0)
+    stats: dict
+
+
+class BatchLP:
+    """Shared part (A, c, row lower bounds) of all node LPs of one MILP, resident on one GPU.
+
+    Canonical form of the reference (base_node.py:683-710): ``min c.x, A x >= b, l <= x <= u``.
+    """
+
+    def __init__(self, A, b, c, device: int = 0):
+        lib = load_library()
+        A = sp.csr_matrix(A, dtype=np.float64)
+        A.sort_indices()
+        self.m_base, self.n = A.shape
+        self.device = int(device)
+        b = _f64(b, (self.m_base,))
+        c = _f64(c, (self.n,))
+        rowptr = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        colidx = np.ascontiguousarray(A.indices, dtype=np.int32)
+        val = np.ascontiguousarray(A.data, dtype=np.float64)
+        h = _P()
+        _check(lib.blp_create(self.device, self.m_base, self.n, int(A.nnz), _np_ptr(rowptr),
+                              _np_ptr(colidx), _np_ptr(val), _np_ptr(c), _np_ptr(b), C.byref(h)),
+               'blp_create')
+        self._h = h
+        self._lib = lib
+        self._ws = None          # torch tensor owning the device workspace
+
+    # -- bookkeeping ------------------------------------------------------------------------
+    @property
+    def m(self) -> int:
+        return self._lib.blp_num_rows(self._h)
+
+    @property
+    def num_cut_rows(self) -> int:
+        return self.m - self.m_base
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.blp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def append_rows(self, rows, rhs) -> int:
+        """Append cut rows ``rows . x >= rhs`` (lp.addConstraint, base_node.py:459-460).
+        Returns the id of the first new row."""
+        R = sp.csr_matrix(np.atleast_2d(rows) if not sp.issparse(rows) else rows, dtype=np.float64)
+        R.sort_indices()
+        k = R.shape[0]
+        if R.shape[1] != self.n:
+            raise ValueError(f'cut rows have {R.shape[1]} columns, the LP has {self.n}')
+        rhs = _f64(np.atleast_1d(rhs), (k,))
+        first = C.c_int(-1)
+        rowptr = np.ascontiguousarray(R.indptr, dtype=np.int32)
+        colidx = np.ascontiguousarray(R.indices, dtype=np.int32)
+        val = np.ascontiguousarray(R.data, dtype=np.float64)
+        _check(self._lib.blp_append_rows(self._h, k, _np_ptr(rowptr), _np_ptr(colidx), _np_ptr(val),
+                                         _np_ptr(rhs), C.byref(first)), 'blp_append_rows')
+        return first.value
+
+    def truncate_rows(self, m_keep: int):
+        """Drop appended rows with id >= m_keep (lp.removeConstraint, base_node.py:337-338)."""
+        _check(self._lib.blp_truncate_rows(self._h, int(m_keep)), 'blp_truncate_rows')
+
+    # -- host-buffer calls (what the Node classes use) --------------------------------------------
+    def solve_batch(self, lb, ub, row_mask=None, x0=None, y0=None,
+                    integer_indices: Optional[Sequence[int]] = None, opts: Optional[BlpOpts] = None,
+                    want_x: bool = True, want_y: bool = True) -> BatchResult:
+        """Solve B node LPs given per-node bounds ``lb, ub`` of shape [B, n] (host arrays)."""
+        lb = np.ascontiguousarray(np.atleast_2d(lb), dtype=np.float64)
+        B = lb.shape[0]
+        lb = _f64(lb, (B, self.n))
+        ub = _f64(np.atleast_2d(ub), (B, self.n))
+        m, mc = self.m, self.num_cut_rows
+        mask = None
+        if row_mask is not None and mc > 0:
+            mask = np.ascontiguousarray(np.atleast_2d(row_mask), dtype=np.uint8)
+            if mask.shape != (B, mc):
+                raise ValueError(f'row_mask must have shape {(B, mc)}, got {mask.shape}')
+        x0 = None if x0 is None else _f64(np.atleast_2d(x0), (B, self.n))
+        y0 = None if y0 is None else _f64(np.atleast_2d(y0), (B, m))
+        ii = None if integer_indices is None else np.ascontiguousarray(sorted(integer_indices), dtype=np.int32)
+        out = self._alloc_out(B, m, want_x, want_y)
+        st = BlpStats()
+        o = opts if opts is not None else default_opts()
+        _check(self._lib.blp_solve_batch_host(
+            self._h, B, _np_ptr(lb), _np_ptr(ub), _np_ptr(mask), _np_ptr(x0), _np_ptr(y0), _np_ptr(ii),
+            0 if ii is None else len(ii), C.byref(o), _np_ptr(out['obj']), _np_ptr(out['lower']),
+            _np_ptr(out['status']), _np_ptr(out['iters']), _np_ptr(out['x']), _np_ptr(out['y']),
+            _np_ptr(out['frac']), C.byref(st)), 'blp_solve_batch_host')
+        return self._result(out, st)
+
+    def solve_children(self, parent_lb, parent_ub, deltas, row_mask=None, x0=None, y0=None,
+                       integer_indices=None, opts: Optional[BlpOpts] = None, want_x: bool = True,
+                       want_y: bool = True) -> BatchResult:
+        """Solve B children of one parent. ``deltas[k]`` is a list of ``(var, lb, ub)`` bound
+        changes of child k against the parent's bounds (base_node.py:595-600); ``x0, y0`` are the
+        parent's primal / row-dual vectors used as the common warm start."""
+        B = len(deltas)
+        if B < 1:
+            raise ValueError('need at least one child')
+        parent_lb = _f64(parent_lb, (self.n,))
+        parent_ub = _f64(parent_ub, (self.n,))
+        m, mc = self.m, self.num_cut_rows
+        dptr = np.zeros(B + 1, dtype=np.int32)
+        for k, d in enumerate(deltas):
+            dptr[k + 1] = dptr[k] + len(d)
+        flat = [t for d in deltas for t in d]
+        dvar = np.ascontiguousarray([t[0] for t in flat], dtype=np.int32)
+        dlb = np.ascontiguousarray([t[1] for t in flat], dtype=np.float64)
+        dub = np.ascontiguousarray([t[2] for t in flat], dtype=np.float64)
+        mask = None
+        if row_mask is not None and mc > 0:
+            mask = np.ascontiguousarray(np.atleast_2d(row_mask), dtype=np.uint8)
+            if mask.shape != (B, mc):
+                raise ValueError(f'row_mask must have shape {(B, mc)}, got {mask.shape}')
+        x0 = None if x0 is None else _f64(x0, (self.n,))
+        y0 = None if y0 is None else _f64(y0, (m,))
+        ii = None if integer_indices is None else np.ascontiguousarray(sorted(integer_indices), dtype=np.int32)
+        out = self._alloc_out(B, m, want_x, want_y)
+        st = BlpStats()
+        o = opts if opts is not None else default_opts()
+        _check(self._lib.blp_solve_children_host(
+            self._h, B, _np_ptr(parent_lb), _np_ptr(parent_ub), _np_ptr(dptr), _np_ptr(dvar),
+            _np_ptr(dlb), _np_ptr(dub), _np_ptr(mask), _np_ptr(x0), _np_ptr(y0), _np_ptr(ii),
+            0 if ii is None else len(ii), C.byref(o), _np_ptr(out['obj']), _np_ptr(out['lower']),
+            _np_ptr(out['status']), _np_ptr(out['iters']), _np_ptr(out['x']), _np_ptr(out['y']),
+            _np_ptr(out['frac']), C.byref(st)), 'blp_solve_children_host')
+        return self._result(out, st)
+
+    def _alloc_out(self, B, m, want_x, want_y):
+        return dict(obj=np.empty(B), lower=np.empty(B), status=np.empty(B, dtype=np.int32),
+                    iters=np.empty(B, dtype=np.int32), frac=np.empty(B, dtype=np.int32),
+                    x=np.empty((B, self.n)) if want_x else None,
+                    y=np.empty((B, m)) if want_y else None)
+
+    @staticmethod
+    def _result(out, st) -> BatchResult:
+        return BatchResult(objective=out['obj'], lower_bound=out['lower'], status=out['status'],
+                           iterations=out['iters'], frac_idx=out['frac'], x=out['x'], y=out['y'],
+                           stats=st.as_dict())
+
+    # -- device-buffer calls (torch tensors own the memory) --------------------------------------
+    def solve_batch_device(self, lb, ub, row_mask=None, x0=None, y0=None, int_idx=None,
+                           opts: Optional[BlpOpts] = None, want_x=True, want_y=True):
+        """Device-resident form. ``lb, ub``: torch float64 CUDA tensors of shape [n, ld] in the
+        node-fastest layout (ld = leading_dim(B)); ``B`` is taken from ``lb.B`` if present, else
+        from ``ub.shape[1]``. Returns a dict of torch tensors plus 'stats'."""
+        import torch
+        B = int(getattr(lb, 'B', lb.shape[1]))
+        ld = leading_dim(B)
+        m = self.m
+        dev = torch.device('cuda', self.device)
+        for name, t, rows in (('lb', lb, self.n), ('ub', ub, self.n), ('x0', x0, self.n), ('y0', y0, m)):
+            if t is None:
+                continue
+            if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != (rows, ld):
+                raise ValueError(f'{name} must be a contiguous float64 CUDA tensor of shape {(rows, ld)}')
+        need = self._lib.blp_workspace_bytes(self._h, B)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        out = dict(obj=torch.empty(ld, dtype=torch.float64, device=dev),
+                   lower=torch.empty(ld, dtype=torch.float64, device=dev),
+                   status=torch.empty(ld, dtype=torch.int32, device=dev),
+                   iters=torch.empty(ld, dtype=torch.int32, device=dev),
+                   frac=torch.empty(ld, dtype=torch.int32, device=dev),
+                   x=torch.empty((self.n, ld), dtype=torch.float64, device=dev) if want_x else None,
+                   y=torch.empty((m, ld), dtype=torch.float64, device=dev) if want_y else None)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        st = BlpStats()
+        o = opts if opts is not None else default_opts()
+        torch.cuda.current_stream(dev).synchronize()     # inputs were produced on torch's stream
+        _check(self._lib.blp_solve_batch(
+            self._h, B, p(lb), p(ub), p(row_mask), p(x0), p(y0), p(int_idx),
+            0 if int_idx is None else int(int_idx.numel()), C.byref(o), p(self._ws), self._ws.numel(),
+            p(out['obj']), p(out['lower']), p(out['status']), p(out['iters']), p(out['x']), p(out['y']),
+            p(out['frac']), C.byref(st)), 'blp_solve_batch')
+        out['stats'] = st.as_dict()
+        return out
+
+    def spmv_device(self, X, transpose: bool = False, B: Optional[int] = None, out=None):
+        """Y = A X (or A' X) on the unscaled matrix; X: [n or m, ld] float64 CUDA tensor."""
+        import torch
+        B = int(X.shape[1] if B is None else B)
+        ld = leading_dim(B)
+        rows_in = self.m if transpose else self.n
+        rows_out = self.n if transpose else self.m
+        if tuple(X.shape) != (rows_in, ld) or X.dtype != torch.float64 or not X.is_contiguous():
+            raise ValueError(f'X must be contiguous float64 of shape {(rows_in, ld)}')
+        Y = out if out is not None else torch.empty((rows_out, ld), dtype=torch.float64, device=X.device)
+        torch.cuda.current_stream(X.device).synchronize()
+        _check(self._lib.blp_spmv(self._h, B, 1 if transpose else 0, C.c_void_p(X.data_ptr()),
+                                  C.c_void_p(Y.data_ptr())), 'blp_spmv')
+        _check(self._lib.blp_stream_sync(self._h), 'blp_stream_sync')
+        return Y
+
+    def spmv_async(self, X, Y, B: int, transpose: bool = False):
+        """Queue one batched SpMV on the handle's stream without synchronising (benchmarks)."""
+        _check(self._lib.blp_spmv(self._h, B, 1 if transpose else 0, C.c_void_p(X.data_ptr()),
+                                  C.c_void_p(Y.data_ptr())), 'blp_spmv')
+
+    def stream_sync(self):
+        _check(self._lib.blp_stream_sync(self._h), 'blp_stream_sync')
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._lib.blp_stream(self._h) or 0)

@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py — node-LP solves/sec of the batched bound step (BASELINE.json metric).
+
+A *step* is one pass of the hot path over one batch: ``--batch`` open nodes (a slice of the
+synthetic frontier of the named workload, default C5: 50 000 vars x 20 000 rows, ~200k nonzeros)
+are solved to the parity tolerance (rel. KKT 1e-8) by one ``blp_solve_batch`` call per GPU.
+With N GPUs every rank solves its own slice of the frontier (weak scaling: per-GPU batch fixed)
+and the only collective is the 16-byte all-reduce(min) of [incumbent, dual bound] per step.
+
+  value   device-resident inputs (bounds and warm start already in HBM), CUDA-event time on the
+          library's stream, max over ranks;
+  e2e     same metric through the host-buffer plugin call (``BatchLP.solve_batch``): pinned host
+          arrays in, H2D + solve + D2H of objective/status/x/y inside the timed region;
+  roofline  k_primal / k_dual per-launch time from CUDA events around every launch of the timed
+          steps (blp_opts.profile) against the measured HBM copy peak;
+  cpu_baseline  the HiGHS dual-simplex stand-in for the reference's CLP path (oracle/highs_lp.py),
+          warm-started from the root basis, one LP per task on all host cores, bounded sample.
+
+``--impl reference`` times only that CPU path (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, m, density, max dive depth, fixture)
+    'c5': (50000, 20000, 2e-4, 32, 'c5_root.npz'),
+    'c4': (10000, 5000, 2e-3, 16, 'c4_root.npz'),
+    'c3': (500, 300, 0.1, 8, None),
+}
+METRIC = 'node_lp_solves_per_sec'
+UNIT = 'node-LPs/s'
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_instance(name):
+    from simple_mip_solver_b200.instances import grumpy_random_mip, numpy_random_mip
+    n, m, dens, depth, fixture = WORKLOADS[name]
+    if name == 'c3':
+        d = grumpy_random_mip(n, m, density=dens, maxObjCoeff=10, maxConsCoeff=10, tightness=2, rand_seed=2)
+    else:
+        d = numpy_random_mip(n, m, density=dens, seed=2)
+    root = None
+    if fixture and os.path.exists(os.path.join(ROOT, 'bench_data', fixture)):
+        z = np.load(os.path.join(ROOT, 'bench_data', fixture))
+        root = dict(x=z['x'], y=np.maximum(z['y'], 0.0), col_basis=z['col_basis'].astype(np.int32),
+                    row_basis=z['row_basis'].astype(np.int32), objective=float(z['objective']))
+    return d, depth, root
+
+
+def root_by_oracle(d):
+    """Root vertex/basis from the HiGHS oracle (only when no fixture is committed)."""
+    from oracle.highs_lp import HIGHS_INF, HighsLP
+    r = HighsLP(d.A, d.c, d.b, np.full(d.m, HIGHS_INF), d.l, d.u).solve()
+    return dict(x=r.x, y=np.maximum(r.row_dual, 0.0), col_basis=r.col_basis, row_basis=r.row_basis,
+                objective=r.objective)
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+_W = {}
+
+
+def _cpu_init(A, b, c, l, u, col_basis, row_basis):
+    from oracle.highs_lp import HIGHS_INF, HighsLP
+    _W['lp'] = HighsLP(A, c, b, np.full(A.shape[0], HIGHS_INF), l, u)
+    _W['basis'] = (col_basis, row_basis)
+    _W['l'], _W['u'] = l, u
+
+
+def _cpu_solve(deltas):
+    """One node LP on one core: root bounds + deltas, warm start from the root basis (the
+    reference hands the parent's basis to the child, base_node.py:589,608)."""
+    lp = _W['lp']
+    l, u = _W['l'].copy(), _W['u'].copy()
+    for j, lo, hi in deltas:
+        l[j], u[j] = lo, hi
+    lp.set_col_bounds(l, u)
+    lp.set_basis(*_W['basis'])
+    t = time.perf_counter()
+    r = lp.solve()
+    return r.status, r.objective, time.perf_counter() - t
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuArm:
+    def __init__(self, d, root, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        ctx = mp.get_context('fork')
+        self.pool = ctx.Pool(cores, initializer=_cpu_init,
+                             initargs=(d.A, d.b, d.c, d.l, d.u, root['col_basis'], root['row_basis']))
+
+    def run(self, deltas_list):
+        t = time.perf_counter()
+        out = self.pool.map(_cpu_solve, deltas_list, chunksize=1)
+        return out, time.perf_counter() - t
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+# ------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.idx}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        # samples under load: the upper half of the observed clocks
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {'sm_mhz': float(np.median(load)) if load else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def node_bytes(n, m):
+    """Algorithmic HBM bytes per node and iteration: primal launch reads
+    xbar, xa, l, u and the gathered y, writes xbar; dual launch reads y and the gathered xbar,
+    writes y."""
+    return 8 * (5 * n + m), 8 * (n + 2 * m)
+
+
+# ------------------------------------------------------------------------------------- main
+def run_reference(args, d, depth, root, rank):
+    """The reference's CPU path (HiGHS-DS stand-in for CLP) on all host cores."""
+    from simple_mip_solver_b200.instances import frontier_nodes
+    if rank != 0:
+        return
+    cores = host_cores()
+    if root is None:
+        root = root_by_oracle(d)
+    per_step = args.cpu_nodes or cores
+    arm = CpuArm(d, root, cores)
+    steps = args.warmup + args.steps
+    times, solved = [], 0
+    for s in range(steps):
+        _, _, deltas = frontier_nodes(d, root['x'], s * per_step, per_step, depth, seed=args.seed)
+        out, dt = arm.run(deltas)
+        if s >= args.warmup:
+            times.append(dt)
+            solved += sum(1 for st, _, _ in out if st in (0, 1, 2))
+    arm.close()
+    total = sum(times)
+    value = solved / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(args.steps, 1),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': workload_config(args, d, per_step),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{per_step} frontier nodes per step on {cores} processes, HiGHS 1.12 dual '
+                                   'simplex (stand-in for CLP), presolve off, warm start from the root basis'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, d, batch):
+    n, m, dens, depth, _ = WORKLOADS[args.workload]
+    return {'workload': f'{args.workload}: frontier of open-node LPs of a synthetic sparse MILP, {n} vars x {m} rows, '
+                        f'{d.A.nnz} nonzeros, dive depth U{{1..{depth}}}, solved to rel. KKT {args.eps:g}; '
+                        f'{batch} nodes per step per GPU (the 4096-node frontier is swept in slices)',
+            'batch_per_gpu': batch, 'eps_rel': args.eps, 'seed': args.seed,
+            'l2_policy': 'solver state per step exceeds L2 (see state_mb); no flush needed'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='blp', choices=['blp', 'reference'])
+    ap.add_argument('--workload', default='c5', choices=list(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=128, help='open nodes per step per GPU')
+    ap.add_argument('--eps', type=float, default=1e-8)
+    ap.add_argument('--max-iters', type=int, default=400000)
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--cpu-nodes', type=int, default=0, help='CPU arm: nodes per step (default: one per core)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    d, depth, root = load_instance(args.workload)
+    if args.impl == 'reference':
+        run_reference(args, d, depth, root, rank)
+        return
+
+    from simple_mip_solver_b200.instances import frontier_nodes
+    n, m, B = d.n, d.m, args.batch
+    if root is None:
+        root = root_by_oracle(d)
+
+    # ---- CPU baseline first (fork pool before CUDA is initialised), rank 0 at N=1 only ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        k = args.cpu_nodes or cores
+        _, _, deltas = frontier_nodes(d, root['x'], 10_000_000, k, depth, seed=args.seed)
+        arm = CpuArm(d, root, cores)
+        out, dt = arm.run(deltas)
+        arm.close()
+        ok = sum(1 for st, _, _ in out if st in (0, 1, 2))
+        cpu = {'value': ok / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+               'sample': f'{k} frontier nodes of the same workload, one LP per process on {cores} processes, '
+                         f'HiGHS 1.12 dual simplex (stand-in for CLP), presolve off, warm start from the root '
+                         f'basis; {dt:.1f} s wall, mean {np.mean([t for _, _, t in out]):.2f} s per LP per core'}
+        log('cpu_baseline', cpu)
+
+    import torch
+    import torch.distributed as dist
+    from simple_mip_solver_b200 import engine, parallel
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    lp = engine.BatchLP(d.A, d.b, d.c, device=local_rank)
+    ld = engine.leading_dim(B)
+    ext = torch.cuda.ExternalStream(lp.stream_ptr, device=dev)
+    opts = engine.default_opts(eps_rel=args.eps, max_iters=args.max_iters, profile=1)
+    int_idx = torch.arange(n, dtype=torch.int32, device=dev)
+
+    def node_slice(step):
+        first = (step * world + rank) * B
+        return frontier_nodes(d, root['x'], first, B, depth, seed=args.seed)
+
+    def to_device(lbs, ubs):
+        lb = torch.zeros((n, ld), dtype=torch.float64, device=dev)
+        ub = torch.zeros((n, ld), dtype=torch.float64, device=dev)
+        lb[:, :B] = torch.from_numpy(lbs).to(dev).T
+        ub[:, :B] = torch.from_numpy(ubs).to(dev).T
+        return lb.contiguous(), ub.contiguous()
+
+    x0 = torch.from_numpy(root['x']).to(dev)[:, None].expand(n, ld).contiguous()
+    y0 = torch.from_numpy(root['y']).to(dev)[:, None].expand(m, ld).contiguous()
+
+    def exchange(res_obj, res_lower, res_status, res_frac):
+        """16-byte all-reduce(min) of [best integral objective in slice, min open lower bound]."""
+        st = res_status[:B]
+        integral = (st == 0) & (res_frac[:B] < 0)
+        inc = float(res_obj[:B][integral].min().item()) if bool(integral.any()) else float('inf')
+        open_ = (st == 0) & ~integral
+        lowb = float(res_lower[:B][open_].min().item()) if bool(open_.any()) else float('inf')
+        return parallel.allreduce_bounds(inc, lowb, device=dev)
+
+    total_steps = args.warmup + args.steps
+    slices = [node_slice(s) for s in range(total_steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        lp.stream_sync()
+
+    # ---- device-resident arm ----
+    agg = dict(launches=0, solved=0, unsolved=0, infeasible=0, node_iters=0.0, iters=0,
+               primal_ms=0.0, dual_ms=0.0, step_ms=0.0, total_ms=0.0)
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for s in range(total_steps):
+        lb, ub = to_device(slices[s][0], slices[s][1])
+        if s == args.warmup:
+            barrier()
+            if rank == 0:
+                sampler.start()
+            ev0.record(ext)
+        r = lp.solve_batch_device(lb, ub, x0=x0, y0=y0, int_idx=int_idx, opts=opts, want_x=True, want_y=True)
+        exchange(r['obj'], r['lower'], r['status'], r['frac'])
+        if s >= args.warmup:
+            st = r['status'][:B]
+            agg['solved'] += int(((st == 0) | (st == 1) | (st == 2)).sum().item())
+            agg['unsolved'] += int((st == 3).sum().item())
+            agg['infeasible'] += int((st == 1).sum().item())
+            sdict = r['stats']
+            agg['launches'] += sdict['kernel_launches']
+            agg['node_iters'] += sdict['node_iterations']
+            agg['iters'] += sdict['iterations']
+            agg['primal_ms'] += sdict['primal_kernel_ms']
+            agg['dual_ms'] += sdict['dual_kernel_ms']
+            agg['step_ms'] += sdict['step_kernel_ms']
+            agg['total_ms'] += sdict['total_ms']
+        log(f'[rank {rank}] step {s} iters {r["stats"]["iterations"]} total_ms {r["stats"]["total_ms"]:.0f}')
+        del lb, ub
+    ev1.record(ext)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = parallel.allreduce_max(dev_ms, device=dev)
+    sums = parallel.allreduce_sum([agg['solved'], agg['unsolved'], agg['launches'], agg['infeasible']], device=dev)
+    value = sums[0] / (dev_ms * 1e-3)
+
+    # ---- end-to-end arm: pinned host buffers through the plugin call ----
+    e2e_steps = max(1, args.steps)
+    e2e_slices = [node_slice(total_steps + s) for s in range(1 + e2e_steps)]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hx0 = pin(np.tile(root['x'], (B, 1)))
+    hy0 = pin(np.tile(root['y'], (B, 1)))
+    opts_e = engine.default_opts(eps_rel=args.eps, max_iters=args.max_iters)
+    ints = list(range(n))
+    h2d = d2h = 0
+    e2e_solved = 0
+    t0 = None
+    for s in range(1 + e2e_steps):
+        hlb, hub = pin(e2e_slices[s][0]), pin(e2e_slices[s][1])
+        if s == 1:
+            barrier()
+            t0 = time.perf_counter()
+        rr = lp.solve_batch(hlb, hub, x0=hx0, y0=hy0, integer_indices=ints, opts=opts_e)
+        integral = (rr.status == 0) & (rr.frac_idx < 0)
+        inc = float(rr.objective[integral].min()) if integral.any() else float('inf')
+        open_ = (rr.status == 0) & ~integral
+        lowb = float(rr.lower_bound[open_].min()) if open_.any() else float('inf')
+        parallel.allreduce_bounds(inc, lowb, device=dev)
+        if s >= 1:
+            e2e_solved += int(np.isin(rr.status, (0, 1, 2)).sum())
+            h2d = hlb.nbytes + hub.nbytes + hx0.nbytes + hy0.nbytes + 4 * n
+            d2h = rr.x.nbytes + rr.y.nbytes + rr.objective.nbytes + rr.lower_bound.nbytes + \
+                rr.status.nbytes + rr.iterations.nbytes + rr.frac_idx.nbytes
+    barrier()
+    e2e_s = parallel.allreduce_max(time.perf_counter() - t0, device=dev)
+    e2e_total = parallel.allreduce_sum([e2e_solved], device=dev)[0]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+        pb, db = node_bytes(n, m)
+        bytes_A = 12 * d.A.nnz + 4 * (m + 1)
+        bytes_AT = 12 * d.A.nnz + 4 * (n + 1)
+        launches_each = max(agg['iters'], 1)           # k_primal launches == k_dual launches == iterations
+        primal_bytes = (pb * agg['node_iters'] + bytes_AT * launches_each) / launches_each
+        dual_bytes = (db * agg['node_iters'] + bytes_A * launches_each) / launches_each
+        primal_s = agg['primal_ms'] * 1e-3 / launches_each
+        dual_s = agg['dual_ms'] * 1e-3 / launches_each
+        prim_gbs = primal_bytes / primal_s / 1e9 if primal_s > 0 else 0.0
+        dual_gbs = dual_bytes / dual_s / 1e9 if dual_s > 0 else 0.0
+        state_mb = 8 * ld * (7 * n + 4 * m) / 1e6
+        cfg = workload_config(args, d, B)
+        cfg['state_mb'] = round(state_mb, 1)
+        cfg['timing'] = ('value: CUDA events on the library stream around the K timed steps, max over ranks; '
+                         'steps run with per-launch events (blp_opts.profile, no CUDA graph)')
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dev_ms / max(args.steps, 1), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'e2e': {'value': e2e_total / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps},
+            'gpu_launches': int(sums[2]),
+            'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'kernel': 'k_primal<32,false>', 'achieved': prim_gbs, 'peak': peak,
+                         'unit': 'GB/s', 'frac': prim_gbs / peak, 'traffic': None, 'peak_source': peak_src,
+                         'bytes_per_launch': primal_bytes, 'ms_per_launch': primal_s * 1e3,
+                         'k_dual': {'achieved': dual_gbs, 'frac': dual_gbs / peak, 'bytes_per_launch': dual_bytes,
+                                    'ms_per_launch': dual_s * 1e3},
+                         'iteration_pair': {'achieved': (primal_bytes + dual_bytes) / max(primal_s + dual_s, 1e-12) / 1e9,
+                                            'frac': (primal_bytes + dual_bytes) / max(primal_s + dual_s, 1e-12) / 1e9 / peak}},
+            'cpu_baseline': cpu,
+            'nodes': {'solved': int(sums[0]), 'iteration_limit': int(sums[1]), 'infeasible': int(sums[3]),
+                      'pdhg_iterations_per_step': agg['iters'] / max(args.steps, 1),
+                      'mean_iterations_per_node': agg['node_iters'] / max(agg['solved'] + agg['unsolved'], 1)},
+        }
+        print(json.dumps(line), flush=True)
+    lp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,540 @@
+"""Look-alikes of the CyLP objects the reference's Node API touches, backed by the GPU engine.
+
+The reference keeps a ``CyClpSimplex`` in ``node.lp`` and calls ``lp.dual()`` on it, one node at a
+time (simple_mip_solver/nodes/base_node.py:273, 646). CyLP/CLP are not part of the reference repo
+and are absent here; this module provides the subset of that object protocol the reference uses
+(listed in SURVEY.md section 8b) with a different engine underneath:
+
+* every LP of one MILP shares one ``SharedLP`` — the matrix, objective, row bounds, the pool of
+  appended cut rows and the ``engine.BatchLP`` handle that lives on the GPU;
+* a ``CyClpSimplex`` here is only the per-node part: variable bounds, which cut rows are present,
+  a warm start, an iteration budget and the last solution;
+* ``dual()`` solves one node through the batched CUDA bound step; ``solve_lps([...])`` solves many
+  node LPs of the same MILP in ONE call and leaves each result in its object, so that a later
+  ``dual()`` on an unchanged LP is a cache hit. That is how a frontier of open nodes, or all
+  strong-branching children, reach the kernels as a batch while the search code stays sequential.
+
+There is no CPU solve here: without libblp.so / a GPU, ``dual()`` raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+
+COIN_INFINITY = 1.7976931348623157e308      # what CyClpSimplex.getCoinInfinity() returns (DBL_MAX)
+
+# PDHG iterations granted per unit of ``lp.maxNumIteration`` (the reference counts dual simplex
+# pivots, base_node.py:645; a first-order iteration is far cheaper than a pivot)
+PDHG_ITERS_PER_PIVOT = 512
+
+
+class CyLPArray(np.ndarray):
+    """ndarray subclass with the name the reference imports from cylp.py.modeling.CyLPModel."""
+    __array_priority__ = 5.0
+
+    def __new__(cls, data, info=None):
+        return np.array(data, dtype=np.float64).view(cls)
+
+
+# ------------------------------------------------------------------------------------------------
+# a very small modelling layer: x = lp.addVariable('x', n); lp += l <= x <= u;
+# lp.addConstraint(pi * x >= pi0, name); lp.objective = c * x  (base_node.py:459-460, 592-608)
+class CyLPVar:
+    __array_ufunc__ = None          # make ndarray * var defer to CyLPVar.__rmul__
+
+    def __init__(self, name: str, dim: int):
+        self.name = name
+        self.dim = int(dim)
+        self.lower = CyLPArray(np.zeros(self.dim))
+        self.upper = CyLPArray(np.full(self.dim, COIN_INFINITY))
+        self.indices = np.arange(self.dim)
+        self._pending_lower = None
+
+    def __repr__(self):
+        return f'CyLPVar({self.name!r}, {self.dim})'
+
+    def __hash__(self):
+        return id(self)
+
+    def __eq__(self, other):
+        return self is other
+
+    # coefficient products
+    def __rmul__(self, coefs):
+        return CyLPExpr(self, coefs)
+
+    def __mul__(self, coefs):
+        return CyLPExpr(self, coefs)
+
+    # bounds: "l <= x <= u" evaluates as (l <= x) and (x <= u); the first half parks the lower
+    # bound on the variable, the second half returns the combined bound statement
+    def __ge__(self, lower):
+        self._pending_lower = np.broadcast_to(np.asarray(lower, dtype=float), (self.dim,)).copy()
+        return CyLPBounds(self, self._pending_lower, None)
+
+    def __le__(self, upper):
+        lower, self._pending_lower = self._pending_lower, None
+        upper = np.broadcast_to(np.asarray(upper, dtype=float), (self.dim,)).copy()
+        return CyLPBounds(self, lower, upper)
+
+
+class CyLPBounds:
+    def __init__(self, var, lower, upper):
+        self.var, self.lower, self.upper = var, lower, upper
+
+    def __bool__(self):
+        return True
+
+
+class CyLPExpr:
+    """coefs * x with coefs a vector (one row) or a matrix (several rows)."""
+    __array_ufunc__ = None
+
+    def __init__(self, var: CyLPVar, coefs):
+        self.var = var
+        if sp.issparse(coefs):
+            M = sp.csr_matrix(coefs, dtype=float)
+        else:
+            M = sp.csr_matrix(np.atleast_2d(np.asarray(coefs, dtype=float)))
+        if M.shape[1] != var.dim:
+            raise ValueError(f'coefficients have {M.shape[1]} columns, variable has {var.dim}')
+        self.coefs = M
+        self._pending_lower = None
+
+    def __ge__(self, lower):
+        k = self.coefs.shape[0]
+        lo = np.broadcast_to(np.asarray(lower, dtype=float), (k,)).copy()
+        self._pending_lower = lo
+        return CyLPConstraint(self, lo, np.full(k, COIN_INFINITY))
+
+    def __le__(self, upper):
+        k = self.coefs.shape[0]
+        lo, self._pending_lower = self._pending_lower, None
+        if lo is None:
+            lo = np.full(k, -COIN_INFINITY)
+        up = np.broadcast_to(np.asarray(upper, dtype=float), (k,)).copy()
+        return CyLPConstraint(self, lo, up)
+
+
+class CyLPConstraint:
+    def __init__(self, expr: CyLPExpr, lower, upper, name: Optional[str] = None):
+        self.name = name
+        self.lower = CyLPArray(lower)
+        self.upper = CyLPArray(upper)
+        self.variables = [expr.var]
+        self.varCoefs = {expr.var: expr.coefs}
+        self.nRows = expr.coefs.shape[0]
+        self.isRange = False
+
+    def __bool__(self):
+        return True
+
+
+# ------------------------------------------------------------------------------------------------
+class SharedLP:
+    """What all node LPs of one MILP have in common: ``min c.x, A x >= b`` plus a pool of cut rows.
+
+    Owns the GPU handle. Cut rows are appended to the device matrix the first time an LP that
+    contains them is solved and are switched on per node through the row mask of the batched call.
+    """
+
+    def __init__(self, A, b, c, device: int = 0):
+        self.A = sp.csr_matrix(A, dtype=np.float64)
+        self.m, self.n = self.A.shape
+        self.b = np.asarray(b, dtype=np.float64).reshape(self.m).copy()
+        self.c = np.asarray(c, dtype=np.float64).reshape(self.n).copy()
+        self.device = device
+        self._engine = None
+        self.cut_names: List[str] = []                     # pool order = device row order
+        self.cut_index: Dict[str, int] = {}
+        self.cut_rows: List[Tuple[np.ndarray, float]] = []
+        self._on_device = 0                                # how many pool rows the device has
+        self.solve_calls = 0
+        self.lps_solved = 0
+        self.kernel_launches = 0
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            from simple_mip_solver_b200.engine import BatchLP
+            self._engine = BatchLP(self.A, self.b, self.c, device=self.device)
+        return self._engine
+
+    def register_cut(self, name: str, pi: np.ndarray, pi0: float) -> int:
+        k = self.cut_index.get(name)
+        if k is None:
+            k = len(self.cut_names)
+            self.cut_names.append(name)
+            self.cut_index[name] = k
+            self.cut_rows.append((np.asarray(pi, dtype=np.float64).copy(), float(pi0)))
+        return k
+
+    def sync_cuts(self):
+        if self._on_device < len(self.cut_rows):
+            new = self.cut_rows[self._on_device:]
+            self.engine.append_rows(np.vstack([p for p, _ in new]), np.array([r for _, r in new]))
+            self._on_device = len(self.cut_rows)
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+            self._on_device = 0
+
+
+class CyClpSimplex:
+    """Per-node LP with the attribute/method names of cylp.cy.CyClpSimplex that the reference uses."""
+
+    def __init__(self, shared: Optional[SharedLP] = None, lower=None, upper=None):
+        self._shared = shared
+        self._vars: List[CyLPVar] = []
+        self._l = None if lower is None else CyLPArray(lower)
+        self._u = None if upper is None else CyLPArray(upper)
+        self._cuts: Dict[str, Tuple[np.ndarray, float]] = {}      # cut rows present in this LP
+        self._pending_rows = []                                    # rows added before `shared` exists
+        self._objective = None
+        self.logLevel = 0
+        self.maxNumIteration = 2147483647
+        self.iteration = 0
+        self._status = -1
+        self._obj = 0.0
+        self._x = None
+        self._y = None
+        self._rc = None
+        self._lower_bound = -np.inf
+        self._solved_key = None
+        self._warm: Optional[Tuple[np.ndarray, Dict[str, float], np.ndarray]] = None
+        self._basis = None
+        self.integer_indices_hint: Optional[Sequence[int]] = None
+        self.solver_opts: Dict[str, float] = {}
+        if shared is not None:
+            v = CyLPVar('x', shared.n)
+            self._vars.append(v)
+            if self._l is None:
+                self._l = CyLPArray(np.zeros(shared.n))
+            if self._u is None:
+                self._u = CyLPArray(np.full(shared.n, COIN_INFINITY))
+
+    # ---- model building (the subset the reference exercises) -------------------------------
+    def addVariable(self, name: str, dim: int, isInt: bool = False):
+        assert not self._vars, 'this LP look-alike holds a single variable vector'
+        v = CyLPVar(name, dim)
+        self._vars.append(v)
+        self._l = CyLPArray(np.zeros(dim))
+        self._u = CyLPArray(np.full(dim, COIN_INFINITY))
+        return v
+
+    def getVarByName(self, name: str):
+        for v in self._vars:
+            if v.name == name:
+                return v
+        raise KeyError(name)
+
+    def __iadd__(self, stmt):
+        if isinstance(stmt, CyLPBounds):
+            if stmt.lower is not None:
+                self._l = CyLPArray(stmt.lower)
+            if stmt.upper is not None:
+                self._u = CyLPArray(stmt.upper)
+            self._solved_key = None
+        elif isinstance(stmt, CyLPConstraint):
+            self.addConstraint(stmt)
+        else:
+            raise TypeError(f'cannot add {type(stmt)} to the LP')
+        return self
+
+    def addConstraint(self, cons: CyLPConstraint, name: Optional[str] = None, addMpsNames: bool = True):
+        assert isinstance(cons, CyLPConstraint), 'constraint must come from an expression like pi * x >= pi0'
+        cons.name = name if name is not None else (cons.name or f'R_{id(cons)}')
+        M = cons.varCoefs[cons.variables[0]]
+        if self._shared is None:
+            # base rows of a model under construction: A x >= b only (the canonical form)
+            assert (np.asarray(cons.upper) >= 1e300).all(), 'rows must be one sided: a.x >= b'
+            self._pending_rows.append(cons)
+            return
+        assert (np.asarray(cons.upper) >= 1e300).all(), 'rows must be one sided: a.x >= b'
+        for r in range(M.shape[0]):
+            nm = cons.name if M.shape[0] == 1 else f'{cons.name}_{r}'
+            self._cuts[nm] = (np.asarray(M.getrow(r).todense()).ravel(), float(cons.lower[r]))
+        self._solved_key = None
+
+    def removeConstraint(self, name: str):
+        if name not in self._cuts:
+            raise KeyError(f'no removable constraint named {name!r}')
+        del self._cuts[name]
+        self._solved_key = None
+
+    def _finalize(self, device: int = 0):
+        """Turn a model built with addVariable/addConstraint/objective into a shared LP."""
+        if self._shared is not None:
+            return
+        n = self._vars[0].dim
+        rows = [c.varCoefs[c.variables[0]] for c in self._pending_rows]
+        A = sp.vstack(rows, format='csr') if rows else sp.csr_matrix((0, n))
+        b = np.concatenate([np.asarray(c.lower) for c in self._pending_rows]) if rows else np.zeros(0)
+        c = np.zeros(n) if self._objective is None else np.asarray(self._objective, dtype=float).ravel()
+        self._base_names = [c_.name for c_ in self._pending_rows]
+        self._shared = SharedLP(A, b, c, device=device)
+        self._pending_rows = []
+
+    # ---- attributes read by the reference ------------------------------------------------------
+    @property
+    def variables(self):
+        v = self._vars[0]
+        v.lower, v.upper = self._l, self._u
+        return self._vars
+
+    @property
+    def constraints(self):
+        sh = self._need_shared()
+        x = self._vars[0]
+        base = CyLPConstraint(CyLPExpr(x, sh.A), sh.b, np.full(sh.m, COIN_INFINITY), name='R_base')
+        out = [base]
+        for nm, (pi, pi0) in self._cuts.items():
+            out.append(CyLPConstraint(CyLPExpr(x, pi), [pi0], [COIN_INFINITY], name=nm))
+        return out
+
+    @property
+    def nVariables(self):
+        return self._vars[0].dim
+
+    nCols = nVariables
+
+    @property
+    def nConstraints(self):
+        return self._need_shared().m + len(self._cuts)
+
+    nRows = nConstraints
+
+    @property
+    def variablesLower(self):
+        return self._l
+
+    @variablesLower.setter
+    def variablesLower(self, v):
+        self._l = CyLPArray(v)
+        self._solved_key = None
+
+    @property
+    def variablesUpper(self):
+        return self._u
+
+    @variablesUpper.setter
+    def variablesUpper(self, v):
+        self._u = CyLPArray(v)
+        self._solved_key = None
+
+    @property
+    def constraintsLower(self):
+        sh = self._need_shared()
+        return CyLPArray(np.concatenate([sh.b, [p0 for _, p0 in self._cuts.values()]]))
+
+    @property
+    def constraintsUpper(self):
+        return CyLPArray(np.full(self.nConstraints, COIN_INFINITY))
+
+    @property
+    def coefMatrix(self):
+        sh = self._need_shared()
+        if not self._cuts:
+            return sh.A.tocsc()
+        return sp.vstack([sh.A] + [sp.csr_matrix(p[None, :]) for p, _ in self._cuts.values()]).tocsc()
+
+    @property
+    def objective(self):
+        if self._shared is not None:
+            return CyLPArray(self._shared.c)
+        return self._objective
+
+    @objective.setter
+    def objective(self, value):
+        if isinstance(value, CyLPExpr):
+            value = np.asarray(value.coefs.todense()).ravel()
+        value = CyLPArray(np.asarray(value, dtype=float).ravel())
+        if self._shared is not None:
+            assert np.array_equal(value, self._shared.c), \
+                'the objective is shared by all node LPs of a model and cannot change per node'
+        self._objective = value
+
+    objectiveCoefficients = objective
+
+    @staticmethod
+    def getCoinInfinity():
+        return COIN_INFINITY
+
+    def setInteger(self, idx):
+        pass
+
+    # ---- results ---------------------------------------------------------------------------------
+    def getStatusCode(self):
+        return self._status
+
+    @property
+    def objectiveValue(self):
+        return self._obj
+
+    @property
+    def primalVariableSolution(self):
+        return {'x': self._x}
+
+    @property
+    def dualConstraintSolution(self):
+        sh = self._need_shared()
+        if self._y is None:
+            return {}
+        out = {'R_base': CyLPArray(self._y[:sh.m])}
+        for k, nm in enumerate(self._cuts):
+            out[nm] = CyLPArray([self._y[sh.m + k]])
+        return out
+
+    @property
+    def dualVariableSolution(self):
+        return {'x': self._rc}
+
+    @property
+    def lagrangianBound(self):
+        """Dual objective of the last solve: a valid lower bound on the LP value (new; the
+        iteration-limited dual simplex objective plays this role in the reference, pseudo_cost.py:86)."""
+        return self._lower_bound
+
+    def getBasisStatus(self):
+        """Active-set image of the last primal-dual pair in CLP's coding (1 basic, 2 at upper,
+        3 at lower): a column strictly inside its bounds, or a row with slack, counts as basic.
+        At a non-degenerate vertex this is the simplex basis; elsewhere the count differs from the
+        number of rows and ``BaseNode.tableau`` returns None exactly as the reference does when
+        CLP reports an inconsistent basis (base_node.py:518-519)."""
+        if self._x is None:
+            n, m = self.nVariables, self.nConstraints
+            return np.full(n, 3, dtype=np.int32), np.full(m, 1, dtype=np.int32)
+        tol = 1e-6
+        x = self._x
+        scale = 1.0 + np.abs(x)
+        at_l = x - self._l <= tol * scale
+        at_u = self._u - x <= tol * scale
+        cols = np.where(at_l, 3, np.where(at_u, 2, 1)).astype(np.int32)
+        slack = self.coefMatrix @ x - self.constraintsLower
+        rows = np.where(slack > tol * (1.0 + np.abs(self.constraintsLower)), 1, 3).astype(np.int32)
+        return cols, rows
+
+    def setBasisStatus(self, cols, rows):
+        self._basis = (np.asarray(cols).copy(), np.asarray(rows).copy())
+
+    def set_warm_start(self, x, duals_by_row: Dict[str, float], y_base):
+        """Parent's primal vector and row duals; the analogue of handing the parent's basis to
+        the child (base_node.py:589, 608)."""
+        self._warm = (np.asarray(x, dtype=float).copy(), dict(duals_by_row),
+                      np.asarray(y_base, dtype=float).copy())
+
+    # ---- solving -----------------------------------------------------------------------------------
+    def _need_shared(self) -> SharedLP:
+        if self._shared is None:
+            self._finalize()
+        return self._shared
+
+    def _state_key(self):
+        return (self._l.tobytes(), self._u.tobytes(), tuple(self._cuts), int(self.maxNumIteration))
+
+    def dual(self):
+        if self._solved_key is None or self._solved_key != self._state_key():
+            solve_lps([self])
+        return self._status
+
+    primal = dual
+
+    def copy_for_child(self) -> 'CyClpSimplex':
+        """New per-node LP on the same shared data with copies of bounds and cut membership
+        (what the per-child rebuild of base_node.py:592-608 amounts to)."""
+        child = CyClpSimplex(self._need_shared(), self._l.copy(), self._u.copy())
+        child._cuts = dict(self._cuts)
+        child._objective = self._objective
+        child.integer_indices_hint = self.integer_indices_hint
+        child.solver_opts = self.solver_opts
+        if self._x is not None and self._y is not None:
+            sh = self._shared
+            child.set_warm_start(self._x, {nm: self._y[sh.m + k] for k, nm in enumerate(self._cuts)},
+                                 self._y[:sh.m])
+        return child
+
+
+def solve_lps(lps: Iterable[CyClpSimplex], force: bool = False) -> int:
+    """Solve every not-yet-solved LP in ``lps`` with ONE batched GPU call per shared model.
+
+    Results are stored in each object (status, objective, x, row duals, reduced costs); LPs whose
+    state is unchanged since their last solve are skipped unless ``force``. Returns the number
+    of LPs actually sent to the GPU."""
+    from simple_mip_solver_b200.engine import default_opts
+    groups: Dict[int, List[CyClpSimplex]] = {}
+    for lp in lps:
+        sh = lp._need_shared()
+        if force or lp._solved_key is None or lp._solved_key != lp._state_key():
+            groups.setdefault(id(sh), []).append(lp)
+    sent = 0
+    for todo in groups.values():
+        sh = todo[0]._shared
+        # distinct iteration budgets cannot share a call: split by budget
+        by_budget: Dict[int, List[CyClpSimplex]] = {}
+        for lp in todo:
+            by_budget.setdefault(int(lp.maxNumIteration), []).append(lp)
+        for budget, batch in by_budget.items():
+            _solve_group(sh, batch, budget, default_opts)
+            sent += len(batch)
+    return sent
+
+
+def _solve_group(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_opts):
+    for lp in batch:
+        for nm, (pi, pi0) in lp._cuts.items():
+            sh.register_cut(nm, pi, pi0)
+    sh.sync_cuts()
+    eng = sh.engine
+    B, n, m, mc = len(batch), sh.n, sh.m, len(sh.cut_names)
+    lb = np.empty((B, n))
+    ub = np.empty((B, n))
+    mask = np.zeros((B, mc), dtype=np.uint8) if mc else None
+    any_warm = any(lp._warm is not None for lp in batch)
+    x0 = np.zeros((B, n)) if any_warm else None
+    y0 = np.zeros((B, m + mc)) if any_warm else None
+    for k, lp in enumerate(batch):
+        lb[k] = np.where(lp._l <= -1e30, -np.inf, lp._l)
+        ub[k] = np.where(lp._u >= 1e30, np.inf, lp._u)
+        for nm in lp._cuts:
+            mask[k, sh.cut_index[nm]] = 1
+        if lp._warm is not None:
+            wx, wcuts, wy = lp._warm
+            x0[k] = wx
+            y0[k, :m] = wy
+            for nm, v in wcuts.items():
+                j = sh.cut_index.get(nm)
+                if j is not None and nm in lp._cuts:
+                    y0[k, m + j] = v
+    okw = dict(batch[0].solver_opts)
+    if budget < 2147483647:
+        okw['max_iters'] = int(min(budget * PDHG_ITERS_PER_PIVOT, 2_000_000_000))
+    opts = default_opts(**okw)
+    ints = batch[0].integer_indices_hint
+    res = eng.solve_batch(lb, ub, row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
+    sh.solve_calls += 1
+    sh.lps_solved += B
+    sh.kernel_launches += int(res.stats['kernel_launches'])
+    for k, lp in enumerate(batch):
+        st = int(res.status[k])
+        lp._status = st
+        lp.iteration = int(res.iterations[k])
+        lp._lower_bound = float(res.lower_bound[k])
+        rows = [sh.cut_index[nm] + m for nm in lp._cuts]
+        ysel = np.concatenate([res.y[k, :m], res.y[k, rows]]) if rows else res.y[k, :m].copy()
+        if st == 1:
+            lp._obj, lp._x, lp._y, lp._rc = float('inf'), None, None, None
+        else:
+            x = res.x[k].copy()
+            lp._x = CyLPArray(x)
+            lp._y = ysel
+            full_y = res.y[k]
+            lp._rc = CyLPArray(sh.c - sh.A.T @ full_y[:m] -
+                               (np.vstack([sh.cut_rows[j - m][0] for j in rows]).T @ full_y[rows] if rows else 0.0))
+            # status 3 = budget exhausted: report the Lagrangian bound, the analogue of the
+            # dual-feasible objective an iteration-limited dual simplex returns
+            lp._obj = float(res.objective[k]) if st != 3 else float(res.lower_bound[k])
+        lp._solved_key = lp._state_key()

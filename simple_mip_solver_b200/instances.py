@@ -122,3 +122,53 @@ def random_dive_bounds(data: MipData, x_root: np.ndarray, batch: int, max_depth:
                 lb[k, j] = max(lb[k, j], np.ceil(v)) if np.ceil(v) <= ub[k, j] else lb[k, j]
             deltas.append((k, int(j), lb[k, j], ub[k, j]))
     return lb, ub, deltas
+
+
+def frontier_nodes(data: MipData, x_root: np.ndarray, first: int, count: int, max_depth: int,
+                   seed: int = 0, p_down: float = 0.75):
+    """Bounds of open nodes ``first .. first+count-1`` of a synthetic frontier.
+
+    Node k is reached from the root by depth_k ~ U{1..max_depth} branching decisions on integer
+    variables that are fractional at the root LP vertex ``x_root`` (most fractional first, as
+    ``BaseNode._most_fractional_index`` would pick them), each moving one bound to floor/ceil of
+    the root value as ``BaseNode._base_branch`` does (base_node.py:595-600). An up-branch that
+    would make a row unsatisfiable even with every other variable at its lower bound is turned
+    into a down-branch, so every node passes the row-activity screen and needs a real LP solve.
+    Each node has its own generator seeded by (seed, k): the frontier does not depend on how it
+    is split into batches or over GPUs. Returns (lb, ub) of shape [count, n] and the deltas."""
+    n = data.n
+    ints = np.asarray(data.integer_indices)
+    vals = x_root[ints]
+    frac = np.minimum(vals - np.floor(vals), np.ceil(vals) - vals)
+    order = ints[np.argsort(-frac, kind='stable')]
+    n_frac = int((frac > 1e-4).sum())
+    A = data.A.tocsc()
+    base_act = data.A @ data.l              # activity with everything at its lower bound
+    lb = np.tile(data.l, (count, 1))
+    ub = np.tile(data.u, (count, 1))
+    deltas = []
+    for t in range(count):
+        k = first + t
+        rng = np.random.Generator(np.random.PCG64([seed, k]))
+        depth = int(rng.integers(1, max_depth + 1))
+        pool = order[:max(n_frac, depth)]
+        picks = rng.choice(pool, size=min(depth, pool.size), replace=False)
+        act = base_act.copy()
+        node = []
+        for j in picks:
+            v = x_root[j]
+            lo, hi = lb[t, j], ub[t, j]
+            up = rng.random() >= p_down and np.ceil(v) <= hi and np.ceil(v) > lo
+            if up:
+                col = A.getcol(j)
+                trial = act[col.indices] + col.data * (np.ceil(v) - lo)
+                if (trial < data.b[col.indices] - 1e-9).any():      # rows are A x >= b
+                    up = False
+                else:
+                    act[col.indices] = trial
+                    lb[t, j] = np.ceil(v)
+            if not up:
+                ub[t, j] = max(min(hi, np.floor(v)), lo)
+            node.append((int(j), float(lb[t, j]), float(ub[t, j])))
+        deltas.append(node)
+    return lb, ub, deltas

@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing of the bound step: node sharding and the incumbent / dual-bound exchange.
+
+Node LPs are independent (they share read-only A, c, b), so a frontier is split by node across
+ranks — one process per GPU, each with its own ``engine.BatchLP`` replica of the matrix — and the
+data path needs no collective. The only exchange is a 16-byte all-reduce(min) of
+``[incumbent objective, smallest open-node lower bound]`` after a batch, done with
+``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests). The reference is single
+process; this module has no counterpart there.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+def shard_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [begin, end) of ``total`` nodes owned by ``rank``; sizes differ by <= 1."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f'bad rank/world: {rank}/{world}')
+    base, extra = divmod(total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard_items(items: Sequence, rank: int, world: int) -> List:
+    b, e = shard_bounds(len(items), rank, world)
+    return list(items[b:e])
+
+
+def allreduce_bounds(incumbent: float, dual_bound: float, device=None) -> Tuple[float, float]:
+    """Global (min incumbent objective, min open-node lower bound) over all ranks.
+
+    Without an initialised process group (single GPU) the inputs are returned unchanged."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(incumbent), float(dual_bound)
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' \
+            else torch.device('cpu')
+    t = torch.tensor([incumbent, dual_bound], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    a, b = t.tolist()
+    return float(a), float(b)
+
+
+def allreduce_max(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' \
+            else torch.device('cpu')
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def allreduce_sum(values: Sequence[float], device=None) -> List[float]:
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [float(v) for v in values]
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' \
+            else torch.device('cpu')
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.tolist()]

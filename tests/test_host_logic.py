@@ -1,0 +1,202 @@
+"""CPU tests of the host-side logic (Node classes, BranchAndBound, batched LP plumbing).
+
+The LP arithmetic comes from the HiGHS oracle through tests/helpers.OracleBatchLP (no GPU in this
+suite); what is under test is the Python that the product ships: that it takes the same decisions
+as the UNMODIFIED reference did when it was run here on the HiGHS stand-in
+(tests/golden/make_goldens.py) — same status, optimum, number of evaluated nodes and, node by node,
+the same tree (parent, branching variable, direction, LP value).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import use_oracle_engine
+from simple_mip_solver_b200 import (BaseNode, BranchAndBound, CyLPArray, DepthFirstSearchNode,
+                                    MILPInstance, PseudoCostBranchDepthFirstSearchNode,
+                                    PseudoCostBranchNode)
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+SCALE1 = json.load(open(os.path.join(GOLD, 'scale_1_models.json')))
+EXAMPLES = json.load(open(os.path.join(GOLD, 'example_models.json')))
+
+CASES = {
+    'BaseNode': (BaseNode, dict(gomory_cuts=False)),
+    'DepthFirstSearchNode': (DepthFirstSearchNode, dict(gomory_cuts=False)),
+    'PseudoCostBranchNode': (PseudoCostBranchNode, dict(pseudo_costs={}, gomory_cuts=False)),
+    'PseudoCostBranchDepthFirstSearchNode': (PseudoCostBranchDepthFirstSearchNode,
+                                             dict(pseudo_costs={}, gomory_cuts=False)),
+}
+
+
+def unfl(v):
+    return {'inf': float('inf'), '-inf': -float('inf')}.get(v, v) if isinstance(v, str) else v
+
+
+def model_from(rec):
+    return MILPInstance(A=np.array(rec['A']), b=CyLPArray(rec['b']), c=CyLPArray(rec['c']),
+                        l=CyLPArray(rec['l']), u=CyLPArray(rec['u']), sense=['Min', '>='],
+                        integerIndices=list(rec['integer_indices']), numVars=len(rec['c']))
+
+
+def check_against_reference(bb, gold, tree=True):
+    assert bb.status == gold['status']
+    assert bb.objective_value == pytest.approx(unfl(gold['objective']), rel=1e-9, abs=1e-9)
+    assert bb.evaluated_nodes == gold['evaluated_nodes']
+    if gold['solution'] is not None:
+        assert np.allclose(bb.solution, gold['solution'], atol=1e-7)
+    if not tree:
+        return
+    assert set(map(str, bb.tree.nodes)) == set(gold['tree'])
+    for idx, (parent, b_idx, b_dir, obj, feas, mipf) in gold['tree'].items():
+        n = bb.tree.get_node_instances(int(idx))
+        assert bb.tree.get_parent(int(idx)) == parent
+        assert (n._b_idx, n._b_dir) == (b_idx, b_dir)
+        assert n.lp_feasible == feas and n.mip_feasible == mipf
+        if obj is not None and n.objective_value is not None:
+            assert n.objective_value == pytest.approx(unfl(obj), rel=1e-9, abs=1e-9)
+
+
+@pytest.mark.parametrize('label', list(CASES))
+@pytest.mark.parametrize('frontier', [1, 8])
+def test_scale_1_models_same_tree_as_reference(monkeypatch, label, frontier):
+    use_oracle_engine(monkeypatch)
+    Node, kw = CASES[label]
+    for name, rec in SCALE1.items():
+        kwargs = {k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()}
+        bb = BranchAndBound(model_from(rec), Node, frontier_batch=frontier, **kwargs)
+        bb.solve()
+        check_against_reference(bb, rec['reference'][label])
+        assert bb.objective_value == pytest.approx(unfl(rec['mip_optimum']), abs=1e-6), name
+
+
+@pytest.mark.parametrize('label', list(CASES))
+@pytest.mark.parametrize('name', ['no_branch', 'small_branch', 'infeasible', 'infeasible2', 'random', 'cut1',
+                                  'cut2', 'cut3', 'square', 'h3p1', 'h3p1_0', 'h3p1_1', 'h3p1_2', 'h3p1_3',
+                                  'h3p1_4', 'h3p1_5', 'lift_project'])
+def test_example_models_same_tree_as_reference(monkeypatch, name, label):
+    use_oracle_engine(monkeypatch)
+    rec = EXAMPLES[name]
+    Node, kw = CASES[label]
+    kwargs = {k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()}
+    bb = BranchAndBound(model_from(rec), Node, **kwargs)
+    bb.solve()
+    check_against_reference(bb, rec['reference'][label])
+    if 'pseudo_costs' in rec['reference'][label]:
+        pc = bb._kwargs['pseudo_costs']
+        gold = rec['reference'][label]['pseudo_costs']
+        assert set(map(str, pc)) == set(gold)
+        for i, v in gold.items():
+            for d, e in v.items():
+                assert pc[int(i)][d]['times'] == e['times']
+                assert pc[int(i)][d]['cost'] == pytest.approx(e['cost'], rel=1e-7, abs=1e-9)
+
+
+def test_frontier_prefetch_batches_lps(monkeypatch):
+    """With frontier_batch > 1 open nodes reach the engine several at a time, and strong
+    branching children always arrive as one batch — without changing the tree."""
+    eng = use_oracle_engine(monkeypatch)
+    rec = EXAMPLES['random']
+    bb = BranchAndBound(model_from(rec), BaseNode, frontier_batch=16, gomory_cuts=False)
+    bb.solve()
+    check_against_reference(bb, rec['reference']['BaseNode'])
+    assert max(eng.batch_sizes) > 1 and eng.calls < eng.lps
+    batched = eng.calls
+    eng2 = use_oracle_engine(monkeypatch)
+    bb1 = BranchAndBound(model_from(rec), BaseNode, frontier_batch=1, gomory_cuts=False)
+    bb1.solve()
+    assert max(eng2.batch_sizes) == 1 and eng2.calls > batched
+    assert bb1.evaluated_nodes == bb.evaluated_nodes
+    eng3 = use_oracle_engine(monkeypatch)
+    bb2 = BranchAndBound(model_from(rec), PseudoCostBranchNode, pseudo_costs={}, gomory_cuts=False)
+    bb2.solve()
+    assert max(eng3.batch_sizes) >= 4          # 2 children x >= 2 uninitialised variables in one call
+
+
+def test_reference_known_answers_small_branch(monkeypatch):
+    """Pins of the reference's own tests that hold on an exact simplex."""
+    use_oracle_engine(monkeypatch)
+    m = model_from(EXAMPLES['small_branch'])
+    node = BaseNode(m.lp, m.integerIndices, idx=0)
+    node._bound_lp()                                     # test_base_node.py:406-416
+    assert node.objective_value == pytest.approx(-2.75) and node.lp_feasible and not node.mip_feasible
+    assert not node.unbounded
+    assert np.allclose(node.solution, [0, 1.25, 1.5])
+    assert node._most_fractional_index == 2              # test_base_node.py:824-826
+    rtn = node._base_branch(2, next_node_idx=1)          # test_base_node.py:711-763
+    assert list(rtn['left'].lp.variablesUpper) == [10, 10, 1]
+    assert list(rtn['right'].lp.variablesLower) == [0, 0, 2]
+    assert rtn['left']._b_val == 1.5 and rtn['left'].dual_bound == node.objective_value
+    assert rtn['left'].depth == 1 and (rtn['left'].idx, rtn['right'].idx) == (1, 2)
+    assert rtn['next_node_idx'] == 3 and node.children == (1, 2) and not node.is_leaf
+    assert rtn['right'].lineage == (0, 2)
+    for v, want in ((5.5, True), (5, False), (5.999999999999, False), (5.000000000001, False)):
+        assert node._is_fractional(v) is want             # test_base_node.py:802-807
+    # pseudo costs at the root (test_pseudo_cost.py:107-135): idx 1 'left' cost 1, all others 0
+    m = model_from(EXAMPLES['small_branch'])
+    pn = PseudoCostBranchNode(m.lp, m.integerIndices, idx=0)
+    rtn = pn.bound(pseudo_costs={}, gomory_cuts=False)
+    pc = rtn['pseudo_costs']
+    assert set(pc) == {1, 2}
+    assert pc[1]['left']['cost'] == pytest.approx(1.0)
+    assert [pc[i][d]['cost'] for i, d in ((1, 'right'), (2, 'left'), (2, 'right'))] == [0, 0, 0]
+    assert all(pc[i][d]['times'] == 1 for i in (1, 2) for d in ('left', 'right'))
+    # best pseudo cost index (test_pseudo_cost.py:170-179)
+    pn.solution = [0, 1.25, 2.5]
+    pcs = {1: {'right': {'cost': 1, 'times': 1}, 'left': {'cost': 1, 'times': 1}},
+           2: {'right': {'cost': 1, 'times': 1}, 'left': {'cost': 1, 'times': 1}}}
+    assert pn._best_pseudo_costs_index(pcs) == 2
+    pcs[1] = {'right': {'cost': 10, 'times': 1}, 'left': {'cost': 1, 'times': 1}}
+    assert pn._best_pseudo_costs_index(pcs) == 2
+    pcs[1] = {'right': {'cost': 10, 'times': 1}, 'left': {'cost': 10, 'times': 1}}
+    assert pn._best_pseudo_costs_index(pcs) == 1
+
+
+def test_gap_trajectory_and_resume(monkeypatch):
+    """solve() can be resumed after a node limit (test_branch_and_bound.py:267-276)."""
+    use_oracle_engine(monkeypatch)
+    bb = BranchAndBound(model_from(EXAMPLES['small_branch']), BaseNode, node_limit=1, gomory_cuts=False)
+    bb.solve()
+    assert bb.current_gap is None and bb.status == 'stopped on iterations or time'
+    bb.node_limit = 10
+    bb.solve()
+    assert bb.current_gap == pytest.approx(.125)
+    bb.node_limit = float('inf')
+    bb.solve()
+    assert bb.current_gap == 0 and bb.status == 'optimal' and bb.objective_value == -2
+
+
+def test_max_form_model_is_flipped(monkeypatch):
+    use_oracle_engine(monkeypatch)
+    A = np.array([[1, 0, 1], [0, 1, 0]])
+    m = MILPInstance(A=A, b=CyLPArray([1.5, 1.25]), c=CyLPArray([1, 1, 1]), l=CyLPArray([0, 0, 0]),
+                     u=CyLPArray([10, 10, 10]), sense=['Max', '<='], integerIndices=[0, 1, 2], numVars=3)
+    bb = BranchAndBound(m, BaseNode, gomory_cuts=False)
+    assert bb._swapped_constraint_direction and bb.model.sense == '>='
+    bb.solve()
+    assert bb.status == 'optimal' and bb.objective_value == -2
+
+
+def test_assertion_messages():
+    m = model_from(EXAMPLES['small_branch'])
+    with pytest.raises(AssertionError, match='lp must be CyClpSimplex instance'):
+        BaseNode(5, m.integerIndices)
+    with pytest.raises(AssertionError, match='indices must match variables'):
+        BaseNode(m.lp, [4])
+    with pytest.raises(AssertionError, match='indices must be distinct'):
+        BaseNode(m.lp, [0, 0])
+    with pytest.raises(AssertionError, match='none are none or all are none'):
+        BaseNode(m.lp, m.integerIndices, b_idx=1)
+    with pytest.raises(AssertionError, match='we can only branch right or left'):
+        BaseNode(m.lp, m.integerIndices, b_idx=1, b_dir='up', b_val=.5)
+    with pytest.raises(AssertionError, match='model must be cuppy MILPInstance'):
+        BranchAndBound('model', BaseNode)
+    with pytest.raises(AssertionError, match='Node must be a class'):
+        BranchAndBound(m, 'node')
+    with pytest.raises(AssertionError, match='node limit must be positive integer or infinity'):
+        BranchAndBound(m, BaseNode, node_limit=0)
+    with pytest.raises(AssertionError, match='mip_gap is a ratio between 0 and 1'):
+        BranchAndBound(m, BaseNode, mip_gap=2)
+    with pytest.raises(AssertionError, match='next_node_idx is reserved'):
+        BranchAndBound(m, BaseNode, next_node_idx=3)

@@ -124,7 +124,7 @@ def example_models():
             return getattr(em, nm)
         m = BaseAlgorithm._convert_constraints_to_greq(fresh())
         A = m.A.toarray() if sp.issparse(m.A) else np.asarray(m.A, dtype=float)
-        rec = dict(A=A.tolist(), b=[float(v) for v in np.asarray(m.b).ravel()],
+        rec = dict(A=A.tolist(), b=[float(v) for v in m.lp.constraintsLower],   # ('unbounded' passes a short b)
                    c=[float(v) for v in np.asarray(m.lp.objective).ravel()],
                    l=[float(v) for v in m.l], u=[float(min(v, 1e308)) for v in m.u],
                    integer_indices=list(m.integerIndices))

@@ -1,0 +1,87 @@
+"""The CPU oracle (HiGHS dual simplex, oracle/highs_lp.py) against the reference's own
+known-answer tests and against the goldens produced by running the reference here."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle.highs_lp import HIGHS_INF, HighsLP, solve_node_lps
+from oracle.pdhg_numpy import BatchPDHG
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+SCALE1 = json.load(open(os.path.join(GOLD, 'scale_1_models.json')))
+EXAMPLES = json.load(open(os.path.join(GOLD, 'example_models.json')))
+
+
+def lp_of(rec, l=None, u=None):
+    A = sp.csr_matrix(np.array(rec['A']))
+    return HighsLP(A, rec['c'], rec['b'], np.full(A.shape[0], HIGHS_INF),
+                   rec['l'] if l is None else l, rec['u'] if u is None else u)
+
+
+def test_reference_known_answer_lps():
+    # test_base_node.py:394-437 — exact values pinned by the reference's tests
+    r = lp_of(EXAMPLES['small_branch']).solve()
+    assert r.status == 0 and r.objective == pytest.approx(-2.75, abs=1e-12)
+    assert np.allclose(r.x, [0, 1.25, 1.5], atol=1e-12)
+    r = lp_of(EXAMPLES['no_branch']).solve()
+    assert r.status == 0 and r.objective == pytest.approx(-2.0, abs=1e-12)
+    assert np.allclose(r.x, [1, 1, 0], atol=1e-12)
+    assert lp_of(EXAMPLES['infeasible']).solve().status == 1
+    assert lp_of(EXAMPLES['unbounded']).solve().status == 2
+    # children of small_branch on x2 (test_branch_and_bound.py:187): right child infeasible
+    rec = EXAMPLES['small_branch']
+    assert lp_of(rec, l=[0, 0, 2]).solve().status == 1
+    assert lp_of(rec, u=[10, 10, 1]).solve().objective == pytest.approx(-2.75)
+    # cut2 root (test_base_node.py:479-489)
+    assert lp_of(EXAMPLES['cut2']).solve().objective == pytest.approx(-38.0)
+
+
+def test_oracle_matches_reference_run_on_every_fixture():
+    for name, rec in SCALE1.items():
+        r = lp_of(rec).solve()
+        assert r.status == 0
+        assert r.objective == pytest.approx(rec['root_lp']['objective'], rel=1e-12, abs=1e-12), name
+    for name, rec in EXAMPLES.items():
+        if 'root_lp' not in rec or not rec['root_lp']['lp_feasible'] or rec['root_lp']['unbounded']:
+            continue
+        assert lp_of(rec).solve().objective == pytest.approx(rec['root_lp']['objective'], rel=1e-12, abs=1e-12)
+
+
+def test_sanity_values_of_survey():
+    # SURVEY.md 8c table (computed with HiGHS when the survey was written)
+    want = {'constraints_high_variables_high_density_high_max_obj_coeff_high_max_cons_coeff_high_tightness_high':
+            (-44.6046511627907, -11),
+            'constraints_high_variables_high_density_high_max_obj_coeff_high_max_cons_coeff_low_tightness_low':
+            (-111.87084870848709, -80)}
+    for name, (lpv, mipv) in want.items():
+        assert SCALE1[name]['root_lp']['objective'] == pytest.approx(lpv, rel=1e-12)
+        assert SCALE1[name]['mip_optimum'] == pytest.approx(mipv)
+
+
+def test_strong_branch_iteration_limit_is_a_lower_bound():
+    # test_base_node.py:774-785: <= 5 pivots, and the child objective is >= the parent's
+    rec = EXAMPLES['random']
+    A = sp.csr_matrix(np.array(rec['A']))
+    root = lp_of(rec).solve()
+    j = int(np.argmax(np.minimum(root.x - np.floor(root.x), np.ceil(root.x) - root.x)))
+    u = np.array(rec['u']); u[j] = np.floor(root.x[j])
+    out = solve_node_lps(A, rec['b'], rec['c'], [rec['l']], [u], iteration_limit=5,
+                         root_l=np.array(rec['l']), root_u=np.array(rec['u']))
+    assert out[0].iterations <= 5
+    if out[0].status in (0, 3):
+        assert out[0].objective >= root.objective - 1e-9
+
+
+def test_numpy_pdhg_model_agrees_with_simplex():
+    """The numpy model of the device algorithm converges to the simplex optimum (1e-6 bar)."""
+    for name in list(SCALE1)[:12]:
+        rec = SCALE1[name]
+        A = sp.csr_matrix(np.array(rec['A']))
+        p = BatchPDHG(A, np.array(rec['b']), np.array(rec['c']))
+        s = p.solve(np.array(rec['l'])[:, None], np.array(rec['u'])[:, None], max_iters=50000)
+        assert s['status'][0] == 0
+        ref = rec['root_lp']['objective']
+        assert abs(s['obj'][0] - ref) <= 1e-6 * max(1, abs(ref)), name

@@ -1,0 +1,57 @@
+"""Node sharding and the incumbent / dual-bound all-reduce on 2 gloo ranks (CPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from simple_mip_solver_b200 import parallel
+
+
+def test_shard_bounds_cover_everything_once():
+    for total in (0, 1, 7, 4096, 4097):
+        for world in (1, 2, 3, 8):
+            cuts = [parallel.shard_bounds(total, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            sizes = [e - b for b, e in cuts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_bounds(4, 2, 2)
+    assert parallel.allreduce_bounds(1.0, 2.0) == (1.0, 2.0)      # no process group: identity
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    nodes = list(range(10))
+    mine = parallel.shard_items(nodes, rank, world)
+    # each rank "solves" its slice: objective = node id + 0.5, nodes 3 and 8 are integral
+    inc = min([k + 0.5 for k in mine if k in (3, 8)], default=float('inf'))
+    low = min(k + 0.25 for k in mine)
+    g_inc, g_low = parallel.allreduce_bounds(inc, low)
+    t = parallel.allreduce_max(float(rank + 1))
+    s = parallel.allreduce_sum([len(mine), 1.0])
+    out.put((rank, mine, g_inc, g_low, t, s))
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchange():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == [0, 1, 2, 3, 4] and got[1][1] == [5, 6, 7, 8, 9]
+    for _, _, g_inc, g_low, t, s in got:
+        assert g_inc == 3.5 and g_low == 0.25 and t == 2.0 and s == [10.0, 2.0]

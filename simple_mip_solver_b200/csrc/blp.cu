@@ -123,8 +123,8 @@ struct blp_handle_s {
     std::vector<double> c0, b0;
     std::vector<double> dr, dc;
     // device copies
-    DevBuf rowptr, colidx, val, cptr, ridx, cval, c, b, rowscale, colscale, d_dr, d_dc;
-    DevBuf uval, ucval;                // unscaled values, same patterns (blp_spmv)
+    DevBuf rowptr, ent, cptr, cent, c, b, rowscale, colscale, d_dr, d_dc;
+    DevBuf uent, ucent;                // unscaled entries, same patterns (blp_spmv)
     DevProb P{};
     // staging of the host-buffer entry points
     DevBuf s_lb, s_ub, s_x0, s_y0, s_mask, s_x, s_y, s_tmp, s_ws, s_node, s_int, s_delta, s_par;
@@ -171,14 +171,18 @@ int prepare(blp_handle h) {
     const double nb = norm2(bs), nc = norm2(cs);
 
     cudaStream_t s = h->stream;
+    auto pack = [](const HostCsr& a) {
+        std::vector<Ent> e(a.idx.size());
+        for (size_t p = 0; p < e.size(); ++p) e[p] = Ent{a.idx[p], 0, a.val[p]};
+        return e;
+    };
+    const std::vector<Ent> eA = pack(As), eAt = pack(At), eA0 = pack(h->A0), eA0t = pack(A0t);
     CK(upload(h->rowptr, As.ptr, s));
-    CK(upload(h->colidx, As.idx, s));
-    CK(upload(h->val, As.val, s));
+    CK(upload(h->ent, eA, s));
     CK(upload(h->cptr, At.ptr, s));
-    CK(upload(h->ridx, At.idx, s));
-    CK(upload(h->cval, At.val, s));
-    CK(upload(h->uval, h->A0.val, s));
-    CK(upload(h->ucval, A0t.val, s));
+    CK(upload(h->cent, eAt, s));
+    CK(upload(h->uent, eA0, s));
+    CK(upload(h->ucent, eA0t, s));
     CK(upload(h->c, cs, s));
     CK(upload(h->b, bs, s));
     CK(upload(h->rowscale, rowscale, s));
@@ -192,11 +196,9 @@ int prepare(blp_handle h) {
     P.m_base = h->m_base;
     P.n = n;
     P.rowptr = h->rowptr.as<int32_t>();
-    P.colidx = h->colidx.as<int32_t>();
-    P.val = h->val.as<double>();
+    P.ent = h->ent.as<Ent>();
     P.cptr = h->cptr.as<int32_t>();
-    P.ridx = h->ridx.as<int32_t>();
-    P.cval = h->cval.as<double>();
+    P.cent = h->cent.as<Ent>();
     P.c = h->c.as<double>();
     P.b = h->b.as<double>();
     P.rowscale = h->rowscale.as<double>();
@@ -256,8 +258,14 @@ size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
     s.status = cv.take<int32_t>(ld);
     s.iters = cv.take<int32_t>(ld);
     s.restart = cv.take<int32_t>(ld);
+    s.origin = cv.take<int32_t>(ld);
+    s.newpos = cv.take<int32_t>(ld);
     s.partC = cv.take<double>((size_t)kEvalChunks * C_N * ld);
     s.partR = cv.take<double>((size_t)kEvalChunks * R_N * ld);
+    s.fracD = cv.take<double>((size_t)kEvalChunks * ld);
+    s.fracI = cv.take<int32_t>((size_t)kEvalChunks * ld);
+    s.isint = cv.take<uint8_t>(n);
+    s.rowmask = cv.take<uint8_t>((m - h->m_base) * (size_t)ld + 1);
     s.counters = cv.take<int32_t>(8);
     if (S) *S = s;
     return align_up(cv.off, 256);
@@ -323,6 +331,37 @@ void launch_check_rows(const DevProb& P, const DevState& S, const Plan& er, cuda
         case 16: k_check_rows<16><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
         default: k_check_rows<32><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
     }
+}
+
+void launch_harvest(const DevProb& P, const DevState& S, const DevOut& O, const Plan& ec,
+                    const Plan& er, bool want_frac, cudaStream_t st, int* launches) {
+    const double eps = 1e-4;      // variable_epsilon of the reference (utils/tolerance.py:2)
+    if (O.x || want_frac) {
+        const dim3 g(ec.chunks, ec.tiles);
+        switch (ec.NT) {
+            case 1: k_harvest_x<1><<<g, kCtaThreads, 0, st>>>(P, S, O, eps, ec.rows_per_cta); break;
+            case 2: k_harvest_x<2><<<g, kCtaThreads, 0, st>>>(P, S, O, eps, ec.rows_per_cta); break;
+            case 4: k_harvest_x<4><<<g, kCtaThreads, 0, st>>>(P, S, O, eps, ec.rows_per_cta); break;
+            case 8: k_harvest_x<8><<<g, kCtaThreads, 0, st>>>(P, S, O, eps, ec.rows_per_cta); break;
+            case 16: k_harvest_x<16><<<g, kCtaThreads, 0, st>>>(P, S, O, eps, ec.rows_per_cta); break;
+            default: k_harvest_x<32><<<g, kCtaThreads, 0, st>>>(P, S, O, eps, ec.rows_per_cta); break;
+        }
+        ++*launches;
+    }
+    if (O.y) {
+        const dim3 g(er.chunks, er.tiles);
+        switch (er.NT) {
+            case 1: k_harvest_y<1><<<g, kCtaThreads, 0, st>>>(P, S, O, er.rows_per_cta); break;
+            case 2: k_harvest_y<2><<<g, kCtaThreads, 0, st>>>(P, S, O, er.rows_per_cta); break;
+            case 4: k_harvest_y<4><<<g, kCtaThreads, 0, st>>>(P, S, O, er.rows_per_cta); break;
+            case 8: k_harvest_y<8><<<g, kCtaThreads, 0, st>>>(P, S, O, er.rows_per_cta); break;
+            case 16: k_harvest_y<16><<<g, kCtaThreads, 0, st>>>(P, S, O, er.rows_per_cta); break;
+            default: k_harvest_y<32><<<g, kCtaThreads, 0, st>>>(P, S, O, er.rows_per_cta); break;
+        }
+        ++*launches;
+    }
+    k_harvest_nodes<<<(S.B + 127) / 128, 128, 0, st>>>(P, S, O, ec.chunks, eps, want_frac ? 1 : 0);
+    ++*launches;
 }
 
 int elementwise_grid(size_t total) {
@@ -484,21 +523,43 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     void* ws = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256));
     DevState S;
     carve_state(h, B, ws, &S);
-    S.rowmask = (P.m > P.m_base) ? row_mask : nullptr;
+    const bool have_mask = (P.m > P.m_base) && row_mask != nullptr;
+    uint8_t* mask_ws = S.rowmask;
+    if (!have_mask) S.rowmask = nullptr;
+    const bool want_frac = frac_idx != nullptr && int_idx != nullptr && n_int > 0;
+    uint8_t* isint_ws = const_cast<uint8_t*>(S.isint);
+    if (!want_frac) S.isint = nullptr;
+    DevOut O{obj, lower_bound, x, y, status, iters, frac_idx};
 
     const int K = std::min(o.eval_every, o.max_iters);
-    const int rpw = env_int("BLP_ROWS_PER_WARP", 4);
-    const Plan pc = plan_rows(P.n, B, rpw, 0), pr = plan_rows(P.m, B, rpw, 0);
-    const Plan ec = plan_rows(P.n, B, 1, kEvalChunks), er = plan_rows(P.m, B, 1, kEvalChunks);
-    DecideArgs D{ec.chunks, er.chunks, K, o.max_iters, o.eps_rel, o.eps_infeas};
+    const int rpw = env_int("BLP_ROWS_PER_WARP", 8);
+    const int NT = pick_nt(B);
+    DecideArgs D{0, 0, K, o.max_iters, o.eps_rel, o.eps_infeas};
     int launches = 0;
 
     CK(cudaEventRecord(h->ev[0], st));
     CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(int32_t), st));
+    if (have_mask)
+        CK(cudaMemcpyAsync(mask_ws, row_mask, (size_t)(P.m - P.m_base) * S.ld, cudaMemcpyDeviceToDevice, st));
+    if (want_frac) {
+        CK(cudaMemsetAsync(isint_ws, 0, P.n, st));
+        k_set_isint<<<(n_int + 255) / 256, 256, 0, st>>>(int_idx, n_int, P.n, isint_ws);
+        ++launches;
+    }
+    if (x) CK(cudaMemsetAsync(x, 0, (size_t)P.n * S.ld * sizeof(double), st));
+    if (y) CK(cudaMemsetAsync(y, 0, (size_t)P.m * S.ld * sizeof(double), st));
+    if (S.ld > B) {
+        k_out_pad<<<(S.ld - B + 127) / 128, 128, 0, st>>>(O, B, S.ld);
+        ++launches;
+    }
     k_init_nodes<<<(S.ld + 127) / 128, 128, 0, st>>>(P, S);
     k_init_cols<<<elementwise_grid((size_t)P.n * S.ld), kCtaThreads, 0, st>>>(P, S, lb, ub, x0);
     k_init_rows<<<elementwise_grid((size_t)P.m * S.ld), kCtaThreads, 0, st>>>(P, S, y0);
-    launch_check_rows(P, S, er, st);
+    {
+        Plan er0 = plan_rows(P.m, B, 1, kEvalChunks);
+        er0.NT = NT;
+        launch_check_rows(P, S, er0, st);
+    }
     k_count_active<<<(B + 127) / 128, 128, 0, st>>>(S);
     launches += 5;
     CK(cudaGetLastError());
@@ -506,10 +567,38 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     CK(cudaStreamSynchronize(st));
     int active = h->h_counters[0];
 
-    // ---- period graphs (cached on the exact parameter set) ----
+    // plans depend on the current batch width (compaction shrinks it); NT stays fixed for the call
+    auto make_plan = [&](int rows, int width, int rows_per_warp, int max_chunks) {
+        Plan p = plan_rows(rows, width, rows_per_warp, max_chunks);
+        const int pass = kWarps * (32 / NT);
+        p.NT = NT;
+        p.tiles = (width + NT - 1) / NT;
+        int rpc = pass * std::max(rows_per_warp, 1);
+        if (max_chunks > 0) {
+            const int need = (rows + max_chunks - 1) / max_chunks;
+            rpc = std::max(rpc, ((need + pass - 1) / pass) * pass);
+        }
+        p.rows_per_cta = rpc;
+        p.chunks = std::max(1, (rows + rpc - 1) / rpc);
+        return p;
+    };
+    Plan pc = make_plan(P.n, B, rpw, 0), pr = make_plan(P.m, B, rpw, 0);
+    Plan ec = make_plan(P.n, B, 1, kEvalChunks), er = make_plan(P.m, B, 1, kEvalChunks);
+    D.chunksC = ec.chunks;
+    D.chunksR = er.chunks;
+
+    if (active < B) launch_harvest(P, S, O, ec, er, want_frac, st, &launches);    // decided at set-up
+
     const bool profile = o.profile == 1;
     const bool use_graph = o.use_graph && !profile;
-    if (use_graph && active > 0) {
+    if (profile)
+        while ((int)h->prof_ev.size() < 2 * K + 1) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->prof_ev.push_back(e);
+        }
+
+    auto ensure_graphs = [&]() -> int {
         GraphKey key;
         memset(&key, 0, sizeof key);
         key.P = P;
@@ -517,36 +606,52 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         key.D = D;
         key.K = K;
         key.rpw = rpw;
-        if (!h->graph_valid || memcmp(&key, &h->gkey, sizeof key) != 0) {
-            h->drop_graphs();
-            cudaGraph_t g = nullptr;
-            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, st);
-            CK(cudaStreamEndCapture(st, &g));
-            cudaError_t e = cudaGraphInstantiate(&h->g_steps, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) return fail(BLP_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
-            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            launch_eval(P, S, ec, er, D, K, st);
-            CK(cudaStreamEndCapture(st, &g));
-            e = cudaGraphInstantiate(&h->g_eval, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) return fail(BLP_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
-            h->gkey = key;
-            h->graph_valid = true;
-        }
-    }
-    if (profile && (int)h->prof_ev.size() < 2 * K + 1) {
-        while ((int)h->prof_ev.size() < 2 * K + 1) {
-            cudaEvent_t e;
-            CK(cudaEventCreate(&e));
-            h->prof_ev.push_back(e);
-        }
-    }
+        if (h->graph_valid && memcmp(&key, &h->gkey, sizeof key) == 0) return BLP_OK;
+        h->drop_graphs();
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, st);
+        CK(cudaStreamEndCapture(st, &g));
+        cudaError_t e = cudaGraphInstantiate(&h->g_steps, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(BLP_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        launch_eval(P, S, ec, er, D, K, st);
+        CK(cudaStreamEndCapture(st, &g));
+        e = cudaGraphInstantiate(&h->g_eval, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(BLP_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+        h->gkey = key;
+        h->graph_valid = true;
+        return BLP_OK;
+    };
 
-    int total = 0, evals = 0;
+    int total = 0, evals = 0, compactions = 0;
     double step_ms = 0.0, primal_ms = 0.0, dual_ms = 0.0, node_iters = 0.0;
     while (active > 0 && total < o.max_iters) {
+        // retire finished nodes: pack the running ones to the front when that frees node tiles
+        if (o.compact && active < S.B) {
+            const int cur_tiles = (S.B + NT - 1) / NT, new_tiles = (active + NT - 1) / NT;
+            if (new_tiles < cur_tiles && (new_tiles * 8 <= cur_tiles * 7 || cur_tiles <= 16)) {
+                const int oldB = S.B;
+                k_compact_plan<<<1, 1024, 0, st>>>(S);
+                k_compact_vecs<<<elementwise_grid((size_t)(4 * P.n + 2 * P.m) * 32), kCtaThreads, 0, st>>>(P, S, oldB);
+                CK(cudaGetLastError());
+                launches += 2;
+                ++compactions;
+                S.B = active;
+                pc = make_plan(P.n, S.B, rpw, 0);
+                pr = make_plan(P.m, S.B, rpw, 0);
+                ec = make_plan(P.n, S.B, 1, kEvalChunks);
+                er = make_plan(P.m, S.B, 1, kEvalChunks);
+                D.chunksC = ec.chunks;
+                D.chunksR = er.chunks;
+            }
+        }
+        if (use_graph) {
+            int rcg = ensure_graphs();
+            if (rcg != BLP_OK) return rcg;
+        }
         CK(cudaEventRecord(h->ev[2], st));
         if (use_graph) {
             CK(cudaGraphLaunch(h->g_steps, st));
@@ -585,25 +690,14 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         evals += 1;
         launches += 2 * K + 5;
         active = h->h_counters[0];
+        if (h->h_counters[3] > 0) {
+            launch_harvest(P, S, O, ec, er, want_frac, st, &launches);
+            CK(cudaGetLastError());
+        }
         if (o.verbose)
-            fprintf(stderr, "[blp] iters %d  running %d  restarting %d\n", total, active, h->h_counters[1]);
+            fprintf(stderr, "[blp] iters %d  width %d  running %d  restarting %d  finished now %d\n", total,
+                    S.B, active, h->h_counters[1], h->h_counters[3]);
     }
-
-    // ---- outputs ----
-    if (x) {
-        k_out_vec<<<elementwise_grid((size_t)P.n * S.ld), kCtaThreads, 0, st>>>(
-            S.X1, P.dc, 1.0 / P.sb, P.n, S.ld, B, x);
-        ++launches;
-    }
-    if (y) {
-        k_out_vec<<<elementwise_grid((size_t)P.m * S.ld), kCtaThreads, 0, st>>>(
-            S.Y1, P.dr, 1.0 / P.sc, P.m, S.ld, B, y);
-        ++launches;
-    }
-    k_out_nodes<<<(S.ld + 127) / 128, 128, 0, st>>>(P, S, int_idx, int_idx ? n_int : 0, 1e-4, obj,
-                                                   lower_bound, status, iters, frac_idx);
-    ++launches;
-    CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[1], st));
     CK(cudaStreamSynchronize(st));
     if (stats) {
@@ -612,7 +706,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         stats->iterations = total;
         stats->evaluations = evals;
         stats->kernel_launches = launches;
-        stats->compactions = 0;
+        stats->compactions = compactions;
         stats->step_kernel_ms = step_ms;
         stats->total_ms = ms;
         stats->node_iterations = node_iters;
@@ -814,18 +908,17 @@ int blp_spmv(blp_handle h, int B, int transpose, const double* X, double* Y) {
     const int ld = blp_ld(B);
     const int rows = transpose ? h->n : h->A0.rows;
     const int32_t* ptr = transpose ? h->P.cptr : h->P.rowptr;
-    const int32_t* idx = transpose ? h->P.ridx : h->P.colidx;
-    const double* val = transpose ? h->ucval.as<double>() : h->uval.as<double>();
-    const Plan p = plan_rows(rows, B, env_int("BLP_ROWS_PER_WARP", 4), 0);
+    const Ent* ent = transpose ? h->ucent.as<Ent>() : h->uent.as<Ent>();
+    const Plan p = plan_rows(rows, B, env_int("BLP_ROWS_PER_WARP", 8), 0);
     const dim3 g(p.chunks, p.tiles);
     cudaStream_t st = h->stream;
     switch (p.NT) {
-        case 1: k_spmv<1><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
-        case 2: k_spmv<2><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
-        case 4: k_spmv<4><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
-        case 8: k_spmv<8><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
-        case 16: k_spmv<16><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
-        default: k_spmv<32><<<g, kCtaThreads, 0, st>>>(ptr, idx, val, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 1: k_spmv<1><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 2: k_spmv<2><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 4: k_spmv<4><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 8: k_spmv<8><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 16: k_spmv<16><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
+        default: k_spmv<32><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
     }
     CK(cudaGetLastError());
     return BLP_OK;
@@ -843,8 +936,8 @@ int blp_destroy(blp_handle h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->drop_graphs();
-    DevBuf* bufs[] = {&h->rowptr, &h->colidx, &h->val, &h->cptr, &h->ridx, &h->cval, &h->c, &h->b,
-                      &h->rowscale, &h->colscale, &h->d_dr, &h->d_dc, &h->uval, &h->ucval, &h->s_lb,
+    DevBuf* bufs[] = {&h->rowptr, &h->ent, &h->cptr, &h->cent, &h->c, &h->b,
+                      &h->rowscale, &h->colscale, &h->d_dr, &h->d_dc, &h->uent, &h->ucent, &h->s_lb,
                       &h->s_ub, &h->s_x0, &h->s_y0, &h->s_mask, &h->s_x, &h->s_y, &h->s_tmp,
                       &h->s_ws, &h->s_node, &h->s_int, &h->s_delta, &h->s_par};
     for (DevBuf* b : bufs) b->release();

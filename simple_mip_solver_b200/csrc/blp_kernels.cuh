@@ -27,10 +27,17 @@ enum { C_DX2, C_CROSS, C_DRES2, C_CX, C_BND, C_DXA2, C_BOX, C_BOXABS, C_CD, C_NS
 // row-pass accumulators
 enum { R_PRES2, R_BY, R_DY2, R_DYA2, R_BYABS, R_NSUM, R_ADNEG = R_NSUM, R_YMAX, R_N };
 
+// one stored matrix entry; 16 bytes so that a row walk is one 128-bit load per nonzero
+struct __align__(16) Ent {
+    int32_t idx;
+    int32_t pad;
+    double val;
+};
+
 struct DevProb {
     int m, m_base, n;
-    const int32_t* rowptr; const int32_t* colidx; const double* val;     // scaled A   (m x n)
-    const int32_t* cptr;   const int32_t* ridx;   const double* cval;    // scaled A^T (n x m)
+    const int32_t* rowptr; const Ent* ent;       // scaled A   (m x n), CSR
+    const int32_t* cptr;   const Ent* cent;      // scaled A^T (n x m), CSR
     const double* c; const double* b;            // scaled objective / row lower bounds
     const double* rowscale; const double* colscale;   // scaled residual -> unscaled
     const double* dr; const double* dc;
@@ -41,49 +48,60 @@ struct DevState {
     int B, ld;
     double *xbar, *xa, *l, *u, *X1, *DX, *G;       // [n][ld]
     double *y, *ya, *Y1, *DY;                      // [m][ld]
-    const uint8_t* rowmask;                        // [m - m_base][ld] or null
+    uint8_t* rowmask;                              // [m - m_base][ld] (workspace copy) or null
     double *omega, *fpe0, *fpe_prev, *pobj, *dobj; // [ld]
     int32_t *sbase, *fin, *status, *iters, *restart;   // [ld]
+    int32_t *origin, *newpos;                      // [ld] caller's node id of a column; compaction map
     double *partC, *partR;                         // [chunks][C_N][ld], [chunks][R_N][ld]
-    int32_t* counters;                             // [0] active nodes, [1] nodes restarting
+    double* fracD; int32_t* fracI;                 // [chunks][ld] most-fractional partials
+    const uint8_t* isint;                          // [n] 1 = integer column, or null
+    int32_t* counters;                             // see k_tick
+};
+
+// caller-side output arrays (node-fastest, leading dimension ld; entries indexed by ORIGINAL node)
+struct DevOut {
+    double *obj, *lower, *x, *y;
+    int32_t *status, *iters, *frac_idx;
 };
 
 __device__ __forceinline__ bool is_inf(double v) { return fabs(v) >= 1e30; }
 
 // ---------------------------------------------------------------------------------------------
 // gather-dot of one CSR row with a batched vector: sum_p val[p] * V[idx[p]][node]
-// NT == 32: the row is warp-uniform; lanes fetch 32 (index, value) pairs with one coalesced load
-// each and broadcast them by shuffle, so the dependent index->gather chain is one load deep.
-// NT < 32: every lane walks its own row.
+// NT == 32: the row is warp-uniform, so every lane issues the same 128-bit entry load (one
+// broadcast wavefront) and then its own coalesced 8-byte gather; 4 entries are in flight at once.
+// NT < 32: every lane walks the row of its own sub-group.
 template <int NT>
 __device__ __forceinline__ double row_dot(const int32_t* __restrict__ ptr,
-                                          const int32_t* __restrict__ idx,
-                                          const double* __restrict__ val, int row, bool row_ok,
+                                          const Ent* __restrict__ ent, int row, bool row_ok,
                                           const double* __restrict__ V, int ld, int node,
                                           bool node_ok, int lane) {
     double acc = 0.0;
-    if constexpr (NT == 32) {
+    if (NT == 32 || (row_ok && node_ok)) {
         const int p0 = __ldg(ptr + row), p1 = __ldg(ptr + row + 1);
-        for (int base = p0; base < p1; base += 32) {
-            const int cnt = min(32, p1 - base);
-            int myi = 0;
-            double mya = 0.0;
-            if (lane < cnt) {
-                myi = __ldg(idx + base + lane);
-                mya = __ldg(val + base + lane);
+        const double* __restrict__ Vn = V + node;
+        int p = p0;
+        for (; p + 4 <= p1; p += 4) {
+            const int4 e0 = __ldg(reinterpret_cast<const int4*>(ent + p));
+            const int4 e1 = __ldg(reinterpret_cast<const int4*>(ent + p + 1));
+            const int4 e2 = __ldg(reinterpret_cast<const int4*>(ent + p + 2));
+            const int4 e3 = __ldg(reinterpret_cast<const int4*>(ent + p + 3));
+            double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+            if (node_ok) {
+                v0 = Vn[(size_t)e0.x * ld];
+                v1 = Vn[(size_t)e1.x * ld];
+                v2 = Vn[(size_t)e2.x * ld];
+                v3 = Vn[(size_t)e3.x * ld];
             }
-#pragma unroll 4
-            for (int q = 0; q < cnt; ++q) {
-                const int i = __shfl_sync(0xffffffffu, myi, q);
-                const double a = __shfl_sync(0xffffffffu, mya, q);
-                if (node_ok) acc = fma(a, V[(size_t)i * ld + node], acc);
-            }
+            acc = fma(__hiloint2double(e0.w, e0.z), v0, acc);
+            acc = fma(__hiloint2double(e1.w, e1.z), v1, acc);
+            acc = fma(__hiloint2double(e2.w, e2.z), v2, acc);
+            acc = fma(__hiloint2double(e3.w, e3.z), v3, acc);
         }
-    } else {
-        if (row_ok && node_ok) {
-            const int p0 = __ldg(ptr + row), p1 = __ldg(ptr + row + 1);
-            for (int p = p0; p < p1; ++p)
-                acc = fma(__ldg(val + p), V[(size_t)__ldg(idx + p) * ld + node], acc);
+        for (; p < p1; ++p) {
+            const int4 e = __ldg(reinterpret_cast<const int4*>(ent + p));
+            const double v = node_ok ? Vn[(size_t)e.x * ld] : 0.0;
+            acc = fma(__hiloint2double(e.w, e.z), v, acc);
         }
     }
     return acc;
@@ -119,7 +137,7 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
             lo = __ldcs(S.l + e);
             hi = __ldcs(S.u + e);
         }
-        const double g = row_dot<NT>(P.cptr, P.ridx, P.cval, row_ok ? j : 0, row_ok, S.y, S.ld,
+        const double g = row_dot<NT>(P.cptr, P.cent, row_ok ? j : 0, row_ok, S.y, S.ld,
                                      node, node_ok && row_ok, lane);
         if (row_ok && node_ok) {
             const double xc = fma(w, xb - a, a);                  // w xbar + (1-w) xa
@@ -163,7 +181,7 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta) 
             a = __ldcs(S.ya + e);
             if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
         }
-        const double ax = row_dot<NT>(P.rowptr, P.colidx, P.val, row_ok ? i : 0, row_ok, S.xbar,
+        const double ax = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.xbar,
                                       S.ld, node, node_ok && row_ok, lane);
         if (row_ok && node_ok) {
             const double yp = on ? fmax(0.0, yc + sig * (__ldg(P.b + i) - ax)) : 0.0;
@@ -215,7 +233,7 @@ k_eval_cols(const DevProb P, const DevState S, const int rows_per_cta) {
         const int j = jb + sub;
         const bool row_ok = j < r1;
         const size_t e = (size_t)j * S.ld + node;
-        const double gp = row_dot<NT>(P.cptr, P.ridx, P.cval, row_ok ? j : 0, row_ok, S.Y1, S.ld,
+        const double gp = row_dot<NT>(P.cptr, P.cent, row_ok ? j : 0, row_ok, S.Y1, S.ld,
                                       node, node_ok && row_ok, lane);
         if (row_ok && node_ok) {
             const double xp = S.X1[e], dx = S.DX[e], g = S.G[e];
@@ -268,9 +286,9 @@ k_eval_rows(const DevProb P, const DevState S, const int rows_per_cta) {
         const bool row_ok = i < r1;
         const size_t e = (size_t)i * S.ld + node;
         const bool ok = row_ok && node_ok;
-        const double ax = row_dot<NT>(P.rowptr, P.colidx, P.val, row_ok ? i : 0, row_ok, S.X1, S.ld,
+        const double ax = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.X1, S.ld,
                                       node, ok, lane);
-        const double ad = row_dot<NT>(P.rowptr, P.colidx, P.val, row_ok ? i : 0, row_ok, S.G, S.ld,
+        const double ad = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.G, S.ld,
                                       node, ok, lane);
         if (ok) {
             bool on = true;
@@ -303,11 +321,13 @@ struct DecideArgs {
 
 // counters: [0] nodes still running after the evaluation, [1] nodes restarting,
 //           [2] PDHG iterations executed so far (advanced by k_tick at the start of a period,
-//               so one captured period graph can be replayed unchanged)
+//               so one captured period graph can be replayed unchanged),
+//           [3] nodes that got a status in this evaluation (to be harvested)
 __global__ void k_tick(const DevState S, const int steps) {
     S.counters[0] = 0;
     S.counters[1] = 0;
     S.counters[2] += steps;
+    S.counters[3] = 0;
 }
 
 __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) {
@@ -366,6 +386,7 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
         S.fin[node] = 1;
         S.iters[node] = total;
         if (st == 1) S.pobj[node] = INFINITY;
+        atomicAdd(S.counters + 3, 1);
         return;
     }
     atomicAdd(S.counters + 0, 1);
@@ -478,8 +499,8 @@ k_check_rows(const DevProb P, const DevState S, const int rows_per_cta) {
             continue;
         double act = 0.0, mag = 0.0;
         for (int p = __ldg(P.rowptr + i); p < __ldg(P.rowptr + i + 1); ++p) {
-            const double a = __ldg(P.val + p);
-            const size_t e = (size_t)__ldg(P.colidx + p) * S.ld + node;
+            const double a = P.ent[p].val;
+            const size_t e = (size_t)P.ent[p].idx * S.ld + node;
             const double t = a * (a > 0.0 ? S.u[e] : S.l[e]);
             act += t;
             mag += fabs(t);
@@ -509,45 +530,206 @@ __global__ void k_init_nodes(const DevProb P, const DevState S) {
     S.status[node] = 3;
     S.iters[node] = 0;
     S.restart[node] = 0;
+    S.origin[node] = node;
 }
 
-// Epilogue: unscale x', y' into the caller's arrays, per-node scalars, most fractional column.
+// Harvest: nodes that received a status in the last evaluation (fin == 1) hand their results to
+// the caller's arrays at their ORIGINAL node index; afterwards they are marked fin = 2 and the next
+// compaction drops their columns.
+//   k_harvest_x: x = X1 * dc / sb, plus per-chunk partials of the most fractional integer column
+//   k_harvest_y: y = Y1 * dr / sc
+//   k_harvest_nodes: per-node scalars, fold of the fractionality partials (ties -> smaller index)
+template <int NT>
 __global__ void __launch_bounds__(kCtaThreads)
-k_out_vec(const double* __restrict__ src, const double* __restrict__ diag, const double inv,
-          const int rows, const int ld, const int B, double* __restrict__ dst) {
-    const size_t total = (size_t)rows * ld;
-    for (size_t e = (size_t)blockIdx.x * kCtaThreads + threadIdx.x; e < total;
-         e += (size_t)gridDim.x * kCtaThreads) {
-        const int r = (int)(e / ld), node = (int)(e % ld);
-        dst[e] = node < B ? src[e] * diag[r] * inv : 0.0;
+k_harvest_x(const DevProb P, const DevState S, const DevOut O, const double frac_eps,
+            const int rows_per_cta) {
+    constexpr int RW = 32 / NT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = blockIdx.y * NT + (lane % NT);
+    const int sub = lane / NT;
+    const bool node_ok = node < S.B && S.fin[node] == 1;
+    if (__ballot_sync(0xffffffffu, node_ok) == 0) return;     // uniform over the CTA
+    const int org = node_ok ? S.origin[node] : 0;
+    const double inv = 1.0 / P.sb;
+    double best = frac_eps;
+    int besti = 0x7fffffff;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(P.n, r0 + rows_per_cta);
+    for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
+        const int j = jb + sub;
+        if (j < r1 && node_ok) {
+            const double v = S.X1[(size_t)j * S.ld + node] * __ldg(P.dc + j) * inv;
+            if (O.x) O.x[(size_t)j * S.ld + org] = v;
+            if (S.isint && S.isint[j]) {
+                const double dist = fmin(v - floor(v), ceil(v) - v);
+                if (dist > best) { best = dist; besti = j; }      // ascending j per lane: first wins
+            }
+        }
+    }
+    __shared__ double sd[kCtaThreads];
+    __shared__ int si[kCtaThreads];
+    sd[threadIdx.x] = best;
+    si[threadIdx.x] = besti;
+    __syncthreads();
+    if (threadIdx.x < NT) {
+        double bd = sd[threadIdx.x];
+        int bi = si[threadIdx.x];
+        for (int q = threadIdx.x + NT; q < kCtaThreads; q += NT)
+            if (sd[q] > bd || (sd[q] == bd && si[q] < bi)) { bd = sd[q]; bi = si[q]; }
+        const int nd = blockIdx.y * NT + threadIdx.x;
+        if (nd < S.ld) {
+            S.fracD[(size_t)blockIdx.x * S.ld + nd] = bd;
+            S.fracI[(size_t)blockIdx.x * S.ld + nd] = bi;
+        }
     }
 }
 
-__global__ void k_out_nodes(const DevProb P, const DevState S, const int32_t* __restrict__ int_idx,
-                            const int n_int, const double frac_eps, double* __restrict__ obj,
-                            double* __restrict__ lower, int32_t* __restrict__ status,
-                            int32_t* __restrict__ iters, int32_t* __restrict__ frac_idx) {
+template <int NT>
+__global__ void __launch_bounds__(kCtaThreads)
+k_harvest_y(const DevProb P, const DevState S, const DevOut O, const int rows_per_cta) {
+    constexpr int RW = 32 / NT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = blockIdx.y * NT + (lane % NT);
+    const int sub = lane / NT;
+    const bool node_ok = node < S.B && S.fin[node] == 1;
+    if (__ballot_sync(0xffffffffu, node_ok) == 0) return;
+    const int org = node_ok ? S.origin[node] : 0;
+    const double inv = 1.0 / P.sc;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(P.m, r0 + rows_per_cta);
+    for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
+        const int i = ib + sub;
+        if (i < r1 && node_ok)
+            O.y[(size_t)i * S.ld + org] = S.Y1[(size_t)i * S.ld + node] * __ldg(P.dr + i) * inv;
+    }
+}
+
+__global__ void k_harvest_nodes(const DevProb P, const DevState S, const DevOut O, const int chunks,
+                                const double frac_eps, const int have_frac) {
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= S.ld) return;
-    const bool real = node < S.B;
-    const int st = real ? S.status[node] : -1;
-    if (obj) obj[node] = real ? S.pobj[node] : 0.0;
-    if (lower) lower[node] = real ? S.dobj[node] : 0.0;
-    if (status) status[node] = st;
-    if (iters) iters[node] = real ? S.iters[node] : 0;
-    if (frac_idx) {
-        int best = -1;
-        if (st == 0 && int_idx) {
-            double far = frac_eps;
-            const double inv = 1.0 / P.sb;
-            for (int q = 0; q < n_int; ++q) {
-                const int j = int_idx[q];
-                const double v = S.X1[(size_t)j * S.ld + node] * P.dc[j] * inv;
-                const double dist = fmin(v - floor(v), ceil(v) - v);
-                if (dist > far) { far = dist; best = j; }
+    if (node >= S.B || S.fin[node] != 1) return;
+    const int org = S.origin[node];
+    const int st = S.status[node];
+    if (O.obj) O.obj[org] = S.pobj[node];
+    if (O.lower) O.lower[org] = S.dobj[node];
+    if (O.status) O.status[org] = st;
+    if (O.iters) O.iters[org] = S.iters[node];
+    if (O.frac_idx) {
+        int bi = -1;
+        if (st == 0 && have_frac) {
+            double bd = frac_eps;
+            int cand = 0x7fffffff;
+            for (int ch = 0; ch < chunks; ++ch) {
+                const double d = S.fracD[(size_t)ch * S.ld + node];
+                const int i = S.fracI[(size_t)ch * S.ld + node];
+                if (d > bd || (d == bd && i < cand)) { bd = d; cand = i; }
+            }
+            if (cand != 0x7fffffff) bi = cand;
+        }
+        O.frac_idx[org] = bi;
+    }
+    S.fin[node] = 2;
+}
+
+// output slots of the padding columns B..ld-1
+__global__ void k_out_pad(const DevOut O, const int B, const int ld) {
+    const int k = B + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ld) return;
+    if (O.obj) O.obj[k] = 0.0;
+    if (O.lower) O.lower[k] = 0.0;
+    if (O.status) O.status[k] = -1;
+    if (O.iters) O.iters[k] = 0;
+    if (O.frac_idx) O.frac_idx[k] = -1;
+}
+
+// Compaction: running nodes (fin == 0) move to the front of the batch, keeping their order, so
+// that retired node columns stop costing bandwidth. One CTA plans the move and permutes the
+// per-node scalars; k_compact_vecs then moves every state row in place (a column only ever moves
+// to a smaller index, and each warp sweeps its row in ascending order, so nothing unread is
+// overwritten).
+__global__ void __launch_bounds__(1024) k_compact_plan(const DevState S) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < S.B; c0 += 1024) {
+        const int k = c0 + tid;
+        const bool keep = k < S.B && S.fin[k] == 0;
+        double om = 0, f0 = 0, fp = 0, po = 0, dq = 0;
+        int sb = 0, stt = 0, itr = 0, org = 0;
+        if (keep) {
+            om = S.omega[k]; f0 = S.fpe0[k]; fp = S.fpe_prev[k]; po = S.pobj[k]; dq = S.dobj[k];
+            sb = S.sbase[k]; stt = S.status[k]; itr = S.iters[k]; org = S.origin[k];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = base_s;
+        for (int w = 0; w < warp; ++w) before += wsum[w];
+        const int pos = before + __popc(bal & ((1u << lane) - 1u));
+        int total = 0;
+        for (int w = 0; w < 32; ++w) total += wsum[w];
+        __syncthreads();
+        if (k < S.B) S.newpos[k] = keep ? pos : -1;
+        if (keep) {
+            S.omega[pos] = om; S.fpe0[pos] = f0; S.fpe_prev[pos] = fp; S.pobj[pos] = po; S.dobj[pos] = dq;
+            S.sbase[pos] = sb; S.status[pos] = stt; S.iters[pos] = itr; S.origin[pos] = org;
+        }
+        if (tid == 0) base_s += total;
+        __syncthreads();
+    }
+    const int nb = base_s;
+    for (int k = tid; k < S.ld; k += 1024) {
+        S.fin[k] = k < nb ? 0 : 2;
+        S.restart[k] = 0;
+    }
+    if (tid == 0) S.counters[4] = nb;
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_compact_vecs(const DevProb P, const DevState S, const int oldB) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * kCtaThreads + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * kCtaThreads) >> 5;
+    const int mc = S.rowmask ? P.m - P.m_base : 0;
+    const int total = 4 * P.n + 2 * P.m + mc;
+    for (int r = gwarp; r < total; r += nwarps) {
+        if (r < 4 * P.n + 2 * P.m) {
+            double* base;
+            if (r < 4 * P.n) {
+                const int a = r / P.n, j = r % P.n;
+                base = (a == 0 ? S.xbar : a == 1 ? S.xa : a == 2 ? S.l : S.u) + (size_t)j * S.ld;
+            } else {
+                const int q = r - 4 * P.n;
+                base = (q < P.m ? S.y : S.ya) + (size_t)(q % P.m) * S.ld;
+            }
+            for (int c0 = 0; c0 < oldB; c0 += 32) {
+                const int k = c0 + lane;
+                const int p = k < oldB ? S.newpos[k] : -1;
+                const double v = p >= 0 ? base[k] : 0.0;
+                __syncwarp();
+                if (p >= 0) base[p] = v;
+            }
+        } else {
+            uint8_t* base = S.rowmask + (size_t)(r - 4 * P.n - 2 * P.m) * S.ld;
+            for (int c0 = 0; c0 < oldB; c0 += 32) {
+                const int k = c0 + lane;
+                const int p = k < oldB ? S.newpos[k] : -1;
+                const uint8_t v = p >= 0 ? base[k] : 0;
+                __syncwarp();
+                if (p >= 0) base[p] = v;
             }
         }
-        frac_idx[node] = best;
+    }
+}
+
+__global__ void k_set_isint(const int32_t* __restrict__ int_idx, const int n_int, const int n,
+                            uint8_t* __restrict__ isint) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_int) {
+        const int j = int_idx[q];
+        if (j >= 0 && j < n) isint[j] = 1;
     }
 }
 
@@ -555,8 +737,8 @@ __global__ void k_out_nodes(const DevProb P, const DevState S, const int32_t* __
 // Plain batched SpMV on the unscaled matrix (parity tests, SpMV roofline measurement).
 template <int NT>
 __global__ void __launch_bounds__(kCtaThreads)
-k_spmv(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-       const double* __restrict__ val, const int rows, const int B, const int ld,
+k_spmv(const int32_t* __restrict__ ptr, const Ent* __restrict__ ent, const int rows, const int B,
+       const int ld,
        const double* __restrict__ X, double* __restrict__ Y, const int rows_per_cta) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -568,7 +750,7 @@ k_spmv(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
-        const double s = row_dot<NT>(ptr, idx, val, row_ok ? i : 0, row_ok, X, ld, node,
+        const double s = row_dot<NT>(ptr, ent, row_ok ? i : 0, row_ok, X, ld, node,
                                      node_ok && row_ok, lane);
         if (row_ok && node_ok) Y[(size_t)i * ld + node] = s;
     }

@@ -74,11 +74,31 @@ cudaError_t upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
 
 struct Plan {
     int NT, tiles, chunks, rows_per_cta;
+    int cap = 0;              // slab entries staged in shared memory per CTA (step kernels, spmv)
+    size_t smem = 0;          // dynamic shared memory bytes of those kernels
 };
+
+constexpr int kMaxSlabEntries = 2816;       // 44 KB of entries + row pointers stay under 48 KB
+
+// shared-memory needs of a row-chunked kernel: the largest entry count of any chunk, capped
+void plan_slab(Plan& p, const std::vector<int32_t>& ptr, int rows) {
+    int worst = 0;
+    for (int r0 = 0; r0 < rows; r0 += p.rows_per_cta) {
+        const int r1 = std::min(rows, r0 + p.rows_per_cta);
+        worst = std::max(worst, ptr[r1] - ptr[r0]);
+    }
+    p.cap = std::min(worst, kMaxSlabEntries);
+    p.smem = 16 * ((size_t)(p.rows_per_cta + 4) / 4 + (size_t)p.cap);
+}
 
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
+}
+
+double env_dbl(const char* name, double dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atof(s) : dflt;
 }
 
 int pick_nt(int B) {
@@ -120,6 +140,7 @@ struct blp_handle_s {
     cudaStream_t stream = nullptr;
     int m_base = 0, n = 0;
     HostCsr A0;                        // unscaled rows (base + appended cuts)
+    std::vector<int32_t> hptrA, hptrAT; // host copies of the row pointers of A and A' (slab sizing)
     std::vector<double> c0, b0;
     std::vector<double> dr, dc;
     // device copies
@@ -168,6 +189,8 @@ int prepare(blp_handle h) {
     HostCsr At = transpose(As);
     HostCsr A0t = transpose(h->A0);
     const double eta = 0.998 / sigma_max(As, At);
+    h->hptrA = As.ptr;
+    h->hptrAT = At.ptr;
     const double nb = norm2(bs), nc = norm2(cs);
 
     cudaStream_t s = h->stream;
@@ -276,12 +299,12 @@ void launch_steps_nt(const DevProb& P, const DevState& S, const Plan& pc, const 
                      bool major, cudaStream_t st, int which) {
     const dim3 gc(pc.chunks, pc.tiles), gr(pr.chunks, pr.tiles);
     if (which != 1) {
-        if (major) k_primal<NT, true><<<gc, kCtaThreads, 0, st>>>(P, S, it, pc.rows_per_cta);
-        else k_primal<NT, false><<<gc, kCtaThreads, 0, st>>>(P, S, it, pc.rows_per_cta);
+        if (major) k_primal<NT, true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap);
+        else k_primal<NT, false><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap);
     }
     if (which != 0) {
-        if (major) k_dual<NT, true><<<gr, kCtaThreads, 0, st>>>(P, S, it, pr.rows_per_cta);
-        else k_dual<NT, false><<<gr, kCtaThreads, 0, st>>>(P, S, it, pr.rows_per_cta);
+        if (major) k_dual<NT, true><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap);
+        else k_dual<NT, false><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap);
     }
 }
 
@@ -533,8 +556,10 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
 
     const int K = std::min(o.eval_every, o.max_iters);
     const int rpw = env_int("BLP_ROWS_PER_WARP", 8);
-    const int NT = pick_nt(B);
-    DecideArgs D{0, 0, K, o.max_iters, o.eps_rel, o.eps_infeas};
+    int NT = pick_nt(B);     // nodes per warp; re-picked when compaction narrows the batch
+    DecideArgs D{0, 0, K, o.max_iters, o.eps_rel, o.eps_infeas,
+                 env_dbl("BLP_BETA_SUFF", 0.2), env_dbl("BLP_BETA_NEC", 0.8), env_dbl("BLP_BETA_ART", 0.36),
+                 env_dbl("BLP_OMEGA_THETA", 0.5)};
     int launches = 0;
 
     CK(cudaEventRecord(h->ev[0], st));
@@ -583,6 +608,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         return p;
     };
     Plan pc = make_plan(P.n, B, rpw, 0), pr = make_plan(P.m, B, rpw, 0);
+    plan_slab(pc, h->hptrAT, P.n);
+    plan_slab(pr, h->hptrA, P.m);
     Plan ec = make_plan(P.n, B, 1, kEvalChunks), er = make_plan(P.m, B, 1, kEvalChunks);
     D.chunksC = ec.chunks;
     D.chunksR = er.chunks;
@@ -632,7 +659,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         // retire finished nodes: pack the running ones to the front when that frees node tiles
         if (o.compact && active < S.B) {
             const int cur_tiles = (S.B + NT - 1) / NT, new_tiles = (active + NT - 1) / NT;
-            if (new_tiles < cur_tiles && (new_tiles * 8 <= cur_tiles * 7 || cur_tiles <= 16)) {
+            if ((new_tiles < cur_tiles && (new_tiles * 8 <= cur_tiles * 7 || cur_tiles <= 16)) ||
+                pick_nt(active) < NT) {
                 const int oldB = S.B;
                 k_compact_plan<<<1, 1024, 0, st>>>(S);
                 k_compact_vecs<<<elementwise_grid((size_t)(4 * P.n + 2 * P.m) * 32), kCtaThreads, 0, st>>>(P, S, oldB);
@@ -640,8 +668,11 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 launches += 2;
                 ++compactions;
                 S.B = active;
+                NT = pick_nt(S.B);
                 pc = make_plan(P.n, S.B, rpw, 0);
                 pr = make_plan(P.m, S.B, rpw, 0);
+                plan_slab(pc, h->hptrAT, P.n);
+                plan_slab(pr, h->hptrA, P.m);
                 ec = make_plan(P.n, S.B, 1, kEvalChunks);
                 er = make_plan(P.m, S.B, 1, kEvalChunks);
                 D.chunksC = ec.chunks;
@@ -909,16 +940,17 @@ int blp_spmv(blp_handle h, int B, int transpose, const double* X, double* Y) {
     const int rows = transpose ? h->n : h->A0.rows;
     const int32_t* ptr = transpose ? h->P.cptr : h->P.rowptr;
     const Ent* ent = transpose ? h->ucent.as<Ent>() : h->uent.as<Ent>();
-    const Plan p = plan_rows(rows, B, env_int("BLP_ROWS_PER_WARP", 8), 0);
+    Plan p = plan_rows(rows, B, env_int("BLP_ROWS_PER_WARP", 8), 0);
+    plan_slab(p, transpose ? h->hptrAT : h->hptrA, rows);
     const dim3 g(p.chunks, p.tiles);
     cudaStream_t st = h->stream;
     switch (p.NT) {
-        case 1: k_spmv<1><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
-        case 2: k_spmv<2><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
-        case 4: k_spmv<4><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
-        case 8: k_spmv<8><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
-        case 16: k_spmv<16><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
-        default: k_spmv<32><<<g, kCtaThreads, 0, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta); break;
+        case 1: k_spmv<1><<<g, kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap); break;
+        case 2: k_spmv<2><<<g, kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap); break;
+        case 4: k_spmv<4><<<g, kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap); break;
+        case 8: k_spmv<8><<<g, kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap); break;
+        case 16: k_spmv<16><<<g, kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap); break;
+        default: k_spmv<32><<<g, kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap); break;
     }
     CK(cudaGetLastError());
     return BLP_OK;

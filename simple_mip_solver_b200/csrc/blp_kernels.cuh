@@ -108,10 +108,80 @@ __device__ __forceinline__ double row_dot(const int32_t* __restrict__ ptr,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row slab of a CTA in shared memory. The step kernels give every CTA a contiguous chunk of CSR
+// rows; all 256 threads first copy the chunk's row pointers and (when they fit) its entries with
+// coalesced 128-bit loads. A row walk then costs one shared-memory read per nonzero, and the only
+// global round trip on a warp's critical path is the one that matters: the streaming loads and
+// the gathers of the batched vector, all issued together.
+struct Slab {
+    const int* sp;       // shared: absolute row pointers of rows r0 .. r1
+    const int4* se;      // shared: entries [sp[0], sp[nrows]) or nullptr if they did not fit
+    int base;
+};
+
+__device__ __forceinline__ Slab stage_slab(const int32_t* __restrict__ ptr,
+                                           const Ent* __restrict__ ent, const int r0, const int r1,
+                                           const int rows_per_cta, const int cap) {
+    extern __shared__ int4 dyn_smem[];
+    int* sp = reinterpret_cast<int*>(dyn_smem);
+    int4* se = dyn_smem + (rows_per_cta + 4) / 4;
+    const int nrows = r1 - r0;
+    for (int t = threadIdx.x; t <= nrows; t += kCtaThreads) sp[t] = __ldg(ptr + r0 + t);
+    __syncthreads();
+    Slab s;
+    s.sp = sp;
+    s.base = sp[0];
+    s.se = nullptr;
+    const int cnt = sp[nrows] - s.base;
+    if (cnt <= cap) {
+        const int4* __restrict__ src = reinterpret_cast<const int4*>(ent) + s.base;
+        for (int t = threadIdx.x; t < cnt; t += kCtaThreads) se[t] = __ldg(src + t);
+        __syncthreads();
+        s.se = se;
+    }
+    return s;
+}
+
+template <bool SHARED>
+__device__ __forceinline__ double dot_entries(const int4* __restrict__ E, const int p0, const int p1,
+                                              const double* __restrict__ Vn, const int ld,
+                                              const bool node_ok) {
+    double acc = 0.0;
+    for (int p = p0; p < p1; p += 4) {
+        int4 e[4];
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool ok = p + q < p1;
+            if (SHARED) e[q] = ok ? E[p + q] : make_int4(0, 0, 0, 0);
+            else e[q] = ok ? __ldg(E + p + q) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            v[q] = (node_ok && p + q < p1) ? Vn[(size_t)e[q].x * ld] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc = fma(__hiloint2double(e[q].w, e[q].z), v[q], acc);
+    }
+    return acc;
+}
+
+// gather-dot of local row lr of the slab; NT == 32: warp-uniform row, NT < 32: one row per sub-group
+template <int NT>
+__device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict__ ent, const int lr,
+                                           const bool row_ok, const double* __restrict__ V,
+                                           const int ld, const int node, const bool node_ok) {
+    if (NT != 32 && !(row_ok && node_ok)) return 0.0;
+    const int p0 = sl.sp[lr], p1 = sl.sp[lr + 1];
+    const double* __restrict__ Vn = V + node;
+    if (sl.se) return dot_entries<true>(sl.se - sl.base, p0, p1, Vn, ld, node_ok);
+    return dot_entries<false>(reinterpret_cast<const int4*>(ent), p0, p1, Vn, ld, node_ok);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Primal half step, fused  G = A'y  ->  x' = clip(x - tau (c - G), l, u)  ->  xbar = 2x' - x.
 template <int NT, bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads)
-k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta) {
+__global__ void __launch_bounds__(kCtaThreads, 6)
+k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * NT + (lane % NT);
@@ -126,6 +196,7 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
     }
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(P.n, r0 + rows_per_cta);
+    const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
         const int j = jb + sub;
         const bool row_ok = j < r1;
@@ -137,8 +208,8 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
             lo = __ldcs(S.l + e);
             hi = __ldcs(S.u + e);
         }
-        const double g = row_dot<NT>(P.cptr, P.cent, row_ok ? j : 0, row_ok, S.y, S.ld,
-                                     node, node_ok && row_ok, lane);
+        const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, S.y, S.ld, node,
+                                      node_ok && row_ok);
         if (row_ok && node_ok) {
             const double xc = fma(w, xb - a, a);                  // w xbar + (1-w) xa
             const double xp = fmin(fmax(xc - tau * (__ldg(P.c + j) - g), lo), hi);
@@ -154,8 +225,8 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
 
 // Dual half step, fused  s = A xbar  ->  y' = max(0, y + sigma (b - s))  ->  Halpern update of y.
 template <int NT, bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads)
-k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta) {
+__global__ void __launch_bounds__(kCtaThreads, 6)
+k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * NT + (lane % NT);
@@ -170,6 +241,7 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta) 
     }
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(P.m, r0 + rows_per_cta);
+    const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
@@ -181,8 +253,8 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta) 
             a = __ldcs(S.ya + e);
             if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
         }
-        const double ax = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.xbar,
-                                      S.ld, node, node_ok && row_ok, lane);
+        const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, S.xbar, S.ld, node,
+                                       node_ok && row_ok);
         if (row_ok && node_ok) {
             const double yp = on ? fmax(0.0, yc + sig * (__ldg(P.b + i) - ax)) : 0.0;
             S.y[e] = fma(w, (2.0 * yp - yc) - a, a);
@@ -317,6 +389,7 @@ k_eval_rows(const DevProb P, const DevState S, const int rows_per_cta) {
 struct DecideArgs {
     int chunksC, chunksR, steps_in_period, max_iters;
     double eps, eps_inf;
+    double beta_suff, beta_nec, beta_art, theta;    // restart thresholds, primal-weight smoothing
 };
 
 // counters: [0] nodes still running after the evaluation, [1] nodes restarting,
@@ -394,12 +467,12 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
     const int s_now = S.sbase[node] + D.steps_in_period;
     const double f0 = S.fpe0[node], fprev = S.fpe_prev[node];
     const bool first = !(f0 < INFINITY);
-    const bool do_restart = first || fpe <= 0.2 * f0 || (fpe <= 0.8 * f0 && fpe > fprev) ||
-                            (double)s_now >= 0.36 * (double)total;
+    const bool do_restart = first || fpe <= D.beta_suff * f0 || (fpe <= D.beta_nec * f0 && fpe > fprev) ||
+                            (double)s_now >= D.beta_art * (double)total;
     if (do_restart) {
         const double ddx = sqrt(c[C_DXA2]), ddy = sqrt(r[R_DYA2]);
         if (!first && ddx > 1e-10 && ddy > 1e-10)
-            S.omega[node] = exp(0.5 * log(ddy / ddx) + 0.5 * log(omega));
+            S.omega[node] = exp(D.theta * log(ddy / ddx) + (1.0 - D.theta) * log(omega));
         S.fpe0[node] = fpe;
         S.fpe_prev[node] = INFINITY;
         S.sbase[node] = 0;
@@ -739,7 +812,7 @@ template <int NT>
 __global__ void __launch_bounds__(kCtaThreads)
 k_spmv(const int32_t* __restrict__ ptr, const Ent* __restrict__ ent, const int rows, const int B,
        const int ld,
-       const double* __restrict__ X, double* __restrict__ Y, const int rows_per_cta) {
+       const double* __restrict__ X, double* __restrict__ Y, const int rows_per_cta, const int cap) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * NT + (lane % NT);
@@ -747,11 +820,12 @@ k_spmv(const int32_t* __restrict__ ptr, const Ent* __restrict__ ent, const int r
     const bool node_ok = node < B;
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(rows, r0 + rows_per_cta);
+    const Slab sl = stage_slab(ptr, ent, r0, r1, rows_per_cta, cap);
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
-        const double s = row_dot<NT>(ptr, ent, row_ok ? i : 0, row_ok, X, ld, node,
-                                     node_ok && row_ok, lane);
+        const double s = slab_dot<NT>(sl, ent, row_ok ? i - r0 : 0, row_ok, X, ld, node,
+                                      node_ok && row_ok);
         if (row_ok && node_ok) Y[(size_t)i * ld + node] = s;
     }
 }

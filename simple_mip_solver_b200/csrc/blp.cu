@@ -87,8 +87,9 @@ void plan_slab(Plan& p, const std::vector<int32_t>& ptr, int rows) {
         const int r1 = std::min(rows, r0 + p.rows_per_cta);
         worst = std::max(worst, ptr[r1] - ptr[r0]);
     }
-    p.cap = std::min(worst, kMaxSlabEntries);
-    p.smem = 16 * ((size_t)(p.rows_per_cta + 4) / 4 + (size_t)p.cap);
+    const int ptr_slots = (p.rows_per_cta + 4) / 4;
+    p.cap = std::max(0, std::min(worst, kMaxSlabEntries - ptr_slots));
+    p.smem = 16 * ((size_t)ptr_slots + (size_t)p.cap);
 }
 
 int env_int(const char* name, int dflt) {
@@ -118,6 +119,8 @@ Plan plan_rows(int rows, int B, int rows_per_warp, int max_chunks) {
     if (max_chunks > 0) {
         const int need = (rows + max_chunks - 1) / max_chunks;
         rpc = std::max(rpc, ((need + pass - 1) / pass) * pass);
+    } else {
+        while (rpc > 512 && rpc > pass) rpc -= pass;      // step kernels: slab pointers stay small
     }
     p.rows_per_cta = rpc;
     p.chunks = std::max(1, (rows + rpc - 1) / rpc);
@@ -602,6 +605,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         if (max_chunks > 0) {
             const int need = (rows + max_chunks - 1) / max_chunks;
             rpc = std::max(rpc, ((need + pass - 1) / pass) * pass);
+        } else {
+            while (rpc > 512 && rpc > pass) rpc -= pass;
         }
         p.rows_per_cta = rpc;
         p.chunks = std::max(1, (rows + rpc - 1) / rpc);

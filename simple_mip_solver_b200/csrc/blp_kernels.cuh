@@ -1,6 +1,10 @@
 // Device kernels of the batched node-LP bound step (sm_100a, fp64, no tensor cores).
 //
-// Layout: every batched vector is node-fastest, V[row][ld]; a warp owns one node tile
+// Layout: the CALLER's batched vectors are node-fastest, V[row][ld]. The solver's own state is
+// tile-major: nodes are grouped in blocks of 32 and element (row j, node k) lives at
+// ((k / 32) * rows + j) * 32 + k % 32, so the 256-byte segments a node block touches in
+// consecutive rows are contiguous in HBM (long sequential streams per CTA instead of 256-byte
+// pieces ld*8 bytes apart). tix() is that index. A warp owns one node tile
 // (NT nodes, NT in {1,2,4,8,16,32}) and 32/NT consecutive matrix rows at a time, so every
 // vector access of a warp is one contiguous 256-byte segment and the CSR entries of a row are
 // warp-uniform. Work is ordered tile-major (blockIdx.y = tile, blockIdx.x = row chunk) so the
@@ -66,6 +70,11 @@ struct DevOut {
 
 __device__ __forceinline__ bool is_inf(double v) { return fabs(v) >= 1e30; }
 
+// tile-major index of (row, node) in an internal [rows] x [ld] state array
+__device__ __forceinline__ size_t tix(const int row, const int node, const int rows) {
+    return ((size_t)(node >> 5) * rows + row) * 32 + (node & 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // gather-dot of one CSR row with a batched vector: sum_p val[p] * V[idx[p]][node]
 // NT == 32: the row is warp-uniform, so every lane issues the same 128-bit entry load (one
@@ -74,12 +83,12 @@ __device__ __forceinline__ bool is_inf(double v) { return fabs(v) >= 1e30; }
 template <int NT>
 __device__ __forceinline__ double row_dot(const int32_t* __restrict__ ptr,
                                           const Ent* __restrict__ ent, int row, bool row_ok,
-                                          const double* __restrict__ V, int ld, int node,
-                                          bool node_ok, int lane) {
+                                          const double* __restrict__ Vn, bool node_ok) {
+    // Vn: the lane's column inside a tile-major state array (row stride 32 doubles)
+    constexpr int ld = 32;
     double acc = 0.0;
     if (NT == 32 || (row_ok && node_ok)) {
         const int p0 = __ldg(ptr + row), p1 = __ldg(ptr + row + 1);
-        const double* __restrict__ Vn = V + node;
         int p = p0;
         for (; p + 4 <= p1; p += 4) {
             const int4 e0 = __ldg(reinterpret_cast<const int4*>(ent + p));
@@ -146,6 +155,7 @@ template <bool SHARED>
 __device__ __forceinline__ double dot_entries(const int4* __restrict__ E, const int p0, const int p1,
                                               const double* __restrict__ Vn, const int ld,
                                               const bool node_ok) {
+    // ld: distance (in doubles) between consecutive rows of the gathered vector for this lane
     double acc = 0.0;
     for (int p = p0; p < p1; p += 4) {
         int4 e[4];
@@ -168,11 +178,10 @@ __device__ __forceinline__ double dot_entries(const int4* __restrict__ E, const 
 // gather-dot of local row lr of the slab; NT == 32: warp-uniform row, NT < 32: one row per sub-group
 template <int NT>
 __device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict__ ent, const int lr,
-                                           const bool row_ok, const double* __restrict__ V,
-                                           const int ld, const int node, const bool node_ok) {
+                                           const bool row_ok, const double* __restrict__ Vn,
+                                           const int ld, const bool node_ok) {
     if (NT != 32 && !(row_ok && node_ok)) return 0.0;
     const int p0 = sl.sp[lr], p1 = sl.sp[lr + 1];
-    const double* __restrict__ Vn = V + node;
     if (sl.se) return dot_entries<true>(sl.se - sl.base, p0, p1, Vn, ld, node_ok);
     return dot_entries<false>(reinterpret_cast<const int4*>(ent), p0, p1, Vn, ld, node_ok);
 }
@@ -200,7 +209,7 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
     for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
         const int j = jb + sub;
         const bool row_ok = j < r1;
-        const size_t e = (size_t)j * S.ld + node;
+        const size_t e = tix(j, node, P.n);
         double xb = 0, a = 0, lo = 0, hi = 0;
         if (row_ok && node_ok) {       // issue the streaming loads before the gather
             xb = S.xbar[e];
@@ -208,8 +217,8 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
             lo = __ldcs(S.l + e);
             hi = __ldcs(S.u + e);
         }
-        const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, S.y, S.ld, node,
-                                      node_ok && row_ok);
+        const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, S.y + tix(0, node, P.m),
+                                      32, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double xc = fma(w, xb - a, a);                  // w xbar + (1-w) xa
             const double xp = fmin(fmax(xc - tau * (__ldg(P.c + j) - g), lo), hi);
@@ -245,7 +254,7 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
-        const size_t e = (size_t)i * S.ld + node;
+        const size_t e = tix(i, node, P.m);
         double yc = 0, a = 0;
         bool on = true;
         if (row_ok && node_ok) {
@@ -253,8 +262,8 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
             a = __ldcs(S.ya + e);
             if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
         }
-        const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, S.xbar, S.ld, node,
-                                       node_ok && row_ok);
+        const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok,
+                                       S.xbar + tix(0, node, P.n), 32, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double yp = on ? fmax(0.0, yc + sig * (__ldg(P.b + i) - ax)) : 0.0;
             S.y[e] = fma(w, (2.0 * yp - yc) - a, a);
@@ -304,9 +313,9 @@ k_eval_cols(const DevProb P, const DevState S, const int rows_per_cta) {
     for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
         const int j = jb + sub;
         const bool row_ok = j < r1;
-        const size_t e = (size_t)j * S.ld + node;
-        const double gp = row_dot<NT>(P.cptr, P.cent, row_ok ? j : 0, row_ok, S.Y1, S.ld,
-                                      node, node_ok && row_ok, lane);
+        const size_t e = tix(j, node, P.n);
+        const double gp = row_dot<NT>(P.cptr, P.cent, row_ok ? j : 0, row_ok, S.Y1 + tix(0, node, P.m),
+                                      node_ok && row_ok);
         if (row_ok && node_ok) {
             const double xp = S.X1[e], dx = S.DX[e], g = S.G[e];
             const double lo = S.l[e], hi = S.u[e], xa = S.xa[e];
@@ -356,12 +365,10 @@ k_eval_rows(const DevProb P, const DevState S, const int rows_per_cta) {
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
-        const size_t e = (size_t)i * S.ld + node;
+        const size_t e = tix(i, node, P.m);
         const bool ok = row_ok && node_ok;
-        const double ax = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.X1, S.ld,
-                                      node, ok, lane);
-        const double ad = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.G, S.ld,
-                                      node, ok, lane);
+        const double ax = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.X1 + tix(0, node, P.n), ok);
+        const double ad = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.G + tix(0, node, P.n), ok);
         if (ok) {
             bool on = true;
             if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
@@ -497,13 +504,13 @@ k_apply_restart(const DevProb P, const DevState S) {
     const int gwarp = (blockIdx.x * kCtaThreads + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kCtaThreads) >> 5;
     for (int j = gwarp; j < P.n; j += nwarps) {
-        const size_t e = (size_t)j * S.ld + node;
+        const size_t e = tix(j, node, P.n);
         const double v = S.X1[e];
         S.xa[e] = v;
         S.xbar[e] = v;
     }
     for (int i = gwarp; i < P.m; i += nwarps) {
-        const size_t e = (size_t)i * S.ld + node;
+        const size_t e = tix(i, node, P.m);
         const double v = S.Y1[e];
         S.ya[e] = v;
         S.y[e] = v;
@@ -531,8 +538,9 @@ k_init_cols(const DevProb P, const DevState S, const double* __restrict__ lb,
         if (lo > hi) {              // empty box: primal infeasible without any iteration
             S.fin[node] = 1; S.status[node] = 1; S.pobj[node] = INFINITY; S.dobj[node] = INFINITY;
         }
-        S.l[e] = lo; S.u[e] = hi; S.xa[e] = x; S.xbar[e] = x; S.X1[e] = x;
-        S.DX[e] = 0.0; S.G[e] = 0.0;
+        const size_t t = tix(j, node, P.n);
+        S.l[t] = lo; S.u[t] = hi; S.xa[t] = x; S.xbar[t] = x; S.X1[t] = x;
+        S.DX[t] = 0.0; S.G[t] = 0.0;
     }
 }
 
@@ -548,7 +556,8 @@ k_init_rows(const DevProb P, const DevState S, const double* __restrict__ y0) {
             if (i >= P.m_base && S.rowmask && S.rowmask[(size_t)(i - P.m_base) * S.ld + node] == 0)
                 y = 0.0;
         }
-        S.y[e] = y; S.ya[e] = y; S.Y1[e] = y; S.DY[e] = 0.0;
+        const size_t t = tix(i, node, P.m);
+        S.y[t] = y; S.ya[t] = y; S.Y1[t] = y; S.DY[t] = 0.0;
     }
 }
 
@@ -573,7 +582,7 @@ k_check_rows(const DevProb P, const DevState S, const int rows_per_cta) {
         double act = 0.0, mag = 0.0;
         for (int p = __ldg(P.rowptr + i); p < __ldg(P.rowptr + i + 1); ++p) {
             const double a = P.ent[p].val;
-            const size_t e = (size_t)P.ent[p].idx * S.ld + node;
+            const size_t e = tix(P.ent[p].idx, node, P.n);
             const double t = a * (a > 0.0 ? S.u[e] : S.l[e]);
             act += t;
             mag += fabs(t);
@@ -631,7 +640,7 @@ k_harvest_x(const DevProb P, const DevState S, const DevOut O, const double frac
     for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
         const int j = jb + sub;
         if (j < r1 && node_ok) {
-            const double v = S.X1[(size_t)j * S.ld + node] * __ldg(P.dc + j) * inv;
+            const double v = S.X1[tix(j, node, P.n)] * __ldg(P.dc + j) * inv;
             if (O.x) O.x[(size_t)j * S.ld + org] = v;
             if (S.isint && S.isint[j]) {
                 const double dist = fmin(v - floor(v), ceil(v) - v);
@@ -673,7 +682,7 @@ k_harvest_y(const DevProb P, const DevState S, const DevOut O, const int rows_pe
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         if (i < r1 && node_ok)
-            O.y[(size_t)i * S.ld + org] = S.Y1[(size_t)i * S.ld + node] * __ldg(P.dr + i) * inv;
+            O.y[(size_t)i * S.ld + org] = S.Y1[tix(i, node, P.m)] * __ldg(P.dr + i) * inv;
     }
 }
 
@@ -769,20 +778,25 @@ k_compact_vecs(const DevProb P, const DevState S, const int oldB) {
     const int total = 4 * P.n + 2 * P.m + mc;
     for (int r = gwarp; r < total; r += nwarps) {
         if (r < 4 * P.n + 2 * P.m) {
-            double* base;
+            double* arr;
+            int row, rows;
             if (r < 4 * P.n) {
-                const int a = r / P.n, j = r % P.n;
-                base = (a == 0 ? S.xbar : a == 1 ? S.xa : a == 2 ? S.l : S.u) + (size_t)j * S.ld;
+                const int a = r / P.n;
+                arr = a == 0 ? S.xbar : a == 1 ? S.xa : a == 2 ? S.l : S.u;
+                row = r % P.n;
+                rows = P.n;
             } else {
                 const int q = r - 4 * P.n;
-                base = (q < P.m ? S.y : S.ya) + (size_t)(q % P.m) * S.ld;
+                arr = q < P.m ? S.y : S.ya;
+                row = q % P.m;
+                rows = P.m;
             }
             for (int c0 = 0; c0 < oldB; c0 += 32) {
                 const int k = c0 + lane;
                 const int p = k < oldB ? S.newpos[k] : -1;
-                const double v = p >= 0 ? base[k] : 0.0;
+                const double v = p >= 0 ? arr[tix(row, k, rows)] : 0.0;
                 __syncwarp();
-                if (p >= 0) base[p] = v;
+                if (p >= 0) arr[tix(row, p, rows)] = v;
             }
         } else {
             uint8_t* base = S.rowmask + (size_t)(r - 4 * P.n - 2 * P.m) * S.ld;
@@ -824,7 +838,7 @@ k_spmv(const int32_t* __restrict__ ptr, const Ent* __restrict__ ent, const int r
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
-        const double s = slab_dot<NT>(sl, ent, row_ok ? i - r0 : 0, row_ok, X, ld, node,
+        const double s = slab_dot<NT>(sl, ent, row_ok ? i - r0 : 0, row_ok, X + node, ld,
                                       node_ok && row_ok);
         if (row_ok && node_ok) Y[(size_t)i * ld + node] = s;
     }

@@ -155,22 +155,29 @@ template <bool SHARED>
 __device__ __forceinline__ double dot_entries(const int4* __restrict__ E, const int p0, const int p1,
                                               const double* __restrict__ Vn, const int ld,
                                               const bool node_ok) {
-    // ld: distance (in doubles) between consecutive rows of the gathered vector for this lane
+    // ld: distance (in doubles) between consecutive rows of the gathered vector for this lane.
+    // kU gathers are issued back to back before the first one is consumed: the row's critical
+    // path is one memory round trip per kU nonzeros. Only the column index is kept in a register
+    // while the gathers fly; the coefficient is re-read (shared memory / L1) at the multiply.
+    constexpr int kU = 8;
     double acc = 0.0;
-    for (int p = p0; p < p1; p += 4) {
-        int4 e[4];
-        double v[4];
+    for (int p = p0; p < p1; p += kU) {
+        double v[kU];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const bool ok = p + q < p1;
-            if (SHARED) e[q] = ok ? E[p + q] : make_int4(0, 0, 0, 0);
-            else e[q] = ok ? __ldg(E + p + q) : make_int4(0, 0, 0, 0);
+        for (int q = 0; q < kU; ++q) {
+            v[q] = 0.0;
+            if (p + q < p1) {
+                const int col = SHARED ? E[p + q].x : __ldg(&E[p + q].x);
+                if (node_ok) v[q] = Vn[(size_t)col * ld];
+            }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            v[q] = (node_ok && p + q < p1) ? Vn[(size_t)e[q].x * ld] : 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc = fma(__hiloint2double(e[q].w, e[q].z), v[q], acc);
+        for (int q = 0; q < kU; ++q)
+            if (p + q < p1) {
+                const int2 c = SHARED ? *reinterpret_cast<const int2*>(&E[p + q].z)
+                                      : __ldg(reinterpret_cast<const int2*>(&E[p + q].z));
+                acc = fma(__hiloint2double(c.y, c.x), v[q], acc);
+            }
     }
     return acc;
 }
@@ -189,7 +196,7 @@ __device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict
 // ---------------------------------------------------------------------------------------------
 // Primal half step, fused  G = A'y  ->  x' = clip(x - tau (c - G), l, u)  ->  xbar = 2x' - x.
 template <int NT, bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads, 6)
+__global__ void __launch_bounds__(kCtaThreads, 4)
 k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,19 +213,32 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(P.n, r0 + rows_per_cta);
     const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
-    for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
+    const double* __restrict__ yn = S.y + tix(0, node, P.m);
+    // software pipeline over the warp's rows: the streaming loads of the next row are issued
+    // before the gathers of the current one are consumed
+    int jb = r0 + warp * RW;
+    double xb = 0, a = 0, lo = 0, hi = 0;
+    if (jb + sub < r1 && node_ok) {
+        const size_t e = tix(jb + sub, node, P.n);
+        xb = S.xbar[e];
+        a = __ldcs(S.xa + e);
+        lo = __ldcs(S.l + e);
+        hi = __ldcs(S.u + e);
+    }
+    for (; jb < r1; jb += kWarps * RW) {
         const int j = jb + sub;
         const bool row_ok = j < r1;
         const size_t e = tix(j, node, P.n);
-        double xb = 0, a = 0, lo = 0, hi = 0;
-        if (row_ok && node_ok) {       // issue the streaming loads before the gather
-            xb = S.xbar[e];
-            a = __ldcs(S.xa + e);
-            lo = __ldcs(S.l + e);
-            hi = __ldcs(S.u + e);
+        const int jn = j + kWarps * RW;
+        double xb2 = 0, a2 = 0, lo2 = 0, hi2 = 0;
+        if (jn < r1 && node_ok) {
+            const size_t e2 = tix(jn, node, P.n);
+            xb2 = S.xbar[e2];
+            a2 = __ldcs(S.xa + e2);
+            lo2 = __ldcs(S.l + e2);
+            hi2 = __ldcs(S.u + e2);
         }
-        const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, S.y + tix(0, node, P.m),
-                                      32, node_ok && row_ok);
+        const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, yn, 32, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double xc = fma(w, xb - a, a);                  // w xbar + (1-w) xa
             const double xp = fmin(fmax(xc - tau * (__ldg(P.c + j) - g), lo), hi);
@@ -229,12 +249,13 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
                 S.G[e] = g;
             }
         }
+        xb = xb2; a = a2; lo = lo2; hi = hi2;
     }
 }
 
 // Dual half step, fused  s = A xbar  ->  y' = max(0, y + sigma (b - s))  ->  Halpern update of y.
 template <int NT, bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads, 6)
+__global__ void __launch_bounds__(kCtaThreads, 4)
 k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -251,19 +272,29 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(P.m, r0 + rows_per_cta);
     const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
-    for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
+    const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
+    int ib = r0 + warp * RW;
+    double yc = 0, a = 0;
+    if (ib + sub < r1 && node_ok) {
+        const size_t e = tix(ib + sub, node, P.m);
+        yc = S.y[e];
+        a = __ldcs(S.ya + e);
+    }
+    for (; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
         const size_t e = tix(i, node, P.m);
-        double yc = 0, a = 0;
-        bool on = true;
-        if (row_ok && node_ok) {
-            yc = S.y[e];
-            a = __ldcs(S.ya + e);
-            if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
+        const int in = i + kWarps * RW;
+        double yc2 = 0, a2 = 0;
+        if (in < r1 && node_ok) {
+            const size_t e2 = tix(in, node, P.m);
+            yc2 = S.y[e2];
+            a2 = __ldcs(S.ya + e2);
         }
-        const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok,
-                                       S.xbar + tix(0, node, P.n), 32, node_ok && row_ok);
+        bool on = true;
+        if (row_ok && node_ok && i >= P.m_base && S.rowmask)
+            on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
+        const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, xn, 32, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double yp = on ? fmax(0.0, yc + sig * (__ldg(P.b + i) - ax)) : 0.0;
             S.y[e] = fma(w, (2.0 * yp - yc) - a, a);
@@ -272,6 +303,7 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
                 S.DY[e] = yp - yc;
             }
         }
+        yc = yc2; a = a2;
     }
 }
 

@@ -22,6 +22,15 @@
 
 namespace blp {
 
+#ifndef BLP_U
+#define BLP_U 4          // gathers issued back to back per row batch
+#endif
+#ifndef BLP_PREFETCH
+#define BLP_PREFETCH 0   // issue the next row's streaming loads before consuming the gathers
+#endif
+#ifndef BLP_MINB
+#define BLP_MINB 6       // resident CTAs per SM the step kernels are compiled for
+#endif
 constexpr int kCtaThreads = 256;
 constexpr int kWarps = kCtaThreads / 32;
 
@@ -159,7 +168,7 @@ __device__ __forceinline__ double dot_entries(const int4* __restrict__ E, const 
     // kU gathers are issued back to back before the first one is consumed: the row's critical
     // path is one memory round trip per kU nonzeros. Only the column index is kept in a register
     // while the gathers fly; the coefficient is re-read (shared memory / L1) at the multiply.
-    constexpr int kU = 8;
+    constexpr int kU = BLP_U;
     double acc = 0.0;
     for (int p = p0; p < p1; p += kU) {
         double v[kU];
@@ -196,7 +205,7 @@ __device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict
 // ---------------------------------------------------------------------------------------------
 // Primal half step, fused  G = A'y  ->  x' = clip(x - tau (c - G), l, u)  ->  xbar = 2x' - x.
 template <int NT, bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads, 4)
+__global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
 k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -231,12 +240,18 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
         const size_t e = tix(j, node, P.n);
         const int jn = j + kWarps * RW;
         double xb2 = 0, a2 = 0, lo2 = 0, hi2 = 0;
-        if (jn < r1 && node_ok) {
+        if (BLP_PREFETCH && jn < r1 && node_ok) {
             const size_t e2 = tix(jn, node, P.n);
             xb2 = S.xbar[e2];
             a2 = __ldcs(S.xa + e2);
             lo2 = __ldcs(S.l + e2);
             hi2 = __ldcs(S.u + e2);
+        }
+        if (!BLP_PREFETCH && row_ok && node_ok) {
+            xb = S.xbar[e];
+            a = __ldcs(S.xa + e);
+            lo = __ldcs(S.l + e);
+            hi = __ldcs(S.u + e);
         }
         const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, yn, 32, node_ok && row_ok);
         if (row_ok && node_ok) {
@@ -255,7 +270,7 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
 
 // Dual half step, fused  s = A xbar  ->  y' = max(0, y + sigma (b - s))  ->  Halpern update of y.
 template <int NT, bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads, 4)
+__global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
 k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -286,7 +301,7 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
         const size_t e = tix(i, node, P.m);
         const int in = i + kWarps * RW;
         double yc2 = 0, a2 = 0;
-        if (in < r1 && node_ok) {
+        if (BLP_PREFETCH && in < r1 && node_ok) {
             const size_t e2 = tix(in, node, P.m);
             yc2 = S.y[e2];
             a2 = __ldcs(S.ya + e2);
@@ -294,6 +309,10 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
         bool on = true;
         if (row_ok && node_ok && i >= P.m_base && S.rowmask)
             on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
+        if (!BLP_PREFETCH && row_ok && node_ok) {
+            yc = S.y[e];
+            a = __ldcs(S.ya + e);
+        }
         const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, xn, 32, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double yp = on ? fmax(0.0, yc + sig * (__ldg(P.b + i) - ax)) : 0.0;

@@ -19,7 +19,8 @@ from typing import Optional, Sequence
 import numpy as np
 import scipy.sparse as sp
 
-_LIB_PATH = Path(__file__).resolve().parent / 'csrc' / 'libblp.so'
+import os as _os
+_LIB_PATH = Path(_os.environ.get('BLP_LIB') or Path(__file__).resolve().parent / 'csrc' / 'libblp.so')
 _lib = None
 
 INF = 1e30   # |bound| >= INF means "no bound" on the device side

@@ -612,7 +612,18 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         p.chunks = std::max(1, (rows + rpc - 1) / rpc);
         return p;
     };
-    Plan pc = make_plan(P.n, B, rpw, 0), pr = make_plan(P.m, B, rpw, 0);
+    // step kernels: fewer rows per warp when the batch is narrow, so that a handful of running
+    // nodes still spreads over all SMs (the per-iteration latency floor of the solve's tail)
+    auto step_plan = [&](int rows, int width) {
+        int r = rpw;
+        Plan p = make_plan(rows, width, r, 0);
+        while (r > 1 && (long)p.chunks * p.tiles < 148L * 12) {
+            r /= 2;
+            p = make_plan(rows, width, r, 0);
+        }
+        return p;
+    };
+    Plan pc = step_plan(P.n, B), pr = step_plan(P.m, B);
     plan_slab(pc, h->hptrAT, P.n);
     plan_slab(pr, h->hptrA, P.m);
     Plan ec = make_plan(P.n, B, 1, kEvalChunks), er = make_plan(P.m, B, 1, kEvalChunks);
@@ -674,8 +685,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 ++compactions;
                 S.B = active;
                 NT = pick_nt(S.B);
-                pc = make_plan(P.n, S.B, rpw, 0);
-                pr = make_plan(P.m, S.B, rpw, 0);
+                pc = step_plan(P.n, S.B);
+                pr = step_plan(P.m, S.B);
                 plan_slab(pc, h->hptrAT, P.n);
                 plan_slab(pr, h->hptrA, P.m);
                 ec = make_plan(P.n, S.B, 1, kEvalChunks);

@@ -171,20 +171,22 @@ __device__ __forceinline__ double dot_entries(const int4* __restrict__ E, const 
     constexpr int kU = BLP_U;
     double acc = 0.0;
     for (int p = p0; p < p1; p += kU) {
-        int col[kU];
-        double cf[kU], v[kU];
-        // slots past the end of the row re-read the row's last entry with coefficient 0, so the
-        // gathers below are unconditional and all issue before the first multiply
+        double v[kU];
 #pragma unroll
         for (int q = 0; q < kU; ++q) {
-            const int4 e = SHARED ? E[min(p + q, p1 - 1)] : __ldg(E + min(p + q, p1 - 1));
-            col[q] = e.x;
-            cf[q] = (p + q < p1) ? __hiloint2double(e.w, e.z) : 0.0;
+            v[q] = 0.0;
+            if (p + q < p1) {
+                const int col = SHARED ? E[p + q].x : __ldg(&E[p + q].x);
+                if (node_ok) v[q] = Vn[(size_t)col * ld];
+            }
         }
 #pragma unroll
-        for (int q = 0; q < kU; ++q) v[q] = Vn[(size_t)col[q] * ld];
-#pragma unroll
-        for (int q = 0; q < kU; ++q) acc = fma(cf[q], v[q], acc);
+        for (int q = 0; q < kU; ++q)
+            if (p + q < p1) {
+                const int2 c = SHARED ? *reinterpret_cast<const int2*>(&E[p + q].z)
+                                      : __ldg(reinterpret_cast<const int2*>(&E[p + q].z));
+                acc = fma(__hiloint2double(c.y, c.x), v[q], acc);
+            }
     }
     return acc;
 }

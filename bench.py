@@ -317,6 +317,7 @@ def main():
         lp.stream_sync()
 
     # ---- device-resident arm ----
+    iters_all = []
     agg = dict(launches=0, solved=0, unsolved=0, infeasible=0, node_iters=0.0, iters=0,
                primal_ms=0.0, dual_ms=0.0, step_ms=0.0, total_ms=0.0)
     sampler = ClockSampler(local_rank)
@@ -335,6 +336,7 @@ def main():
             agg['solved'] += int(((st == 0) | (st == 1) | (st == 2)).sum().item())
             agg['unsolved'] += int((st == 3).sum().item())
             agg['infeasible'] += int((st == 1).sum().item())
+            iters_all.append(r['iters'][:B].cpu().numpy())
             sdict = r['stats']
             agg['launches'] += sdict['kernel_launches']
             agg['node_iters'] += sdict['node_iterations']
@@ -443,7 +445,8 @@ def main():
             'cpu_baseline': cpu,
             'nodes': {'solved': int(sums[0]), 'iteration_limit': int(sums[1]), 'infeasible': int(sums[3]),
                       'pdhg_iterations_per_step': agg['iters'] / max(args.steps, 1),
-                      'mean_iterations_per_node': agg['node_iters'] / max(agg['solved'] + agg['unsolved'], 1)},
+                      'mean_iterations_per_node': agg['node_iters'] / max(agg['solved'] + agg['unsolved'], 1),
+                      'iterations_p50_p90_max': [float(np.percentile(np.concatenate(iters_all), q)) for q in (50, 90, 100)]},
         }
         print(json.dumps(line), flush=True)
     lp.close()

@@ -292,6 +292,7 @@ size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
     s.fracI = cv.take<int32_t>((size_t)kEvalChunks * ld);
     s.isint = cv.take<uint8_t>(n);
     s.rowmask = cv.take<uint8_t>((m - h->m_base) * (size_t)ld + 1);
+    s.dbg = cv.take<double>((size_t)ld * 8);
     s.counters = cv.take<int32_t>(8);
     if (S) *S = s;
     return align_up(cv.off, 256);
@@ -553,6 +554,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     uint8_t* mask_ws = S.rowmask;
     if (!have_mask) S.rowmask = nullptr;
     const bool want_frac = frac_idx != nullptr && int_idx != nullptr && n_int > 0;
+    if (o.verbose < 2) S.dbg = nullptr;
     uint8_t* isint_ws = const_cast<uint8_t*>(S.isint);
     if (!want_frac) S.isint = nullptr;
     DevOut O{obj, lower_bound, x, y, status, iters, frac_idx};
@@ -740,6 +742,14 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         if (h->h_counters[3] > 0) {
             launch_harvest(P, S, O, ec, er, want_frac, st, &launches);
             CK(cudaGetLastError());
+        }
+        if (o.verbose >= 2) {
+            double t[8 * 4];
+            const int kshow = std::min(4, S.B);
+            CK(cudaMemcpy(t, S.dbg, sizeof(double) * 8 * kshow, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < kshow; ++k)
+                fprintf(stderr, "[blp]   col %d: rp %.2e rd %.2e gap %.2e fpe %.2e omega %.3e since_restart %.0f pobj %.9e dobj %.9e\n",
+                        k, t[8 * k], t[8 * k + 1], t[8 * k + 2], t[8 * k + 3], t[8 * k + 4], t[8 * k + 5], t[8 * k + 6], t[8 * k + 7]);
         }
         if (o.verbose)
             fprintf(stderr, "[blp] iters %d  width %d  running %d  restarting %d  finished now %d\n", total,

@@ -68,6 +68,7 @@ struct DevState {
     double *partC, *partR;                         // [chunks][C_N][ld], [chunks][R_N][ld]
     double* fracD; int32_t* fracI;                 // [chunks][ld] most-fractional partials
     const uint8_t* isint;                          // [n] 1 = integer column, or null
+    double* dbg;                                   // [ld][8] per-node trace of the last evaluation, or null
     int32_t* counters;                             // see k_tick
 };
 
@@ -493,6 +494,11 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
     const double rg = fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj));
     S.pobj[node] = pobj;
     S.dobj[node] = dobj;
+    if (S.dbg) {
+        double* t = S.dbg + (size_t)node * 8;
+        t[0] = rp; t[1] = rd; t[2] = rg; t[3] = fpe; t[4] = omega; t[5] = (double)S.sbase[node];
+        t[6] = pobj; t[7] = dobj;
+    }
     const int total = S.counters[2];
     const bool last = total >= D.max_iters;
     int st = -1;

@@ -44,7 +44,8 @@ enum blp_status {
 };
 
 typedef struct blp_opts {
-    double eps_rel;        /* relative KKT tolerance (primal, dual, gap); default 1e-8 */
+    double eps_rel;        /* relative KKT tolerance (primal, dual, gap); default 1e-7: bounds the objective
+                              error by ~5e-7 relative; 1e-8 is SURVEY 8d's figure */
     double eps_infeas;     /* relative size a Farkas certificate must reach; default 1e-9 */
     int max_iters;         /* PDHG iteration cap per call (the analogue of lp.maxNumIteration,
                               base_node.py:645); nodes still running get status 3. default 400000 */

@@ -411,7 +411,7 @@ extern "C" {
 
 void blp_default_opts(blp_opts* o) {
     if (!o) return;
-    o->eps_rel = 1e-8;
+    o->eps_rel = 1e-7;
     o->eps_infeas = 1e-9;
     o->max_iters = 400000;
     o->eval_every = 64;

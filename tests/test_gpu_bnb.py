@@ -179,3 +179,21 @@ def test_cut_rows_through_node_api(blp_lib):
         assert float(np.dot(pi, kids['left'].solution)) >= rhs - 1e-5 * max(1.0, abs(rhs))   # solver tolerance is relative
         assert 'cut_test_0' in kids['left'].lp.dualConstraintSolution
     assert 'cut_test_0' not in kids['right'].lp.dualConstraintSolution
+
+
+def test_default_bound_with_gomory_rounds(blp_lib):
+    """BaseNode.bound() with the reference's defaults (gomory_cuts=True, up to 10 cut rounds,
+    base_node.py:137-230, 365): cut rows are generated from the active-set basis of the GPU
+    solution, appended through lp.addConstraint and re-solved on the GPU. The MIP optimum must be
+    the reference's; how many rounds help depends on the vertex and is not pinned."""
+    used_cuts = 0
+    for name, rec in list(SCALE1.items()) + [(k, EXAMPLES[k]) for k in ('small_branch', 'cut1', 'cut2', 'cut3', 'square')]:
+        gold = rec['reference']['BaseNode_gomory']
+        bb = BranchAndBound(model_from(rec), BaseNode)
+        bb.solve()
+        assert bb.status == gold['status'] == 'optimal', name
+        assert rel(bb.objective_value, unfl(gold['objective'])) <= 1e-6, (name, bb.objective_value, gold['objective'])
+        used_cuts += bb._kwargs.get('total_number_gmic_added', 0)
+        bb.model.lp._shared.close()
+    print('GMI cuts appended over all instances:', used_cuts)
+    assert used_cuts > 0

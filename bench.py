@@ -172,10 +172,12 @@ class ClockSampler:
 
 
 def node_bytes(n, m):
-    """Algorithmic HBM bytes per node and iteration: primal launch reads
-    xbar, xa, l, u and the gathered y, writes xbar; dual launch reads y and the gathered xbar,
-    writes y."""
-    return 8 * (5 * n + m), 8 * (n + 2 * m)
+    """Algorithmic HBM bytes per node and iteration. SURVEY.md section 8d counts 8(6n+3m) with dense
+    per-node bounds; the kernels keep the bounds of a 32-node block as one reference value per row
+    plus a deviation mask (nodes differ from the root in a few entries), which is the variant
+    SURVEY 8d allows with formula 8(4n+3m): the primal launch reads xbar, xa and the gathered y and
+    writes xbar (3n+m); the dual launch reads y and the gathered xbar and writes y (n+2m)."""
+    return 8 * (3 * n + m), 8 * (n + 2 * m)
 
 
 # ------------------------------------------------------------------------------------- main
@@ -436,7 +438,7 @@ def main():
                          'traffic': None, 'peak_source': peak_src, 'bytes_per_launch': pair_bytes,
                          'ms_per_launch': pair_s * 1e3,
                          'measured': 'CUDA events around every period graph (64 iterations) of the timed steps; '
-                                     'bytes = 8(6n+3m) per running node and iteration + both matrices',
+                                     'bytes = 8(4n+3m) per running node and iteration + both matrices (bounds kept as block reference + mask)',
                          'k_primal': {'achieved': prim_gbs, 'frac': prim_gbs / peak, 'bytes_per_launch': primal_bytes,
                                       'ms_per_launch': primal_s * 1e3},
                          'k_dual': {'achieved': dual_gbs, 'frac': dual_gbs / peak, 'bytes_per_launch': dual_bytes,

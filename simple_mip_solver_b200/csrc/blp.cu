@@ -293,6 +293,9 @@ size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
     s.isint = cv.take<uint8_t>(n);
     s.rowmask = cv.take<uint8_t>((m - h->m_base) * (size_t)ld + 1);
     s.dbg = cv.take<double>((size_t)ld * 8);
+    s.lref = cv.take<double>(n * (size_t)(ld / 32));
+    s.uref = cv.take<double>(n * (size_t)(ld / 32));
+    s.lumask = cv.take<uint32_t>(n * (size_t)(ld / 32));
     s.counters = cv.take<int32_t>(8);
     if (S) *S = s;
     return align_up(cv.off, 256);
@@ -590,8 +593,9 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         er0.NT = NT;
         launch_check_rows(P, S, er0, st);
     }
+    k_build_lumask<<<elementwise_grid((size_t)P.n * (S.ld / 32) * 32), kCtaThreads, 0, st>>>(P, S);
     k_count_active<<<(B + 127) / 128, 128, 0, st>>>(S);
-    launches += 5;
+    launches += 6;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_counters, S.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -683,9 +687,10 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 k_compact_plan<<<1, 1024, 0, st>>>(S);
                 k_compact_vecs<<<elementwise_grid((size_t)(4 * P.n + 2 * P.m) * 32), kCtaThreads, 0, st>>>(P, S, oldB);
                 CK(cudaGetLastError());
-                launches += 2;
-                ++compactions;
                 S.B = active;
+                k_build_lumask<<<elementwise_grid((size_t)P.n * ((S.B + 31) / 32) * 32), kCtaThreads, 0, st>>>(P, S);
+                launches += 3;
+                ++compactions;
                 NT = pick_nt(S.B);
                 pc = step_plan(P.n, S.B);
                 pr = step_plan(P.m, S.B);

@@ -69,6 +69,11 @@ struct DevState {
     double* fracD; int32_t* fracI;                 // [chunks][ld] most-fractional partials
     const uint8_t* isint;                          // [n] 1 = integer column, or null
     double* dbg;                                   // [ld][8] per-node trace of the last evaluation, or null
+    // bounds of a 32-node block are mostly identical (nodes differ from the root in a few entries):
+    // lref/uref hold the block's reference bound per row, lumask the nodes that deviate from it;
+    // the primal step reads the dense l,u of a row only for those nodes. Layout [block][row].
+    double *lref, *uref;
+    uint32_t* lumask;
     int32_t* counters;                             // see k_tick
 };
 
@@ -251,8 +256,15 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
         if (!BLP_PREFETCH && row_ok && node_ok) {
             xb = S.xbar[e];
             a = __ldcs(S.xa + e);
-            lo = __ldcs(S.l + e);
-            hi = __ldcs(S.u + e);
+            const size_t fi = (size_t)(node >> 5) * P.n + j;
+            const uint32_t mk = __ldg(S.lumask + fi);
+            if ((mk >> (node & 31)) & 1u) {
+                lo = __ldcs(S.l + e);
+                hi = __ldcs(S.u + e);
+            } else {
+                lo = __ldg(S.lref + fi);
+                hi = __ldg(S.uref + fi);
+            }
         }
         const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, yn, 32, node_ok && row_ok);
         if (row_ok && node_ok) {
@@ -647,6 +659,30 @@ k_check_rows(const DevProb P, const DevState S, const int rows_per_cta) {
         const double bi = __ldg(P.b + i);
         if (bi - act > 1e-9 * (fabs(bi) + mag) + 1e-300) {
             S.fin[node] = 1; S.status[node] = 1; S.pobj[node] = INFINITY; S.dobj[node] = INFINITY;
+        }
+    }
+}
+
+// (re)build the per-block reference bounds and deviation masks from the dense l,u state
+__global__ void __launch_bounds__(kCtaThreads)
+k_build_lumask(const DevProb P, const DevState S) {
+    const int lane = threadIdx.x & 31;
+    const size_t gwarp = ((size_t)blockIdx.x * kCtaThreads + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * kCtaThreads) >> 5;
+    const int blocks = (S.B + 31) >> 5;
+    const size_t total = (size_t)blocks * P.n;
+    for (size_t w = gwarp; w < total; w += nwarps) {
+        const int blk = (int)(w / P.n), j = (int)(w % P.n);
+        const int node = blk * 32 + lane;
+        const size_t e = tix(j, node, P.n);
+        const double lo = S.l[e], hi = S.u[e];
+        const double lr = __shfl_sync(0xffffffffu, lo, 0), ur = __shfl_sync(0xffffffffu, hi, 0);
+        const bool dev = node < S.B && (lo != lr || hi != ur);
+        const unsigned mk = __ballot_sync(0xffffffffu, dev);
+        if (lane == 0) {
+            S.lumask[w] = mk;
+            S.lref[w] = lr;
+            S.uref[w] = ur;
         }
     }
 }

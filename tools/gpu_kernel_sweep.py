@@ -19,7 +19,7 @@ for dens in [float(a) for a in sys.argv[1:]] or [1e-7, 5e-5, 2e-4, 1e-3]:
     r = lp.solve_batch_device(lb, ub, opts=o, want_x=False, want_y=False)
     s = r['stats']
     pm, dm = s['primal_kernel_ms'] / s['iterations'], s['dual_kernel_ms'] / s['iterations']
-    pb = 8 * B * (5 * n + m) / 1e9
+    pb = 8 * B * (3 * n + m) / 1e9
     db = 8 * B * (n + 2 * m) / 1e9
     print(f'density {dens:g} nnz {d.A.nnz}: primal {pm:.3f} ms ({pb / pm * 1e3:.0f} GB/s algo)  dual {dm:.3f} ms ({db / dm * 1e3:.0f} GB/s algo)', flush=True)
     lp.close()

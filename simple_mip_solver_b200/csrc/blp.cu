@@ -74,6 +74,7 @@ cudaError_t upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
 
 struct Plan {
     int NT, tiles, chunks, rows_per_cta;
+    int V = 1;                // nodes per lane: 2 selects the k_primal2 / k_dual2 kernels
     int cap = 0;              // slab entries staged in shared memory per CTA (step kernels, spmv)
     size_t smem = 0;          // dynamic shared memory bytes of those kernels
 };
@@ -318,6 +319,18 @@ void launch_steps_nt(const DevProb& P, const DevState& S, const Plan& pc, const 
 // which: 0 primal only, 1 dual only, 2 both
 void launch_steps(const DevProb& P, const DevState& S, const Plan& pc, const Plan& pr, int it,
                   bool major, cudaStream_t st, int which = 2) {
+    if (pc.V == 2) {
+        const dim3 gc(pc.chunks, pc.tiles), gr(pr.chunks, pr.tiles);
+        if (which != 1) {
+            if (major) k_primal2<true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap);
+            else k_primal2<false><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap);
+        }
+        if (which != 0) {
+            if (major) k_dual2<true><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap);
+            else k_dual2<false><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap);
+        }
+        return;
+    }
     switch (pc.NT) {
         case 1: launch_steps_nt<1>(P, S, pc, pr, it, major, st, which); break;
         case 2: launch_steps_nt<2>(P, S, pc, pr, it, major, st, which); break;
@@ -424,7 +437,7 @@ void blp_default_opts(blp_opts* o) {
     o->profile = 0;
 }
 
-int blp_ld(int B) { return B <= 0 ? 0 : (B + 31) / 32 * 32; }
+int blp_ld(int B) { return B <= 0 ? 0 : (B + kBlk - 1) / kBlk * kBlk; }
 
 const char* blp_last_error(void) { return g_err.c_str(); }
 
@@ -620,12 +633,23 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     };
     // step kernels: fewer rows per warp when the batch is narrow, so that a handful of running
     // nodes still spreads over all SMs (the per-iteration latency floor of the solve's tail)
+    const bool allow_v2 = env_int("BLP_V2", 1) != 0;
     auto step_plan = [&](int rows, int width) {
         int r = rpw;
         Plan p = make_plan(rows, width, r, 0);
+        const bool v2 = allow_v2 && width >= kBlk;
+        auto shape = [&](Plan& q, int rr) {
+            if (!v2) return;
+            q.V = 2;                                   // a warp = one row x 64 nodes
+            q.tiles = (width + kBlk - 1) / kBlk;
+            q.rows_per_cta = kWarps * std::max(rr, 1);
+            q.chunks = std::max(1, (rows + q.rows_per_cta - 1) / q.rows_per_cta);
+        };
+        shape(p, r);
         while (r > 1 && (long)p.chunks * p.tiles < 148L * 12) {
             r /= 2;
             p = make_plan(rows, width, r, 0);
+            shape(p, r);
         }
         return p;
     };
@@ -654,7 +678,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         key.S = S;
         key.D = D;
         key.K = K;
-        key.rpw = rpw;
+        key.rpw = rpw | (allow_v2 ? 1 << 16 : 0);
         if (h->graph_valid && memcmp(&key, &h->gkey, sizeof key) == 0) return BLP_OK;
         h->drop_graphs();
         cudaGraph_t g = nullptr;

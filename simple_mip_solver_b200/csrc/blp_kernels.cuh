@@ -1,8 +1,8 @@
 // Device kernels of the batched node-LP bound step (sm_100a, fp64, no tensor cores).
 //
 // Layout: the CALLER's batched vectors are node-fastest, V[row][ld]. The solver's own state is
-// tile-major: nodes are grouped in blocks of 32 and element (row j, node k) lives at
-// ((k / 32) * rows + j) * 32 + k % 32, so the 256-byte segments a node block touches in
+// tile-major: nodes are grouped in blocks of 64 and element (row j, node k) lives at
+// ((k / 64) * rows + j) * 64 + k % 64, so the 512-byte segments a node block touches in
 // consecutive rows are contiguous in HBM (long sequential streams per CTA instead of 256-byte
 // pieces ld*8 bytes apart). tix() is that index. A warp owns one node tile
 // (NT nodes, NT in {1,2,4,8,16,32}) and 32/NT consecutive matrix rows at a time, so every
@@ -32,6 +32,7 @@ namespace blp {
 #define BLP_MINB 6       // resident CTAs per SM the step kernels are compiled for
 #endif
 constexpr int kCtaThreads = 256;
+constexpr int kBlk = 64;      // nodes per layout block (row stride of a lane's column, in doubles)
 constexpr int kWarps = kCtaThreads / 32;
 
 // column-pass accumulators (sums first, then maxima)
@@ -87,7 +88,7 @@ __device__ __forceinline__ bool is_inf(double v) { return fabs(v) >= 1e30; }
 
 // tile-major index of (row, node) in an internal [rows] x [ld] state array
 __device__ __forceinline__ size_t tix(const int row, const int node, const int rows) {
-    return ((size_t)(node >> 5) * rows + row) * 32 + (node & 31);
+    return ((size_t)(node >> 6) * rows + row) * kBlk + (node & (kBlk - 1));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -100,7 +101,7 @@ __device__ __forceinline__ double row_dot(const int32_t* __restrict__ ptr,
                                           const Ent* __restrict__ ent, int row, bool row_ok,
                                           const double* __restrict__ Vn, bool node_ok) {
     // Vn: the lane's column inside a tile-major state array (row stride 32 doubles)
-    constexpr int ld = 32;
+    constexpr int ld = kBlk;
     double acc = 0.0;
     if (NT == 32 || (row_ok && node_ok)) {
         const int p0 = __ldg(ptr + row), p1 = __ldg(ptr + row + 1);
@@ -266,7 +267,7 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
                 hi = __ldg(S.uref + fi);
             }
         }
-        const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, yn, 32, node_ok && row_ok);
+        const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, yn, kBlk, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double xc = fma(w, xb - a, a);                  // w xbar + (1-w) xa
             const double xp = fmin(fmax(xc - tau * (__ldg(P.c + j) - g), lo), hi);
@@ -326,7 +327,7 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
             yc = S.y[e];
             a = __ldcs(S.ya + e);
         }
-        const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, xn, 32, node_ok && row_ok);
+        const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, xn, kBlk, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double yp = on ? fmax(0.0, yc + sig * (__ldg(P.b + i) - ax)) : 0.0;
             S.y[e] = fma(w, (2.0 * yp - yc) - a, a);
@@ -336,6 +337,161 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
             }
         }
         yc = yc2; a = a2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-nodes-per-lane step kernels (batches of >= 64 nodes). A warp owns one matrix row for a
+// whole 64-node block: every state access is one 128-bit load/store per lane (512 contiguous
+// bytes per warp), and the per-row instruction overhead (index arithmetic, entry reads, loop
+// control) is spent once per 64 nodes instead of once per 32 — the one-node-per-lane kernels
+// issue ~170 instructions per row and are issue-bound, not bandwidth-bound
+// (profiles/r1b_full_step_kernels.md).
+#ifndef BLP_MINB2
+#define BLP_MINB2 4
+#endif
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 ldcs2(const double* p) {
+    return __ldcs(reinterpret_cast<const double2*>(p));
+}
+__device__ __forceinline__ void st2(double* p, const double2 v, const bool k0, const bool k1) {
+    if (k0 && k1) *reinterpret_cast<double2*>(p) = v;
+    else if (k0) p[0] = v.x;
+    else if (k1) p[1] = v.y;
+}
+
+template <bool SHARED>
+__device__ __forceinline__ void dot2_entries(const int4* __restrict__ E, const int p0, const int p1,
+                                             const double* __restrict__ Vn, double& g0, double& g1) {
+    constexpr int kU = BLP_U;
+    for (int p = p0; p < p1; p += kU) {
+        double2 v[kU];
+#pragma unroll
+        for (int q = 0; q < kU; ++q) {
+            v[q] = make_double2(0.0, 0.0);
+            if (p + q < p1) {
+                const int col = SHARED ? E[p + q].x : __ldg(&E[p + q].x);
+                v[q] = ld2(Vn + (size_t)col * kBlk);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kU; ++q)
+            if (p + q < p1) {
+                const int2 c = SHARED ? *reinterpret_cast<const int2*>(&E[p + q].z)
+                                      : __ldg(reinterpret_cast<const int2*>(&E[p + q].z));
+                const double cf = __hiloint2double(c.y, c.x);
+                g0 = fma(cf, v[q].x, g0);
+                g1 = fma(cf, v[q].y, g1);
+            }
+    }
+}
+
+__device__ __forceinline__ void slab_dot2(const Slab& sl, const Ent* __restrict__ ent, const int lr,
+                                          const double* __restrict__ Vn, double& g0, double& g1) {
+    const int p0 = sl.sp[lr], p1 = sl.sp[lr + 1];
+    if (sl.se) dot2_entries<true>(sl.se - sl.base, p0, p1, Vn, g0, g1);
+    else dot2_entries<false>(reinterpret_cast<const int4*>(ent), p0, p1, Vn, g0, g1);
+}
+
+template <bool MAJOR>
+__global__ void __launch_bounds__(kCtaThreads, BLP_MINB2)
+k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = blockIdx.y * kBlk + lane * 2;             // this lane: nodes node, node + 1
+    const bool k0 = node < S.B && S.fin[node] == 0;
+    const bool k1 = node + 1 < S.B && S.fin[node + 1] == 0;
+    if (__ballot_sync(0xffffffffu, k0 || k1) == 0) return;     // whole block retired
+    double w0 = 0, w1 = 0, tau0 = 0, tau1 = 0;
+    if (k0) {
+        const int s = S.sbase[node] + it;
+        w0 = (double)s / (double)(s + 1);
+        tau0 = P.eta / S.omega[node];
+    }
+    if (k1) {
+        const int s = S.sbase[node + 1] + it;
+        w1 = (double)s / (double)(s + 1);
+        tau1 = P.eta / S.omega[node + 1];
+    }
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(P.n, r0 + rows_per_cta);
+    const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
+    const size_t base = tix(0, node, P.n);
+    const double* __restrict__ yn = S.y + tix(0, node, P.m);
+    const size_t fblk = (size_t)(node >> 5) * P.n;
+    const unsigned bit = node & 31;
+    for (int j = r0 + warp; j < r1; j += kWarps) {
+        const size_t e = base + (size_t)j * kBlk;
+        const double2 xb = ld2(S.xbar + e);
+        const double2 a = ldcs2(S.xa + e);
+        const uint32_t mk = (__ldg(S.lumask + fblk + j) >> bit) & 3u;
+        double lo0 = __ldg(S.lref + fblk + j), hi0 = __ldg(S.uref + fblk + j);
+        double lo1 = lo0, hi1 = hi0;
+        if (mk) {                                              // a node of this lane deviates
+            const double2 l2 = ldcs2(S.l + e), u2 = ldcs2(S.u + e);
+            if (mk & 1u) { lo0 = l2.x; hi0 = u2.x; }
+            if (mk & 2u) { lo1 = l2.y; hi1 = u2.y; }
+        }
+        double g0 = 0.0, g1 = 0.0;
+        slab_dot2(sl, P.cent, j - r0, yn, g0, g1);
+        const double cj = __ldg(P.c + j);
+        const double xc0 = fma(w0, xb.x - a.x, a.x), xc1 = fma(w1, xb.y - a.y, a.y);
+        const double xp0 = fmin(fmax(xc0 - tau0 * (cj - g0), lo0), hi0);
+        const double xp1 = fmin(fmax(xc1 - tau1 * (cj - g1), lo1), hi1);
+        st2(S.xbar + e, make_double2(2.0 * xp0 - xc0, 2.0 * xp1 - xc1), k0, k1);
+        if constexpr (MAJOR) {
+            st2(S.X1 + e, make_double2(xp0, xp1), k0, k1);
+            st2(S.DX + e, make_double2(xp0 - xc0, xp1 - xc1), k0, k1);
+            st2(S.G + e, make_double2(g0, g1), k0, k1);
+        }
+    }
+}
+
+template <bool MAJOR>
+__global__ void __launch_bounds__(kCtaThreads, BLP_MINB2)
+k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = blockIdx.y * kBlk + lane * 2;
+    const bool k0 = node < S.B && S.fin[node] == 0;
+    const bool k1 = node + 1 < S.B && S.fin[node + 1] == 0;
+    if (__ballot_sync(0xffffffffu, k0 || k1) == 0) return;
+    double w0 = 0, w1 = 0, sig0 = 0, sig1 = 0;
+    if (k0) {
+        const int s = S.sbase[node] + it;
+        w0 = (double)(s + 1) / (double)(s + 2);
+        sig0 = P.eta * S.omega[node];
+    }
+    if (k1) {
+        const int s = S.sbase[node + 1] + it;
+        w1 = (double)(s + 1) / (double)(s + 2);
+        sig1 = P.eta * S.omega[node + 1];
+    }
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(P.m, r0 + rows_per_cta);
+    const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
+    const size_t base = tix(0, node, P.m);
+    const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
+    for (int i = r0 + warp; i < r1; i += kWarps) {
+        const size_t e = base + (size_t)i * kBlk;
+        const double2 yc = ld2(S.y + e);
+        const double2 a = ldcs2(S.ya + e);
+        bool on0 = true, on1 = true;
+        if (i >= P.m_base && S.rowmask) {
+            const uint8_t* mrow = S.rowmask + (size_t)(i - P.m_base) * S.ld + node;
+            on0 = mrow[0] != 0;
+            on1 = mrow[1] != 0;
+        }
+        double ax0 = 0.0, ax1 = 0.0;
+        slab_dot2(sl, P.ent, i - r0, xn, ax0, ax1);
+        const double bi = __ldg(P.b + i);
+        const double yp0 = on0 ? fmax(0.0, yc.x + sig0 * (bi - ax0)) : 0.0;
+        const double yp1 = on1 ? fmax(0.0, yc.y + sig1 * (bi - ax1)) : 0.0;
+        st2(S.y + e, make_double2(fma(w0, (2.0 * yp0 - yc.x) - a.x, a.x),
+                                  fma(w1, (2.0 * yp1 - yc.y) - a.y, a.y)), k0, k1);
+        if constexpr (MAJOR) {
+            st2(S.Y1 + e, make_double2(yp0, yp1), k0, k1);
+            st2(S.DY + e, make_double2(yp0 - yc.x, yp1 - yc.y), k0, k1);
+        }
     }
 }
 

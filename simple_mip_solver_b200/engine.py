@@ -119,7 +119,7 @@ def default_opts(**kw) -> BlpOpts:
 
 
 def leading_dim(B: int) -> int:
-    return (B + 31) // 32 * 32
+    return (B + 63) // 64 * 64
 
 
 @dataclass

@@ -62,7 +62,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(engine.EXPORTED_SYMBOLS)
     o = engine.default_opts()
     assert o.eps_rel == 1e-7 and o.eval_every == 64 and o.max_iters == 400000
-    assert lib.blp_ld(1) == 32 and lib.blp_ld(33) == 64
+    assert lib.blp_ld(1) == 64 and lib.blp_ld(65) == 128
     assert engine.load_library().blp_version().decode().endswith('sm_100a')
 
 

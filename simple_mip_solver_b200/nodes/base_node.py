@@ -219,6 +219,14 @@ class BaseNode:
         if self.lp_feasible and len(self._integer_indices):
             vals = self.solution[self._integer_indices]
             self.mip_feasible = bool(np.max(np.abs(np.round(vals) - vals)) <= variable_epsilon)
+            if self.mip_feasible and not self.unbounded:
+                # A simplex vertex that passes this test is integral to machine precision; a
+                # first-order solution is integral to the solve tolerance. Snap the integer
+                # variables so that an incumbent's objective is the objective of an integral point.
+                x = np.array(self.solution, dtype=float)
+                x[self._integer_indices] = np.round(vals)
+                self.solution = CyLPArray(x)
+                self.objective_value = float(np.dot(np.asarray(self.lp.objective), x))
         else:
             self.mip_feasible = bool(self.lp_feasible)
 

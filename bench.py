@@ -233,7 +233,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='blp', choices=['blp', 'reference'])
     ap.add_argument('--workload', default='c5', choices=list(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=256, help='open nodes per step per GPU')
+    ap.add_argument('--batch', type=int, default=512, help='open nodes per step per GPU')
     ap.add_argument('--eps', type=float, default=1e-7)
     ap.add_argument('--max-iters', type=int, default=400000)
     ap.add_argument('--seed', type=int, default=0)

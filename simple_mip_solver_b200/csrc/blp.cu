@@ -77,11 +77,45 @@ struct Plan {
     int V = 1;                // nodes per lane: 2 selects the k_primal2 / k_dual2 kernels
     int cap = 0;              // slab entries staged in shared memory per CTA (step kernels, spmv)
     size_t smem = 0;          // dynamic shared memory bytes of those kernels
+    const int* chunk_ptr = nullptr;   // device: row range of every CTA (step kernels)
 };
 
 constexpr int kMaxSlabEntries = 2816;       // 44 KB of entries + row pointers stay under 48 KB
 
-// shared-memory needs of a row-chunked kernel: the largest entry count of any chunk, capped
+// Row ranges of the step-kernel CTAs: at most rows_per_cta rows and about 4x the average entry
+// count per chunk; a long row (dense cut row) gets a chunk of its own and is then gathered by all
+// warps of the CTA together. Also sizes the shared-memory slab (largest chunk, capped).
+void plan_chunks(Plan& p, const std::vector<int32_t>& ptr, int rows, std::vector<int32_t>& bounds) {
+    const long nnz = ptr[rows];
+    const long budget = std::max<long>(4 * ((nnz * p.rows_per_cta + rows - 1) / std::max(rows, 1)), kLongRow);
+    bounds.clear();
+    bounds.push_back(0);
+    int worst = 0;
+    int r = 0;
+    while (r < rows) {
+        int r1 = r;
+        long cnt = 0;
+        while (r1 < rows && r1 - r < p.rows_per_cta) {
+            const long len = ptr[r1 + 1] - ptr[r1];
+            if (len > kLongRow) {                 // long row: alone in its chunk
+                if (r1 == r) { cnt = len; ++r1; }
+                break;
+            }
+            if (r1 > r && cnt + len > budget) break;
+            cnt += len;
+            ++r1;
+        }
+        worst = std::max<long>(worst, cnt);
+        bounds.push_back(r1);
+        r = r1;
+    }
+    p.chunks = (int)bounds.size() - 1;
+    const int ptr_slots = (p.rows_per_cta + 4) / 4;
+    p.cap = std::max(0, std::min(worst, kMaxSlabEntries - ptr_slots));
+    p.smem = 16 * ((size_t)ptr_slots + (size_t)p.cap);
+}
+
+// spmv keeps uniform chunks
 void plan_slab(Plan& p, const std::vector<int32_t>& ptr, int rows) {
     int worst = 0;
     for (int r0 = 0; r0 < rows; r0 += p.rows_per_cta) {
@@ -150,6 +184,8 @@ struct blp_handle_s {
     // device copies
     DevBuf rowptr, ent, cptr, cent, c, b, rowscale, colscale, d_dr, d_dc;
     DevBuf uent, ucent;                // unscaled entries, same patterns (blp_spmv)
+    DevBuf chunkC, chunkR;             // row ranges of the step-kernel CTAs (primal / dual)
+    std::vector<int32_t> h_chunkC, h_chunkR;
     DevProb P{};
     // staging of the host-buffer entry points
     DevBuf s_lb, s_ub, s_x0, s_y0, s_mask, s_x, s_y, s_tmp, s_ws, s_node, s_int, s_delta, s_par;
@@ -307,12 +343,12 @@ void launch_steps_nt(const DevProb& P, const DevState& S, const Plan& pc, const 
                      bool major, cudaStream_t st, int which) {
     const dim3 gc(pc.chunks, pc.tiles), gr(pr.chunks, pr.tiles);
     if (which != 1) {
-        if (major) k_primal<NT, true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap);
-        else k_primal<NT, false><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap);
+        if (major) k_primal<NT, true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr);
+        else k_primal<NT, false><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr);
     }
     if (which != 0) {
-        if (major) k_dual<NT, true><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap);
-        else k_dual<NT, false><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap);
+        if (major) k_dual<NT, true><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr);
+        else k_dual<NT, false><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr);
     }
 }
 
@@ -322,12 +358,12 @@ void launch_steps(const DevProb& P, const DevState& S, const Plan& pc, const Pla
     if (pc.V == 2) {
         const dim3 gc(pc.chunks, pc.tiles), gr(pr.chunks, pr.tiles);
         if (which != 1) {
-            if (major) k_primal2<true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap);
-            else k_primal2<false><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap);
+            if (major) k_primal2<true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr);
+            else k_primal2<false><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr);
         }
         if (which != 0) {
-            if (major) k_dual2<true><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap);
-            else k_dual2<false><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap);
+            if (major) k_dual2<true><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr);
+            else k_dual2<false><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr);
         }
         return;
     }
@@ -654,8 +690,16 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         return p;
     };
     Plan pc = step_plan(P.n, B), pr = step_plan(P.m, B);
-    plan_slab(pc, h->hptrAT, P.n);
-    plan_slab(pr, h->hptrA, P.m);
+    auto finish_step_plans = [&]() -> int {
+        plan_chunks(pc, h->hptrAT, P.n, h->h_chunkC);
+        plan_chunks(pr, h->hptrA, P.m, h->h_chunkR);
+        CK(upload(h->chunkC, h->h_chunkC, st));
+        CK(upload(h->chunkR, h->h_chunkR, st));
+        pc.chunk_ptr = h->chunkC.as<int32_t>();
+        pr.chunk_ptr = h->chunkR.as<int32_t>();
+        return BLP_OK;
+    };
+    if ((rc = finish_step_plans()) != BLP_OK) return rc;
     Plan ec = make_plan(P.n, B, 1, kEvalChunks), er = make_plan(P.m, B, 1, kEvalChunks);
     D.chunksC = ec.chunks;
     D.chunksR = er.chunks;
@@ -718,8 +762,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 NT = pick_nt(S.B);
                 pc = step_plan(P.n, S.B);
                 pr = step_plan(P.m, S.B);
-                plan_slab(pc, h->hptrAT, P.n);
-                plan_slab(pr, h->hptrA, P.m);
+                if ((rc = finish_step_plans()) != BLP_OK) return rc;
                 ec = make_plan(P.n, S.B, 1, kEvalChunks);
                 er = make_plan(P.m, S.B, 1, kEvalChunks);
                 D.chunksC = ec.chunks;
@@ -1024,7 +1067,7 @@ int blp_destroy(blp_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->drop_graphs();
     DevBuf* bufs[] = {&h->rowptr, &h->ent, &h->cptr, &h->cent, &h->c, &h->b,
-                      &h->rowscale, &h->colscale, &h->d_dr, &h->d_dc, &h->uent, &h->ucent, &h->s_lb,
+                      &h->rowscale, &h->colscale, &h->d_dr, &h->d_dc, &h->uent, &h->ucent, &h->chunkC, &h->chunkR, &h->s_lb,
                       &h->s_ub, &h->s_x0, &h->s_y0, &h->s_mask, &h->s_x, &h->s_y, &h->s_tmp,
                       &h->s_ws, &h->s_node, &h->s_int, &h->s_delta, &h->s_par};
     for (DevBuf* b : bufs) b->release();

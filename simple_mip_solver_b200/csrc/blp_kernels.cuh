@@ -213,7 +213,8 @@ __device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict
 // Primal half step, fused  G = A'y  ->  x' = clip(x - tau (c - G), l, u)  ->  xbar = 2x' - x.
 template <int NT, bool MAJOR>
 __global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
-k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
+k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
+        const int* __restrict__ chunk_ptr) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * NT + (lane % NT);
@@ -226,8 +227,8 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
         w = (double)s / (double)(s + 1);
         tau = P.eta / S.omega[node];
     }
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(P.n, r0 + rows_per_cta);
+    const int r0 = __ldg(chunk_ptr + blockIdx.x);
+    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
     const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
     // software pipeline over the warp's rows: the streaming loads of the next row are issued
@@ -285,7 +286,8 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
 // Dual half step, fused  s = A xbar  ->  y' = max(0, y + sigma (b - s))  ->  Halpern update of y.
 template <int NT, bool MAJOR>
 __global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
-k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
+k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
+        const int* __restrict__ chunk_ptr) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * NT + (lane % NT);
@@ -298,8 +300,8 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
         w = (double)(s + 1) / (double)(s + 2);
         sig = P.eta * S.omega[node];
     }
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(P.m, r0 + rows_per_cta);
+    const int r0 = __ldg(chunk_ptr + blockIdx.x);
+    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
     const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
     int ib = r0 + warp * RW;
@@ -394,9 +396,35 @@ __device__ __forceinline__ void slab_dot2(const Slab& sl, const Ent* __restrict_
     else dot2_entries<false>(reinterpret_cast<const int4*>(ent), p0, p1, Vn, g0, g1);
 }
 
+// A chunk that consists of ONE long row (a dense cut row, typically) is shared by all warps of the
+// CTA: each warp gathers a slice of the row's entries, the partial sums meet in shared memory.
+constexpr int kLongRow = 96;
+
+__device__ __forceinline__ void coop_dot2(const Slab& sl, const Ent* __restrict__ ent,
+                                          const double* __restrict__ Vn, const int warp, const int lane,
+                                          double& g0, double& g1) {
+    __shared__ double2 red[kWarps][32];
+    const int p0 = sl.sp[0], p1 = sl.sp[1];
+    const int seg = ((p1 - p0 + kWarps - 1) / kWarps + BLP_U - 1) / BLP_U * BLP_U;
+    const int a = min(p1, p0 + warp * seg), b = min(p1, a + seg);
+    double s0 = 0.0, s1 = 0.0;
+    if (sl.se) dot2_entries<true>(sl.se - sl.base, a, b, Vn, s0, s1);
+    else dot2_entries<false>(reinterpret_cast<const int4*>(ent), a, b, Vn, s0, s1);
+    red[warp][lane] = make_double2(s0, s1);
+    __syncthreads();
+    g0 = 0.0;
+    g1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        g0 += red[w][lane].x;
+        g1 += red[w][lane].y;
+    }
+}
+
 template <bool MAJOR>
 __global__ void __launch_bounds__(kCtaThreads, BLP_MINB2)
-k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
+k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
+          const int* __restrict__ chunk_ptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * kBlk + lane * 2;             // this lane: nodes node, node + 1
     const bool k0 = node < S.B && S.fin[node] == 0;
@@ -413,13 +441,19 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
         w1 = (double)s / (double)(s + 1);
         tau1 = P.eta / S.omega[node + 1];
     }
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(P.n, r0 + rows_per_cta);
+    const int r0 = __ldg(chunk_ptr + blockIdx.x);
+    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
     const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.n);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
     const size_t fblk = (size_t)(node >> 5) * P.n;
     const unsigned bit = node & 31;
+    const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
+    double cg0 = 0.0, cg1 = 0.0;
+    if (coop) {
+        coop_dot2(sl, P.cent, yn, warp, lane, cg0, cg1);
+        if (warp != 0) return;
+    }
     for (int j = r0 + warp; j < r1; j += kWarps) {
         const size_t e = base + (size_t)j * kBlk;
         const double2 xb = ld2(S.xbar + e);
@@ -432,8 +466,8 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
             if (mk & 1u) { lo0 = l2.x; hi0 = u2.x; }
             if (mk & 2u) { lo1 = l2.y; hi1 = u2.y; }
         }
-        double g0 = 0.0, g1 = 0.0;
-        slab_dot2(sl, P.cent, j - r0, yn, g0, g1);
+        double g0 = cg0, g1 = cg1;
+        if (!coop) slab_dot2(sl, P.cent, j - r0, yn, g0, g1);
         const double cj = __ldg(P.c + j);
         const double xc0 = fma(w0, xb.x - a.x, a.x), xc1 = fma(w1, xb.y - a.y, a.y);
         const double xp0 = fmin(fmax(xc0 - tau0 * (cj - g0), lo0), hi0);
@@ -449,7 +483,8 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
 
 template <bool MAJOR>
 __global__ void __launch_bounds__(kCtaThreads, BLP_MINB2)
-k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap) {
+k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
+          const int* __restrict__ chunk_ptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * kBlk + lane * 2;
     const bool k0 = node < S.B && S.fin[node] == 0;
@@ -466,11 +501,17 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
         w1 = (double)(s + 1) / (double)(s + 2);
         sig1 = P.eta * S.omega[node + 1];
     }
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(P.m, r0 + rows_per_cta);
+    const int r0 = __ldg(chunk_ptr + blockIdx.x);
+    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
     const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.m);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
+    const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
+    double cg0 = 0.0, cg1 = 0.0;
+    if (coop) {
+        coop_dot2(sl, P.ent, xn, warp, lane, cg0, cg1);
+        if (warp != 0) return;
+    }
     for (int i = r0 + warp; i < r1; i += kWarps) {
         const size_t e = base + (size_t)i * kBlk;
         const double2 yc = ld2(S.y + e);
@@ -481,8 +522,8 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
             on0 = mrow[0] != 0;
             on1 = mrow[1] != 0;
         }
-        double ax0 = 0.0, ax1 = 0.0;
-        slab_dot2(sl, P.ent, i - r0, xn, ax0, ax1);
+        double ax0 = cg0, ax1 = cg1;
+        if (!coop) slab_dot2(sl, P.ent, i - r0, xn, ax0, ax1);
         const double bi = __ldg(P.b + i);
         const double yp0 = on0 ? fmax(0.0, yc.x + sig0 * (bi - ax0)) : 0.0;
         const double yp1 = on1 ? fmax(0.0, yc.y + sig1 * (bi - ax1)) : 0.0;

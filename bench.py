@@ -273,11 +273,15 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from simple_mip_solver_b200 import engine, parallel
+    from simple_mip_solver_b200 import _build, engine, parallel
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    if local_rank == 0:
+        _build.build_extension()          # no-op when libblp.so is newer than its sources
+    if world > 1:
+        dist.barrier()
 
     lp = engine.BatchLP(d.A, d.b, d.c, device=local_rank)
     ld = engine.leading_dim(B)

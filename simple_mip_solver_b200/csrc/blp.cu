@@ -801,10 +801,11 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         step_ms += ms;
         if (profile)
             for (int it = 0; it < K; ++it) {
-                CK(cudaEventElapsedTime(&ms, h->prof_ev[2 * it], h->prof_ev[2 * it + 1]));
-                primal_ms += ms;
-                CK(cudaEventElapsedTime(&ms, h->prof_ev[2 * it + 1], h->prof_ev[2 * it + 2]));
-                dual_ms += ms;
+                float t = 0.f;
+                CK(cudaEventElapsedTime(&t, h->prof_ev[2 * it], h->prof_ev[2 * it + 1]));
+                primal_ms += t;
+                CK(cudaEventElapsedTime(&t, h->prof_ev[2 * it + 1], h->prof_ev[2 * it + 2]));
+                dual_ms += t;
             }
         node_iters += (double)active * K;
         total += K;
@@ -824,8 +825,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                         k, t[8 * k], t[8 * k + 1], t[8 * k + 2], t[8 * k + 3], t[8 * k + 4], t[8 * k + 5], t[8 * k + 6], t[8 * k + 7]);
         }
         if (o.verbose)
-            fprintf(stderr, "[blp] iters %d  width %d  running %d  restarting %d  finished now %d\n", total,
-                    S.B, active, h->h_counters[1], h->h_counters[3]);
+            fprintf(stderr, "[blp] iters %d  width %d  running %d  restarting %d  finished now %d  steps_ms %.3f\n",
+                    total, S.B, active, h->h_counters[1], h->h_counters[3], ms);
     }
     CK(cudaEventRecord(h->ev[1], st));
     CK(cudaStreamSynchronize(st));

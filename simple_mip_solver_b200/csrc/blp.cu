@@ -611,7 +611,10 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     if (!want_frac) S.isint = nullptr;
     DevOut O{obj, lower_bound, x, y, status, iters, frac_idx};
 
-    const int K = std::min(o.eval_every, o.max_iters);
+    // evaluation period: eval_every at first, 4x that once a node batch has run 32 periods (an
+    // evaluation costs about three iterations; late in a solve nothing changes within 64 of them)
+    const int K0 = std::min(o.eval_every, o.max_iters);
+    int K = K0;
     const int rpw = env_int("BLP_ROWS_PER_WARP", 8);
     int NT = pick_nt(B);     // nodes per warp; re-picked when compaction narrows the batch
     DecideArgs D{0, 0, K, o.max_iters, o.eps_rel, o.eps_infeas,
@@ -709,7 +712,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     const bool profile = o.profile == 1;
     const bool use_graph = o.use_graph && !profile;
     if (profile)
-        while ((int)h->prof_ev.size() < 2 * K + 1) {
+        while ((int)h->prof_ev.size() < 2 * 4 * K0 + 1) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
             h->prof_ev.push_back(e);
@@ -767,6 +770,14 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 er = make_plan(P.m, S.B, 1, kEvalChunks);
                 D.chunksC = ec.chunks;
                 D.chunksR = er.chunks;
+            }
+        }
+        {
+            int want = (total >= 32 * K0 && env_int("BLP_ADAPTIVE_EVAL", 1)) ? 4 * K0 : K0;
+            want = std::min(want, o.max_iters - total);
+            if (want != K) {
+                K = want;
+                D.steps_in_period = K;
             }
         }
         if (use_graph) {

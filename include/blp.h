@@ -19,7 +19,8 @@
  *     2 dual infeasible (unbounded), 3 iteration limit.
  *   - "device" pointers are CUDA device pointers owned by the caller (torch tensors in the Python
  *     host layer) and borrowed for the duration of the call. Batched vectors are stored
- *     node-fastest: element (j, k) of an [rows][ld] array lives at j*ld + k, ld = blp_ld(B).
+ *     node-fastest: element (j, k) of an [rows][ld] array lives at j*ld + k, ld = blp_ld(B)
+ *     (B rounded up to a multiple of 64).
  *   - a handle is bound to one GPU and one CUDA stream and is not thread safe.
  *   - infinite bounds: any |v| >= 1e30 (CLP's getCoinInfinity() is DBL_MAX) or IEEE inf.
  */

@@ -2,12 +2,10 @@
 //
 // Layout: the CALLER's batched vectors are node-fastest, V[row][ld]. The solver's own state is
 // tile-major: nodes are grouped in blocks of 64 and element (row j, node k) lives at
-// ((k / 64) * rows + j) * 64 + k % 64, so the 512-byte segments a node block touches in
-// consecutive rows are contiguous in HBM (long sequential streams per CTA instead of 256-byte
-// pieces ld*8 bytes apart). tix() is that index. A warp owns one node tile
-// (NT nodes, NT in {1,2,4,8,16,32}) and 32/NT consecutive matrix rows at a time, so every
-// vector access of a warp is one contiguous 256-byte segment and the CSR entries of a row are
-// warp-uniform. Work is ordered tile-major (blockIdx.y = tile, blockIdx.x = row chunk) so the
+// ((k / 64) * rows + j) * 64 + k % 64 (tix()), so the 512-byte segments a node block touches in
+// consecutive rows are contiguous in HBM. A warp owns one matrix row (or 32/NT rows) for a tile of
+// nodes, so every state access of a warp is one contiguous segment and the CSR entries of a row
+// are warp-uniform. Work is ordered tile-major (blockIdx.y = tile, blockIdx.x = row chunk) so the
 // CTAs resident at any moment share a few node tiles and the gathered vector of those tiles is
 // served from L2 after its first (compulsory) read from HBM.
 //
@@ -15,7 +13,7 @@
 //     x' = clip(x - tau (c - A'y), l, u),   y' = max(0, y + sigma (b - A (2x' - x)))
 // one step is  z+ = w (2 T(z) - z) + (1 - w) z_anchor,  w = (s+1)/(s+2), s = steps since restart.
 // State kept per node column: xbar = 2x' - x (gathered by the dual step; the next primal step
-// rebuilds x = w xbar + (1-w) xa from it), xa, l, u, y, ya.
+// rebuilds x = w xbar + (1-w) xa from it), xa, l, u (+ block reference bounds and masks), y, ya.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -24,9 +22,6 @@ namespace blp {
 
 #ifndef BLP_U
 #define BLP_U 4          // gathers issued back to back per row batch
-#endif
-#ifndef BLP_PREFETCH
-#define BLP_PREFETCH 0   // issue the next row's streaming loads before consuming the gathers
 #endif
 #ifndef BLP_MINB
 #define BLP_MINB 6       // resident CTAs per SM the step kernels are compiled for
@@ -214,7 +209,7 @@ __device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict
 template <int NT, bool MAJOR>
 __global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
 k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-        const int* __restrict__ chunk_ptr) {
+         const int* __restrict__ chunk_ptr) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * NT + (lane % NT);
@@ -231,31 +226,12 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
     const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
     const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
-    // software pipeline over the warp's rows: the streaming loads of the next row are issued
-    // before the gathers of the current one are consumed
-    int jb = r0 + warp * RW;
-    double xb = 0, a = 0, lo = 0, hi = 0;
-    if (jb + sub < r1 && node_ok) {
-        const size_t e = tix(jb + sub, node, P.n);
-        xb = S.xbar[e];
-        a = __ldcs(S.xa + e);
-        lo = __ldcs(S.l + e);
-        hi = __ldcs(S.u + e);
-    }
-    for (; jb < r1; jb += kWarps * RW) {
+    for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
         const int j = jb + sub;
         const bool row_ok = j < r1;
         const size_t e = tix(j, node, P.n);
-        const int jn = j + kWarps * RW;
-        double xb2 = 0, a2 = 0, lo2 = 0, hi2 = 0;
-        if (BLP_PREFETCH && jn < r1 && node_ok) {
-            const size_t e2 = tix(jn, node, P.n);
-            xb2 = S.xbar[e2];
-            a2 = __ldcs(S.xa + e2);
-            lo2 = __ldcs(S.l + e2);
-            hi2 = __ldcs(S.u + e2);
-        }
-        if (!BLP_PREFETCH && row_ok && node_ok) {
+        double xb = 0, a = 0, lo = 0, hi = 0;
+        if (row_ok && node_ok) {       // streaming loads first, the gathers follow at once
             xb = S.xbar[e];
             a = __ldcs(S.xa + e);
             const size_t fi = (size_t)(node >> 5) * P.n + j;
@@ -279,7 +255,6 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
                 S.G[e] = g;
             }
         }
-        xb = xb2; a = a2; lo = lo2; hi = hi2;
     }
 }
 
@@ -287,7 +262,7 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
 template <int NT, bool MAJOR>
 __global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
 k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-        const int* __restrict__ chunk_ptr) {
+       const int* __restrict__ chunk_ptr) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * NT + (lane % NT);
@@ -304,30 +279,16 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
     const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
     const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
-    int ib = r0 + warp * RW;
-    double yc = 0, a = 0;
-    if (ib + sub < r1 && node_ok) {
-        const size_t e = tix(ib + sub, node, P.m);
-        yc = S.y[e];
-        a = __ldcs(S.ya + e);
-    }
-    for (; ib < r1; ib += kWarps * RW) {
+    for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
         const size_t e = tix(i, node, P.m);
-        const int in = i + kWarps * RW;
-        double yc2 = 0, a2 = 0;
-        if (BLP_PREFETCH && in < r1 && node_ok) {
-            const size_t e2 = tix(in, node, P.m);
-            yc2 = S.y[e2];
-            a2 = __ldcs(S.ya + e2);
-        }
+        double yc = 0, a = 0;
         bool on = true;
-        if (row_ok && node_ok && i >= P.m_base && S.rowmask)
-            on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
-        if (!BLP_PREFETCH && row_ok && node_ok) {
+        if (row_ok && node_ok) {
             yc = S.y[e];
             a = __ldcs(S.ya + e);
+            if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
         }
         const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, xn, kBlk, node_ok && row_ok);
         if (row_ok && node_ok) {
@@ -338,7 +299,6 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
                 S.DY[e] = yp - yc;
             }
         }
-        yc = yc2; a = a2;
     }
 }
 

@@ -1,0 +1,131 @@
+"""The CyLP / cuppy / gimpy look-alikes: the calls the reference makes on them behave the same."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import use_oracle_engine
+from simple_mip_solver_b200.compat import (COIN_INFINITY, BinaryTree, CyClpSimplex, CyLPArray, MILPInstance,
+                                           SharedLP, read_mps, solve_lps)
+
+
+def _lp():
+    A = sp.csr_matrix(np.array([[-1., 0, -1], [0, -1, 0]]))
+    return CyClpSimplex(SharedLP(A, [-1.5, -1.25], [-1, -1, -1]), [0, 0, 0], [10, 10, 10])
+
+
+def test_protocol_attributes():
+    lp = _lp()
+    assert lp.nVariables == lp.nCols == 3 and lp.nConstraints == 2
+    assert len(lp.variables) == 1 and lp.variables[0].name == 'x' and lp.getVarByName('x').dim == 3
+    assert lp.getCoinInfinity() >= 1e300
+    assert np.array_equal(lp.constraintsLower, [-1.5, -1.25]) and (lp.constraintsUpper >= 1e300).all()
+    assert lp.coefMatrix.shape == (2, 3) and sp.issparse(lp.coefMatrix)
+    assert np.array_equal(lp.objective, [-1, -1, -1])
+    c0 = lp.constraints[0]
+    assert c0.nRows == 2 and c0.varCoefs[lp.getVarByName('x')].shape == (2, 3)
+    lp.variablesUpper = CyLPArray([5, 5, 5])            # test_base_node.py:126-128 sets bounds
+    assert list(lp.variablesUpper) == [5, 5, 5]
+    cols, rows = lp.getBasisStatus()
+    assert cols.dtype == np.int32 and len(cols) == 3 and len(rows) == 2
+
+
+def test_modelling_expressions_and_cut_rows(monkeypatch):
+    use_oracle_engine(monkeypatch)
+    lp = _lp()
+    x = lp.getVarByName('x')
+    lp.addConstraint(CyLPArray([-1, -1, -1]) * x >= -2.5, 'cut_a')        # base_node.py:459-460
+    assert lp.nConstraints == 3 and lp.coefMatrix.shape == (3, 3)
+    assert [c.name for c in lp.constraints] == ['R_base', 'cut_a']
+    lp.dual()
+    assert lp.getStatusCode() == 0 and lp.objectiveValue == pytest.approx(-2.5)
+    duals = lp.dualConstraintSolution
+    assert set(duals) == {'R_base', 'cut_a'} and duals['cut_a'][0] > 0
+    assert lp.primalVariableSolution['x'].shape == (3,)
+    lp.removeConstraint('cut_a')                                          # base_node.py:337-338
+    lp.dual()
+    assert lp.objectiveValue == pytest.approx(-2.75)
+    with pytest.raises(KeyError):
+        lp.removeConstraint('cut_a')
+    # bounds statement and building a model from scratch (base_node.py:592-608 style)
+    new = CyClpSimplex()
+    y = new.addVariable('x', 3)
+    new += CyLPArray([0, 0, 0]) <= y <= CyLPArray([10, 10, 1])
+    new.addConstraint(CyLPArray([-1.5, -1.25]) <= np.array([[-1., 0, -1], [0, -1, 0]]) * y <= CyLPArray([COIN_INFINITY] * 2), 'R')
+    new.objective = CyLPArray([-1, -1, -1]) * y
+    new.dual()
+    assert new.getStatusCode() == 0 and new.objectiveValue == pytest.approx(-2.75)
+    assert list(new.variablesUpper) == [10, 10, 1]
+
+
+def test_solve_lps_batches_and_caches(monkeypatch):
+    eng = use_oracle_engine(monkeypatch)
+    lp = _lp()
+    kids = [lp.copy_for_child() for _ in range(3)]
+    kids[0].variablesUpper[2] = 1
+    kids[1].variablesLower[2] = 2
+    assert solve_lps([lp] + kids) == 4 and eng.calls == 1 and eng.batch_sizes == [4]
+    assert [k.getStatusCode() for k in kids] == [0, 1, 0]
+    assert kids[1].objectiveValue == float('inf') and kids[1].primalVariableSolution['x'] is None
+    assert solve_lps([lp] + kids) == 0                    # unchanged LPs are cache hits
+    lp.dual()
+    assert eng.calls == 1
+    kids[2].variablesUpper[0] = 0.5                       # an in-place bound change invalidates the cache
+    kids[2].dual()
+    assert eng.calls == 2
+    kids[0].maxNumIteration = 5                           # a different budget goes in its own call
+    kids[1].variablesLower[2] = 0
+    assert solve_lps(kids) == 2 and eng.calls == 4
+
+
+def test_milp_instance_forms():
+    A = np.array([[1, 0, 1], [0, 1, 0]])
+    m = MILPInstance(A=A, b=CyLPArray([1.5, 1.25]), c=CyLPArray([1, 1, 1]), l=CyLPArray([0, 0, 0]),
+                     u=CyLPArray([10, 10, 10]), sense=['Max', '<='], integerIndices=[0, 1, 2], numVars=3)
+    assert m.sense == '<=' and list(m.lp.objective) == [-1, -1, -1]          # maximisation is negated
+    g = MILPInstance(A=-A, b=-CyLPArray([1.5, 1.25]), c=-CyLPArray([1, 1, 1]), sense=['Min', '>='],
+                     integerIndices=[0], numVars=3)
+    assert g.sense == '>=' and (g.u >= 1e300).all() and (g.l == 0).all()
+    assert isinstance(g.lp, CyClpSimplex) and g.lp.nConstraints == 2
+
+
+def test_mps_reader(tmp_path):
+    text = """NAME          BLANK
+ROWS
+ N  OBJROW
+ L  R_1_0
+ L  R_1_1
+COLUMNS
+    x_0  OBJROW  -3.  R_1_0  7.
+    x_0  R_1_1  2.
+    x_1  OBJROW  -5.
+    x_2  OBJROW  -1.  R_1_1  4.
+RHS
+    RHS  R_1_0  9.  R_1_1  6.
+BOUNDS
+ UI BOUND  x_0  10.
+ UI BOUND  x_1  10.
+ UP BOUND  x_2  3.5
+ENDATA
+"""
+    p = tmp_path / 'm.mps'
+    p.write_text(text)
+    mdl = read_mps(str(p))
+    assert mdl.A.shape == (2, 3) and mdl.row_senses == ['L', 'L']
+    assert np.array_equal(mdl.A.toarray(), [[7, 0, 0], [2, 0, 4]])           # x_1: an empty column
+    assert list(mdl.rhs) == [9, 6] and list(mdl.c) == [-3, -5, -1]
+    assert mdl.integer_indices == [0, 1] and list(mdl.u) == [10, 10, 3.5] and list(mdl.l) == [0, 0, 0]
+    inst = MILPInstance(file_name=str(p))
+    assert inst.sense == '<=' and inst.integerIndices == [0, 1] and inst.numVars == 3
+
+
+def test_binary_tree():
+    t = BinaryTree()
+    t.add_root(0, node='r')
+    t.add_left_child(1, 0, node='l')
+    t.add_right_child(2, 0, node='rr')
+    assert 1 in t and 3 not in t and t.get_children(0) == [1, 2] and t.get_parent(2) == 0
+    assert t.nodes[1].attr['node'] == 'l' and t.get_node_attr(2, 'node') == 'rr'
+    with pytest.raises(AssertionError):
+        t.add_left_child(3, 0)
+    with pytest.raises(AssertionError):
+        t.add_left_child(2, 1)

@@ -197,3 +197,35 @@ def test_default_bound_with_gomory_rounds(blp_lib):
         bb.model.lp._shared.close()
     print('GMI cuts appended over all instances:', used_cuts)
     assert used_cuts > 0
+
+
+def test_disjunctive_cut_nodes(blp_lib):
+    """DisjunctiveCutBoundNode as a caller of the GPU bound step; its CGLP is solved by the same
+    engine (reference usage: test_simple_mip_solver/helpers.py:75-126)."""
+    from simple_mip_solver_b200 import (CutGeneratingLP, DisjunctiveCutBoundNode,
+                                        DisjunctiveCutBoundPseudoCostBranchNode)
+    recs = list(SCALE1.items())[::9] + [(k, EXAMPLES[k]) for k in ('cut1', 'cut2', 'lift_project')]
+    created = 0
+    for name, rec in recs:
+        tree = BranchAndBound(model_from(rec), BaseNode, node_limit=8, gomory_cuts=False)
+        tree.solve()
+        cglp = CutGeneratingLP(tree, tree.root_node.idx)
+        pi, pi0 = cglp.solve()
+        assert pi is not None
+        # validity on the integer points of the model (small boxes only)
+        A, b = np.array(rec['A']), np.array(rec['b'])
+        if len(rec['c']) <= 4:
+            import itertools
+            for p in itertools.product(*[range(int(lo), int(min(hi, lo + 6)) + 1) for lo, hi in zip(rec['l'], rec['u'])]):
+                p = np.array(p, dtype=float)
+                if (A @ p >= b - 1e-9).all():
+                    assert float(np.dot(pi, p)) >= pi0 - 1e-5 * max(1.0, abs(pi0)), (name, p)
+        for Node, extra in ((DisjunctiveCutBoundNode, dict(gomory_cuts=False)),
+                            (DisjunctiveCutBoundPseudoCostBranchNode, dict(pseudo_costs={}, gomory_cuts=False))):
+            bb = BranchAndBound(model_from(rec), Node, cglp=cglp, **extra)
+            bb.solve()
+            want = rec.get('mip_optimum', rec['reference']['BaseNode']['objective'])
+            assert bb.status == 'optimal' and rel(bb.objective_value, unfl(want)) <= 1e-6, (name, bb.objective_value, want)
+            created += bb._kwargs['total_number_cglp_created']
+            bb.model.lp._shared.close()
+    assert created > 0

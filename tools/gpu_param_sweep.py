@@ -10,9 +10,7 @@ d, depth, root = bench.load_instance(sys.argv[1] if len(sys.argv) > 1 else 'c5')
 lp = engine.BatchLP(d.A, d.b, d.c)
 lbs, ubs, _ = frontier_nodes(d, root['x'], 0, B, depth, seed=0)
 x0 = np.tile(root['x'], (B, 1)); y0 = np.tile(root['y'], (B, 1))
-configs = [dict(), dict(BLP_BETA_SUFF='0.1'), dict(BLP_BETA_SUFF='0.3'), dict(BLP_BETA_NEC='0.9'), dict(BLP_BETA_NEC='0.6'),
-           dict(BLP_BETA_ART='0.2'), dict(BLP_BETA_ART='0.5'), dict(BLP_OMEGA_THETA='0.2'), dict(BLP_OMEGA_THETA='0.8'),
-           dict(BLP_BETA_SUFF='0.3', BLP_BETA_ART='0.2')]
+configs = [dict(BLP_OMEGA_THETA=t, BLP_BETA_ART=a) for t in ('0.0', '0.05', '0.1', '0.2', '0.3') for a in ('0.36', '0.2')]
 for cfg in configs:
     for k in ('BLP_BETA_SUFF', 'BLP_BETA_NEC', 'BLP_BETA_ART', 'BLP_OMEGA_THETA'):
         os.environ.pop(k, None)

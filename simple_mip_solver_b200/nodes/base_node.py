@@ -337,35 +337,66 @@ class BaseNode:
 
     def _find_gomory_cuts(self: T) -> Dict[int, Tuple[CyLPArray, float]]:
         """Gomory mixed integer cuts from the rows of the LP tableau that belong to fractional
-        basic integer variables (reference :468-511; Conforti et al. 5.31), vectorised."""
+        basic integer variables (reference :468-511; Conforti et al. 5.31), vectorised.
+
+        Two things differ from the reference, both because the LP solution here is a first-order
+        one and not a simplex vertex. (1) The basis is the active set of the solution; it is only
+        used if the basic solution it defines (computed exactly from the basis matrix) reproduces
+        the solver's x, and the right-hand side of a tableau row is taken from that basic solution,
+        not from the approximate x. (2) Nonbasic variables sitting at a nonzero bound (a branching
+        bound, an upper bound) are shifted/complemented to zero first; the reference's formula
+        assumes nonbasics at zero and is the special case without shifts (its pinned ``cut3``
+        example, test_base_node.py:654-684, gives the same cut)."""
         cuts = {}
         tableau = self.tableau
         if tableau is None:
             return cuts
-        n = self.lp.nVariables
+        n, m = self.lp.nVariables, self.lp.nConstraints
+        col_stat, row_stat = self.lp.getBasisStatus()
         basic = self.basic_variable_indices
-        is_basic = np.zeros(tableau.shape[1], dtype=bool)
+        is_basic = np.zeros(n + m, dtype=bool)
         is_basic[basic] = True
-        is_int = np.zeros(n, dtype=bool)
+        is_int = np.zeros(n + m, dtype=bool)
         is_int[self._integer_indices] = True
         A = self.lp.coefMatrix
-        b = np.asarray(self.lp.constraintsLower)
+        b = np.asarray(self.lp.constraintsLower, dtype=float)
+        l = np.asarray(self.lp.variablesLower, dtype=float)
+        u = np.asarray(self.lp.variablesUpper, dtype=float)
+        # nonbasic values: structural at lower / upper bound, slack (A x - b) at zero
+        at_upper = np.concatenate([col_stat == 2, np.zeros(m, dtype=bool)])
+        offset = np.concatenate([np.where(col_stat == 2, u, l), np.zeros(m)])
+        offset[is_basic] = 0.0
+        if not np.isfinite(offset).all():
+            return cuts
+        sign = np.where(at_upper, -1.0, 1.0)
+        full = np.concatenate((A.toarray(), -np.identity(m)), axis=1)
+        try:
+            x_basic = np.linalg.solve(full[:, basic], b - full @ offset)
+        except np.linalg.LinAlgError:
+            return cuts
+        z = offset.copy()
+        z[basic] = x_basic
+        if np.max(np.abs(z[:n] - self.solution) / (1.0 + np.abs(self.solution))) > 1e-5:
+            return cuts                      # the active set is not the basis of this solution
+        is_int &= np.abs(offset - np.round(offset)) <= 1e-9          # shifted variable stays integer
         eps = good_coefficient_approximation_epsilon
         for row_idx, j in enumerate(basic):
-            if j >= n or not is_int[j] or not self._is_fractional(float(self.solution[j])):
+            if j >= n or j not in self._integer_indices or not self._is_fractional(float(x_basic[row_idx])):
                 continue
-            f0 = self._get_fraction(float(self.solution[j]))
+            f0 = self._get_fraction(float(x_basic[row_idx]))
             if f0 < eps or f0 + eps > 1:
                 continue
-            row = np.where(is_basic, 0.0, tableau[row_idx])
-            a, s = row[:n], row[n:]
-            f = a - np.floor(a)
+            row = np.where(is_basic, 0.0, tableau[row_idx] * sign)   # coefficients of the shifted nonbasics
+            f = row - np.floor(row)
             pi_int = np.where(f <= f0, f / f0, (1 - f) / (1 - f0))
-            pi_cont = np.where(a > 0, a / f0, -a / (1 - f0))
-            pi = np.where(is_int, pi_int, pi_cont)
-            pi_s = np.where(s > 0, s / f0, -s / (1 - f0))
-            # slack s = A x - b  =>  (pi + A' pi_s) . x >= 1 + pi_s . b
-            cuts[row_idx] = (CyLPArray(pi + A.T @ pi_s), float(1 + np.dot(pi_s, b)))
+            pi_cont = np.where(row > 0, row / f0, -row / (1 - f0))
+            pi_shift = np.where(is_int, pi_int, pi_cont)
+            pi_shift[is_basic] = 0.0
+            # sum pi' x' >= 1 with x'_j = sign_j (x_j - offset_j) for structurals, slack = A x - b
+            pi_x, pi_s = pi_shift[:n] * sign[:n], pi_shift[n:]
+            coefs = pi_x + A.T @ pi_s
+            rhs = 1.0 + float(np.dot(pi_x, offset[:n])) + float(np.dot(pi_s, b))
+            cuts[row_idx] = (CyLPArray(coefs), rhs)
         return cuts
 
     @property

@@ -425,6 +425,14 @@ def main():
         dual_s = prof['dual_kernel_ms'] * 1e-3 / it_prof
         prim_gbs = primal_bytes / primal_s / 1e9 if primal_s > 0 else 0.0
         dual_gbs = dual_bytes / dual_s / 1e9 if dual_s > 0 else 0.0
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1c_traffic.json')))
+            if tr['workload'] == args.workload and tr['batch'] == B:
+                # DRAM read+write bytes of one k_primal2 + one k_dual2 launch at full batch width (ncu)
+                traffic = tr['k_primal2_dram_bytes_per_launch'] + tr['k_dual2_dram_bytes_per_launch']
+        except Exception:
+            pass
         state_mb = 8 * ld * (7 * n + 4 * m) / 1e6
         cfg = workload_config(args, d, B)
         cfg['state_mb'] = round(state_mb, 1)
@@ -439,7 +447,10 @@ def main():
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': 'PDHG iteration = k_primal + k_dual (one launch each)',
                          'achieved': pair_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': pair_gbs / peak,
-                         'traffic': None, 'peak_source': peak_src, 'bytes_per_launch': pair_bytes,
+                         'traffic': traffic, 'traffic_note': 'ncu dram read+write of one iteration at FULL batch width '
+                         '(profiles/r1c_traffic.json); bytes_per_launch is the average over the timed steps, '
+                         'where finished nodes have been compacted away', 'full_width_bytes': (pb + db) * B + bytes_A + bytes_AT,
+                         'peak_source': peak_src, 'bytes_per_launch': pair_bytes,
                          'ms_per_launch': pair_s * 1e3,
                          'measured': 'CUDA events around every period graph (64 iterations) of the timed steps; '
                                      'bytes = 8(4n+3m) per running node and iteration + both matrices (bounds kept as block reference + mask)',

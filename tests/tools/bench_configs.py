@@ -7,7 +7,7 @@ Writes gpurun_out/configs.json.
 """
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench
 from simple_mip_solver_b200 import engine
 from simple_mip_solver_b200.instances import frontier_nodes, grumpy_random_mip

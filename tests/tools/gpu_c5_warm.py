@@ -1,7 +1,7 @@
 """How many PDHG iterations do warm-started dive nodes need at the C4/C5 shapes? (exploration)"""
 import json, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from simple_mip_solver_b200 import engine
 from simple_mip_solver_b200.instances import numpy_random_mip, random_dive_bounds
 from oracle.highs_lp import HighsLP, HIGHS_INF

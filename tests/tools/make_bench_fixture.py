@@ -2,7 +2,7 @@
 duals and basis under bench_data/ (the warm start both bench arms branch from)."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from simple_mip_solver_b200.instances import numpy_random_mip
 from oracle.highs_lp import HighsLP, HIGHS_INF
 

@@ -1,7 +1,7 @@
 """Run the reference's own unittest modules on the HiGHS stand-in (oracle/ref_stubs.py).
 Usage: python tools/run_reference_tests.py test_simple_mip_solver.test_nodes.test_base_node ..."""
 import os, sys, unittest
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ref_stubs
 ref_stubs.install()
 if not hasattr(unittest.TestCase, 'assertRegexpMatches'):

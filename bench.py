@@ -235,7 +235,7 @@ def main():
     ap.add_argument('--workload', default='c5', choices=list(WORKLOADS))
     ap.add_argument('--batch', type=int, default=512, help='open nodes per step per GPU')
     ap.add_argument('--eps', type=float, default=1e-7)
-    ap.add_argument('--max-iters', type=int, default=400000)
+    ap.add_argument('--max-iters', type=int, default=2000000)
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--cpu-nodes', type=int, default=0, help='CPU arm: nodes per step (default: one per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

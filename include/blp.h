@@ -49,7 +49,7 @@ typedef struct blp_opts {
                               error by ~5e-7 relative; 1e-8 is SURVEY 8d's figure */
     double eps_infeas;     /* relative size a Farkas certificate must reach; default 1e-9 */
     int max_iters;         /* PDHG iteration cap per call (the analogue of lp.maxNumIteration,
-                              base_node.py:645); nodes still running get status 3. default 400000 */
+                              base_node.py:645); nodes still running get status 3. default 2000000 */
     int eval_every;        /* iterations between KKT / restart evaluations; default 64 */
     int use_graph;         /* 1: replay each evaluation period as one CUDA graph; default 1 */
     int compact;           /* 1: retire finished nodes by compacting the batch; default 1 */

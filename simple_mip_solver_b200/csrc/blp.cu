@@ -465,7 +465,7 @@ void blp_default_opts(blp_opts* o) {
     if (!o) return;
     o->eps_rel = 1e-7;
     o->eps_infeas = 1e-9;
-    o->max_iters = 400000;
+    o->max_iters = 2000000;
     o->eval_every = 64;
     o->use_graph = 1;
     o->compact = 1;

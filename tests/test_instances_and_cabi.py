@@ -61,7 +61,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), f'{sym} declared in blp.h but not exported'
     assert declared == set(engine.EXPORTED_SYMBOLS)
     o = engine.default_opts()
-    assert o.eps_rel == 1e-7 and o.eval_every == 64 and o.max_iters == 400000
+    assert o.eps_rel == 1e-7 and o.eval_every == 64 and o.max_iters == 2000000
     assert lib.blp_ld(1) == 64 and lib.blp_ld(65) == 128
     assert engine.load_library().blp_version().decode().endswith('sm_100a')
 

@@ -184,3 +184,30 @@ def test_sparse_dive_nodes_c4_shape(blp_lib):
         if ref.status == 0:
             assert _rel(r.objective[k], ref.objective) <= REL, (k, r.objective[k], ref.objective)
     lp.close()
+
+
+def test_device_most_fractional_index_matches_host_rule(blp_lib):
+    """frac_idx (index work, must be exact): the device's most fractional integer column equals
+    BaseNode._most_fractional_index (base_node.py:544-562: distance > 1e-4, first wins ties)
+    evaluated on the x the call returned — with a ragged integer set."""
+    eng = _engine(blp_lib)
+    d = numpy_random_mip(800, 400, density=0.02, seed=9)
+    rng = np.random.default_rng(1)
+    ints = sorted(rng.choice(d.n, size=333, replace=False).tolist())
+    from simple_mip_solver_b200.instances import frontier_nodes
+    lbs, ubs, _ = frontier_nodes(d, np.full(d.n, 0.5), 0, 70, 5, seed=3, p_down=0.9)
+    lp = eng.BatchLP(d.A, d.b, d.c)
+    r = lp.solve_batch(lbs, ubs, integer_indices=ints)
+    ii = np.asarray(ints)
+    for k in range(70):
+        if r.status[k] != 0:
+            assert r.frac_idx[k] == -1
+            continue
+        v = r.x[k, ii]
+        dist = np.minimum(v - np.floor(v), np.ceil(v) - v)
+        j = int(np.argmax(dist))
+        want = int(ii[j]) if dist[j] > 1e-4 else -1
+        assert r.frac_idx[k] == want, (k, r.frac_idx[k], want)
+    none = lp.solve_batch(lbs[:3], ubs[:3])                      # no integer set: all -1
+    assert (none.frac_idx == -1).all()
+    lp.close()

@@ -175,6 +175,7 @@ struct GraphKey {
 
 struct blp_handle_s {
     int device = 0;
+    int num_sms = 0, coop_ok = 0;      // SM count; cooperative launch supported
     cudaStream_t stream = nullptr;
     int m_base = 0, n = 0;
     HostCsr A0;                        // unscaled rows (base + appended cuts)
@@ -443,6 +444,35 @@ void launch_harvest(const DevProb& P, const DevState& S, const DevOut& O, const 
     ++*launches;
 }
 
+// One evaluation period of a narrow batch (one-node-per-lane kernels) as ONE cooperative launch.
+// Returns cudaErrorNotSupported when the grid cannot be made co-resident.
+cudaError_t launch_period_coop(blp_handle h, const DevProb& P, const DevState& S, const Plan& pc,
+                               const Plan& pr, int K, cudaStream_t st) {
+    const void* fn = nullptr;
+    switch (pc.NT) {
+        case 1: fn = (const void*)k_period_coop<1>; break;
+        case 2: fn = (const void*)k_period_coop<2>; break;
+        case 4: fn = (const void*)k_period_coop<4>; break;
+        case 8: fn = (const void*)k_period_coop<8>; break;
+        case 16: fn = (const void*)k_period_coop<16>; break;
+        default: fn = (const void*)k_period_coop<32>; break;
+    }
+    const size_t smem = std::max(pc.smem, pr.smem);
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kCtaThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorNotSupported;
+    const int items = std::max(pc.chunks, pr.chunks) * pc.tiles;
+    const int grid = std::max(1, std::min(occ * h->num_sms, items));
+    CoopPlan C{pc.rows_per_cta, pc.cap, pc.chunks, pr.rows_per_cta, pr.cap, pr.chunks, pc.tiles,
+               pc.chunk_ptr, pr.chunk_ptr};
+    DevProb Pc = P;
+    DevState Sc = S;
+    int Kc = K;
+    void* args[] = {&Pc, &Sc, &Kc, &C};
+    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kCtaThreads), args, smem, st);
+}
+
 int elementwise_grid(size_t total) {
     size_t g = (total + kCtaThreads - 1) / kCtaThreads;
     return (int)std::min<size_t>(std::max<size_t>(g, 1), 148 * 16);
@@ -514,6 +544,8 @@ int blp_create(int device, int m, int n, int64_t nnz, const int32_t* rowptr, con
     h->A0.val.assign(val, val + nnz);
     h->c0.assign(c, c + n);
     h->b0.assign(row_lb, row_lb + m);
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->coop_ok, cudaDevAttrCooperativeLaunch, device);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_counters, 8 * sizeof(int32_t));
     for (int q = 0; q < 4 && e == cudaSuccess; ++q) e = cudaEventCreate(&h->ev[q]);
@@ -718,6 +750,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
             h->prof_ev.push_back(e);
         }
 
+    bool coop = false;          // this period's steps run as one cooperative launch
+    const bool allow_coop = h->coop_ok && env_int("BLP_COOP", 1) != 0;
     auto ensure_graphs = [&]() -> int {
         GraphKey key;
         memset(&key, 0, sizeof key);
@@ -725,16 +759,19 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         key.S = S;
         key.D = D;
         key.K = K;
-        key.rpw = rpw | (allow_v2 ? 1 << 16 : 0);
+        key.rpw = rpw | (allow_v2 ? 1 << 16 : 0) | (coop ? 1 << 17 : 0);
         if (h->graph_valid && memcmp(&key, &h->gkey, sizeof key) == 0) return BLP_OK;
         h->drop_graphs();
         cudaGraph_t g = nullptr;
-        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, st);
-        CK(cudaStreamEndCapture(st, &g));
-        cudaError_t e = cudaGraphInstantiate(&h->g_steps, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) return fail(BLP_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+        cudaError_t e = cudaSuccess;
+        if (!coop) {
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, st);
+            CK(cudaStreamEndCapture(st, &g));
+            e = cudaGraphInstantiate(&h->g_steps, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(BLP_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+        }
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         launch_eval(P, S, ec, er, D, K, st);
         CK(cudaStreamEndCapture(st, &g));
@@ -780,12 +817,22 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 D.steps_in_period = K;
             }
         }
+        coop = use_graph && allow_coop && pc.V == 1;
         if (use_graph) {
             int rcg = ensure_graphs();
             if (rcg != BLP_OK) return rcg;
         }
         CK(cudaEventRecord(h->ev[2], st));
-        if (use_graph) {
+        if (coop) {
+            cudaError_t ce = launch_period_coop(h, P, S, pc, pr, K, st);
+            if (ce != cudaSuccess) {                      // grid not co-resident etc.: graph path
+                cudaGetLastError();
+                coop = false;
+                int rcg = ensure_graphs();
+                if (rcg != BLP_OK) return rcg;
+                CK(cudaGraphLaunch(h->g_steps, st));
+            }
+        } else if (use_graph) {
             CK(cudaGraphLaunch(h->g_steps, st));
         } else if (profile) {
             CK(cudaEventRecord(h->prof_ev[0], st));
@@ -821,7 +868,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         node_iters += (double)active * K;
         total += K;
         evals += 1;
-        launches += 2 * K + 5;
+        launches += (coop ? 1 : 2 * K) + 5;
         active = h->h_counters[0];
         if (h->h_counters[3] > 0) {
             launch_harvest(P, S, O, ec, er, want_frac, st, &launches);

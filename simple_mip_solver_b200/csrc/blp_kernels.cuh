@@ -16,6 +16,7 @@
 // rebuilds x = w xbar + (1-w) xa from it), xa, l, u (+ block reference bounds and masks), y, ya.
 #pragma once
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 namespace blp {
@@ -207,12 +208,12 @@ __device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict
 // ---------------------------------------------------------------------------------------------
 // Primal half step, fused  G = A'y  ->  x' = clip(x - tau (c - G), l, u)  ->  xbar = 2x' - x.
 template <int NT, bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
-k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-         const int* __restrict__ chunk_ptr) {
+__device__ __forceinline__ void primal_chunk(const DevProb& P, const DevState& S, const int it,
+                                             const int rows_per_cta, const int cap,
+                                             const int* __restrict__ chunk_ptr, const int cx, const int cy) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int node = blockIdx.y * NT + (lane % NT);
+    const int node = cy * NT + (lane % NT);
     const int sub = lane / NT;
     const bool node_ok = node < S.B && S.fin[node] == 0;
     if (__ballot_sync(0xffffffffu, node_ok) == 0) return;     // whole node tile retired
@@ -222,8 +223,8 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
         w = (double)s / (double)(s + 1);
         tau = P.eta / S.omega[node];
     }
-    const int r0 = __ldg(chunk_ptr + blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
+    const int r0 = __ldg(chunk_ptr + cx);
+    const int r1 = __ldg(chunk_ptr + cx + 1);
     const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
     for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
@@ -258,14 +259,21 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
     }
 }
 
-// Dual half step, fused  s = A xbar  ->  y' = max(0, y + sigma (b - s))  ->  Halpern update of y.
 template <int NT, bool MAJOR>
 __global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
-k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-       const int* __restrict__ chunk_ptr) {
+k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
+         const int* __restrict__ chunk_ptr) {
+    primal_chunk<NT, MAJOR>(P, S, it, rows_per_cta, cap, chunk_ptr, blockIdx.x, blockIdx.y);
+}
+
+// Dual half step, fused  s = A xbar  ->  y' = max(0, y + sigma (b - s))  ->  Halpern update of y.
+template <int NT, bool MAJOR>
+__device__ __forceinline__ void dual_chunk(const DevProb& P, const DevState& S, const int it,
+                                           const int rows_per_cta, const int cap,
+                                           const int* __restrict__ chunk_ptr, const int cx, const int cy) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int node = blockIdx.y * NT + (lane % NT);
+    const int node = cy * NT + (lane % NT);
     const int sub = lane / NT;
     const bool node_ok = node < S.B && S.fin[node] == 0;
     if (__ballot_sync(0xffffffffu, node_ok) == 0) return;     // whole node tile retired
@@ -275,8 +283,8 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
         w = (double)(s + 1) / (double)(s + 2);
         sig = P.eta * S.omega[node];
     }
-    const int r0 = __ldg(chunk_ptr + blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
+    const int r0 = __ldg(chunk_ptr + cx);
+    const int r1 = __ldg(chunk_ptr + cx + 1);
     const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
@@ -299,6 +307,45 @@ k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, 
                 S.DY[e] = yp - yc;
             }
         }
+    }
+}
+
+template <int NT, bool MAJOR>
+__global__ void __launch_bounds__(kCtaThreads, BLP_MINB)
+k_dual(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
+       const int* __restrict__ chunk_ptr) {
+    dual_chunk<NT, MAJOR>(P, S, it, rows_per_cta, cap, chunk_ptr, blockIdx.x, blockIdx.y);
+}
+
+// One whole evaluation period (K iterations) of a NARROW batch as a single cooperative launch:
+// the grid loops over the (row chunk, node tile) work items of the primal step, meets at a grid
+// barrier, does the dual step, meets again. Two launches per iteration cost ~20 us when only a
+// few nodes are running (tiny LPs, the tail of a batch); two grid barriers cost a few.
+// The gpu-scope fence inside grid.sync() also drops stale L1 lines of the vectors other CTAs wrote.
+struct CoopPlan {
+    int rpcC, capC, nchC, rpcR, capR, nchR, tiles;
+    const int* chunkC;
+    const int* chunkR;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kCtaThreads, 4)
+k_period_coop(const DevProb P, const DevState S, const int K, const CoopPlan C) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int it = 0; it < K; ++it) {
+        const bool major = it == K - 1;
+        for (int w = blockIdx.x; w < C.nchC * C.tiles; w += gridDim.x) {
+            if (major) primal_chunk<NT, true>(P, S, it, C.rpcC, C.capC, C.chunkC, w % C.nchC, w / C.nchC);
+            else primal_chunk<NT, false>(P, S, it, C.rpcC, C.capC, C.chunkC, w % C.nchC, w / C.nchC);
+            __syncthreads();            // the row slab in shared memory is reused by the next item
+        }
+        grid.sync();
+        for (int w = blockIdx.x; w < C.nchR * C.tiles; w += gridDim.x) {
+            if (major) dual_chunk<NT, true>(P, S, it, C.rpcR, C.capR, C.chunkR, w % C.nchR, w / C.nchR);
+            else dual_chunk<NT, false>(P, S, it, C.rpcR, C.capR, C.chunkR, w % C.nchR, w / C.nchR);
+            __syncthreads();
+        }
+        grid.sync();
     }
 }
 

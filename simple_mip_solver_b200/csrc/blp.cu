@@ -463,7 +463,10 @@ cudaError_t launch_period_coop(blp_handle h, const DevProb& P, const DevState& S
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorNotSupported;
     const int items = std::max(pc.chunks, pr.chunks) * pc.tiles;
-    const int grid = std::max(1, std::min(occ * h->num_sms, items));
+    // worth it only for small LPs, where every CTA gets at most one work item per phase; with
+    // more rows than that (the tail of a large batch) two graph launches are as fast (measured)
+    if (items > occ * h->num_sms) return cudaErrorNotSupported;
+    const int grid = std::max(1, items);
     CoopPlan C{pc.rows_per_cta, pc.cap, pc.chunks, pr.rows_per_cta, pr.cap, pr.chunks, pc.tiles,
                pc.chunk_ptr, pr.chunk_ptr};
     DevProb Pc = P;
@@ -708,7 +711,9 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     auto step_plan = [&](int rows, int width) {
         int r = rpw;
         Plan p = make_plan(rows, width, r, 0);
-        const bool v2 = allow_v2 && width >= kBlk;
+        // two nodes per lane pay off when a launch has real work; tiny LPs stay on the
+        // one-node-per-lane kernels, which can run a whole period as one cooperative launch
+        const bool v2 = allow_v2 && width >= kBlk && (long)std::max(P.n, P.m) * width >= (1L << 20);
         auto shape = [&](Plan& q, int rr) {
             if (!v2) return;
             q.V = 2;                                   // a warp = one row x 64 nodes
@@ -751,6 +756,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         }
 
     bool coop = false;          // this period's steps run as one cooperative launch
+    bool coop_rejected = false; // the current plan does not fit a cooperative grid
     const bool allow_coop = h->coop_ok && env_int("BLP_COOP", 1) != 0;
     auto ensure_graphs = [&]() -> int {
         GraphKey key;
@@ -803,6 +809,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 pc = step_plan(P.n, S.B);
                 pr = step_plan(P.m, S.B);
                 if ((rc = finish_step_plans()) != BLP_OK) return rc;
+                coop_rejected = false;
                 ec = make_plan(P.n, S.B, 1, kEvalChunks);
                 er = make_plan(P.m, S.B, 1, kEvalChunks);
                 D.chunksC = ec.chunks;
@@ -817,7 +824,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 D.steps_in_period = K;
             }
         }
-        coop = use_graph && allow_coop && pc.V == 1;
+        coop = use_graph && allow_coop && pc.V == 1 && !coop_rejected;
         if (use_graph) {
             int rcg = ensure_graphs();
             if (rcg != BLP_OK) return rcg;
@@ -825,9 +832,10 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         CK(cudaEventRecord(h->ev[2], st));
         if (coop) {
             cudaError_t ce = launch_period_coop(h, P, S, pc, pr, K, st);
-            if (ce != cudaSuccess) {                      // grid not co-resident etc.: graph path
+            if (ce != cudaSuccess) {                      // too many rows / not co-resident: graph path
                 cudaGetLastError();
                 coop = false;
+                coop_rejected = true;
                 int rcg = ensure_graphs();
                 if (rcg != BLP_OK) return rcg;
                 CK(cudaGraphLaunch(h->g_steps, st));

@@ -157,6 +157,18 @@ class BatchPDHG:
                     ynorm = np.abs(yp).sum(0) * np.abs(b).max() + 1e-300
                     infeas = (farkas > eps_inf * (np.abs(b * yp).sum(0) + np.abs(box).sum(0) + 1e-300)) \
                         & (farkas > 0) & active & ~conv
+                    # the same certificate from the dual step dy = y' - y (offset-free ray estimate)
+                    gd = gp - g
+                    dpos, dneg = np.maximum(gd, 0), np.minimum(gd, 0)
+                    dbox = np.where(dpos > 0, dpos * np.where(fin_u, u, INF), 0) \
+                        + np.where(dneg < 0, dneg * np.where(fin_l, l, -INF), 0)
+                    dymax = np.abs(dy).max(0)
+                    with np.errstate(invalid='ignore'):
+                        fstep = (b * dy).sum(0) - dbox.sum(0)
+                        step_ok = np.isfinite(dbox).all(0) & (dymax > 0) \
+                            & (fstep > 1e-6 * (np.abs(b * dy).sum(0) + np.abs(np.where(np.isfinite(dbox), dbox, 0)).sum(0))) \
+                            & ((-dy).max(0) <= 1e-8 * dymax)
+                    infeas |= step_ok & active & ~conv
                     # dual infeasibility (unbounded) certificate from the primal iterate
                     xnorm = np.abs(xp).max(0) + 1e-300
                     d = xp / xnorm

@@ -32,10 +32,11 @@ constexpr int kBlk = 64;      // nodes per layout block (row stride of a lane's 
 constexpr int kWarps = kCtaThreads / 32;
 
 // column-pass accumulators (sums first, then maxima)
-enum { C_DX2, C_CROSS, C_DRES2, C_CX, C_BND, C_DXA2, C_BOX, C_BOXABS, C_CD, C_NSUM,
-       C_DMAX = C_NSUM, C_DVIOL, C_RAYVIOL, C_N };
+enum { C_DX2, C_CROSS, C_DRES2, C_CX, C_BND, C_DXA2, C_BOX, C_BOXABS, C_CD, C_DBOX, C_DBOXABS, C_NSUM,
+       C_DMAX = C_NSUM, C_DVIOL, C_RAYVIOL, C_DRAYVIOL, C_N };
 // row-pass accumulators
-enum { R_PRES2, R_BY, R_DY2, R_DYA2, R_BYABS, R_NSUM, R_ADNEG = R_NSUM, R_YMAX, R_N };
+enum { R_PRES2, R_BY, R_DY2, R_DYA2, R_BYABS, R_BD, R_BDABS, R_NSUM,
+       R_ADNEG = R_NSUM, R_YMAX, R_DYMAX, R_DYNEG, R_N };
 
 // one stored matrix entry; 16 bytes so that a row walk is one 128-bit load per nonzero
 struct __align__(16) Ent {
@@ -605,6 +606,14 @@ k_eval_cols(const DevProb P, const DevState S, const int rows_per_cta) {
             else if (gp < 0.0) { if (fl) box = gp * lo; else acc[C_RAYVIOL] = fmax(acc[C_RAYVIOL], -gp); }
             acc[C_BOX] += box;
             acc[C_BOXABS] += fabs(box);
+            // the same Farkas box term for the dual STEP dy = y' - y (A'dy = gp - g): on an
+            // infeasible LP the step converges to the certificate ray, free of the offset y' carries
+            const double gd = gp - g;
+            double dbox = 0.0;
+            if (gd > 0.0) { if (fu) dbox = gd * hi; else acc[C_DRAYVIOL] = fmax(acc[C_DRAYVIOL], gd); }
+            else if (gd < 0.0) { if (fl) dbox = gd * lo; else acc[C_DRAYVIOL] = fmax(acc[C_DRAYVIOL], -gd); }
+            acc[C_DBOX] += dbox;
+            acc[C_DBOXABS] += fabs(dbox);
             acc[C_CD] = fma(cj, d, acc[C_CD]);
             acc[C_DMAX] = fmax(acc[C_DMAX], fabs(d));
             if (fl) acc[C_DVIOL] = fmax(acc[C_DVIOL], -d);
@@ -652,6 +661,10 @@ k_eval_rows(const DevProb P, const DevState S, const int rows_per_cta) {
                 acc[R_DYA2] = fma(t, t, acc[R_DYA2]);
                 acc[R_ADNEG] = fmax(acc[R_ADNEG], -ad);
                 acc[R_YMAX] = fmax(acc[R_YMAX], yp);
+                acc[R_BD] = fma(bi, dy, acc[R_BD]);
+                acc[R_BDABS] += fabs(bi * dy);
+                acc[R_DYMAX] = fmax(acc[R_DYMAX], fabs(dy));
+                acc[R_DYNEG] = fmax(acc[R_DYNEG], -dy);
             }
         }
     }
@@ -726,6 +739,11 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
         const double farkas = r[R_BY] - c[C_BOX];
         if (farkas > 0.0 && farkas > D.eps_inf * (r[R_BYABS] + c[C_BOXABS]) &&
             c[C_RAYVIOL] <= 1e-8 * r[R_YMAX])
+            st = 1;
+        // ... and from the dual step dy >= 0 (it reaches the ray long before y' is dominated by it)
+        const double fstep = r[R_BD] - c[C_DBOX];
+        if (st < 0 && r[R_DYMAX] > 0.0 && fstep > 1e-6 * (r[R_BDABS] + c[C_DBOXABS]) &&
+            c[C_DRAYVIOL] <= 1e-8 * r[R_DYMAX] && r[R_DYNEG] <= 1e-8 * r[R_DYMAX])
             st = 1;
         // primal ray d = x' - xa: c.d < 0, A d >= 0, d respects finite bounds => unbounded
         const double dmax = c[C_DMAX];

@@ -204,7 +204,7 @@ def test_disjunctive_cut_nodes(blp_lib):
     engine (reference usage: test_simple_mip_solver/helpers.py:75-126)."""
     from simple_mip_solver_b200 import (CutGeneratingLP, DisjunctiveCutBoundNode,
                                         DisjunctiveCutBoundPseudoCostBranchNode)
-    recs = list(SCALE1.items())[::9] + [(k, EXAMPLES[k]) for k in ('cut1', 'cut2', 'lift_project')]
+    recs = list(SCALE1.items())[::16] + [(k, EXAMPLES[k]) for k in ('cut1', 'cut2', 'lift_project')]
     created = 0
     for name, rec in recs:
         tree = BranchAndBound(model_from(rec), BaseNode, node_limit=8, gomory_cuts=False)

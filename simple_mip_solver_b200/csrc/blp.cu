@@ -276,7 +276,7 @@ int prepare(blp_handle h) {
     P.bnorm0 = norm2(h->b0);
     P.cnorm0 = norm2(h->c0);
     P.cinf_s = cinf;
-    P.omega0 = (nb > 1e-12 && nc > 1e-12) ? nc / nb : 1.0;
+    P.omega0 = ((nb > 1e-12 && nc > 1e-12) ? nc / nb : 1.0) * env_dbl("BLP_OMEGA0_SCALE", 1.0);
     h->drop_graphs();
     return BLP_OK;
 }

@@ -457,7 +457,8 @@ cudaError_t launch_period_coop(blp_handle h, const DevProb& P, const DevState& S
         case 16: fn = (const void*)k_period_coop<16>; break;
         default: fn = (const void*)k_period_coop<32>; break;
     }
-    const size_t smem = std::max(pc.smem, pr.smem);
+    const size_t smem = pc.smem + pr.smem;        // both slabs stay resident for the whole period
+    if (smem > 48 * 1024) return cudaErrorNotSupported;
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kCtaThreads, smem);
     if (e != cudaSuccess) return e;

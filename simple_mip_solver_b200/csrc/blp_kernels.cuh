@@ -141,12 +141,14 @@ struct Slab {
     int base;
 };
 
+extern __shared__ int4 dyn_smem[];
+
 __device__ __forceinline__ Slab stage_slab(const int32_t* __restrict__ ptr,
                                            const Ent* __restrict__ ent, const int r0, const int r1,
-                                           const int rows_per_cta, const int cap) {
-    extern __shared__ int4 dyn_smem[];
-    int* sp = reinterpret_cast<int*>(dyn_smem);
-    int4* se = dyn_smem + (rows_per_cta + 4) / 4;
+                                           const int rows_per_cta, const int cap,
+                                           int4* const smem_base = dyn_smem) {
+    int* sp = reinterpret_cast<int*>(smem_base);
+    int4* se = smem_base + (rows_per_cta + 4) / 4;
     const int nrows = r1 - r0;
     for (int t = threadIdx.x; t <= nrows; t += kCtaThreads) sp[t] = __ldg(ptr + r0 + t);
     __syncthreads();
@@ -211,7 +213,8 @@ __device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict
 template <int NT, bool MAJOR>
 __device__ __forceinline__ void primal_chunk(const DevProb& P, const DevState& S, const int it,
                                              const int rows_per_cta, const int cap,
-                                             const int* __restrict__ chunk_ptr, const int cx, const int cy) {
+                                             const int* __restrict__ chunk_ptr, const int cx, const int cy,
+                                             const Slab* pre = nullptr) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = cy * NT + (lane % NT);
@@ -226,7 +229,7 @@ __device__ __forceinline__ void primal_chunk(const DevProb& P, const DevState& S
     }
     const int r0 = __ldg(chunk_ptr + cx);
     const int r1 = __ldg(chunk_ptr + cx + 1);
-    const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
+    const Slab sl = pre ? *pre : stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
     for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
         const int j = jb + sub;
@@ -271,7 +274,8 @@ k_primal(const DevProb P, const DevState S, const int it, const int rows_per_cta
 template <int NT, bool MAJOR>
 __device__ __forceinline__ void dual_chunk(const DevProb& P, const DevState& S, const int it,
                                            const int rows_per_cta, const int cap,
-                                           const int* __restrict__ chunk_ptr, const int cx, const int cy) {
+                                           const int* __restrict__ chunk_ptr, const int cx, const int cy,
+                                           const Slab* pre = nullptr) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = cy * NT + (lane % NT);
@@ -286,7 +290,7 @@ __device__ __forceinline__ void dual_chunk(const DevProb& P, const DevState& S, 
     }
     const int r0 = __ldg(chunk_ptr + cx);
     const int r1 = __ldg(chunk_ptr + cx + 1);
-    const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
+    const Slab sl = pre ? *pre : stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
@@ -333,18 +337,25 @@ template <int NT>
 __global__ void __launch_bounds__(kCtaThreads, 4)
 k_period_coop(const DevProb P, const DevState S, const int K, const CoopPlan C) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    // the launch gives every CTA at most one primal and one dual work item; their row slabs are
+    // staged in shared memory once and serve all K iterations
+    const int w = blockIdx.x;
+    const bool hasC = w < C.nchC * C.tiles, hasR = w < C.nchR * C.tiles;
+    const int cxC = w % C.nchC, cyC = w / C.nchC, cxR = w % C.nchR, cyR = w / C.nchR;
+    Slab slC{nullptr, nullptr, 0}, slR{nullptr, nullptr, 0};
+    int4* const baseR = dyn_smem + (C.rpcC + 4) / 4 + C.capC;
+    if (hasC) slC = stage_slab(P.cptr, P.cent, __ldg(C.chunkC + cxC), __ldg(C.chunkC + cxC + 1), C.rpcC, C.capC);
+    if (hasR) slR = stage_slab(P.rowptr, P.ent, __ldg(C.chunkR + cxR), __ldg(C.chunkR + cxR + 1), C.rpcR, C.capR, baseR);
     for (int it = 0; it < K; ++it) {
         const bool major = it == K - 1;
-        for (int w = blockIdx.x; w < C.nchC * C.tiles; w += gridDim.x) {
-            if (major) primal_chunk<NT, true>(P, S, it, C.rpcC, C.capC, C.chunkC, w % C.nchC, w / C.nchC);
-            else primal_chunk<NT, false>(P, S, it, C.rpcC, C.capC, C.chunkC, w % C.nchC, w / C.nchC);
-            __syncthreads();            // the row slab in shared memory is reused by the next item
+        if (hasC) {
+            if (major) primal_chunk<NT, true>(P, S, it, C.rpcC, C.capC, C.chunkC, cxC, cyC, &slC);
+            else primal_chunk<NT, false>(P, S, it, C.rpcC, C.capC, C.chunkC, cxC, cyC, &slC);
         }
         grid.sync();
-        for (int w = blockIdx.x; w < C.nchR * C.tiles; w += gridDim.x) {
-            if (major) dual_chunk<NT, true>(P, S, it, C.rpcR, C.capR, C.chunkR, w % C.nchR, w / C.nchR);
-            else dual_chunk<NT, false>(P, S, it, C.rpcR, C.capR, C.chunkR, w % C.nchR, w / C.nchR);
-            __syncthreads();
+        if (hasR) {
+            if (major) dual_chunk<NT, true>(P, S, it, C.rpcR, C.capR, C.chunkR, cxR, cyR, &slR);
+            else dual_chunk<NT, false>(P, S, it, C.rpcR, C.capR, C.chunkR, cxR, cyR, &slR);
         }
         grid.sync();
     }

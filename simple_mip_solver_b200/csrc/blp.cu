@@ -458,7 +458,11 @@ cudaError_t launch_period_coop(blp_handle h, const DevProb& P, const DevState& S
         default: fn = (const void*)k_period_coop<32>; break;
     }
     const size_t smem = pc.smem + pr.smem;        // both slabs stay resident for the whole period
-    if (smem > 48 * 1024) return cudaErrorNotSupported;
+    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    if (smem > 48 * 1024) {
+        cudaError_t ea = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return ea;
+    }
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kCtaThreads, smem);
     if (e != cudaSuccess) return e;

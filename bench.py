@@ -4,6 +4,8 @@
 A *step* is one pass of the hot path over one batch: ``--batch`` open nodes (a slice of the
 synthetic frontier of the named workload, default C5: 50 000 vars x 20 000 rows, ~200k nonzeros)
 are solved to the parity tolerance (rel. KKT 1e-7; --eps 1e-8 for SURVEY 8d's figure) by one ``blp_solve_batch`` call per GPU.
+``--slots`` of them are resident at a time (blp_opts.max_active): a node that finishes hands its
+slot to the next pending node of the slice, so the step kernels sweep a constant batch width.
 With N GPUs every rank solves its own slice of the frontier (weak scaling: per-GPU batch fixed)
 and the only collective is the 16-byte all-reduce(min) of [incumbent, dual bound] per step.
 
@@ -221,8 +223,11 @@ def workload_config(args, d, batch):
     n, m, dens, depth, _ = WORKLOADS[args.workload]
     return {'workload': f'{args.workload}: frontier of open-node LPs of a synthetic sparse MILP, {n} vars x {m} rows, '
                         f'{d.A.nnz} nonzeros, dive depth U{{1..{depth}}}, solved to rel. KKT {args.eps:g}; '
-                        f'{batch} nodes per step per GPU (the 4096-node frontier is swept in slices)',
-            'batch_per_gpu': batch, 'eps_rel': args.eps, 'seed': args.seed,
+                        f'{batch} nodes per step per GPU (the 4096-node frontier is swept in slices), '
+                        f'{min(args.slots, batch) if args.slots > 0 else batch} of them resident at a time '
+                        f'(finished nodes hand their slot to pending ones)',
+            'batch_per_gpu': batch, 'resident_slots': min(args.slots, batch) if args.slots > 0 else batch,
+            'eps_rel': args.eps, 'seed': args.seed,
             'l2_policy': 'solver state per step exceeds L2 (see state_mb); no flush needed'}
 
 
@@ -233,7 +238,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='blp', choices=['blp', 'reference'])
     ap.add_argument('--workload', default='c5', choices=list(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=512, help='open nodes per step per GPU')
+    ap.add_argument('--batch', type=int, default=1024, help='open nodes per step per GPU')
+    ap.add_argument('--slots', type=int, default=512,
+                    help='nodes resident at a time (blp_opts.max_active); 0 = the whole batch')
     ap.add_argument('--eps', type=float, default=1e-7)
     ap.add_argument('--max-iters', type=int, default=2000000)
     ap.add_argument('--seed', type=int, default=0)
@@ -285,8 +292,10 @@ def main():
 
     lp = engine.BatchLP(d.A, d.b, d.c, device=local_rank)
     ld = engine.leading_dim(B)
+    W = min(args.slots, B) if args.slots > 0 else B           # resident node slots
+    ldW = engine.leading_dim(W)
     ext = torch.cuda.ExternalStream(lp.stream_ptr, device=dev)
-    opts = engine.default_opts(eps_rel=args.eps, max_iters=args.max_iters)
+    opts = engine.default_opts(eps_rel=args.eps, max_iters=args.max_iters, max_active=W)
     opts_prof = engine.default_opts(eps_rel=args.eps, max_iters=min(args.max_iters, 1024), profile=1)
     int_idx = torch.arange(n, dtype=torch.int32, device=dev)
 
@@ -294,11 +303,12 @@ def main():
         first = (step * world + rank) * B
         return frontier_nodes(d, root['x'], first, B, depth, seed=args.seed)
 
-    def to_device(lbs, ubs):
-        lb = torch.zeros((n, ld), dtype=torch.float64, device=dev)
-        ub = torch.zeros((n, ld), dtype=torch.float64, device=dev)
-        lb[:, :B] = torch.from_numpy(lbs).to(dev).T
-        ub[:, :B] = torch.from_numpy(ubs).to(dev).T
+    def to_device(lbs, ubs, count=B):
+        ldc = engine.leading_dim(count)
+        lb = torch.zeros((n, ldc), dtype=torch.float64, device=dev)
+        ub = torch.zeros((n, ldc), dtype=torch.float64, device=dev)
+        lb[:, :count] = torch.from_numpy(lbs[:count]).to(dev).T
+        ub[:, :count] = torch.from_numpy(ubs[:count]).to(dev).T
         return lb.contiguous(), ub.contiguous()
 
     x0 = torch.from_numpy(root['x']).to(dev)[:, None].expand(n, ld).contiguous()
@@ -325,7 +335,7 @@ def main():
     # ---- device-resident arm ----
     iters_all = []
     agg = dict(launches=0, solved=0, unsolved=0, infeasible=0, node_iters=0.0, iters=0,
-               primal_ms=0.0, dual_ms=0.0, step_ms=0.0, total_ms=0.0)
+               primal_ms=0.0, dual_ms=0.0, step_ms=0.0, total_ms=0.0, refills=0)
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for s in range(total_steps):
@@ -351,19 +361,20 @@ def main():
             agg['dual_ms'] += sdict['dual_kernel_ms']
             agg['step_ms'] += sdict['step_kernel_ms']
             agg['total_ms'] += sdict['total_ms']
+            agg['refills'] += sdict['refills']
         log(f'[rank {rank}] step {s} iters {r["stats"]["iterations"]} total_ms {r["stats"]["total_ms"]:.0f}')
         del lb, ub
     ev1.record(ext)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    # per-kernel split: the first 1024 iterations of the last timed slice once more (full batch
-    # width) with CUDA events around every k_primal / k_dual launch (blp_opts.profile: no CUDA
-    # graph; not part of `value`)
+    # per-kernel split: the first 1024 iterations of the first W nodes of the last timed slice once
+    # more (full batch width) with CUDA events around every k_primal / k_dual launch
+    # (blp_opts.profile: no CUDA graph; not part of `value`)
     prof = None
     if rank == 0:
-        lb, ub = to_device(slices[-1][0], slices[-1][1])
-        prof = lp.solve_batch_device(lb, ub, x0=x0, y0=y0, int_idx=int_idx, opts=opts_prof,
-                                     want_x=False, want_y=False)['stats']
+        lb, ub = to_device(slices[-1][0], slices[-1][1], W)
+        prof = lp.solve_batch_device(lb, ub, x0=x0[:, :ldW].contiguous(), y0=y0[:, :ldW].contiguous(),
+                                     int_idx=int_idx, opts=opts_prof, want_x=False, want_y=False)['stats']
         del lb, ub
     dev_ms = ev0.elapsed_time(ev1)
     dev_ms = parallel.allreduce_max(dev_ms, device=dev)
@@ -376,7 +387,7 @@ def main():
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     hx0 = pin(np.tile(root['x'], (B, 1)))
     hy0 = pin(np.tile(root['y'], (B, 1)))
-    opts_e = engine.default_opts(eps_rel=args.eps, max_iters=args.max_iters)
+    opts_e = engine.default_opts(eps_rel=args.eps, max_iters=args.max_iters, max_active=W)
     ints = list(range(n))
     h2d = d2h = 0
     e2e_solved = 0
@@ -428,12 +439,12 @@ def main():
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1c_traffic.json')))
-            if tr['workload'] == args.workload and tr['batch'] == B:
+            if tr['workload'] == args.workload and tr['batch'] == W:
                 # DRAM read+write bytes of one k_primal2 + one k_dual2 launch at full batch width (ncu)
                 traffic = tr['k_primal2_dram_bytes_per_launch'] + tr['k_dual2_dram_bytes_per_launch']
         except Exception:
             pass
-        state_mb = 8 * ld * (7 * n + 4 * m) / 1e6
+        state_mb = 8 * ldW * (7 * n + 4 * m) / 1e6
         cfg = workload_config(args, d, B)
         cfg['state_mb'] = round(state_mb, 1)
         cfg['timing'] = 'value: CUDA events on the library stream around the K timed steps, max over ranks'
@@ -449,7 +460,7 @@ def main():
                          'achieved': pair_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': pair_gbs / peak,
                          'traffic': traffic, 'traffic_note': 'ncu dram read+write of one iteration at FULL batch width '
                          '(profiles/r1c_traffic.json); bytes_per_launch is the average over the timed steps, '
-                         'where finished nodes have been compacted away', 'full_width_bytes': (pb + db) * B + bytes_A + bytes_AT,
+                         'where slots of finished nodes are refilled while nodes are pending and the tail of a step is compacted', 'full_width_bytes': (pb + db) * W + bytes_A + bytes_AT,
                          'peak_source': peak_src, 'bytes_per_launch': pair_bytes,
                          'ms_per_launch': pair_s * 1e3,
                          'measured': 'CUDA events around every period graph (64 iterations) of the timed steps; '
@@ -462,6 +473,7 @@ def main():
             'cpu_baseline': cpu,
             'nodes': {'solved': int(sums[0]), 'iteration_limit': int(sums[1]), 'infeasible': int(sums[3]),
                       'pdhg_iterations_per_step': agg['iters'] / max(args.steps, 1),
+                      'refills_per_step': agg['refills'] / max(args.steps, 1),
                       'mean_iterations_per_node': agg['node_iters'] / max(agg['solved'] + agg['unsolved'], 1),
                       'iterations_p50_p90_max': [float(np.percentile(np.concatenate(iters_all), q)) for q in (50, 90, 100)]},
         }

@@ -56,6 +56,13 @@ typedef struct blp_opts {
     int verbose;           /* 1: print one line per evaluation to stderr */
     int profile;           /* 1: no graphs; time every k_primal / k_dual launch with CUDA events
                               (blp_stats.primal_kernel_ms / dual_kernel_ms). default 0 */
+    int max_active;        /* node slots resident at once (continuous batching). 0 or >= B: all B nodes
+                              are resident. With 0 < max_active < B the first max_active nodes start,
+                              and whenever nodes finish the next pending ones take over their slots, so
+                              a long frontier (branch_and_bound.py:215-266 evaluates it one node at a
+                              time) is swept at constant batch width with state for max_active nodes
+                              only. max_iters then counts per node from its own start and may be
+                              overshot by less than one evaluation period. default 0 */
 } blp_opts;
 
 typedef struct blp_stats {
@@ -68,6 +75,7 @@ typedef struct blp_stats {
     double node_iterations;    /* sum over iterations of the number of node columns swept */
     double primal_kernel_ms;   /* profile mode: device time of all k_primal launches */
     double dual_kernel_ms;     /* profile mode: device time of all k_dual launches */
+    int refills;               /* nodes that entered through a freed slot (max_active < B) */
 } blp_stats;
 
 /* default options */
@@ -76,8 +84,13 @@ void blp_default_opts(blp_opts* o);
 /* leading dimension (in elements) of every [rows][ld] batched array for a batch of B nodes */
 int blp_ld(int B);
 
-/* bytes of device workspace blp_solve_batch needs for B nodes (depends on m incl. appended rows) */
-size_t blp_workspace_bytes(blp_handle h, int B);
+/* node slots a call with B nodes and these options keeps resident: max_active if 0 < max_active < B,
+ * else B (opts may be NULL) */
+int blp_slots(int B, const blp_opts* opts);
+
+/* bytes of device workspace blp_solve_batch needs for W = blp_slots(B, opts) resident nodes
+ * (depends on m incl. appended rows) */
+size_t blp_workspace_bytes(blp_handle h, int W);
 
 /*
  * Build the shared part of all node LPs on GPU `device`: CSR of A (m x n), its transpose, the
@@ -114,7 +127,7 @@ int blp_num_cols(blp_handle h);
  *   row_mask    [m-m_base][ld] uint8, 1 = cut row present in node k's LP; NULL = all present
  *   x0, y0      [n][ld],[m][ld] warm start (parent's primal / row duals), NULL = cold
  *   int_idx     [n_int]        int32 integer column ids in ascending order (for frac_idx), or NULL
- *   workspace   blp_workspace_bytes(h, B) bytes
+ *   workspace   blp_workspace_bytes(h, blp_slots(B, opts)) bytes
  * outputs (each may be NULL):
  *   obj         [ld]  primal objective c.x at termination (+inf where status == 1)
  *   lower_bound [ld]  Lagrangian bound b.y + sum_j min((c-A'y)_j l_j, (c-A'y)_j u_j)

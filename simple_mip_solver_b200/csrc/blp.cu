@@ -324,6 +324,9 @@ size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
     s.restart = cv.take<int32_t>(ld);
     s.origin = cv.take<int32_t>(ld);
     s.newpos = cv.take<int32_t>(ld);
+    s.start = cv.take<int32_t>(ld);
+    s.fresh = cv.take<int32_t>(ld);
+    s.newlist = cv.take<int32_t>(ld);
     s.partC = cv.take<double>((size_t)kEvalChunks * C_N * ld);
     s.partR = cv.take<double>((size_t)kEvalChunks * R_N * ld);
     s.fracD = cv.take<double>((size_t)kEvalChunks * ld);
@@ -401,15 +404,16 @@ void launch_eval(const DevProb& P, const DevState& S, const Plan& ec, const Plan
     k_apply_restart<<<dim3(rchunks, (S.ld + 31) / 32), kCtaThreads, 0, st>>>(P, S);
 }
 
-void launch_check_rows(const DevProb& P, const DevState& S, const Plan& er, cudaStream_t st) {
+void launch_check_rows(const DevProb& P, const DevState& S, const Plan& er, int only_fresh,
+                       cudaStream_t st) {
     const dim3 g(er.chunks, er.tiles);
     switch (er.NT) {
-        case 1: k_check_rows<1><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
-        case 2: k_check_rows<2><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
-        case 4: k_check_rows<4><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
-        case 8: k_check_rows<8><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
-        case 16: k_check_rows<16><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
-        default: k_check_rows<32><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta); break;
+        case 1: k_check_rows<1><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta, only_fresh); break;
+        case 2: k_check_rows<2><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta, only_fresh); break;
+        case 4: k_check_rows<4><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta, only_fresh); break;
+        case 8: k_check_rows<8><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta, only_fresh); break;
+        case 16: k_check_rows<16><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta, only_fresh); break;
+        default: k_check_rows<32><<<g, kCtaThreads, 0, st>>>(P, S, er.rows_per_cta, only_fresh); break;
     }
 }
 
@@ -489,8 +493,10 @@ int elementwise_grid(size_t total) {
 int check_opts(const blp_opts* in, blp_opts* o) {
     blp_default_opts(o);
     if (in) *o = *in;
-    if (!(o->eps_rel > 0.0) || !(o->eps_infeas > 0.0) || o->max_iters < 1 || o->eval_every < 1)
-        return fail(BLP_ERR_ARG, "blp_opts: eps_rel/eps_infeas must be > 0, max_iters/eval_every >= 1");
+    if (!(o->eps_rel > 0.0) || !(o->eps_infeas > 0.0) || o->max_iters < 1 || o->eval_every < 1 ||
+        o->max_active < 0)
+        return fail(BLP_ERR_ARG, "blp_opts: eps_rel/eps_infeas must be > 0, max_iters/eval_every >= 1, "
+                                 "max_active >= 0");
     return BLP_OK;
 }
 
@@ -509,6 +515,11 @@ void blp_default_opts(blp_opts* o) {
     o->compact = 1;
     o->verbose = 0;
     o->profile = 0;
+    o->max_active = 0;
+}
+
+int blp_slots(int B, const blp_opts* o) {
+    return (o && o->max_active > 0 && o->max_active < B) ? o->max_active : B;
 }
 
 int blp_ld(int B) { return B <= 0 ? 0 : (B + kBlk - 1) / kBlk * kBlk; }
@@ -627,21 +638,26 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                     double* x, double* y, int32_t* frac_idx, blp_stats* stats) {
     if (!h) return fail(BLP_ERR_ARG, "blp_solve_batch: NULL handle");
     if (B < 1 || !lb || !ub) return fail(BLP_ERR_ARG, "blp_solve_batch: need B >= 1 and lb/ub");
-    if (!workspace || workspace_bytes < blp_workspace_bytes(h, B))
-        return fail(BLP_ERR_NOMEM, "blp_solve_batch: workspace of %zu bytes, need %zu", workspace_bytes,
-                    blp_workspace_bytes(h, B));
     if (frac_idx && int_idx == nullptr && n_int > 0)
         return fail(BLP_ERR_ARG, "blp_solve_batch: n_int > 0 with int_idx NULL");
     blp_opts o;
     int rc = check_opts(opts_in, &o);
     if (rc != BLP_OK) return rc;
+    // W node slots are resident at once; with W < B (blp_opts.max_active) the other nodes wait
+    // in the caller's arrays and take over the slots of finished ones (continuous batching)
+    const int W = blp_slots(B, &o);
+    const bool refill_mode = W < B;
+    const int ld_in = blp_ld(B);
+    if (!workspace || workspace_bytes < blp_workspace_bytes(h, W))
+        return fail(BLP_ERR_NOMEM, "blp_solve_batch: workspace of %zu bytes, need %zu", workspace_bytes,
+                    blp_workspace_bytes(h, W));
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const DevProb& P = h->P;
 
     void* ws = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(workspace), 256));
     DevState S;
-    carve_state(h, B, ws, &S);
+    carve_state(h, W, ws, &S);
     const bool have_mask = (P.m > P.m_base) && row_mask != nullptr;
     uint8_t* mask_ws = S.rowmask;
     if (!have_mask) S.rowmask = nullptr;
@@ -649,14 +665,14 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     if (o.verbose < 2) S.dbg = nullptr;
     uint8_t* isint_ws = const_cast<uint8_t*>(S.isint);
     if (!want_frac) S.isint = nullptr;
-    DevOut O{obj, lower_bound, x, y, status, iters, frac_idx};
+    DevOut O{obj, lower_bound, x, y, status, iters, frac_idx, ld_in};
 
     // evaluation period: eval_every at first, 4x that once a node batch has run 32 periods (an
     // evaluation costs about three iterations; late in a solve nothing changes within 64 of them)
     const int K0 = std::min(o.eval_every, o.max_iters);
     int K = K0;
     const int rpw = env_int("BLP_ROWS_PER_WARP", 8);
-    int NT = pick_nt(B);     // nodes per warp; re-picked when compaction narrows the batch
+    int NT = pick_nt(W);     // nodes per warp; re-picked when compaction narrows the batch
     DecideArgs D{0, 0, K, o.max_iters, o.eps_rel, o.eps_infeas,
                  env_dbl("BLP_BETA_SUFF", 0.2), env_dbl("BLP_BETA_NEC", 0.8), env_dbl("BLP_BETA_ART", 0.36),
                  env_dbl("BLP_OMEGA_THETA", 0.05)};
@@ -665,28 +681,28 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     CK(cudaEventRecord(h->ev[0], st));
     CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(int32_t), st));
     if (have_mask)
-        CK(cudaMemcpyAsync(mask_ws, row_mask, (size_t)(P.m - P.m_base) * S.ld, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpy2DAsync(mask_ws, S.ld, row_mask, ld_in, S.ld, P.m - P.m_base, cudaMemcpyDeviceToDevice, st));
     if (want_frac) {
         CK(cudaMemsetAsync(isint_ws, 0, P.n, st));
         k_set_isint<<<(n_int + 255) / 256, 256, 0, st>>>(int_idx, n_int, P.n, isint_ws);
         ++launches;
     }
-    if (x) CK(cudaMemsetAsync(x, 0, (size_t)P.n * S.ld * sizeof(double), st));
-    if (y) CK(cudaMemsetAsync(y, 0, (size_t)P.m * S.ld * sizeof(double), st));
-    if (S.ld > B) {
-        k_out_pad<<<(S.ld - B + 127) / 128, 128, 0, st>>>(O, B, S.ld);
+    if (x) CK(cudaMemsetAsync(x, 0, (size_t)P.n * ld_in * sizeof(double), st));
+    if (y) CK(cudaMemsetAsync(y, 0, (size_t)P.m * ld_in * sizeof(double), st));
+    if (ld_in > B) {
+        k_out_pad<<<(ld_in - B + 127) / 128, 128, 0, st>>>(O, B, ld_in);
         ++launches;
     }
     k_init_nodes<<<(S.ld + 127) / 128, 128, 0, st>>>(P, S);
-    k_init_cols<<<elementwise_grid((size_t)P.n * S.ld), kCtaThreads, 0, st>>>(P, S, lb, ub, x0);
-    k_init_rows<<<elementwise_grid((size_t)P.m * S.ld), kCtaThreads, 0, st>>>(P, S, y0);
+    k_init_cols<<<elementwise_grid((size_t)P.n * S.ld), kCtaThreads, 0, st>>>(P, S, lb, ub, x0, ld_in);
+    k_init_rows<<<elementwise_grid((size_t)P.m * S.ld), kCtaThreads, 0, st>>>(P, S, y0, ld_in);
     {
-        Plan er0 = plan_rows(P.m, B, 1, kEvalChunks);
+        Plan er0 = plan_rows(P.m, W, 1, kEvalChunks);
         er0.NT = NT;
-        launch_check_rows(P, S, er0, st);
+        launch_check_rows(P, S, er0, 0, st);
     }
     k_build_lumask<<<elementwise_grid((size_t)P.n * (S.ld / 32) * 32), kCtaThreads, 0, st>>>(P, S);
-    k_count_active<<<(B + 127) / 128, 128, 0, st>>>(S);
+    k_count_active<<<(W + 127) / 128, 128, 0, st>>>(S);
     launches += 6;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_counters, S.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -734,7 +750,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         }
         return p;
     };
-    Plan pc = step_plan(P.n, B), pr = step_plan(P.m, B);
+    Plan pc = step_plan(P.n, W), pr = step_plan(P.m, W);
     auto finish_step_plans = [&]() -> int {
         plan_chunks(pc, h->hptrAT, P.n, h->h_chunkC);
         plan_chunks(pr, h->hptrA, P.m, h->h_chunkR);
@@ -745,11 +761,35 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         return BLP_OK;
     };
     if ((rc = finish_step_plans()) != BLP_OK) return rc;
-    Plan ec = make_plan(P.n, B, 1, kEvalChunks), er = make_plan(P.m, B, 1, kEvalChunks);
+    Plan ec = make_plan(P.n, W, 1, kEvalChunks), er = make_plan(P.m, W, 1, kEvalChunks);
     D.chunksC = ec.chunks;
     D.chunksR = er.chunks;
 
-    if (active < B) launch_harvest(P, S, O, ec, er, want_frac, st, &launches);    // decided at set-up
+    if (active < W) launch_harvest(P, S, O, ec, er, want_frac, st, &launches);    // decided at set-up
+
+    // continuous batching: pending nodes next .. B-1 take over the slots of harvested ones
+    int next = W, refills = 0;
+    auto refill = [&]() -> int {
+        while (next < B && active < S.B) {
+            const int nnew = std::min(B - next, S.B - active);
+            k_refill_plan<<<1, 1024, 0, st>>>(P, S, next, nnew);
+            k_refill_cols<<<elementwise_grid((size_t)P.n * nnew), kCtaThreads, 0, st>>>(P, S, lb, ub, x0, ld_in, nnew);
+            k_refill_rows<<<elementwise_grid((size_t)P.m * nnew), kCtaThreads, 0, st>>>(P, S, y0, row_mask, ld_in, nnew);
+            launch_check_rows(P, S, er, 1, st);
+            k_build_lumask<<<elementwise_grid((size_t)P.n * ((S.B + 31) / 32) * 32), kCtaThreads, 0, st>>>(P, S);
+            k_count_active<<<(S.B + 127) / 128, 128, 0, st>>>(S);
+            launches += 6;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(h->h_counters, S.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            next += nnew;
+            refills += nnew;
+            active = h->h_counters[0];
+            if (h->h_counters[3] > 0) launch_harvest(P, S, O, ec, er, want_frac, st, &launches);
+        }
+        return BLP_OK;
+    };
+    if ((rc = refill()) != BLP_OK) return rc;
 
     const bool profile = o.profile == 1;
     const bool use_graph = o.use_graph && !profile;
@@ -796,9 +836,10 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
 
     int total = 0, evals = 0, compactions = 0;
     double step_ms = 0.0, primal_ms = 0.0, dual_ms = 0.0, node_iters = 0.0;
-    while (active > 0 && total < o.max_iters) {
+    while (active > 0 && (refill_mode || total < o.max_iters)) {
         // retire finished nodes: pack the running ones to the front when that frees node tiles
-        if (o.compact && active < S.B) {
+        // (while nodes are pending, freed slots are refilled instead)
+        if (o.compact && active < S.B && next >= B) {
             const int cur_tiles = (S.B + NT - 1) / NT, new_tiles = (active + NT - 1) / NT;
             if ((new_tiles < cur_tiles && (new_tiles * 8 <= cur_tiles * 7 || cur_tiles <= 16)) ||
                 pick_nt(active) < NT) {
@@ -823,7 +864,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         }
         {
             int want = (total >= 32 * K0 && env_int("BLP_ADAPTIVE_EVAL", 1)) ? 4 * K0 : K0;
-            want = std::min(want, o.max_iters - total);
+            if (!refill_mode) want = std::min(want, o.max_iters - total);
             if (want != K) {
                 K = want;
                 D.steps_in_period = K;
@@ -883,9 +924,11 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         evals += 1;
         launches += (coop ? 1 : 2 * K) + 5;
         active = h->h_counters[0];
-        if (h->h_counters[3] > 0) {
+        const int finished_now = h->h_counters[3], restarting = h->h_counters[1];
+        if (finished_now > 0) {
             launch_harvest(P, S, O, ec, er, want_frac, st, &launches);
             CK(cudaGetLastError());
+            if ((rc = refill()) != BLP_OK) return rc;
         }
         if (o.verbose >= 2) {
             double t[8 * 4];
@@ -897,7 +940,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         }
         if (o.verbose)
             fprintf(stderr, "[blp] iters %d  width %d  running %d  restarting %d  finished now %d  steps_ms %.3f\n",
-                    total, S.B, active, h->h_counters[1], h->h_counters[3], ms);
+                    total, S.B, active, restarting, finished_now, ms);
     }
     CK(cudaEventRecord(h->ev[1], st));
     CK(cudaStreamSynchronize(st));
@@ -913,6 +956,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         stats->node_iterations = node_iters;
         stats->primal_kernel_ms = primal_ms;
         stats->dual_kernel_ms = dual_ms;
+        stats->refills = refills;
     }
     return BLP_OK;
 }
@@ -973,7 +1017,7 @@ int finish_host(blp_handle h, int B, int ld, const NodeOut& no, bool want_x, boo
     return BLP_OK;
 }
 
-int stage_common(blp_handle h, int B, int ld, const uint8_t* row_mask, const int32_t* int_idx,
+int stage_common(blp_handle h, int B, int W, int ld, const uint8_t* row_mask, const int32_t* int_idx,
                  int n_int, bool want_x, bool want_y, const uint8_t** d_mask,
                  const int32_t** d_int) {
     cudaStream_t st = h->stream;
@@ -996,7 +1040,7 @@ int stage_common(blp_handle h, int B, int ld, const uint8_t* row_mask, const int
     if (want_x) CK(h->s_x.ensure((size_t)n * ld * sizeof(double)));
     if (want_y) CK(h->s_y.ensure((size_t)m * ld * sizeof(double)));
     CK(h->s_node.ensure((size_t)ld * (2 * sizeof(double) + 3 * sizeof(int32_t))));
-    CK(h->s_ws.ensure(blp_workspace_bytes(h, B)));
+    CK(h->s_ws.ensure(blp_workspace_bytes(h, W)));
     CK(cudaGetLastError());
     return BLP_OK;
 }
@@ -1019,7 +1063,8 @@ int blp_solve_batch_host(blp_handle h, int B, const double* lb, const double* ub
     if (y0 && (rc = stage_in(h, h->s_y0, y0, B, m, ld))) return rc;
     const uint8_t* d_mask;
     const int32_t* d_int;
-    if ((rc = stage_common(h, B, ld, row_mask, int_idx, n_int, x != nullptr, y != nullptr, &d_mask, &d_int)))
+    if ((rc = stage_common(h, B, blp_slots(B, opts), ld, row_mask, int_idx, n_int, x != nullptr, y != nullptr,
+                           &d_mask, &d_int)))
         return rc;
     NodeOut no = node_out(h, ld);
     rc = blp_solve_batch(h, B, h->s_lb.as<double>(), h->s_ub.as<double>(), d_mask,
@@ -1091,7 +1136,8 @@ int blp_solve_children_host(blp_handle h, int B, const double* parent_lb, const 
     const uint8_t* d_mask;
     const int32_t* d_int;
     int rc;
-    if ((rc = stage_common(h, B, ld, row_mask, int_idx, n_int, x != nullptr, y != nullptr, &d_mask, &d_int)))
+    if ((rc = stage_common(h, B, blp_slots(B, opts), ld, row_mask, int_idx, n_int, x != nullptr, y != nullptr,
+                           &d_mask, &d_int)))
         return rc;
     NodeOut no = node_out(h, ld);
     rc = blp_solve_batch(h, B, h->s_lb.as<double>(), h->s_ub.as<double>(), d_mask,

@@ -63,6 +63,8 @@ struct DevState {
     double *omega, *fpe0, *fpe_prev, *pobj, *dobj; // [ld]
     int32_t *sbase, *fin, *status, *iters, *restart;   // [ld]
     int32_t *origin, *newpos;                      // [ld] caller's node id of a column; compaction map
+    int32_t *start, *fresh, *newlist;              // [ld] iteration count at which the slot's node was loaded;
+                                                   //      1 = loaded by the last refill; slots of that refill
     double *partC, *partR;                         // [chunks][C_N][ld], [chunks][R_N][ld]
     double* fracD; int32_t* fracI;                 // [chunks][ld] most-fractional partials
     const uint8_t* isint;                          // [n] 1 = integer column, or null
@@ -79,6 +81,7 @@ struct DevState {
 struct DevOut {
     double *obj, *lower, *x, *y;
     int32_t *status, *iters, *frac_idx;
+    int ld;                                        // leading dimension of the caller's arrays
 };
 
 __device__ __forceinline__ bool is_inf(double v) { return fabs(v) >= 1e30; }
@@ -739,7 +742,7 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
         t[0] = rp; t[1] = rd; t[2] = rg; t[3] = fpe; t[4] = omega; t[5] = (double)S.sbase[node];
         t[6] = pobj; t[7] = dobj;
     }
-    const int total = S.counters[2];
+    const int total = S.counters[2] - S.start[node];      // iterations this node has run
     const bool last = total >= D.max_iters;
     int st = -1;
     if (rp <= D.eps && rd <= D.eps && rg <= D.eps) {
@@ -823,7 +826,7 @@ k_apply_restart(const DevProb P, const DevState S) {
 // Set-up: scale the per-node bounds into the solver's space and build the start point.
 __global__ void __launch_bounds__(kCtaThreads)
 k_init_cols(const DevProb P, const DevState S, const double* __restrict__ lb,
-            const double* __restrict__ ub, const double* __restrict__ x0) {
+            const double* __restrict__ ub, const double* __restrict__ x0, const int ld_in) {
     const size_t total = (size_t)P.n * S.ld;
     for (size_t e = (size_t)blockIdx.x * kCtaThreads + threadIdx.x; e < total;
          e += (size_t)gridDim.x * kCtaThreads) {
@@ -831,10 +834,11 @@ k_init_cols(const DevProb P, const DevState S, const double* __restrict__ lb,
         double lo = 0.0, hi = 0.0, x = 0.0;
         if (node < S.B) {
             const double f = P.sb / P.dc[j];
-            const double a = lb[e], b = ub[e];
+            const size_t ei = (size_t)j * ld_in + node;
+            const double a = lb[ei], b = ub[ei];
             lo = is_inf(a) ? (a > 0 ? INFINITY : -INFINITY) : a * f;
             hi = is_inf(b) ? (b > 0 ? INFINITY : -INFINITY) : b * f;
-            x = x0 ? x0[e] * f : 0.0;
+            x = x0 ? x0[ei] * f : 0.0;
             x = fmin(fmax(x, lo), hi);
         }
         if (lo > hi) {              // empty box: primal infeasible without any iteration
@@ -847,14 +851,14 @@ k_init_cols(const DevProb P, const DevState S, const double* __restrict__ lb,
 }
 
 __global__ void __launch_bounds__(kCtaThreads)
-k_init_rows(const DevProb P, const DevState S, const double* __restrict__ y0) {
+k_init_rows(const DevProb P, const DevState S, const double* __restrict__ y0, const int ld_in) {
     const size_t total = (size_t)P.m * S.ld;
     for (size_t e = (size_t)blockIdx.x * kCtaThreads + threadIdx.x; e < total;
          e += (size_t)gridDim.x * kCtaThreads) {
         const int i = (int)(e / S.ld), node = (int)(e % S.ld);
         double y = 0.0;
         if (node < S.B && y0) {
-            y = fmax(0.0, y0[e] * P.sc / P.dr[i]);
+            y = fmax(0.0, y0[(size_t)i * ld_in + node] * P.sc / P.dr[i]);
             if (i >= P.m_base && S.rowmask && S.rowmask[(size_t)(i - P.m_base) * S.ld + node] == 0)
                 y = 0.0;
         }
@@ -868,12 +872,13 @@ k_init_rows(const DevProb P, const DevState S, const double* __restrict__ y0) {
 // activity over the node's box stays below its lower bound proves the node LP infeasible.
 template <int NT>
 __global__ void __launch_bounds__(kCtaThreads)
-k_check_rows(const DevProb P, const DevState S, const int rows_per_cta) {
+k_check_rows(const DevProb P, const DevState S, const int rows_per_cta, const int only_fresh) {
     constexpr int RW = 32 / NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int node = blockIdx.y * NT + (lane % NT);
     const int sub = lane / NT;
-    const bool node_ok = node < S.B;
+    const bool node_ok = node < S.B && (!only_fresh || S.fresh[node] != 0);
+    if (__ballot_sync(0xffffffffu, node_ok) == 0) return;
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(P.m, r0 + rows_per_cta);
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
@@ -920,9 +925,13 @@ k_build_lumask(const DevProb P, const DevState S) {
     }
 }
 
+// counters[0] += running nodes, counters[3] += nodes decided at set-up and not yet harvested
 __global__ void k_count_active(const DevState S) {
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node < S.B && S.fin[node] == 0) atomicAdd(S.counters + 0, 1);
+    if (node >= S.B) return;
+    const int f = S.fin[node];
+    if (f == 0) atomicAdd(S.counters + 0, 1);
+    else if (f == 1) atomicAdd(S.counters + 3, 1);
 }
 
 __global__ void k_init_nodes(const DevProb P, const DevState S) {
@@ -939,6 +948,105 @@ __global__ void k_init_nodes(const DevProb P, const DevState S) {
     S.iters[node] = 0;
     S.restart[node] = 0;
     S.origin[node] = node;
+    S.start[node] = 0;
+    S.fresh[node] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Refill (continuous batching, blp_opts.max_active < B): the batch holds S.B node SLOTS; a slot
+// whose node has been harvested (fin == 2) takes the next pending node of the caller's batch, so
+// the step kernels keep sweeping a full-width batch while a long frontier drains, instead of
+// narrowing towards the slowest node of every slice.
+//   k_refill_plan (one CTA): free slots in ascending order get nodes next, next+1, ... (nnew of
+//                 them); per-slot scalars are reset; newlist[q] = slot of the q-th new node
+//   k_refill_cols / k_refill_rows: the new slots' state columns, as k_init_cols / k_init_rows
+__global__ void __launch_bounds__(1024) k_refill_plan(const DevProb P, const DevState S, const int next,
+                                                      const int nnew) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    const int now = S.counters[2];
+    for (int c0 = 0; c0 < S.B; c0 += 1024) {
+        const int k = c0 + tid;
+        const bool free_slot = k < S.B && S.fin[k] == 2;
+        const unsigned bal = __ballot_sync(0xffffffffu, free_slot);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int before = base_s;
+        for (int w = 0; w < warp; ++w) before += wsum[w];
+        const int q = before + __popc(bal & ((1u << lane) - 1u));
+        int total = 0;
+        for (int w = 0; w < 32; ++w) total += wsum[w];
+        __syncthreads();
+        const bool take = free_slot && q < nnew;
+        if (k < S.B) S.fresh[k] = take ? 1 : 0;
+        if (take) {
+            S.newlist[q] = k;
+            S.origin[k] = next + q;
+            S.start[k] = now;
+            S.omega[k] = P.omega0;
+            S.fpe0[k] = INFINITY;
+            S.fpe_prev[k] = INFINITY;
+            S.pobj[k] = 0.0;
+            S.dobj[k] = -INFINITY;
+            S.sbase[k] = 0;
+            S.fin[k] = 0;
+            S.status[k] = 3;
+            S.iters[k] = 0;
+            S.restart[k] = 0;
+        }
+        if (tid == 0) base_s += total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        S.counters[0] = 0;
+        S.counters[3] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_refill_cols(const DevProb P, const DevState S, const double* __restrict__ lb,
+              const double* __restrict__ ub, const double* __restrict__ x0, const int ld_in,
+              const int nnew) {
+    const size_t total = (size_t)P.n * nnew;
+    for (size_t e = (size_t)blockIdx.x * kCtaThreads + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * kCtaThreads) {
+        const int j = (int)(e / nnew), slot = S.newlist[e % nnew];
+        const size_t ei = (size_t)j * ld_in + S.origin[slot];
+        const double f = P.sb / P.dc[j];
+        const double a = lb[ei], b = ub[ei];
+        const double lo = is_inf(a) ? (a > 0 ? INFINITY : -INFINITY) : a * f;
+        const double hi = is_inf(b) ? (b > 0 ? INFINITY : -INFINITY) : b * f;
+        const double x = fmin(fmax(x0 ? x0[ei] * f : 0.0, lo), hi);
+        if (lo > hi) {
+            S.fin[slot] = 1; S.status[slot] = 1; S.pobj[slot] = INFINITY; S.dobj[slot] = INFINITY;
+        }
+        const size_t t = tix(j, slot, P.n);
+        S.l[t] = lo; S.u[t] = hi; S.xa[t] = x; S.xbar[t] = x; S.X1[t] = x;
+        S.DX[t] = 0.0; S.G[t] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_refill_rows(const DevProb P, const DevState S, const double* __restrict__ y0,
+              const uint8_t* __restrict__ row_mask, const int ld_in, const int nnew) {
+    const size_t total = (size_t)P.m * nnew;
+    for (size_t e = (size_t)blockIdx.x * kCtaThreads + threadIdx.x; e < total;
+         e += (size_t)gridDim.x * kCtaThreads) {
+        const int i = (int)(e / nnew), slot = S.newlist[e % nnew];
+        const int org = S.origin[slot];
+        bool on = true;
+        if (i >= P.m_base && S.rowmask) {
+            const uint8_t v = row_mask[(size_t)(i - P.m_base) * ld_in + org];
+            S.rowmask[(size_t)(i - P.m_base) * S.ld + slot] = v;
+            on = v != 0;
+        }
+        const double y = (y0 && on) ? fmax(0.0, y0[(size_t)i * ld_in + org] * P.sc / P.dr[i]) : 0.0;
+        const size_t t = tix(i, slot, P.m);
+        S.y[t] = y; S.ya[t] = y; S.Y1[t] = y; S.DY[t] = 0.0;
+    }
 }
 
 // Harvest: nodes that received a status in the last evaluation (fin == 1) hand their results to
@@ -967,7 +1075,7 @@ k_harvest_x(const DevProb P, const DevState S, const DevOut O, const double frac
         const int j = jb + sub;
         if (j < r1 && node_ok) {
             const double v = S.X1[tix(j, node, P.n)] * __ldg(P.dc + j) * inv;
-            if (O.x) O.x[(size_t)j * S.ld + org] = v;
+            if (O.x) O.x[(size_t)j * O.ld + org] = v;
             if (S.isint && S.isint[j]) {
                 const double dist = fmin(v - floor(v), ceil(v) - v);
                 if (dist > best) { best = dist; besti = j; }      // ascending j per lane: first wins
@@ -1008,7 +1116,7 @@ k_harvest_y(const DevProb P, const DevState S, const DevOut O, const int rows_pe
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         if (i < r1 && node_ok)
-            O.y[(size_t)i * S.ld + org] = S.Y1[tix(i, node, P.m)] * __ldg(P.dr + i) * inv;
+            O.y[(size_t)i * O.ld + org] = S.Y1[tix(i, node, P.m)] * __ldg(P.dr + i) * inv;
     }
 }
 
@@ -1065,10 +1173,10 @@ __global__ void __launch_bounds__(1024) k_compact_plan(const DevState S) {
         const int k = c0 + tid;
         const bool keep = k < S.B && S.fin[k] == 0;
         double om = 0, f0 = 0, fp = 0, po = 0, dq = 0;
-        int sb = 0, stt = 0, itr = 0, org = 0;
+        int sb = 0, stt = 0, itr = 0, org = 0, beg = 0;
         if (keep) {
             om = S.omega[k]; f0 = S.fpe0[k]; fp = S.fpe_prev[k]; po = S.pobj[k]; dq = S.dobj[k];
-            sb = S.sbase[k]; stt = S.status[k]; itr = S.iters[k]; org = S.origin[k];
+            sb = S.sbase[k]; stt = S.status[k]; itr = S.iters[k]; org = S.origin[k]; beg = S.start[k];
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) wsum[warp] = __popc(bal);
@@ -1083,6 +1191,7 @@ __global__ void __launch_bounds__(1024) k_compact_plan(const DevState S) {
         if (keep) {
             S.omega[pos] = om; S.fpe0[pos] = f0; S.fpe_prev[pos] = fp; S.pobj[pos] = po; S.dobj[pos] = dq;
             S.sbase[pos] = sb; S.status[pos] = stt; S.iters[pos] = itr; S.origin[pos] = org;
+            S.start[pos] = beg;
         }
         if (tid == 0) base_s += total;
         __syncthreads();

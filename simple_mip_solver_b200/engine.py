@@ -33,14 +33,14 @@ class BlpError(RuntimeError):
 class BlpOpts(C.Structure):
     _fields_ = [('eps_rel', C.c_double), ('eps_infeas', C.c_double), ('max_iters', C.c_int),
                 ('eval_every', C.c_int), ('use_graph', C.c_int), ('compact', C.c_int),
-                ('verbose', C.c_int), ('profile', C.c_int)]
+                ('verbose', C.c_int), ('profile', C.c_int), ('max_active', C.c_int)]
 
 
 class BlpStats(C.Structure):
     _fields_ = [('iterations', C.c_int), ('evaluations', C.c_int), ('kernel_launches', C.c_int),
                 ('compactions', C.c_int), ('step_kernel_ms', C.c_double), ('total_ms', C.c_double),
                 ('node_iterations', C.c_double), ('primal_kernel_ms', C.c_double),
-                ('dual_kernel_ms', C.c_double)]
+                ('dual_kernel_ms', C.c_double), ('refills', C.c_int)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -50,6 +50,7 @@ _P = C.c_void_p
 _SIGNATURES = {
     'blp_default_opts': (None, [C.POINTER(BlpOpts)]),
     'blp_ld': (C.c_int, [C.c_int]),
+    'blp_slots': (C.c_int, [C.c_int, C.POINTER(BlpOpts)]),
     'blp_workspace_bytes': (C.c_size_t, [_P, C.c_int]),
     'blp_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     'blp_append_rows': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_int)]),
@@ -295,7 +296,8 @@ class BatchLP:
                 continue
             if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != (rows, ld):
                 raise ValueError(f'{name} must be a contiguous float64 CUDA tensor of shape {(rows, ld)}')
-        need = self._lib.blp_workspace_bytes(self._h, B)
+        o = opts if opts is not None else default_opts()
+        need = self._lib.blp_workspace_bytes(self._h, self._lib.blp_slots(B, C.byref(o)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -308,7 +310,6 @@ class BatchLP:
                    y=torch.empty((m, ld), dtype=torch.float64, device=dev) if want_y else None)
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         st = BlpStats()
-        o = opts if opts is not None else default_opts()
         torch.cuda.current_stream(dev).synchronize()     # inputs were produced on torch's stream
         _check(self._lib.blp_solve_batch(
             self._h, B, p(lb), p(ub), p(row_mask), p(x0), p(y0), p(int_idx),

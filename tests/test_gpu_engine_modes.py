@@ -98,3 +98,82 @@ def test_iteration_budget_returns_lagrangian_bound(blp_lib):
     both = lim & (full.status == 0)
     assert (short.lower_bound[both] <= full.objective[both] + 1e-6 * np.abs(full.objective[both])).all()
     assert (short.iterations[lim] == 256).all()
+
+
+def test_continuous_batching_matches_resident_batch(blp_lib):
+    """blp_opts.max_active < B: pending nodes take over the slots of finished ones. Every node
+    must end with the same status, an objective equal within the solve tolerance and its own
+    iteration count (counted from the moment it was loaded)."""
+    from simple_mip_solver_b200 import engine as eng
+    d, lbs, ubs = _instance()
+    B = lbs.shape[0]
+    lbs, ubs = lbs.copy(), ubs.copy()
+    lbs[97, 5], ubs[97, 5] = 3.0, 2.0          # empty boxes among the pending nodes: status 1
+    lbs[149, 0], ubs[149, 0] = 1.0, 0.0        # without an iteration, also as the very last node
+    base = _solve(eng, d, lbs, ubs)
+    assert base.status[97] == 1 and base.status[149] == 1
+    for slots in (64, 40, 7):
+        r = _solve(eng, d, lbs, ubs, max_active=slots)
+        assert r.stats['refills'] == B - slots
+        assert r.stats['compactions'] > 0                     # the tail still compacts
+        assert np.array_equal(r.status, base.status)
+        ok = base.status == 0
+        assert np.allclose(r.objective[ok], base.objective[ok], rtol=5e-7, atol=1e-9)
+        assert np.allclose(r.lower_bound[ok], base.lower_bound[ok], rtol=5e-7, atol=1e-9)
+        assert (r.iterations[ok] > 0).all() and r.iterations[97] == 0 and r.iterations[149] == 0
+        # per-node iteration counts stay in the range of the resident solve (own clock, not the batch's)
+        assert r.iterations[ok].max() <= 2 * base.iterations[ok].max()
+        assert np.isinf(r.objective[97]) and np.isinf(r.objective[149])
+        # x is the point the objective was computed at
+        assert np.allclose((r.x[ok] * d.c).sum(1), r.objective[ok], rtol=1e-9, atol=1e-9)
+    # max_active >= B is the resident batch itself
+    _same(base, _solve(eng, d, lbs, ubs, max_active=B))
+    _same(base, _solve(eng, d, lbs, ubs, max_active=10 * B))
+
+
+def test_continuous_batching_iteration_budget_is_per_node(blp_lib):
+    from simple_mip_solver_b200 import engine as eng
+    d, lbs, ubs = _instance()
+    r = _solve(eng, d, lbs[:96], ubs[:96], max_active=32, max_iters=256)
+    lim = r.status == 3
+    assert lim.sum() > 10
+    assert (r.iterations[lim] >= 256).all() and (r.iterations[lim] < 256 + 256).all()
+    full = _solve(eng, d, lbs[:96], ubs[:96])
+    both = lim & (full.status == 0)
+    assert (r.lower_bound[both] <= full.objective[both] + 1e-6 * np.abs(full.objective[both])).all()
+
+
+def test_continuous_batching_carries_row_masks_and_warm_starts(blp_lib):
+    """Refilled slots read their own row mask, x0 and y0 columns from the caller's arrays."""
+    from oracle.highs_lp import HIGHS_INF, HighsLP
+    from simple_mip_solver_b200 import engine as eng
+    d = numpy_random_mip(600, 300, density=0.02, seed=7)
+    root = HighsLP(d.A, d.c, d.b, np.full(d.m, HIGHS_INF), d.l, d.u).solve()
+    B = 80
+    lbs, ubs, _ = frontier_nodes(d, root.x, 0, B, 6, seed=1)
+    rng = np.random.default_rng(3)
+    rows, rhs = [], []
+    for k in range(6):
+        S = rng.choice(d.n, size=60, replace=False)
+        row = np.zeros(d.n)
+        row[S] = -1.0
+        rows.append(row)
+        rhs.append(-np.floor(root.x[S].sum()))
+    lp = eng.BatchLP(d.A, d.b, d.c)
+    lp.append_rows(np.array(rows), np.array(rhs))
+    masks = (rng.random((B, 6)) < 0.5).astype(np.uint8)
+    x0 = np.tile(root.x, (B, 1))
+    y0 = np.hstack([np.tile(np.maximum(root.row_dual, 0), (B, 1)), np.zeros((B, 6))])
+    res = lp.solve_batch(lbs, ubs, row_mask=masks, x0=x0, y0=y0, opts=eng.default_opts(max_active=24))
+    lp.close()
+    assert res.stats['refills'] == B - 24
+    for k in range(0, B, 3):
+        h = HighsLP(d.A, d.c, d.b, np.full(d.m, HIGHS_INF), lbs[k], ubs[k])
+        for t in np.flatnonzero(masks[k]):
+            h.add_row(rows[t], rhs[t])
+        ref = h.solve()
+        assert res.status[k] == ref.status, k
+        if ref.status == 0:
+            assert abs(res.objective[k] - ref.objective) <= 1e-6 * max(1.0, abs(ref.objective)), k
+    ok = res.status == 0
+    assert (res.y[ok][:, d.m:][masks[ok] == 0] == 0).all()

@@ -74,8 +74,7 @@ cudaError_t upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
 
 struct Plan {
     int NT, tiles, chunks, rows_per_cta;
-    int V = 1;                // 2: two nodes per lane (k_primal2 / k_dual2); 3: the same with the
-                              //    cp.async ring pipeline (k_primal3 / k_dual3)
+    int V = 1;                // nodes per lane: 2 selects the k_primal2 / k_dual2 kernels
     int cap = 0;              // slab entries staged in shared memory per CTA (step kernels, spmv)
     size_t smem = 0;          // dynamic shared memory bytes of those kernels
     const int* chunk_ptr = nullptr;   // device: row range of every CTA (step kernels)
@@ -86,8 +85,7 @@ constexpr int kMaxSlabEntries = 2816;       // 44 KB of entries + row pointers s
 // Row ranges of the step-kernel CTAs: at most rows_per_cta rows and about 4x the average entry
 // count per chunk; a long row (dense cut row) gets a chunk of its own and is then gathered by all
 // warps of the CTA together. Also sizes the shared-memory slab (largest chunk, capped).
-void plan_chunks(Plan& p, const std::vector<int32_t>& ptr, int rows, std::vector<int32_t>& bounds,
-                 int meta_per_row) {
+void plan_chunks(Plan& p, const std::vector<int32_t>& ptr, int rows, std::vector<int32_t>& bounds) {
     const long nnz = ptr[rows];
     const long budget = std::max<long>(4 * ((nnz * p.rows_per_cta + rows - 1) / std::max(rows, 1)), kLongRow);
     bounds.clear();
@@ -115,8 +113,6 @@ void plan_chunks(Plan& p, const std::vector<int32_t>& ptr, int rows, std::vector
     const int ptr_slots = (p.rows_per_cta + 4) / 4;
     p.cap = std::max(0, std::min(worst, kMaxSlabEntries - ptr_slots));
     p.smem = 16 * ((size_t)ptr_slots + (size_t)p.cap);
-    if (p.V == 3)       // staged row data + rings
-        p.smem += (size_t)meta_per_row * p.rows_per_cta + ring_bytes(meta_per_row == kMetaPrimal ? kRingP : kRingD);
 }
 
 // spmv keeps uniform chunks
@@ -196,6 +192,11 @@ struct blp_handle_s {
     DevBuf s_lb, s_ub, s_x0, s_y0, s_mask, s_x, s_y, s_tmp, s_ws, s_node, s_int, s_delta, s_par;
     int32_t* h_counters = nullptr;     // pinned
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // node tiles are independent chains of launches: inside a period graph they run as up to
+    // kLanes parallel branches, so the tail of one branch's kernel overlaps the next kernel of another
+    static constexpr int kLanes = 4;
+    cudaStream_t side[kLanes - 1] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kLanes - 1] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> prof_ev;
     // cached period graphs
     bool graph_valid = false;
@@ -360,30 +361,20 @@ void launch_steps_nt(const DevProb& P, const DevState& S, const Plan& pc, const 
     }
 }
 
-// which: 0 primal only, 1 dual only, 2 both
+// which: 0 primal only, 1 dual only, 2 both. The two-nodes-per-lane kernels can be launched for a
+// sub-range of node tiles [tile0, tile0 + ntiles) (ntiles < 0: all), see ensure_graphs.
 void launch_steps(const DevProb& P, const DevState& S, const Plan& pc, const Plan& pr, int it,
-                  bool major, cudaStream_t st, int which = 2) {
-    if (pc.V == 3) {
-        const dim3 gc(pc.chunks, pc.tiles), gr(pr.chunks, pr.tiles);
-        if (which != 1) {
-            if (major) k_primal3<true><<<gc, kCta3, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr);
-            else k_primal3<false><<<gc, kCta3, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr);
-        }
-        if (which != 0) {
-            if (major) k_dual3<true><<<gr, kCta3, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr);
-            else k_dual3<false><<<gr, kCta3, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr);
-        }
-        return;
-    }
+                  bool major, cudaStream_t st, int which = 2, int tile0 = 0, int ntiles = -1) {
     if (pc.V == 2) {
-        const dim3 gc(pc.chunks, pc.tiles), gr(pr.chunks, pr.tiles);
+        const int nt = ntiles < 0 ? pc.tiles : ntiles;
+        const dim3 gc(pc.chunks, nt), gr(pr.chunks, nt);
         if (which != 1) {
-            if (major) k_primal2<true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr);
-            else k_primal2<false><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr);
+            if (major) k_primal2<true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr, tile0);
+            else k_primal2<false><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr, tile0);
         }
         if (which != 0) {
-            if (major) k_dual2<true><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr);
-            else k_dual2<false><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr);
+            if (major) k_dual2<true><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr, tile0);
+            else k_dual2<false><<<gr, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr, tile0);
         }
         return;
     }
@@ -582,15 +573,13 @@ int blp_create(int device, int m, int n, int64_t nnz, const int32_t* rowptr, con
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->coop_ok, cudaDevAttrCooperativeLaunch, device);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    {   // the ring kernels use more than 48 KB of dynamic shared memory
-        const int big = 200 * 1024;
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_primal3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_primal3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dual3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dual3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    }
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_counters, 8 * sizeof(int32_t));
     for (int q = 0; q < 4 && e == cudaSuccess; ++q) e = cudaEventCreate(&h->ev[q]);
+    for (int q = 0; q < blp_handle_s::kLanes - 1 && e == cudaSuccess; ++q) {
+        e = cudaStreamCreateWithFlags(&h->side[q], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[q], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         blp_destroy(h);
         return fail(BLP_ERR_CUDA, "blp_create: %s", cudaGetErrorString(e));
@@ -752,19 +741,18 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     // step kernels: fewer rows per warp when the batch is narrow, so that a handful of running
     // nodes still spreads over all SMs (the per-iteration latency floor of the solve's tail)
     const bool allow_v2 = env_int("BLP_V2", 1) != 0;
-    const bool allow_v3 = allow_v2 && env_int("BLP_V3", 1) != 0;
-    const int rpw3 = env_int("BLP_ROWS_PER_WARP3", 16);
+    const int graph_lanes = env_int("BLP_GRAPH_LANES", 2);
     auto step_plan = [&](int rows, int width) {
+        int r = rpw;
+        Plan p = make_plan(rows, width, r, 0);
         // two nodes per lane pay off when a launch has real work; tiny LPs stay on the
         // one-node-per-lane kernels, which can run a whole period as one cooperative launch
         const bool v2 = allow_v2 && width >= kBlk && (long)std::max(P.n, P.m) * width >= (1L << 20);
-        int r = (v2 && allow_v3) ? rpw3 : rpw;
-        Plan p = make_plan(rows, width, r, 0);
         auto shape = [&](Plan& q, int rr) {
             if (!v2) return;
-            q.V = allow_v3 ? 3 : 2;                    // a warp = one row x 64 nodes
+            q.V = 2;                                   // a warp = one row x 64 nodes
             q.tiles = (width + kBlk - 1) / kBlk;
-            q.rows_per_cta = (allow_v3 ? kWarps3 : kWarps) * std::max(rr, 1);
+            q.rows_per_cta = kWarps * std::max(rr, 1);
             q.chunks = std::max(1, (rows + q.rows_per_cta - 1) / q.rows_per_cta);
         };
         shape(p, r);
@@ -777,8 +765,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     };
     Plan pc = step_plan(P.n, W), pr = step_plan(P.m, W);
     auto finish_step_plans = [&]() -> int {
-        plan_chunks(pc, h->hptrAT, P.n, h->h_chunkC, kMetaPrimal);
-        plan_chunks(pr, h->hptrA, P.m, h->h_chunkR, kMetaDual);
+        plan_chunks(pc, h->hptrAT, P.n, h->h_chunkC);
+        plan_chunks(pr, h->hptrA, P.m, h->h_chunkR);
         CK(upload(h->chunkC, h->h_chunkC, st));
         CK(upload(h->chunkR, h->h_chunkR, st));
         pc.chunk_ptr = h->chunkC.as<int32_t>();
@@ -835,14 +823,31 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         key.S = S;
         key.D = D;
         key.K = K;
-        key.rpw = rpw | (allow_v2 ? 1 << 16 : 0) | (coop ? 1 << 17 : 0) | (allow_v3 ? 1 << 18 : 0) | (rpw3 << 20);
+        key.rpw = rpw | (allow_v2 ? 1 << 16 : 0) | (coop ? 1 << 17 : 0) | (graph_lanes << 20);
         if (h->graph_valid && memcmp(&key, &h->gkey, sizeof key) == 0) return BLP_OK;
         h->drop_graphs();
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaSuccess;
         if (!coop) {
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, st);
+            const int lanes = pc.V == 2 ? std::max(1, std::min({graph_lanes, pc.tiles, (int)blp_handle_s::kLanes})) : 1;
+            if (lanes == 1) {
+                for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, st);
+            } else {
+                // branch b owns the node tiles [b*T/lanes, (b+1)*T/lanes): its 2K launches depend
+                // only on each other, the branches meet again at the end of the period
+                CK(cudaEventRecord(h->ev_fork, st));
+                for (int b = 0; b < lanes; ++b) {
+                    cudaStream_t sb = b == 0 ? st : h->side[b - 1];
+                    if (b) CK(cudaStreamWaitEvent(sb, h->ev_fork, 0));
+                    const int t0 = (int)((long)pc.tiles * b / lanes), t1 = (int)((long)pc.tiles * (b + 1) / lanes);
+                    for (int it = 0; it < K; ++it) launch_steps(P, S, pc, pr, it, it == K - 1, sb, 2, t0, t1 - t0);
+                    if (b) {
+                        CK(cudaEventRecord(h->ev_join[b - 1], sb));
+                        CK(cudaStreamWaitEvent(st, h->ev_join[b - 1], 0));
+                    }
+                }
+            }
             CK(cudaStreamEndCapture(st, &g));
             e = cudaGraphInstantiate(&h->g_steps, g, 0);
             cudaGraphDestroy(g);
@@ -1215,6 +1220,9 @@ int blp_destroy(blp_handle h) {
                       &h->s_ws, &h->s_node, &h->s_int, &h->s_delta, &h->s_par};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_join) if (e) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (cudaStream_t s : h->side) if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     if (h->h_counters) cudaFreeHost(h->h_counters);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -153,7 +153,7 @@ __device__ __forceinline__ Slab stage_slab(const int32_t* __restrict__ ptr,
     int* sp = reinterpret_cast<int*>(smem_base);
     int4* se = smem_base + (rows_per_cta + 4) / 4;
     const int nrows = r1 - r0;
-    for (int t = threadIdx.x; t <= nrows; t += blockDim.x) sp[t] = __ldg(ptr + r0 + t);
+    for (int t = threadIdx.x; t <= nrows; t += kCtaThreads) sp[t] = __ldg(ptr + r0 + t);
     __syncthreads();
     Slab s;
     s.sp = sp;
@@ -162,7 +162,7 @@ __device__ __forceinline__ Slab stage_slab(const int32_t* __restrict__ ptr,
     const int cnt = sp[nrows] - s.base;
     if (cnt <= cap) {
         const int4* __restrict__ src = reinterpret_cast<const int4*>(ent) + s.base;
-        for (int t = threadIdx.x; t < cnt; t += blockDim.x) se[t] = __ldg(src + t);
+        for (int t = threadIdx.x; t < cnt; t += kCtaThreads) se[t] = __ldg(src + t);
         __syncthreads();
         s.se = se;
     }
@@ -424,10 +424,10 @@ constexpr int kLongRow = 96;
 
 __device__ __forceinline__ void coop_dot2(const Slab& sl, const Ent* __restrict__ ent,
                                           const double* __restrict__ Vn, const int warp, const int lane,
-                                          const int nw, double& g0, double& g1) {
+                                          double& g0, double& g1) {
     __shared__ double2 red[kWarps][32];
     const int p0 = sl.sp[0], p1 = sl.sp[1];
-    const int seg = ((p1 - p0 + nw - 1) / nw + BLP_U - 1) / BLP_U * BLP_U;
+    const int seg = ((p1 - p0 + kWarps - 1) / kWarps + BLP_U - 1) / BLP_U * BLP_U;
     const int a = min(p1, p0 + warp * seg), b = min(p1, a + seg);
     double s0 = 0.0, s1 = 0.0;
     if (sl.se) dot2_entries<true>(sl.se - sl.base, a, b, Vn, s0, s1);
@@ -436,48 +436,36 @@ __device__ __forceinline__ void coop_dot2(const Slab& sl, const Ent* __restrict_
     __syncthreads();
     g0 = 0.0;
     g1 = 0.0;
-    for (int w = 0; w < nw; ++w) {
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
         g0 += red[w][lane].x;
         g1 += red[w][lane].y;
     }
 }
 
-// per-lane constants of a step-kernel launch: the lane's two nodes, their Halpern weights and steps
-struct Lane2 {
-    int node;
-    bool k0, k1;
-    double w0, w1, s0, s1;        // s = tau (primal launch) or sigma (dual launch)
-};
-
-template <bool PRIMAL>
-__device__ __forceinline__ bool lane2_setup(const DevProb& P, const DevState& S, const int it,
-                                            const int lane, Lane2& L) {
-    L.node = blockIdx.y * kBlk + lane * 2;                     // this lane: nodes node, node + 1
-    L.k0 = L.node < S.B && S.fin[L.node] == 0;
-    L.k1 = L.node + 1 < S.B && S.fin[L.node + 1] == 0;
-    if (__ballot_sync(0xffffffffu, L.k0 || L.k1) == 0) return false;     // whole block retired
-    L.w0 = L.w1 = L.s0 = L.s1 = 0.0;
-    if (L.k0) {
-        const int s = S.sbase[L.node] + it;
-        L.w0 = PRIMAL ? (double)s / (double)(s + 1) : (double)(s + 1) / (double)(s + 2);
-        L.s0 = PRIMAL ? P.eta / S.omega[L.node] : P.eta * S.omega[L.node];
-    }
-    if (L.k1) {
-        const int s = S.sbase[L.node + 1] + it;
-        L.w1 = PRIMAL ? (double)s / (double)(s + 1) : (double)(s + 1) / (double)(s + 2);
-        L.s1 = PRIMAL ? P.eta / S.omega[L.node + 1] : P.eta * S.omega[L.node + 1];
-    }
-    return true;
-}
-
-// rows r0 .. r1 of the primal step with register-staged gathers (slab already in shared memory)
 template <bool MAJOR>
-__device__ __forceinline__ void primal2_rows(const DevProb& P, const DevState& S, const Slab& sl,
-                                             const int r0, const int r1, const Lane2& L,
-                                             const int lane, const int warp, const int nw = kWarps) {
-    const int node = L.node;
-    const bool k0 = L.k0, k1 = L.k1;
-    const double w0 = L.w0, w1 = L.w1, tau0 = L.s0, tau1 = L.s1;
+__global__ void __launch_bounds__(kCtaThreads, BLP_MINB2)
+k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
+          const int* __restrict__ chunk_ptr, const int tile0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = (tile0 + blockIdx.y) * kBlk + lane * 2;   // this lane: nodes node, node + 1
+    const bool k0 = node < S.B && S.fin[node] == 0;
+    const bool k1 = node + 1 < S.B && S.fin[node + 1] == 0;
+    if (__ballot_sync(0xffffffffu, k0 || k1) == 0) return;     // whole block retired
+    double w0 = 0, w1 = 0, tau0 = 0, tau1 = 0;
+    if (k0) {
+        const int s = S.sbase[node] + it;
+        w0 = (double)s / (double)(s + 1);
+        tau0 = P.eta / S.omega[node];
+    }
+    if (k1) {
+        const int s = S.sbase[node + 1] + it;
+        w1 = (double)s / (double)(s + 1);
+        tau1 = P.eta / S.omega[node + 1];
+    }
+    const int r0 = __ldg(chunk_ptr + blockIdx.x);
+    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
+    const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.n);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
     const size_t fblk = (size_t)(node >> 5) * P.n;
@@ -485,10 +473,10 @@ __device__ __forceinline__ void primal2_rows(const DevProb& P, const DevState& S
     const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
     double cg0 = 0.0, cg1 = 0.0;
     if (coop) {
-        coop_dot2(sl, P.cent, yn, warp, lane, nw, cg0, cg1);
+        coop_dot2(sl, P.cent, yn, warp, lane, cg0, cg1);
         if (warp != 0) return;
     }
-    for (int j = r0 + warp; j < r1; j += nw) {
+    for (int j = r0 + warp; j < r1; j += kWarps) {
         const size_t e = base + (size_t)j * kBlk;
         const double2 xb = ld2(S.xbar + e);
         const double2 a = ldcs2(S.xa + e);
@@ -517,33 +505,36 @@ __device__ __forceinline__ void primal2_rows(const DevProb& P, const DevState& S
 
 template <bool MAJOR>
 __global__ void __launch_bounds__(kCtaThreads, BLP_MINB2)
-k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-          const int* __restrict__ chunk_ptr) {
+k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
+        const int* __restrict__ chunk_ptr, const int tile0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Lane2 L;
-    if (!lane2_setup<true>(P, S, it, lane, L)) return;
+    const int node = (tile0 + blockIdx.y) * kBlk + lane * 2;
+    const bool k0 = node < S.B && S.fin[node] == 0;
+    const bool k1 = node + 1 < S.B && S.fin[node + 1] == 0;
+    if (__ballot_sync(0xffffffffu, k0 || k1) == 0) return;
+    double w0 = 0, w1 = 0, sig0 = 0, sig1 = 0;
+    if (k0) {
+        const int s = S.sbase[node] + it;
+        w0 = (double)(s + 1) / (double)(s + 2);
+        sig0 = P.eta * S.omega[node];
+    }
+    if (k1) {
+        const int s = S.sbase[node + 1] + it;
+        w1 = (double)(s + 1) / (double)(s + 2);
+        sig1 = P.eta * S.omega[node + 1];
+    }
     const int r0 = __ldg(chunk_ptr + blockIdx.x);
     const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
-    const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
-    primal2_rows<MAJOR>(P, S, sl, r0, r1, L, lane, warp);
-}
-
-template <bool MAJOR>
-__device__ __forceinline__ void dual2_rows(const DevProb& P, const DevState& S, const Slab& sl,
-                                           const int r0, const int r1, const Lane2& L,
-                                           const int lane, const int warp, const int nw = kWarps) {
-    const int node = L.node;
-    const bool k0 = L.k0, k1 = L.k1;
-    const double w0 = L.w0, w1 = L.w1, sig0 = L.s0, sig1 = L.s1;
+    const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.m);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
     const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
     double cg0 = 0.0, cg1 = 0.0;
     if (coop) {
-        coop_dot2(sl, P.ent, xn, warp, lane, nw, cg0, cg1);
+        coop_dot2(sl, P.ent, xn, warp, lane, cg0, cg1);
         if (warp != 0) return;
     }
-    for (int i = r0 + warp; i < r1; i += nw) {
+    for (int i = r0 + warp; i < r1; i += kWarps) {
         const size_t e = base + (size_t)i * kBlk;
         const double2 yc = ld2(S.y + e);
         const double2 a = ldcs2(S.ya + e);
@@ -565,258 +556,6 @@ __device__ __forceinline__ void dual2_rows(const DevProb& P, const DevState& S, 
             st2(S.DY + e, make_double2(yp0 - yc.x, yp1 - yc.y), k0, k1);
         }
     }
-}
-
-template <bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads, BLP_MINB2)
-k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-        const int* __restrict__ chunk_ptr) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Lane2 L;
-    if (!lane2_setup<false>(P, S, it, lane, L)) return;
-    const int r0 = __ldg(chunk_ptr + blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
-    const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
-    dual2_rows<MAJOR>(P, S, sl, r0, r1, L, lane, warp);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Pipelined two-nodes-per-lane step kernels (k_primal3 / k_dual3). ncu of k_primal2 / k_dual2
-// shows no saturated unit (DRAM 45 %, L2 35 %, issue 30-47 %) and warps stalled on the long
-// scoreboard 75 % of the time: with the gathered values staged in registers a warp has one row in
-// flight and pays 2-3 dependent memory round trips per row, and 64 registers per thread cap the
-// SM at 32 warps. Here every warp owns a ring of kRing 512-byte slots in shared memory and runs
-// ahead of its arithmetic with cp.async (LDGSTS, 16 bytes per lane, no register staging): a matrix
-// row occupies the slots [own vector, anchor, gathered rows of the other vector ...] and is one
-// commit group; a warp issues rows as long as they fit into the free part of its ring (up to
-// kRing slots = 16 KB in flight per warp whatever the row lengths are) and consumes them in order.
-// A lane only ever reads back the 16 bytes it copied itself, so the ring needs no barrier.
-// Arithmetic and summation order are those of k_primal2 / k_dual2: results are bit-identical.
-#ifndef BLP_RING_P
-#define BLP_RING_P 16        // 512-byte slots per warp, primal launch (power of two)
-#endif
-#ifndef BLP_RING_D
-#define BLP_RING_D 32        // dual launch
-#endif
-#ifndef BLP_CPASYNC
-#define BLP_CPASYNC "ca"     // ca: through L1 (lanes of one sector coalesce); cg: L1 bypass
-#endif
-constexpr int kRingP = BLP_RING_P, kRingD = BLP_RING_D;
-static_assert((kRingP & (kRingP - 1)) == 0 && kRingP >= 8 && (kRingD & (kRingD - 1)) == 0 && kRingD >= 8,
-              "ring sizes must be powers of two");
-constexpr int kCta3 = 128, kWarps3 = kCta3 / 32;           // CTA of the ring kernels
-constexpr int ring_bytes(const int ring) { return kWarps3 * ring * 512; }   // per CTA
-constexpr int kRingRows = 8;                               // rows (= commit groups) in flight per warp, at most
-constexpr int kMetaPrimal = 48, kMetaDual = 8;             // staged bytes per row besides the CSR slab
-
-__device__ __forceinline__ void cp_async16(const unsigned smem_dst, const void* gsrc) {
-    asm volatile("cp.async." BLP_CPASYNC ".shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-// wait until at most n (0..kRingRows-1) of this thread's most recent commit groups are pending
-__device__ __forceinline__ void cp_async_wait_dyn(const int n) {
-    switch (n) {
-        case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
-        case 6: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 7;\n" ::: "memory"); break;
-    }
-}
-
-// The shared pipeline of a warp over its rows first, first + kWarps3, ... < r1. One commit group
-// per row: [own vector, anchor, gathered rows ...]; rows are issued while they fit into the free
-// part of the ring, consumed in order. A row that cannot fit the ring at all (more than kRing - 2
-// entries) is never issued: when its turn comes the pipeline is empty and slow(row) handles it.
-// fin(row, own, anchor, g0, g1) finishes a row.
-template <int kRing, class Fin, class Slow>
-__device__ __forceinline__ void ring_rows(const Slab& sl, const int r0, const int r1, const int warp,
-                                          const int lane, const unsigned ring_s, const double2* __restrict__ ring,
-                                          const double* __restrict__ own, const double* __restrict__ anchor,
-                                          const double* __restrict__ other, Fin fin, Slow slow) {
-    const int4* __restrict__ E = sl.se - sl.base;
-    const unsigned lane_s = ring_s + lane * 16;
-    int prow = r0 + warp, crow = prow;
-    unsigned head = 0, tail = 0;                  // slot counters (monotonic; ring position = counter & (kRing-1))
-    int inflight = 0;
-    while (crow < r1) {
-        // producer: run ahead as far as the ring allows
-        while (prow < r1 && inflight < kRingRows) {
-            const int p0 = sl.sp[prow - r0], p1 = sl.sp[prow - r0 + 1];
-            const int need = p1 - p0 + 2;
-            if (need > kRing) {
-                if (inflight) break;              // drain first; then the consumer takes the slow path
-                break;
-            }
-            if ((int)(head - tail) + need > kRing) break;
-            cp_async16(lane_s + ((head & (kRing - 1)) << 9), own + (size_t)prow * kBlk);
-            cp_async16(lane_s + (((head + 1) & (kRing - 1)) << 9), anchor + (size_t)prow * kBlk);
-            head += 2;
-            for (int p = p0; p < p1; ++p) {
-                cp_async16(lane_s + ((head & (kRing - 1)) << 9), other + (size_t)E[p].x * kBlk);
-                ++head;
-            }
-            cp_async_commit();
-            ++inflight;
-            prow += kWarps3;
-        }
-        if (inflight == 0) {                      // crow is a row too long for the ring
-            slow(crow);
-            crow += kWarps3;
-            prow = crow;
-            continue;
-        }
-        cp_async_wait_dyn(inflight - 1);          // the oldest row has landed
-        const int p0 = sl.sp[crow - r0], p1 = sl.sp[crow - r0 + 1];
-        const double2 a = ring[(tail & (kRing - 1)) * 32];
-        const double2 b = ring[((tail + 1) & (kRing - 1)) * 32];
-        tail += 2;
-        double g0 = 0.0, g1 = 0.0;
-        for (int p = p0; p < p1; ++p) {
-            const double2 v = ring[(tail & (kRing - 1)) * 32];
-            ++tail;
-            const int2 c = *reinterpret_cast<const int2*>(&E[p].z);
-            const double cf = __hiloint2double(c.y, c.x);
-            g0 = fma(cf, v.x, g0);
-            g1 = fma(cf, v.y, g1);
-        }
-        fin(crow, a, b, g0, g1);
-        --inflight;
-        crow += kWarps3;
-    }
-}
-
-template <bool MAJOR>
-__global__ void __launch_bounds__(kCta3, 4)
-k_primal3(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-          const int* __restrict__ chunk_ptr) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Lane2 L;
-    if (!lane2_setup<true>(P, S, it, lane, L)) return;
-    const int r0 = __ldg(chunk_ptr + blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
-    // shared memory: [row pointers | entries (cap) | c, lref x2, uref x2, lumask x2 per row | rings]
-    int4* const meta = dyn_smem + (rows_per_cta + 4) / 4 + cap;
-    double* const sC = reinterpret_cast<double*>(meta);
-    double* const sLref = sC + rows_per_cta;                   // [2][rows_per_cta]: the tile's two 32-node blocks
-    double* const sUref = sLref + 2 * rows_per_cta;
-    uint32_t* const sMask = reinterpret_cast<uint32_t*>(sUref + 2 * rows_per_cta);
-    double2* const ring = reinterpret_cast<double2*>(reinterpret_cast<char*>(meta) + (size_t)kMetaPrimal * rows_per_cta) +
-                          warp * kRingP * 32;
-    const int nrows = r1 - r0;
-    const size_t fb0 = (size_t)(blockIdx.y * 2) * P.n + r0;
-    for (int t = threadIdx.x; t < nrows; t += kCta3) {
-        sC[t] = __ldg(P.c + r0 + t);
-        sLref[t] = __ldg(S.lref + fb0 + t);
-        sUref[t] = __ldg(S.uref + fb0 + t);
-        sMask[t] = __ldg(S.lumask + fb0 + t);
-    }
-    if (blockIdx.y * kBlk + 32 < S.ld) {                       // second block of the tile exists
-        const size_t fb1 = fb0 + P.n;
-        for (int t = threadIdx.x; t < nrows; t += kCta3) {
-            sLref[rows_per_cta + t] = __ldg(S.lref + fb1 + t);
-            sUref[rows_per_cta + t] = __ldg(S.uref + fb1 + t);
-            sMask[rows_per_cta + t] = __ldg(S.lumask + fb1 + t);
-        }
-    }
-    const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);   // barriers inside cover the meta too
-    if (sl.se == nullptr || (nrows == 1 && sl.sp[1] - sl.sp[0] > kLongRow)) {
-        primal2_rows<MAJOR>(P, S, sl, r0, r1, L, lane, warp, kWarps3);  // slab too large / long row: register path
-        return;
-    }
-    const int node = L.node;
-    const bool k0 = L.k0, k1 = L.k1;
-    const double w0 = L.w0, w1 = L.w1, tau0 = L.s0, tau1 = L.s1;
-    const size_t base = tix(0, node, P.n);
-    const int half = (lane >> 4) * rows_per_cta;               // this lane's 32-node block
-    const unsigned bit = node & 31;
-    const double* __restrict__ yn = S.y + tix(0, node, P.m);
-    auto fin = [&](const int j, const double2 xb, const double2 a, const double g0, const double g1) {
-                  const int t = j - r0;
-                  const size_t e = base + (size_t)j * kBlk;
-                  const uint32_t mk = (sMask[half + t] >> bit) & 3u;
-                  double lo0 = sLref[half + t], hi0 = sUref[half + t];
-                  double lo1 = lo0, hi1 = hi0;
-                  if (mk) {                                    // a node of this lane deviates
-                      const double2 l2 = ldcs2(S.l + e), u2 = ldcs2(S.u + e);
-                      if (mk & 1u) { lo0 = l2.x; hi0 = u2.x; }
-                      if (mk & 2u) { lo1 = l2.y; hi1 = u2.y; }
-                  }
-                  const double cj = sC[t];
-                  const double xc0 = fma(w0, xb.x - a.x, a.x), xc1 = fma(w1, xb.y - a.y, a.y);
-                  const double xp0 = fmin(fmax(xc0 - tau0 * (cj - g0), lo0), hi0);
-                  const double xp1 = fmin(fmax(xc1 - tau1 * (cj - g1), lo1), hi1);
-                  st2(S.xbar + e, make_double2(2.0 * xp0 - xc0, 2.0 * xp1 - xc1), k0, k1);
-                  if constexpr (MAJOR) {
-                      st2(S.X1 + e, make_double2(xp0, xp1), k0, k1);
-                      st2(S.DX + e, make_double2(xp0 - xc0, xp1 - xc1), k0, k1);
-                      st2(S.G + e, make_double2(g0, g1), k0, k1);
-                  }
-              };
-    ring_rows<kRingP>(sl, r0, r1, warp, lane, (unsigned)__cvta_generic_to_shared(ring), ring + lane, S.xbar + base,
-              S.xa + base, yn, fin, [&](const int j) {         // a row longer than the ring: register path
-                  const size_t e = base + (size_t)j * kBlk;
-                  const double2 xb = ld2(S.xbar + e), a = ldcs2(S.xa + e);
-                  double g0 = 0.0, g1 = 0.0;
-                  slab_dot2(sl, P.cent, j - r0, yn, g0, g1);
-                  fin(j, xb, a, g0, g1);
-              });
-}
-
-template <bool MAJOR>
-__global__ void __launch_bounds__(kCta3, 3)
-k_dual3(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-        const int* __restrict__ chunk_ptr) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Lane2 L;
-    if (!lane2_setup<false>(P, S, it, lane, L)) return;
-    const int r0 = __ldg(chunk_ptr + blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
-    int4* const meta = dyn_smem + (rows_per_cta + 4) / 4 + cap;
-    double* const sB = reinterpret_cast<double*>(meta);
-    double2* const ring = reinterpret_cast<double2*>(reinterpret_cast<char*>(meta) + (size_t)kMetaDual * rows_per_cta) +
-                          warp * kRingD * 32;
-    const int nrows = r1 - r0;
-    for (int t = threadIdx.x; t < nrows; t += kCta3) sB[t] = __ldg(P.b + r0 + t);
-    const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
-    if (sl.se == nullptr || (nrows == 1 && sl.sp[1] - sl.sp[0] > kLongRow)) {
-        dual2_rows<MAJOR>(P, S, sl, r0, r1, L, lane, warp, kWarps3);
-        return;
-    }
-    const int node = L.node;
-    const bool k0 = L.k0, k1 = L.k1;
-    const double w0 = L.w0, w1 = L.w1, sig0 = L.s0, sig1 = L.s1;
-    const size_t base = tix(0, node, P.m);
-    const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
-    auto fin = [&](const int i, const double2 yc, const double2 a, const double ax0, const double ax1) {
-                  const size_t e = base + (size_t)i * kBlk;
-                  bool on0 = true, on1 = true;
-                  if (i >= P.m_base && S.rowmask) {
-                      const uint8_t* mrow = S.rowmask + (size_t)(i - P.m_base) * S.ld + node;
-                      on0 = mrow[0] != 0;
-                      on1 = mrow[1] != 0;
-                  }
-                  const double bi = sB[i - r0];
-                  const double yp0 = on0 ? fmax(0.0, yc.x + sig0 * (bi - ax0)) : 0.0;
-                  const double yp1 = on1 ? fmax(0.0, yc.y + sig1 * (bi - ax1)) : 0.0;
-                  st2(S.y + e, make_double2(fma(w0, (2.0 * yp0 - yc.x) - a.x, a.x),
-                                            fma(w1, (2.0 * yp1 - yc.y) - a.y, a.y)), k0, k1);
-                  if constexpr (MAJOR) {
-                      st2(S.Y1 + e, make_double2(yp0, yp1), k0, k1);
-                      st2(S.DY + e, make_double2(yp0 - yc.x, yp1 - yc.y), k0, k1);
-                  }
-              };
-    ring_rows<kRingD>(sl, r0, r1, warp, lane, (unsigned)__cvta_generic_to_shared(ring), ring + lane, S.y + base,
-              S.ya + base, xn, fin, [&](const int i) {
-                  const size_t e = base + (size_t)i * kBlk;
-                  const double2 yc = ld2(S.y + e), a = ldcs2(S.ya + e);
-                  double ax0 = 0.0, ax1 = 0.0;
-                  slab_dot2(sl, P.ent, i - r0, xn, ax0, ax1);
-                  fin(i, yc, a, ax0, ax1);
-              });
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,6 +1,5 @@
-"""Ring-pipelined step kernels (k_primal3/k_dual3) vs the register-staged ones (k_primal2/k_dual2)
-at the C5 shape: per-launch time (profile mode, CUDA events around every launch), per-iteration
-time inside the period graph, and bit-equality of the results after a fixed number of iterations."""
+"""Parallel graph branches over node-tile groups (BLP_GRAPH_LANES): time per PDHG iteration inside
+the period graph at the C5 shape for a few batch widths, and bit-equality of the results."""
 import os, sys, hashlib
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +11,7 @@ from simple_mip_solver_b200.instances import frontier_nodes
 d, depth, root = bench.load_instance('c5')
 n, m = d.n, d.m
 dev = torch.device('cuda', 0)
-widths = [int(a) for a in sys.argv[1:]] or [512, 4096]
+widths = [int(a) for a in sys.argv[1:]] or [128, 512, 1024]
 lp = engine.BatchLP(d.A, d.b, d.c)
 pbn, dbn = 8 * (3 * n + m), 8 * (n + 2 * m)
 for B in widths:
@@ -26,20 +25,15 @@ for B in widths:
     x0 = torch.from_numpy(root['x']).to(dev)[:, None].expand(n, ld).contiguous()
     y0 = torch.from_numpy(root['y']).to(dev)[:, None].expand(m, ld).contiguous()
     ref = None
-    for env in ({'BLP_V3': '0'}, {'BLP_V3': '1', 'BLP_ROWS_PER_WARP3': '8'}, {'BLP_V3': '1', 'BLP_ROWS_PER_WARP3': '16'},
-                {'BLP_V3': '1', 'BLP_ROWS_PER_WARP3': '32'}):
-        os.environ.update(env)
-        op = engine.default_opts(max_iters=256, eval_every=64, profile=1)
+    for lanes in os.environ.get('SWEEP_LANES', '1,2,3,4').split(','):
+        os.environ['BLP_GRAPH_LANES'] = lanes
         og = engine.default_opts(max_iters=1024, eval_every=64)
-        lp.solve_batch_device(lb, ub, x0=x0, y0=y0, opts=op, want_x=False, want_y=False)
-        s = lp.solve_batch_device(lb, ub, x0=x0, y0=y0, opts=op, want_x=False, want_y=False)['stats']
+        lp.solve_batch_device(lb, ub, x0=x0, y0=y0, opts=og, want_x=False, want_y=False)
         r = lp.solve_batch_device(lb, ub, x0=x0, y0=y0, opts=og, want_x=True, want_y=False)
         g = r['stats']
-        pm, dm = s['primal_kernel_ms'] / s['iterations'], s['dual_kernel_ms'] / s['iterations']
         sig = hashlib.sha1(r['lower'][:B].cpu().numpy().tobytes() + r['x'][:, :B].cpu().numpy().tobytes()).hexdigest()[:12]
-        if ref is None:
-            ref = sig
+        ref = ref or sig
         it_us = 1e3 * g['step_kernel_ms'] / g['iterations']
-        print(f'B {B} {env}: primal {pm*1e3:.1f} us ({pbn*B/pm/1e6:.0f} GB/s)  dual {dm*1e3:.1f} us ({dbn*B/dm/1e6:.0f} GB/s)  '
-              f'graph {it_us:.1f} us/iter ({(pbn+dbn)*B/it_us/1e3:.0f} GB/s)  result {sig} {"same" if sig == ref else "DIFFERENT"}', flush=True)
+        print(f'B {B} lanes {lanes}: graph {it_us:.1f} us/iter ({(pbn+dbn)*B/it_us/1e3:.0f} GB/s)  result {sig} '
+              f'{"same" if sig == ref else "DIFFERENT"}', flush=True)
 lp.close()

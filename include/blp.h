@@ -194,6 +194,32 @@ const char* blp_last_error(void);
 /* library / build identification, e.g. "blp 0.1 sm_100a" */
 const char* blp_version(void);
 
+/*
+ * MPS reader (host only, no GPU needed). Replaces: MILPInstance(file_name=...) of the reference's
+ * tests (test_simple_mip_solver/helpers.py:42, example_models.py:43-48), which reads the model through
+ * CLP's MPS reader. Dialect: what CLP writes — free whitespace-separated fields, sections NAME / ROWS /
+ * COLUMNS / RHS / BOUNDS / ENDATA, integer columns flagged by UI / LI / BV bounds or MARKER lines,
+ * optional set names; RANGES are ignored; empty rows and columns are kept.
+ * The model is returned as written: rows with their sense 'L' / 'G' / 'E' and right-hand side (the caller
+ * brings it into the solver's ">=" form as base_algorithm.py:53-59 does), objective c with offset,
+ * bounds l, u (IEEE +-inf for missing ones), ascending integer column ids.
+ *   blp_mps_read   parse `path`; on error returns BLP_ERR_ARG and blp_mps_last_error() has the text
+ *   blp_mps_dims   row / column / nonzero / integer-column counts
+ *   blp_mps_copy   fill caller arrays: CSR rowptr[m+1], colidx[nnz], val[nnz] (columns ascending within
+ *                  a row, duplicates summed), rhs[m], sense[m], c[n], *obj_offset, l[n], u[n],
+ *                  int_idx[n_int]; any pointer may be NULL
+ */
+typedef struct blp_mps_s* blp_mps;
+int blp_mps_read(const char* path, blp_mps* out);
+int blp_mps_dims(blp_mps mps, int32_t* m, int32_t* n, int64_t* nnz, int32_t* n_int);
+int blp_mps_copy(blp_mps mps, int32_t* rowptr, int32_t* colidx, double* val, double* rhs, char* sense,
+                 double* c, double* obj_offset, double* l, double* u, int32_t* int_idx);
+const char* blp_mps_name(blp_mps mps);
+const char* blp_mps_row_name(blp_mps mps, int32_t i);
+const char* blp_mps_col_name(blp_mps mps, int32_t j);
+int blp_mps_free(blp_mps mps);
+const char* blp_mps_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

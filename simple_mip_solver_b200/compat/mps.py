@@ -1,21 +1,20 @@
-"""Small MPS reader for the reference's fixtures.
+"""MPS input: thin binding of the native reader in libblp.so (``blp_mps_*``, include/blp.h).
 
 The reference loads its random test models with ``MILPInstance(file_name=...)``
-(test_simple_mip_solver/helpers.py:42), which goes through CLP's MPS reader. The fixtures under
-``scale_1_models`` / ``example_models`` are CLP-written: whitespace separated fields, sections
-ROWS / COLUMNS / RHS / BOUNDS / ENDATA, integer columns flagged by ``UI`` bounds (or MARKER
-lines). This reader accepts that dialect (plus RANGES-free general MPS) and returns raw arrays;
-it tolerates empty rows and empty columns, which several fixtures contain.
+(test_simple_mip_solver/helpers.py:42), which goes through CLP's MPS reader; the fixtures under
+``scale_1_models`` / ``example_models`` are CLP-written. The parsing is done in C++
+(csrc/blp_mps.cpp); this module only wraps the arrays. A pure-Python
+restatement of the same dialect lives in ``oracle/mps_py.py`` and is used by the tests as the
+checker, never here.
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass, field
-from typing import Dict, List
+from typing import List
 
 import numpy as np
 import scipy.sparse as sp
-
-_INF = float('inf')
 
 
 @dataclass
@@ -34,114 +33,33 @@ class MpsModel:
 
 
 def read_mps(path: str) -> MpsModel:
-    mdl = MpsModel()
-    obj_row = None
-    row_idx: Dict[str, int] = {}
-    col_idx: Dict[str, int] = {}
-    entries = []                      # (row, col, value)
-    obj_coefs: Dict[int, float] = {}
-    rhs_vals: Dict[int, float] = {}
-    lower: Dict[int, float] = {}
-    upper: Dict[int, float] = {}
-    integer = set()
-    in_int_marker = False
-    section = None
-
-    def col_of(name):
-        j = col_idx.get(name)
-        if j is None:
-            j = len(mdl.col_names)
-            col_idx[name] = j
-            mdl.col_names.append(name)
-            if in_int_marker:
-                integer.add(j)
-        return j
-
-    with open(path) as fh:
-        for raw in fh:
-            if not raw.strip() or raw.lstrip().startswith('*'):
-                continue
-            tok = raw.split()
-            if not raw[0].isspace():                      # section header
-                section = tok[0].upper()
-                if section == 'NAME' and len(tok) > 1:
-                    mdl.name = tok[1]
-                if section == 'ENDATA':
-                    break
-                continue
-            if section == 'ROWS':
-                sense, name = tok[0].upper(), tok[1]
-                if sense == 'N':
-                    if obj_row is None:
-                        obj_row = name
-                else:
-                    row_idx[name] = len(mdl.row_names)
-                    mdl.row_names.append(name)
-                    mdl.row_senses.append(sense)
-            elif section == 'COLUMNS':
-                if len(tok) >= 3 and tok[1].upper() == "'MARKER'":
-                    in_int_marker = tok[2].upper() == "'INTORG'"
-                    continue
-                j = col_of(tok[0])
-                for k in range(1, len(tok) - 1, 2):
-                    rname, val = tok[k], float(tok[k + 1])
-                    if rname == obj_row:
-                        obj_coefs[j] = val
-                    elif rname in row_idx:
-                        entries.append((row_idx[rname], j, val))
-            elif section == 'RHS':
-                start = 1 if len(tok) % 2 == 1 else 0     # optional set name
-                for k in range(start, len(tok) - 1, 2):
-                    rname, val = tok[k], float(tok[k + 1])
-                    if rname == obj_row:
-                        mdl.obj_offset = -val
-                    elif rname in row_idx:
-                        rhs_vals[row_idx[rname]] = val
-            elif section == 'BOUNDS':
-                kind = tok[0].upper()
-                # "UI BOUND x_0 100." (set name present) or "UI x_0 100."
-                if kind in ('FR', 'MI', 'PL', 'BV'):
-                    cname = tok[2] if len(tok) >= 3 else tok[1]
-                    val = None
-                else:
-                    cname = tok[2] if len(tok) >= 4 else tok[1]
-                    val = float(tok[-1])
-                j = col_of(cname)
-                if kind == 'UP':
-                    upper[j] = val
-                    if val < 0 and j not in lower:
-                        lower[j] = -_INF
-                elif kind == 'UI':
-                    upper[j] = val
-                    integer.add(j)
-                elif kind == 'LO':
-                    lower[j] = val
-                elif kind == 'LI':
-                    lower[j] = val
-                    integer.add(j)
-                elif kind == 'FX':
-                    lower[j] = upper[j] = val
-                elif kind == 'FR':
-                    lower[j], upper[j] = -_INF, _INF
-                elif kind == 'MI':
-                    lower[j] = -_INF
-                elif kind == 'PL':
-                    upper[j] = _INF
-                elif kind == 'BV':
-                    lower[j], upper[j] = 0.0, 1.0
-                    integer.add(j)
-            # RANGES and anything else: not produced by the reference's writer; ignored.
-
-    n, m = len(mdl.col_names), len(mdl.row_names)
-    if entries:
-        r, cidx, v = zip(*entries)
-    else:
-        r, cidx, v = (), (), ()
-    mdl.A = sp.csr_matrix((np.asarray(v, dtype=float), (np.asarray(r, dtype=int),
-                                                        np.asarray(cidx, dtype=int))), shape=(m, n))
-    mdl.rhs = np.array([rhs_vals.get(i, 0.0) for i in range(m)])
-    mdl.c = np.array([obj_coefs.get(j, 0.0) for j in range(n)])
-    mdl.l = np.array([lower.get(j, 0.0) for j in range(n)])
-    mdl.u = np.array([upper.get(j, _INF) for j in range(n)])
-    mdl.integer_indices = sorted(integer)
+    """Parse an MPS file with the native reader. Raises ``BlpError`` if the file cannot be read
+    or libblp.so has not been built (there is no Python fallback)."""
+    from ..engine import BlpError, load_library
+    lib = load_library()
+    h = C.c_void_p()
+    if lib.blp_mps_read(str(path).encode(), C.byref(h)) != 0:
+        raise BlpError(lib.blp_mps_last_error().decode())
+    try:
+        m, n, n_int, nnz = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        lib.blp_mps_dims(h, C.byref(m), C.byref(n), C.byref(nnz), C.byref(n_int))
+        m, n, nnz, n_int = m.value, n.value, nnz.value, n_int.value
+        rowptr = np.zeros(m + 1, dtype=np.int32)
+        colidx = np.zeros(nnz, dtype=np.int32)
+        val = np.zeros(nnz)
+        rhs, sense = np.zeros(m), np.zeros(m, dtype='S1')
+        c, l, u = np.zeros(n), np.zeros(n), np.zeros(n)
+        ints = np.zeros(n_int, dtype=np.int32)
+        off = C.c_double(0.0)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        lib.blp_mps_copy(h, p(rowptr), p(colidx), p(val), p(rhs), p(sense), p(c),
+                         C.cast(C.byref(off), C.c_void_p), p(l), p(u), p(ints))
+        mdl = MpsModel(name=lib.blp_mps_name(h).decode(),
+                       row_names=[lib.blp_mps_row_name(h, i).decode() for i in range(m)],
+                       row_senses=[s.decode() for s in sense],
+                       col_names=[lib.blp_mps_col_name(h, j).decode() for j in range(n)],
+                       A=sp.csr_matrix((val, colidx, rowptr), shape=(m, n)), rhs=rhs, c=c,
+                       obj_offset=off.value, l=l, u=u, integer_indices=[int(j) for j in ints])
+    finally:
+        lib.blp_mps_free(h)
     return mdl

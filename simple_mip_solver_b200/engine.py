@@ -72,6 +72,15 @@ _SIGNATURES = {
     'blp_destroy': (C.c_int, [_P]),
     'blp_last_error': (C.c_char_p, []),
     'blp_version': (C.c_char_p, []),
+    'blp_mps_read': (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    'blp_mps_dims': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                               C.POINTER(C.c_int32)]),
+    'blp_mps_copy': (C.c_int, [_P] * 11),
+    'blp_mps_name': (C.c_char_p, [_P]),
+    'blp_mps_row_name': (C.c_char_p, [_P, C.c_int32]),
+    'blp_mps_col_name': (C.c_char_p, [_P, C.c_int32]),
+    'blp_mps_free': (C.c_int, [_P]),
+    'blp_mps_last_error': (C.c_char_p, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -174,12 +174,14 @@ class ClockSampler:
 
 
 def node_bytes(n, m):
-    """Algorithmic HBM bytes per node and iteration. SURVEY.md section 8d counts 8(6n+3m) with dense
-    per-node bounds; the kernels keep the bounds of a 32-node block as one reference value per row
-    plus a deviation mask (nodes differ from the root in a few entries), which is the variant
-    SURVEY 8d allows with formula 8(4n+3m): the primal launch reads xbar, xa and the gathered y and
-    writes xbar (3n+m); the dual launch reads y and the gathered xbar and writes y (n+2m)."""
-    return 8 * (3 * n + m), 8 * (n + 2 * m)
+    """Algorithmic HBM bytes per node and iteration, as the kernels' state representation requires
+    them. SURVEY.md section 8d counts 8(6n+3m) with dense per-node bounds and 8(4n+3m) with bounds
+    kept as deltas, which is what the kernels do (one reference bound per row and 32-node block plus
+    a deviation mask); since the Halpern anchors are stored in fp32 the count is
+      primal launch: xbar read + write (16n), anchor xa (4n), gathered y (8m)
+      dual launch:   y read + write (16m), anchor ya (4m), gathered xbar (8n)
+    = 28(n+m) per node and iteration (1.96 MB at C5; 8(4n+3m) would be 2.08 MB)."""
+    return 20 * n + 8 * m, 8 * n + 20 * m
 
 
 # ------------------------------------------------------------------------------------- main
@@ -464,7 +466,7 @@ def main():
                          'peak_source': peak_src, 'bytes_per_launch': pair_bytes,
                          'ms_per_launch': pair_s * 1e3,
                          'measured': 'CUDA events around every period graph (64 iterations) of the timed steps; '
-                                     'bytes = 8(4n+3m) per running node and iteration + both matrices (bounds kept as block reference + mask)',
+                                     'bytes = 28(n+m) per running node and iteration + both matrices (bounds kept as block reference + mask, fp32 anchors)',
                          'k_primal': {'achieved': prim_gbs, 'frac': prim_gbs / peak, 'bytes_per_launch': primal_bytes,
                                       'ms_per_launch': primal_s * 1e3},
                          'k_dual': {'achieved': dual_gbs, 'frac': dual_gbs / peak, 'bytes_per_launch': dual_bytes,

@@ -8,7 +8,9 @@ Problem (the canonical node LP of the reference, base_node.py:259-286):
 
     min c.x  s.t.  A x >= b (row-masked), l_k <= x <= u_k        for every node k of a batch
 
-Vectors are stored node-fastest, X[n, B], exactly as on the device.
+Vectors are stored node-fastest, X[n, B], exactly as on the device. One deliberate difference: the
+device rounds the Halpern anchors to fp32 at every restart (any fixed anchor is a valid Halpern
+anchor); this model keeps them in fp64.
 """
 from __future__ import annotations
 

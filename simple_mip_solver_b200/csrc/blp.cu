@@ -307,14 +307,14 @@ size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
     s.B = B;
     s.ld = ld;
     s.xbar = cv.take<double>(n * ld);
-    s.xa = cv.take<double>(n * ld);
+    s.xa = cv.take<anc_t>(n * ld);
     s.l = cv.take<double>(n * ld);
     s.u = cv.take<double>(n * ld);
     s.X1 = cv.take<double>(n * ld);
     s.DX = cv.take<double>(n * ld);
     s.G = cv.take<double>(n * ld);
     s.y = cv.take<double>(m * ld);
-    s.ya = cv.take<double>(m * ld);
+    s.ya = cv.take<anc_t>(m * ld);
     s.Y1 = cv.take<double>(m * ld);
     s.DY = cv.take<double>(m * ld);
     s.omega = cv.take<double>(ld);

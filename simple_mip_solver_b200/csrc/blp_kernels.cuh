@@ -27,6 +27,21 @@ namespace blp {
 #ifndef BLP_MINB
 #define BLP_MINB 6       // resident CTAs per SM the step kernels are compiled for
 #endif
+// Halpern anchors xa, ya are stored in fp32 (BLP_ANCHOR32=1). Any fixed point a is a valid Halpern
+// anchor (z+ = w R(z) + (1-w) a converges to a fixed point of R for every a); a restart therefore
+// sets the anchor to the fp32 rounding of the restart point and keeps the current point in fp64.
+// The iterates stay within |a - z0| / (k+1) of the sequence anchored at z0 itself. Saves 4 of the
+// 8 anchor bytes read per state element and iteration.
+#ifndef BLP_ANCHOR32
+#define BLP_ANCHOR32 1
+#endif
+#if BLP_ANCHOR32
+using anc_t = float;
+using anc2_t = float2;
+#else
+using anc_t = double;
+using anc2_t = double2;
+#endif
 constexpr int kCtaThreads = 256;
 constexpr int kBlk = 64;      // nodes per layout block (row stride of a lane's column, in doubles)
 constexpr int kWarps = kCtaThreads / 32;
@@ -57,8 +72,9 @@ struct DevProb {
 
 struct DevState {
     int B, ld;
-    double *xbar, *xa, *l, *u, *X1, *DX, *G;       // [n][ld]
-    double *y, *ya, *Y1, *DY;                      // [m][ld]
+    double *xbar, *l, *u, *X1, *DX, *G;            // [n][ld]
+    double *y, *Y1, *DY;                           // [m][ld]
+    anc_t *xa, *ya;                                // [n][ld], [m][ld] Halpern anchors
     uint8_t* rowmask;                              // [m - m_base][ld] (workspace copy) or null
     double *omega, *fpe0, *fpe_prev, *pobj, *dobj; // [ld]
     int32_t *sbase, *fin, *status, *iters, *restart;   // [ld]
@@ -241,7 +257,7 @@ __device__ __forceinline__ void primal_chunk(const DevProb& P, const DevState& S
         double xb = 0, a = 0, lo = 0, hi = 0;
         if (row_ok && node_ok) {       // streaming loads first, the gathers follow at once
             xb = S.xbar[e];
-            a = __ldcs(S.xa + e);
+            a = (double)__ldcs(S.xa + e);
             const size_t fi = (size_t)(node >> 5) * P.n + j;
             const uint32_t mk = __ldg(S.lumask + fi);
             if ((mk >> (node & 31)) & 1u) {
@@ -303,7 +319,7 @@ __device__ __forceinline__ void dual_chunk(const DevProb& P, const DevState& S, 
         bool on = true;
         if (row_ok && node_ok) {
             yc = S.y[e];
-            a = __ldcs(S.ya + e);
+            a = (double)__ldcs(S.ya + e);
             if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
         }
         const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, xn, kBlk, node_ok && row_ok);
@@ -378,6 +394,10 @@ k_period_coop(const DevProb P, const DevState S, const int K, const CoopPlan C) 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ double2 ldcs2(const double* p) {
     return __ldcs(reinterpret_cast<const double2*>(p));
+}
+__device__ __forceinline__ double2 ldcs2(const float* p) {     // two fp32 anchors, widened
+    const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+    return make_double2((double)v.x, (double)v.y);
 }
 __device__ __forceinline__ void st2(double* p, const double2 v, const bool k0, const bool k1) {
     if (k0 && k1) *reinterpret_cast<double2*>(p) = v;
@@ -601,7 +621,7 @@ k_eval_cols(const DevProb P, const DevState S, const int rows_per_cta) {
                                       node_ok && row_ok);
         if (row_ok && node_ok) {
             const double xp = S.X1[e], dx = S.DX[e], g = S.G[e];
-            const double lo = S.l[e], hi = S.u[e], xa = S.xa[e];
+            const double lo = S.l[e], hi = S.u[e], xa = (double)S.xa[e];
             const double cj = __ldg(P.c + j), cs = __ldg(P.colscale + j);
             const bool fl = !is_inf(lo), fu = !is_inf(hi);
             acc[C_DX2] = fma(dx, dx, acc[C_DX2]);
@@ -664,7 +684,7 @@ k_eval_rows(const DevProb P, const DevState S, const int rows_per_cta) {
             bool on = true;
             if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
             if (on) {
-                const double yp = S.Y1[e], dy = S.DY[e], ya = S.ya[e];
+                const double yp = S.Y1[e], dy = S.DY[e], ya = (double)S.ya[e];
                 const double bi = __ldg(P.b + i);
                 const double pr = fmax(bi - ax, 0.0) * __ldg(P.rowscale + i);
                 acc[R_PRES2] = fma(pr, pr, acc[R_PRES2]);
@@ -811,13 +831,13 @@ k_apply_restart(const DevProb P, const DevState S) {
     for (int j = gwarp; j < P.n; j += nwarps) {
         const size_t e = tix(j, node, P.n);
         const double v = S.X1[e];
-        S.xa[e] = v;
+        S.xa[e] = (anc_t)v;
         S.xbar[e] = v;
     }
     for (int i = gwarp; i < P.m; i += nwarps) {
         const size_t e = tix(i, node, P.m);
         const double v = S.Y1[e];
-        S.ya[e] = v;
+        S.ya[e] = (anc_t)v;
         S.y[e] = v;
     }
 }
@@ -845,7 +865,7 @@ k_init_cols(const DevProb P, const DevState S, const double* __restrict__ lb,
             S.fin[node] = 1; S.status[node] = 1; S.pobj[node] = INFINITY; S.dobj[node] = INFINITY;
         }
         const size_t t = tix(j, node, P.n);
-        S.l[t] = lo; S.u[t] = hi; S.xa[t] = x; S.xbar[t] = x; S.X1[t] = x;
+        S.l[t] = lo; S.u[t] = hi; S.xa[t] = (anc_t)x; S.xbar[t] = x; S.X1[t] = x;
         S.DX[t] = 0.0; S.G[t] = 0.0;
     }
 }
@@ -863,7 +883,7 @@ k_init_rows(const DevProb P, const DevState S, const double* __restrict__ y0, co
                 y = 0.0;
         }
         const size_t t = tix(i, node, P.m);
-        S.y[t] = y; S.ya[t] = y; S.Y1[t] = y; S.DY[t] = 0.0;
+        S.y[t] = y; S.ya[t] = (anc_t)y; S.Y1[t] = y; S.DY[t] = 0.0;
     }
 }
 
@@ -1024,7 +1044,7 @@ k_refill_cols(const DevProb P, const DevState S, const double* __restrict__ lb,
             S.fin[slot] = 1; S.status[slot] = 1; S.pobj[slot] = INFINITY; S.dobj[slot] = INFINITY;
         }
         const size_t t = tix(j, slot, P.n);
-        S.l[t] = lo; S.u[t] = hi; S.xa[t] = x; S.xbar[t] = x; S.X1[t] = x;
+        S.l[t] = lo; S.u[t] = hi; S.xa[t] = (anc_t)x; S.xbar[t] = x; S.X1[t] = x;
         S.DX[t] = 0.0; S.G[t] = 0.0;
     }
 }
@@ -1045,7 +1065,7 @@ k_refill_rows(const DevProb P, const DevState S, const double* __restrict__ y0,
         }
         const double y = (y0 && on) ? fmax(0.0, y0[(size_t)i * ld_in + org] * P.sc / P.dr[i]) : 0.0;
         const size_t t = tix(i, slot, P.m);
-        S.y[t] = y; S.ya[t] = y; S.Y1[t] = y; S.DY[t] = 0.0;
+        S.y[t] = y; S.ya[t] = (anc_t)y; S.Y1[t] = y; S.DY[t] = 0.0;
     }
 }
 
@@ -1211,27 +1231,26 @@ k_compact_vecs(const DevProb P, const DevState S, const int oldB) {
     const int nwarps = (gridDim.x * kCtaThreads) >> 5;
     const int mc = S.rowmask ? P.m - P.m_base : 0;
     const int total = 4 * P.n + 2 * P.m + mc;
+    // one state row (512-byte segments of all node blocks) per warp and pass
+    auto move_row = [&](auto* arr, const int row, const int rows) {
+        for (int c0 = 0; c0 < oldB; c0 += 32) {
+            const int k = c0 + lane;
+            const int p = k < oldB ? S.newpos[k] : -1;
+            const auto v = p >= 0 ? arr[tix(row, k, rows)] : 0;
+            __syncwarp();
+            if (p >= 0) arr[tix(row, p, rows)] = v;
+        }
+    };
     for (int r = gwarp; r < total; r += nwarps) {
         if (r < 4 * P.n + 2 * P.m) {
-            double* arr;
-            int row, rows;
             if (r < 4 * P.n) {
-                const int a = r / P.n;
-                arr = a == 0 ? S.xbar : a == 1 ? S.xa : a == 2 ? S.l : S.u;
-                row = r % P.n;
-                rows = P.n;
+                const int a = r / P.n, row = r % P.n;
+                if (a == 1) move_row(S.xa, row, P.n);
+                else move_row(a == 0 ? S.xbar : a == 2 ? S.l : S.u, row, P.n);
             } else {
-                const int q = r - 4 * P.n;
-                arr = q < P.m ? S.y : S.ya;
-                row = q % P.m;
-                rows = P.m;
-            }
-            for (int c0 = 0; c0 < oldB; c0 += 32) {
-                const int k = c0 + lane;
-                const int p = k < oldB ? S.newpos[k] : -1;
-                const double v = p >= 0 ? arr[tix(row, k, rows)] : 0.0;
-                __syncwarp();
-                if (p >= 0) arr[tix(row, p, rows)] = v;
+                const int q = r - 4 * P.n, row = q % P.m;
+                if (q < P.m) move_row(S.y, row, P.m);
+                else move_row(S.ya, row, P.m);
             }
         } else {
             uint8_t* base = S.rowmask + (size_t)(r - 4 * P.n - 2 * P.m) * S.ld;

@@ -742,12 +742,13 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     // nodes still spreads over all SMs (the per-iteration latency floor of the solve's tail)
     const bool allow_v2 = env_int("BLP_V2", 1) != 0;
     const int graph_lanes = env_int("BLP_GRAPH_LANES", 2);
+    const int rpw2 = env_int("BLP_ROWS_PER_WARP2", 16);   // two-nodes-per-lane kernels: 128 rows per CTA
     auto step_plan = [&](int rows, int width) {
-        int r = rpw;
-        Plan p = make_plan(rows, width, r, 0);
         // two nodes per lane pay off when a launch has real work; tiny LPs stay on the
         // one-node-per-lane kernels, which can run a whole period as one cooperative launch
         const bool v2 = allow_v2 && width >= kBlk && (long)std::max(P.n, P.m) * width >= (1L << 20);
+        int r = v2 ? rpw2 : rpw;
+        Plan p = make_plan(rows, width, r, 0);
         auto shape = [&](Plan& q, int rr) {
             if (!v2) return;
             q.V = 2;                                   // a warp = one row x 64 nodes
@@ -823,7 +824,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         key.S = S;
         key.D = D;
         key.K = K;
-        key.rpw = rpw | (allow_v2 ? 1 << 16 : 0) | (coop ? 1 << 17 : 0) | (graph_lanes << 20);
+        key.rpw = rpw | (rpw2 << 8) | (allow_v2 ? 1 << 16 : 0) | (coop ? 1 << 17 : 0) | (graph_lanes << 20);
         if (h->graph_valid && memcmp(&key, &h->gkey, sizeof key) == 0) return BLP_OK;
         h->drop_graphs();
         cudaGraph_t g = nullptr;

@@ -388,7 +388,7 @@ k_period_coop(const DevProb P, const DevState S, const int K, const CoopPlan C) 
 // issue ~170 instructions per row and are issue-bound, not bandwidth-bound
 // (profiles/r1b_full_step_kernels.md).
 #ifndef BLP_MINB2
-#define BLP_MINB2 4
+#define BLP_MINB2 5
 #endif
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }

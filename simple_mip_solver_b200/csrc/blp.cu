@@ -743,11 +743,12 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     const bool allow_v2 = env_int("BLP_V2", 1) != 0;
     const int graph_lanes = env_int("BLP_GRAPH_LANES", 2);
     const int rpw2 = env_int("BLP_ROWS_PER_WARP2", 16);   // two-nodes-per-lane kernels: 128 rows per CTA
-    auto step_plan = [&](int rows, int width) {
+    const int rpw2p = env_int("BLP_ROWS_PER_WARP2P", rpw2);
+    auto step_plan = [&](int rows, int width, bool primal = false) {
         // two nodes per lane pay off when a launch has real work; tiny LPs stay on the
         // one-node-per-lane kernels, which can run a whole period as one cooperative launch
         const bool v2 = allow_v2 && width >= kBlk && (long)std::max(P.n, P.m) * width >= (1L << 20);
-        int r = v2 ? rpw2 : rpw;
+        int r = v2 ? (primal ? rpw2p : rpw2) : rpw;
         Plan p = make_plan(rows, width, r, 0);
         auto shape = [&](Plan& q, int rr) {
             if (!v2) return;
@@ -764,7 +765,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         }
         return p;
     };
-    Plan pc = step_plan(P.n, W), pr = step_plan(P.m, W);
+    Plan pc = step_plan(P.n, W, true), pr = step_plan(P.m, W);
     auto finish_step_plans = [&]() -> int {
         plan_chunks(pc, h->hptrAT, P.n, h->h_chunkC);
         plan_chunks(pr, h->hptrA, P.m, h->h_chunkR);
@@ -824,7 +825,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         key.S = S;
         key.D = D;
         key.K = K;
-        key.rpw = rpw | (rpw2 << 8) | (allow_v2 ? 1 << 16 : 0) | (coop ? 1 << 17 : 0) | (graph_lanes << 20);
+        key.rpw = rpw | (rpw2 << 8) | (rpw2p << 24) | (allow_v2 ? 1 << 16 : 0) | (coop ? 1 << 17 : 0) | (graph_lanes << 20);
         if (h->graph_valid && memcmp(&key, &h->gkey, sizeof key) == 0) return BLP_OK;
         h->drop_graphs();
         cudaGraph_t g = nullptr;
@@ -883,7 +884,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 launches += 3;
                 ++compactions;
                 NT = pick_nt(S.B);
-                pc = step_plan(P.n, S.B);
+                pc = step_plan(P.n, S.B, true);
                 pr = step_plan(P.m, S.B);
                 if ((rc = finish_step_plans()) != BLP_OK) return rc;
                 coop_rejected = false;

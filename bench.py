@@ -378,6 +378,25 @@ def main():
         prof = lp.solve_batch_device(lb, ub, x0=x0[:, :ldW].contiguous(), y0=y0[:, :ldW].contiguous(),
                                      int_idx=int_idx, opts=opts_prof, want_x=False, want_y=False)['stats']
         del lb, ub
+    # plain batched SpMV (BASELINE.json's second figure): Y = A X and G = A' Y at the resident width,
+    # CUDA events on the library stream, operands larger than L2; not part of `value`
+    spmv = None
+    if rank == 0:
+        spmv = {}
+        for name, tr, rin, rout in (('A', False, n, m), ('AT', True, m, n)):
+            X = torch.randn((rin, ldW), dtype=torch.float64, device=dev)
+            Y = torch.empty((rout, ldW), dtype=torch.float64, device=dev)
+            torch.cuda.synchronize(dev)
+            for _ in range(3):
+                lp.spmv_async(X, Y, W, transpose=tr)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(ext)
+            for _ in range(20):
+                lp.spmv_async(X, Y, W, transpose=tr)
+            s1.record(ext)
+            lp.stream_sync()
+            spmv[name] = s0.elapsed_time(s1) / 20.0
+            del X, Y
     dev_ms = ev0.elapsed_time(ev1)
     dev_ms = parallel.allreduce_max(dev_ms, device=dev)
     sums = parallel.allreduce_sum([agg['solved'], agg['unsolved'], agg['launches'], agg['infeasible']], device=dev)
@@ -472,6 +491,12 @@ def main():
                          'k_dual': {'achieved': dual_gbs, 'frac': dual_gbs / peak, 'bytes_per_launch': dual_bytes,
                                     'ms_per_launch': dual_s * 1e3},
                          'split_measured': 'first 1024 iterations of the last timed slice (full batch width) re-run with CUDA events around every launch'},
+            'spmv': {'unit': 'GB/s', 'batch': W, 'note': 'plain batched SpMV on the unscaled matrix, node-fastest '
+                     'operands [rows][ld]; bytes = 12 nnz + 4(rows+1) + 8 B (n + m); CUDA events over 20 launches',
+                     'A': {'ms': spmv['A'], 'achieved': (bytes_A + 8 * W * (n + m)) / spmv['A'] / 1e6,
+                           'frac': (bytes_A + 8 * W * (n + m)) / spmv['A'] / 1e6 / peak},
+                     'AT': {'ms': spmv['AT'], 'achieved': (bytes_AT + 8 * W * (n + m)) / spmv['AT'] / 1e6,
+                            'frac': (bytes_AT + 8 * W * (n + m)) / spmv['AT'] / 1e6 / peak}},
             'cpu_baseline': cpu,
             'nodes': {'solved': int(sums[0]), 'iteration_limit': int(sums[1]), 'infeasible': int(sums[3]),
                       'pdhg_iterations_per_step': agg['iters'] / max(args.steps, 1),

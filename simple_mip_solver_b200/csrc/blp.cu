@@ -1188,10 +1188,20 @@ int blp_spmv(blp_handle h, int B, int transpose, const double* X, double* Y) {
     const int rows = transpose ? h->n : h->A0.rows;
     const int32_t* ptr = transpose ? h->P.cptr : h->P.rowptr;
     const Ent* ent = transpose ? h->ucent.as<Ent>() : h->uent.as<Ent>();
+    cudaStream_t st = h->stream;
+    if (B >= kBlk && env_int("BLP_V2", 1) != 0) {               // two nodes per lane
+        Plan p;
+        p.rows_per_cta = kWarps * env_int("BLP_ROWS_PER_WARP2", 16);
+        p.chunks = std::max(1, (rows + p.rows_per_cta - 1) / p.rows_per_cta);
+        p.tiles = ld / kBlk;
+        plan_slab(p, transpose ? h->hptrAT : h->hptrA, rows);
+        k_spmv2<<<dim3(p.chunks, p.tiles), kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap);
+        CK(cudaGetLastError());
+        return BLP_OK;
+    }
     Plan p = plan_rows(rows, B, env_int("BLP_ROWS_PER_WARP", 8), 0);
     plan_slab(p, transpose ? h->hptrAT : h->hptrA, rows);
     const dim3 g(p.chunks, p.tiles);
-    cudaStream_t st = h->stream;
     switch (p.NT) {
         case 1: k_spmv<1><<<g, kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap); break;
         case 2: k_spmv<2><<<g, kCtaThreads, p.smem, st>>>(ptr, ent, rows, B, ld, X, Y, p.rows_per_cta, p.cap); break;

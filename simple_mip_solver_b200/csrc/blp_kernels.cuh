@@ -405,9 +405,12 @@ __device__ __forceinline__ void st2(double* p, const double2 v, const bool k0, c
     else if (k1) p[1] = v.y;
 }
 
+// ld: distance (in doubles) between consecutive rows of the gathered vector (kBlk for the solver's
+// tile-major state, the caller's leading dimension for blp_spmv)
 template <bool SHARED>
 __device__ __forceinline__ void dot2_entries(const int4* __restrict__ E, const int p0, const int p1,
-                                             const double* __restrict__ Vn, double& g0, double& g1) {
+                                             const double* __restrict__ Vn, double& g0, double& g1,
+                                             const int ld = kBlk) {
     constexpr int kU = BLP_U;
     for (int p = p0; p < p1; p += kU) {
         double2 v[kU];
@@ -416,7 +419,7 @@ __device__ __forceinline__ void dot2_entries(const int4* __restrict__ E, const i
             v[q] = make_double2(0.0, 0.0);
             if (p + q < p1) {
                 const int col = SHARED ? E[p + q].x : __ldg(&E[p + q].x);
-                v[q] = ld2(Vn + (size_t)col * kBlk);
+                v[q] = ld2(Vn + (size_t)col * ld);
             }
         }
 #pragma unroll
@@ -432,10 +435,11 @@ __device__ __forceinline__ void dot2_entries(const int4* __restrict__ E, const i
 }
 
 __device__ __forceinline__ void slab_dot2(const Slab& sl, const Ent* __restrict__ ent, const int lr,
-                                          const double* __restrict__ Vn, double& g0, double& g1) {
+                                          const double* __restrict__ Vn, double& g0, double& g1,
+                                          const int ld = kBlk) {
     const int p0 = sl.sp[lr], p1 = sl.sp[lr + 1];
-    if (sl.se) dot2_entries<true>(sl.se - sl.base, p0, p1, Vn, g0, g1);
-    else dot2_entries<false>(reinterpret_cast<const int4*>(ent), p0, p1, Vn, g0, g1);
+    if (sl.se) dot2_entries<true>(sl.se - sl.base, p0, p1, Vn, g0, g1, ld);
+    else dot2_entries<false>(reinterpret_cast<const int4*>(ent), p0, p1, Vn, g0, g1, ld);
 }
 
 // A chunk that consists of ONE long row (a dense cut row, typically) is shared by all warps of the
@@ -1295,6 +1299,26 @@ k_spmv(const int32_t* __restrict__ ptr, const Ent* __restrict__ ent, const int r
         const double s = slab_dot<NT>(sl, ent, row_ok ? i - r0 : 0, row_ok, X + node, ld,
                                       node_ok && row_ok);
         if (row_ok && node_ok) Y[(size_t)i * ld + node] = s;
+    }
+}
+
+// The same with two nodes per lane (B >= 64): a warp owns one matrix row for 64 nodes, every access is
+// one 128-bit load / store per lane, the CSR chunk of the CTA is staged in shared memory.
+__global__ void __launch_bounds__(kCtaThreads, BLP_MINB2)
+k_spmv2(const int32_t* __restrict__ ptr, const Ent* __restrict__ ent, const int rows, const int B,
+        const int ld, const double* __restrict__ X, double* __restrict__ Y, const int rows_per_cta,
+        const int cap) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = blockIdx.y * kBlk + lane * 2;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(rows, r0 + rows_per_cta);
+    const Slab sl = stage_slab(ptr, ent, r0, r1, rows_per_cta, cap);
+    const bool k0 = node < B, k1 = node + 1 < B;
+    if (node >= ld) return;                                    // ld is a multiple of 64: never taken
+    for (int i = r0 + warp; i < r1; i += kWarps) {
+        double g0 = 0.0, g1 = 0.0;
+        slab_dot2(sl, ent, i - r0, X + node, g0, g1, ld);
+        st2(Y + (size_t)i * ld + node, make_double2(g0, g1), k0, k1);
     }
 }
 

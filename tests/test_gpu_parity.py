@@ -24,7 +24,7 @@ def _engine(blp_lib):
     return engine
 
 
-@pytest.mark.parametrize('B', [1, 3, 8, 32, 45, 130])
+@pytest.mark.parametrize('B', [1, 3, 8, 32, 45, 64, 130, 300])
 @pytest.mark.parametrize('shape', [(7, 5, 0.5), (300, 500, 0.1), (2000, 5000, 0.004)])
 def test_spmv_matches_scipy(blp_lib, B, shape):
     import torch

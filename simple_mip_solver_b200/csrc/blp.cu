@@ -85,7 +85,11 @@ constexpr int kMaxSlabEntries = 2816;       // 44 KB of entries + row pointers s
 // Row ranges of the step-kernel CTAs: at most rows_per_cta rows and about 4x the average entry
 // count per chunk; a long row (dense cut row) gets a chunk of its own and is then gathered by all
 // warps of the CTA together. Also sizes the shared-memory slab (largest chunk, capped).
-void plan_chunks(Plan& p, const std::vector<int32_t>& ptr, int rows, std::vector<int32_t>& bounds) {
+// Output: pairs (first row, end row), one per chunk, the chunks with the most entries first — CTAs
+// are dispatched in blockIdx order, so the slow long-row chunks (appended cut rows sit at the END of
+// the matrix) start at once instead of forming the tail of every launch.
+void plan_chunks(Plan& p, const std::vector<int32_t>& ptr, int rows, std::vector<int32_t>& pairs) {
+    std::vector<int32_t> bounds;
     const long nnz = ptr[rows];
     const long budget = std::max<long>(4 * ((nnz * p.rows_per_cta + rows - 1) / std::max(rows, 1)), kLongRow);
     bounds.clear();
@@ -110,6 +114,20 @@ void plan_chunks(Plan& p, const std::vector<int32_t>& ptr, int rows, std::vector
         r = r1;
     }
     p.chunks = (int)bounds.size() - 1;
+    std::vector<int32_t> order(p.chunks);
+    for (int q = 0; q < p.chunks; ++q) order[q] = q;
+    auto weight = [&](int q) { return ptr[bounds[q + 1]] - ptr[bounds[q]]; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {      // long-row chunks first, the rest in row order
+        const bool la = bounds[a + 1] - bounds[a] == 1 && weight(a) > kLongRow;
+        const bool lb = bounds[b + 1] - bounds[b] == 1 && weight(b) > kLongRow;
+        if (la != lb) return la;
+        return la ? weight(a) > weight(b) : false;
+    });
+    pairs.resize(2 * (size_t)p.chunks);
+    for (int q = 0; q < p.chunks; ++q) {
+        pairs[2 * q] = bounds[order[q]];
+        pairs[2 * q + 1] = bounds[order[q] + 1];
+    }
     const int ptr_slots = (p.rows_per_cta + 4) / 4;
     p.cap = std::max(0, std::min(worst, kMaxSlabEntries - ptr_slots));
     p.smem = 16 * ((size_t)ptr_slots + (size_t)p.cap);

@@ -227,6 +227,53 @@ __device__ __forceinline__ double slab_dot(const Slab& sl, const Ent* __restrict
     return dot_entries<false>(reinterpret_cast<const int4*>(ent), p0, p1, Vn, ld, node_ok);
 }
 
+// A chunk that consists of ONE long row (a dense cut row, typically) is shared by all threads of
+// the CTA in the one-node-per-lane kernels too: thread t gathers the entries p0 + t / NT,
+// p0 + t / NT + 256 / NT, ... for node t % NT (the NT threads of a slice read NT consecutive
+// doubles), the partial sums meet in shared memory and are folded in slice order, so the result is
+// deterministic. Without it one warp walks the row alone: 400 entries = 100 dependent round trips,
+// which made every iteration of a NARROW batch with cut rows 1.5x slower.
+// Returns the dot for node (cy * NT + t % NT) in the threads t < NT, which are the lanes that own
+// row r0 in the regular mapping (warp 0, sub-group 0).
+constexpr int kLongRow = 96;
+
+template <int NT>
+__device__ __forceinline__ double coop_dot_nt(const Slab& sl, const Ent* __restrict__ ent,
+                                              const double* __restrict__ V, const int rows_v,
+                                              const int cy, const DevState& S) {
+    constexpr int NS = kCtaThreads / NT;                      // slices of the row
+    __shared__ double red[kCtaThreads];
+    const int nl = threadIdx.x % NT, slice = threadIdx.x / NT;
+    const int node = cy * NT + nl;
+    const bool ok = node < S.B && S.fin[node] == 0;
+    const double* __restrict__ Vn = V + tix(0, ok ? node : cy * NT, rows_v);
+    const int p0 = sl.sp[0], p1 = sl.sp[1];
+    const int4* __restrict__ E = sl.se ? sl.se - sl.base : reinterpret_cast<const int4*>(ent);
+    double acc = 0.0;
+    for (int p = p0 + slice; p < p1; p += 4 * NS) {            // four independent gathers in flight
+        double v[4], cf[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int pq = p + q * NS;
+            v[q] = 0.0;
+            cf[q] = 0.0;
+            if (pq < p1) {
+                const int4 e = sl.se ? E[pq] : __ldg(E + pq);
+                cf[q] = __hiloint2double(e.w, e.z);
+                v[q] = Vn[(size_t)e.x * kBlk];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc = fma(cf[q], v[q], acc);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < NT)
+        for (int q = 0; q < NS; ++q) r += red[q * NT + threadIdx.x];
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Primal half step, fused  G = A'y  ->  x' = clip(x - tau (c - G), l, u)  ->  xbar = 2x' - x.
 template <int NT, bool MAJOR>
@@ -246,10 +293,16 @@ __device__ __forceinline__ void primal_chunk(const DevProb& P, const DevState& S
         w = (double)s / (double)(s + 1);
         tau = P.eta / S.omega[node];
     }
-    const int r0 = __ldg(chunk_ptr + cx);
-    const int r1 = __ldg(chunk_ptr + cx + 1);
+    const int r0 = __ldg(chunk_ptr + 2 * cx);              // chunk cx = rows [r0, r1); heaviest chunks first
+    const int r1 = __ldg(chunk_ptr + 2 * cx + 1);
     const Slab sl = pre ? *pre : stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
+    const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
+    double cg = 0.0;
+    if (coop) {
+        cg = coop_dot_nt<NT>(sl, P.cent, S.y, P.m, cy, S);
+        if (threadIdx.x >= NT) return;
+    }
     for (int jb = r0 + warp * RW; jb < r1; jb += kWarps * RW) {
         const int j = jb + sub;
         const bool row_ok = j < r1;
@@ -268,7 +321,7 @@ __device__ __forceinline__ void primal_chunk(const DevProb& P, const DevState& S
                 hi = __ldg(S.uref + fi);
             }
         }
-        const double g = slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, yn, kBlk, node_ok && row_ok);
+        const double g = coop ? cg : slab_dot<NT>(sl, P.cent, row_ok ? j - r0 : 0, row_ok, yn, kBlk, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double xc = fma(w, xb - a, a);                  // w xbar + (1-w) xa
             const double xp = fmin(fmax(xc - tau * (__ldg(P.c + j) - g), lo), hi);
@@ -307,10 +360,16 @@ __device__ __forceinline__ void dual_chunk(const DevProb& P, const DevState& S, 
         w = (double)(s + 1) / (double)(s + 2);
         sig = P.eta * S.omega[node];
     }
-    const int r0 = __ldg(chunk_ptr + cx);
-    const int r1 = __ldg(chunk_ptr + cx + 1);
+    const int r0 = __ldg(chunk_ptr + 2 * cx);              // chunk cx = rows [r0, r1); heaviest chunks first
+    const int r1 = __ldg(chunk_ptr + 2 * cx + 1);
     const Slab sl = pre ? *pre : stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
+    const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
+    double cg = 0.0;
+    if (coop) {
+        cg = coop_dot_nt<NT>(sl, P.ent, S.xbar, P.n, cy, S);
+        if (threadIdx.x >= NT) return;
+    }
     for (int ib = r0 + warp * RW; ib < r1; ib += kWarps * RW) {
         const int i = ib + sub;
         const bool row_ok = i < r1;
@@ -322,7 +381,7 @@ __device__ __forceinline__ void dual_chunk(const DevProb& P, const DevState& S, 
             a = (double)__ldcs(S.ya + e);
             if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;
         }
-        const double ax = slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, xn, kBlk, node_ok && row_ok);
+        const double ax = coop ? cg : slab_dot<NT>(sl, P.ent, row_ok ? i - r0 : 0, row_ok, xn, kBlk, node_ok && row_ok);
         if (row_ok && node_ok) {
             const double yp = on ? fmax(0.0, yc + sig * (__ldg(P.b + i) - ax)) : 0.0;
             S.y[e] = fma(w, (2.0 * yp - yc) - a, a);
@@ -363,8 +422,8 @@ k_period_coop(const DevProb P, const DevState S, const int K, const CoopPlan C) 
     const int cxC = w % C.nchC, cyC = w / C.nchC, cxR = w % C.nchR, cyR = w / C.nchR;
     Slab slC{nullptr, nullptr, 0}, slR{nullptr, nullptr, 0};
     int4* const baseR = dyn_smem + (C.rpcC + 4) / 4 + C.capC;
-    if (hasC) slC = stage_slab(P.cptr, P.cent, __ldg(C.chunkC + cxC), __ldg(C.chunkC + cxC + 1), C.rpcC, C.capC);
-    if (hasR) slR = stage_slab(P.rowptr, P.ent, __ldg(C.chunkR + cxR), __ldg(C.chunkR + cxR + 1), C.rpcR, C.capR, baseR);
+    if (hasC) slC = stage_slab(P.cptr, P.cent, __ldg(C.chunkC + 2 * cxC), __ldg(C.chunkC + 2 * cxC + 1), C.rpcC, C.capC);
+    if (hasR) slR = stage_slab(P.rowptr, P.ent, __ldg(C.chunkR + 2 * cxR), __ldg(C.chunkR + 2 * cxR + 1), C.rpcR, C.capR, baseR);
     for (int it = 0; it < K; ++it) {
         const bool major = it == K - 1;
         if (hasC) {
@@ -444,7 +503,6 @@ __device__ __forceinline__ void slab_dot2(const Slab& sl, const Ent* __restrict_
 
 // A chunk that consists of ONE long row (a dense cut row, typically) is shared by all warps of the
 // CTA: each warp gathers a slice of the row's entries, the partial sums meet in shared memory.
-constexpr int kLongRow = 96;
 
 __device__ __forceinline__ void coop_dot2(const Slab& sl, const Ent* __restrict__ ent,
                                           const double* __restrict__ Vn, const int warp, const int lane,
@@ -487,8 +545,8 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
         w1 = (double)s / (double)(s + 1);
         tau1 = P.eta / S.omega[node + 1];
     }
-    const int r0 = __ldg(chunk_ptr + blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
+    const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
+    const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
     const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.n);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
@@ -547,8 +605,8 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
         w1 = (double)(s + 1) / (double)(s + 2);
         sig1 = P.eta * S.omega[node + 1];
     }
-    const int r0 = __ldg(chunk_ptr + blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + blockIdx.x + 1);
+    const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
+    const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
     const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.m);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);

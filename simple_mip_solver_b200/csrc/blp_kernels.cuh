@@ -148,6 +148,45 @@ __device__ __forceinline__ double row_dot(const int32_t* __restrict__ ptr,
     return acc;
 }
 
+// The same walk for TWO batched vectors at once (the evaluation's A x' and A d): one pass over the
+// row's entries, eight gathers in flight, so a 400-entry cut row costs 50 dependent round trips
+// per evaluation instead of 200.
+template <int NT>
+__device__ __forceinline__ void row_dot_pair(const int32_t* __restrict__ ptr, const Ent* __restrict__ ent,
+                                             int row, bool row_ok, const double* __restrict__ Vn,
+                                             const double* __restrict__ Wn, bool node_ok, double& accv,
+                                             double& accw) {
+    constexpr int ld = kBlk;
+    accv = 0.0;
+    accw = 0.0;
+    if (NT == 32 || (row_ok && node_ok)) {
+        const int p0 = __ldg(ptr + row), p1 = __ldg(ptr + row + 1);
+        for (int p = p0; p < p1; p += 4) {
+            int4 e[4];
+            double v[4], w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[q] = 0.0;
+                w[q] = 0.0;
+                e[q] = make_int4(0, 0, 0, 0);
+                if (p + q < p1) {
+                    e[q] = __ldg(reinterpret_cast<const int4*>(ent + p + q));
+                    if (node_ok) {
+                        v[q] = Vn[(size_t)e[q].x * ld];
+                        w[q] = Wn[(size_t)e[q].x * ld];
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double cf = __hiloint2double(e[q].w, e[q].z);
+                accv = fma(cf, v[q], accv);
+                accw = fma(cf, w[q], accw);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row slab of a CTA in shared memory. The step kernels give every CTA a contiguous chunk of CSR
 // rows; all 256 threads first copy the chunk's row pointers and (when they fit) its entries with
@@ -740,8 +779,9 @@ k_eval_rows(const DevProb P, const DevState S, const int rows_per_cta) {
         const bool row_ok = i < r1;
         const size_t e = tix(i, node, P.m);
         const bool ok = row_ok && node_ok;
-        const double ax = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.X1 + tix(0, node, P.n), ok);
-        const double ad = row_dot<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.G + tix(0, node, P.n), ok);
+        double ax, ad;
+        row_dot_pair<NT>(P.rowptr, P.ent, row_ok ? i : 0, row_ok, S.X1 + tix(0, node, P.n), S.G + tix(0, node, P.n),
+                         ok, ax, ad);
         if (ok) {
             bool on = true;
             if (i >= P.m_base && S.rowmask) on = S.rowmask[(size_t)(i - P.m_base) * S.ld + node] != 0;

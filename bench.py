@@ -293,6 +293,7 @@ def main():
         dist.barrier()
 
     lp = engine.BatchLP(d.A, d.b, d.c, device=local_rank)
+    use_comm = lp.comm_init()                 # blp_allreduce_min over NCCL when world > 1
     ld = engine.leading_dim(B)
     W = min(args.slots, B) if args.slots > 0 else B           # resident node slots
     ldW = engine.leading_dim(W)
@@ -323,7 +324,7 @@ def main():
         inc = float(res_obj[:B][integral].min().item()) if bool(integral.any()) else float('inf')
         open_ = (st == 0) & ~integral
         lowb = float(res_lower[:B][open_].min().item()) if bool(open_.any()) else float('inf')
-        return parallel.allreduce_bounds(inc, lowb, device=dev)
+        return parallel.allreduce_bounds(inc, lowb, device=dev, lp=lp if use_comm else None)
 
     total_steps = args.warmup + args.steps
     slices = [node_slice(s) for s in range(total_steps)]
@@ -423,7 +424,7 @@ def main():
         inc = float(rr.objective[integral].min()) if integral.any() else float('inf')
         open_ = (rr.status == 0) & ~integral
         lowb = float(rr.lower_bound[open_].min()) if open_.any() else float('inf')
-        parallel.allreduce_bounds(inc, lowb, device=dev)
+        parallel.allreduce_bounds(inc, lowb, device=dev, lp=lp if use_comm else None)
         if s >= 1:
             e2e_solved += int(np.isin(rr.status, (0, 1, 2)).sum())
             h2d = hlb.nbytes + hub.nbytes + hx0.nbytes + hy0.nbytes + 4 * n

@@ -191,6 +191,22 @@ int blp_destroy(blp_handle h);
 
 const char* blp_last_error(void);
 
+/*
+ * Multi-GPU exchange. Node LPs are independent, so a frontier is split by node
+ * over one process per GPU and the data path has no collective; after a batch the ranks agree on
+ *   two_vals[0] = best integer-feasible objective found (the incumbent, branch_and_bound.py:258-262)
+ *   two_vals[1] = smallest lower bound of the nodes still open (BranchAndBound.dual_bound, :199-201)
+ * with one 16-byte ncclAllReduce(min) over NVLink on the handle's stream. NCCL is bound at run time
+ * (dlopen of libnccl.so.2, or $BLP_NCCL_LIB).
+ *   blp_comm_unique_id  rank 0 creates the 128-byte NCCL id; the host distributes it to all ranks
+ *   blp_comm_init       every rank joins with (nranks, rank, id); collective
+ *   blp_allreduce_min   two_vals: HOST pointer, in/out; identity on a handle without communicator
+ */
+int blp_comm_unique_id(char id[128]);
+int blp_comm_init(blp_handle h, int nranks, int rank, const char id[128]);
+int blp_allreduce_min(blp_handle h, double* two_vals);
+int blp_comm_destroy(blp_handle h);
+
 /* library / build identification, e.g. "blp 0.1 sm_100a" */
 const char* blp_version(void);
 

@@ -8,6 +8,7 @@
 #include "../../include/blp.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -216,6 +217,10 @@ struct blp_handle_s {
     cudaStream_t side[kLanes - 1] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[kLanes - 1] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> prof_ev;
+    // multi-GPU exchange (blp_comm_init): NCCL communicator of this rank and a 16-byte device buffer
+    void* comm = nullptr;
+    int comm_ranks = 1;
+    double* d_pair = nullptr;
     // cached period graphs
     bool graph_valid = false;
     GraphKey gkey{};
@@ -230,6 +235,51 @@ struct blp_handle_s {
 };
 
 namespace {
+
+// ---- NCCL, bound at run time -----------------------------------------------------------------
+// The only collective of the path is the 16-byte all-reduce(min) of [incumbent, dual bound]
+// (SURVEY section 8e). libnccl is opened with dlopen so that libblp.so has no link-time
+// dependency on it: a process that has torch loaded gets torch's copy, any other host the system one.
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclFloat64 = 8, kNcclMin = 3;      // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.lib ? &api : nullptr;
+    tried = true;
+    const char* names[] = {getenv("BLP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return nullptr;
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.lib, "ncclAllReduce"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+        dlclose(api.lib);
+        api.lib = nullptr;
+        return nullptr;
+    }
+    return &api;
+}
+
+int nccl_fail(const NcclApi* a, const char* what, int rc) {
+    return fail(BLP_ERR_CUDA, "%s: NCCL error %d (%s)", what, rc,
+                (a && a->GetErrorString) ? a->GetErrorString(rc) : "?");
+}
 
 // (re)build scaling, transpose, step size and the device copies of the shared LP data
 int prepare(blp_handle h) {
@@ -1239,10 +1289,68 @@ int blp_stream_sync(blp_handle h) {
     return BLP_OK;
 }
 
+int blp_comm_unique_id(char id[128]) {
+    if (!id) return fail(BLP_ERR_ARG, "blp_comm_unique_id: id is NULL");
+    NcclApi* a = nccl_api();
+    if (!a) return fail(BLP_ERR_STATE, "blp_comm_unique_id: libnccl.so.2 not found (set BLP_NCCL_LIB)");
+    NcclId u;
+    const int rc = a->GetUniqueId(&u);
+    if (rc) return nccl_fail(a, "ncclGetUniqueId", rc);
+    memcpy(id, u.internal, 128);
+    return BLP_OK;
+}
+
+int blp_comm_init(blp_handle h, int nranks, int rank, const char id[128]) {
+    if (!h || !id) return fail(BLP_ERR_ARG, "blp_comm_init: NULL handle or id");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(BLP_ERR_ARG, "blp_comm_init: rank %d of %d", rank, nranks);
+    if (h->comm) return fail(BLP_ERR_STATE, "blp_comm_init: the handle already has a communicator");
+    NcclApi* a = nccl_api();
+    if (!a) return fail(BLP_ERR_STATE, "blp_comm_init: libnccl.so.2 not found (set BLP_NCCL_LIB)");
+    CK(cudaSetDevice(h->device));
+    NcclId u;
+    memcpy(u.internal, id, 128);
+    const int rc = a->CommInitRank(&h->comm, nranks, u, rank);
+    if (rc) {
+        h->comm = nullptr;
+        return nccl_fail(a, "ncclCommInitRank", rc);
+    }
+    h->comm_ranks = nranks;
+    if (!h->d_pair) CK(cudaMalloc(&h->d_pair, 2 * sizeof(double)));
+    return BLP_OK;
+}
+
+int blp_allreduce_min(blp_handle h, double* two_vals) {
+    if (!h || !two_vals) return fail(BLP_ERR_ARG, "blp_allreduce_min: NULL handle or values");
+    if (!h->comm || h->comm_ranks == 1) return BLP_OK;        // a world of one rank: identity
+    NcclApi* a = nccl_api();
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_pair, two_vals, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const int rc = a->AllReduce(h->d_pair, h->d_pair, 2, kNcclFloat64, kNcclMin, h->comm, h->stream);
+    if (rc) return nccl_fail(a, "ncclAllReduce", rc);
+    CK(cudaMemcpyAsync(two_vals, h->d_pair, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BLP_OK;
+}
+
+int blp_comm_destroy(blp_handle h) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_comm_destroy: NULL handle");
+    if (h->comm) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        NcclApi* a = nccl_api();
+        if (a) a->CommDestroy(h->comm);
+        h->comm = nullptr;
+        h->comm_ranks = 1;
+    }
+    return BLP_OK;
+}
+
 int blp_destroy(blp_handle h) {
     if (!h) return BLP_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    blp_comm_destroy(h);
+    if (h->d_pair) cudaFree(h->d_pair);
     h->drop_graphs();
     DevBuf* bufs[] = {&h->rowptr, &h->ent, &h->cptr, &h->cent, &h->c, &h->b,
                       &h->rowscale, &h->colscale, &h->d_dr, &h->d_dc, &h->uent, &h->ucent, &h->chunkC, &h->chunkR, &h->s_lb,

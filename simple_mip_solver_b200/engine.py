@@ -72,6 +72,10 @@ _SIGNATURES = {
     'blp_destroy': (C.c_int, [_P]),
     'blp_last_error': (C.c_char_p, []),
     'blp_version': (C.c_char_p, []),
+    'blp_comm_unique_id': (C.c_int, [C.c_char_p]),
+    'blp_comm_init': (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),
+    'blp_allreduce_min': (C.c_int, [_P, C.POINTER(C.c_double)]),
+    'blp_comm_destroy': (C.c_int, [_P]),
     'blp_mps_read': (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     'blp_mps_dims': (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                C.POINTER(C.c_int32)]),
@@ -348,6 +352,29 @@ class BatchLP:
         """Queue one batched SpMV on the handle's stream without synchronising (benchmarks)."""
         _check(self._lib.blp_spmv(self._h, B, 1 if transpose else 0, C.c_void_p(X.data_ptr()),
                                   C.c_void_p(Y.data_ptr())), 'blp_spmv')
+
+    # -- multi-GPU exchange (one process per GPU) -------------------------------------------------
+    def comm_init(self):
+        """Join the NCCL communicator of the library with the ranks of the initialised
+        ``torch.distributed`` process group: rank 0 creates the id (blp_comm_unique_id), the group
+        broadcasts its 128 bytes, every rank calls blp_comm_init. No-op for a single rank."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return False
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _check(self._lib.blp_comm_unique_id(buf), 'blp_comm_unique_id')
+        box = [buf.raw]
+        dist.broadcast_object_list(box, src=0)
+        _check(self._lib.blp_comm_init(self._h, world, rank, box[0]), 'blp_comm_init')
+        return True
+
+    def allreduce_min(self, incumbent: float, dual_bound: float):
+        """Global (min incumbent, min open lower bound) through blp_allreduce_min."""
+        v = (C.c_double * 2)(float(incumbent), float(dual_bound))
+        _check(self._lib.blp_allreduce_min(self._h, v), 'blp_allreduce_min')
+        return float(v[0]), float(v[1])
 
     def stream_sync(self):
         _check(self._lib.blp_stream_sync(self._h), 'blp_stream_sync')

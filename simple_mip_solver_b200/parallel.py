@@ -3,8 +3,9 @@
 Node LPs are independent (they share read-only A, c, b), so a frontier is split by node across
 ranks — one process per GPU, each with its own ``engine.BatchLP`` replica of the matrix — and the
 data path needs no collective. The only exchange is a 16-byte all-reduce(min) of
-``[incumbent objective, smallest open-node lower bound]`` after a batch, done with
-``torch.distributed`` (NCCL over NVLink on GPUs; gloo in the CPU tests). The reference is single
+``[incumbent objective, smallest open-node lower bound]`` after a batch: on GPUs the library's own
+``blp_allreduce_min`` (NCCL over NVLink on the handle's stream, communicator bootstrapped through the
+``torch.distributed`` group), in the CPU tests ``torch.distributed`` with gloo. The reference is single
 process; this module has no counterpart there.
 """
 from __future__ import annotations
@@ -26,10 +27,15 @@ def shard_items(items: Sequence, rank: int, world: int) -> List:
     return list(items[b:e])
 
 
-def allreduce_bounds(incumbent: float, dual_bound: float, device=None) -> Tuple[float, float]:
+def allreduce_bounds(incumbent: float, dual_bound: float, device=None, lp=None) -> Tuple[float, float]:
     """Global (min incumbent objective, min open-node lower bound) over all ranks.
 
-    Without an initialised process group (single GPU) the inputs are returned unchanged."""
+    With ``lp`` (an ``engine.BatchLP`` whose ``comm_init()`` has been called) the exchange is the
+    library's own 16-byte ncclAllReduce on its stream (``blp_allreduce_min``); otherwise it goes
+    through ``torch.distributed`` (gloo in the CPU tests). Without an initialised process group
+    (single GPU) the inputs are returned unchanged."""
+    if lp is not None:
+        return lp.allreduce_min(incumbent, dual_bound)
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -77,3 +77,19 @@ def test_product_fails_loudly_without_gpu_or_library(monkeypatch, tmp_path):
     monkeypatch.setattr(engine, '_LIB_PATH', tmp_path / 'missing.so')
     with pytest.raises(engine.BlpError, match='no CPU fallback'):
         engine.load_library()
+
+
+def test_comm_entry_points_without_a_gpu():
+    """blp_comm_unique_id binds NCCL at run time (no GPU needed); the handle-taking entry points
+    reject a NULL handle with an error code and a message instead of crashing."""
+    from simple_mip_solver_b200 import engine
+    lib = engine.load_library()
+    a, b = ctypes.create_string_buffer(128), ctypes.create_string_buffer(128)
+    assert lib.blp_comm_unique_id(a) == 0 and lib.blp_comm_unique_id(b) == 0
+    assert a.raw != b.raw and any(a.raw)
+    assert lib.blp_comm_unique_id(None) == -1
+    v = (ctypes.c_double * 2)(1.0, 2.0)
+    assert lib.blp_allreduce_min(None, v) == -1 and b'NULL' in lib.blp_last_error()
+    assert lib.blp_comm_init(None, 2, 0, a) == -1
+    assert lib.blp_comm_destroy(None) == -1
+    assert list(v) == [1.0, 2.0]

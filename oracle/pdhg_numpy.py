@@ -86,7 +86,7 @@ class BatchPDHG:
         self.cnorm0 = np.linalg.norm(self.c0)
 
     def solve(self, lb, ub, eps=1e-8, max_iters=200000, K=64, row_mask=None, x0=None, y0=None,
-              reflect=True, restart_to='pdhg', theta=0.5, verbose=False, eps_inf=1e-9, omega_init=None):
+              reflect=True, restart_to='pdhg', theta=0.5, verbose=False, eps_inf=1e-9, omega_init=None, balance=0.3):
         """lb, ub: [n, B] (unscaled). Returns dict of per-node arrays."""
         n, m = self.n, self.m
         lb = np.asarray(lb, float).reshape(n, -1)
@@ -204,6 +204,15 @@ class BatchPDHG:
                     good = do_restart & (ddx > 1e-10) & (ddy > 1e-10) & np.isfinite(fpe0)
                     omega = np.where(good, np.exp(theta * np.log(np.where(good, ddy / np.maximum(ddx, 1e-300), 1))
                                                   + (1 - theta) * np.log(omega)), omega)
+                    # residual balancing (k_decide, BLP_OMEGA_BALANCE): push the weight towards the lagging
+                    # criterion — the primal residual shrinks with the dual step, the gap with the primal step
+                    if balance > 0:
+                        with np.errstate(divide='ignore', invalid='ignore'):
+                            lr = np.clip(np.log(rp / rg), -1.0, 1.0)
+                        fb = omega * np.exp(balance * np.where(np.isfinite(lr), lr, 0.0))
+                        ok = do_restart & np.isfinite(fpe0) & (rp > 0) & (rg > 0) \
+                            & (fb <= 1e4 * self.omega0) & (fb >= 1e-4 * self.omega0)
+                        omega = np.where(ok, fb, omega)
                     rs = do_restart[None, :]
                     xn = np.where(rs, zx, xn); yn = np.where(rs, zy, yn)
                     xa = np.where(rs, zx, xa); ya = np.where(rs, zy, ya)

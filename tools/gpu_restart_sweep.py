@@ -14,6 +14,10 @@ lp = engine.BatchLP(d.A, d.b, d.c)
 cases = [{}, {'BLP_OMEGA_THETA': '0'}, {'BLP_BETA_ART': '0.7'}, {'BLP_BETA_ART': '1.0'}, {'BLP_BETA_ART': '3.0'},
          {'BLP_OMEGA_THETA': '0', 'BLP_BETA_ART': '0.5'}, {'BLP_OMEGA_THETA': '0', 'BLP_BETA_ART': '0.7'},
          {'BLP_OMEGA_THETA': '0', 'BLP_BETA_ART': '1.0'}]
+if os.environ.get('SWEEP_BALANCE'):      # residual-balancing feedback on the primal weight (k_decide)
+    cases = [{}, {'BLP_OMEGA_THETA': '0'}, {'BLP_OMEGA_THETA': '0', 'BLP_OMEGA_BALANCE': '0.3'},
+             {'BLP_OMEGA_THETA': '0', 'BLP_OMEGA_BALANCE': '0.1'}, {'BLP_OMEGA_BALANCE': '0.3'},
+             {'BLP_OMEGA_THETA': '0.02'}]
 if os.environ.get('SWEEP_COLD'):
     x0 = y0 = None
 for env in cases:

@@ -9,7 +9,7 @@ cost GPU minutes. Uses the oracle's scaling and the bench fixtures; never import
     python tests/tools/cpu_pdhg_lab.py c5 1:2 trace                  # convergence trace of node 1
 
 Variants: base | frozen (theta=0) | theta<v> | tb<k> (theta .05 + residual balance k) |
-bal<k> (theta 0 + balance k) | dz<d>_<k> (balance k with dead zone d) | rho<v> (reflection) |
+bal<k> (theta 0 + balance k) | dz<d>_<k> (balance k with dead zone d) | rho<v> (reflection) | ex<b> (balance .3 + restart point extrapolated by b) |
 art<v> (artificial restart constant) | om<f> (frozen weight f x omega0) | cold | trace
 
 Findings of round 1: on the C4/C5 frontiers the iteration is in its
@@ -38,7 +38,7 @@ INF = float('inf')
 
 def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=0.05, omega_init=None,
            art=0.36, suff=0.2, nec=0.8, trace=False, long_after=32, balance=0.0, bal_clip=1.0,
-           bal_dead=0.0, rho=1.0):
+           bal_dead=0.0, rho=1.0, extrap=0.0):
     """One node, the device algorithm: reflected Halpern PDHG, evaluation every K (4K after
     ``long_after`` periods) iterations, restart to T(z), primal weight updated at restarts."""
     n, m = P.n, P.m
@@ -94,8 +94,13 @@ def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=
                             lr = np.log(rp / rg)
                             lr = np.sign(lr) * max(abs(lr) - bal_dead, 0.0)
                             omega *= np.exp(balance * np.clip(lr, -bal_clip, bal_clip))
-                    xn, yn = xp, yp
-                    xa, ya = xp.copy(), yp.copy()
+                    if extrap > 0 and np.isfinite(fpe0):       # extrapolated restart point (tried: see DESIGN)
+                        zx = np.clip(xp + extrap * (xp - xa), l, u)
+                        zy = np.maximum(yp + extrap * (yp - ya), 0)
+                    else:
+                        zx, zy = xp, yp
+                    xn, yn = zx, zy
+                    xa, ya = zx.copy(), zy.copy()
                     fpe0, fpe_prev, t = fpe, INF, -1
                     if trace:
                         hist[-1][-1] = why
@@ -119,6 +124,7 @@ def variant_kwargs(v, P):
                          ('bal', lambda s: dict(theta=0.0, balance=float(s))),
                          ('dz', lambda s: dict(bal_dead=float(s.split('_')[0]), balance=float(s.split('_')[1]))),
                          ('rho', lambda s: dict(rho=float(s))),
+                         ('ex', lambda s: dict(balance=0.3, extrap=float(s))),
                          ('art', lambda s: dict(art=float(s))),
                          ('om', lambda s: dict(theta=0.0, omega_init=P.omega0 * float(s)))):
         if v.startswith(prefix):

@@ -86,7 +86,7 @@ class BatchPDHG:
         self.cnorm0 = np.linalg.norm(self.c0)
 
     def solve(self, lb, ub, eps=1e-8, max_iters=200000, K=64, row_mask=None, x0=None, y0=None,
-              reflect=True, restart_to='pdhg', theta=0.5, verbose=False, eps_inf=1e-9, omega_init=None, balance=0.3):
+              reflect=True, restart_to='pdhg', theta=0.5, verbose=False, eps_inf=1e-9, omega_init=None, balance=0.3, balance_dead=0.25):
         """lb, ub: [n, B] (unscaled). Returns dict of per-node arrays."""
         n, m = self.n, self.m
         lb = np.asarray(lb, float).reshape(n, -1)
@@ -208,7 +208,8 @@ class BatchPDHG:
                     # criterion — the primal residual shrinks with the dual step, the gap with the primal step
                     if balance > 0:
                         with np.errstate(divide='ignore', invalid='ignore'):
-                            lr = np.clip(np.log(rp / rg), -1.0, 1.0)
+                            lr = np.log(rp / rg)
+                            lr = np.sign(lr) * np.clip(np.abs(lr) - balance_dead, 0.0, 1.0)
                         fb = omega * np.exp(balance * np.where(np.isfinite(lr), lr, 0.0))
                         ok = do_restart & np.isfinite(fpe0) & (rp > 0) & (rg > 0) \
                             & (fb <= 1e4 * self.omega0) & (fb >= 1e-4 * self.omega0)

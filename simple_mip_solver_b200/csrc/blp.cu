@@ -755,7 +755,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     int NT = pick_nt(W);     // nodes per warp; re-picked when compaction narrows the batch
     DecideArgs D{0, 0, K, o.max_iters, o.eps_rel, o.eps_infeas,
                  env_dbl("BLP_BETA_SUFF", 0.2), env_dbl("BLP_BETA_NEC", 0.8), env_dbl("BLP_BETA_ART", 0.36),
-                 env_dbl("BLP_OMEGA_THETA", 0.05), env_dbl("BLP_OMEGA_BALANCE", 0.3)};
+                 env_dbl("BLP_OMEGA_THETA", 0.05), env_dbl("BLP_OMEGA_BALANCE", 0.3),
+                 env_dbl("BLP_OMEGA_DEADZONE", 0.25)};
     int launches = 0;
 
     CK(cudaEventRecord(h->ev[0], st));

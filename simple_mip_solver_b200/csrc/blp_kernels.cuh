@@ -814,7 +814,7 @@ struct DecideArgs {
     int chunksC, chunksR, steps_in_period, max_iters;
     double eps, eps_inf;
     double beta_suff, beta_nec, beta_art, theta;    // restart thresholds, primal-weight smoothing
-    double balance;   // primal-weight feedback on the lagging criterion (0 = off), see k_decide
+    double balance, balance_dead;   // primal-weight feedback on the lagging criterion (0 = off), see k_decide
 };
 
 // counters: [0] nodes still running after the evaluation, [1] nodes restarting,
@@ -912,9 +912,12 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
         // residual balancing: the primal residual shrinks with the dual step (omega up), the
         // duality gap with the primal step (omega down); push towards whichever criterion lags
         // (bench fixtures: same mean iteration count, slowest node of a 256-node batch 12-25 % earlier;
-        // the feedback alone may move omega at most 1e4 either way from its initial value)
+        // the feedback alone may move omega at most 1e4 either way from its initial value;
+        // criteria within a factor exp(dead zone) of each other count as balanced)
         if (!first && D.balance > 0.0 && rp > 0.0 && rg > 0.0) {
-            const double fb = om * exp(D.balance * fmin(fmax(log(rp / rg), -1.0), 1.0));
+            const double lr = log(rp / rg);
+            const double ex = copysign(fmin(fmax(fabs(lr) - D.balance_dead, 0.0), 1.0), lr);
+            const double fb = om * exp(D.balance * ex);
             if (fb <= 1e4 * P.omega0 && fb >= 1e-4 * P.omega0) om = fb;
         }
         S.omega[node] = om;

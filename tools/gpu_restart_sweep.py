@@ -18,6 +18,8 @@ if os.environ.get('SWEEP_BALANCE'):      # residual-balancing feedback on the pr
     cases = [{}, {'BLP_OMEGA_THETA': '0'}, {'BLP_OMEGA_THETA': '0', 'BLP_OMEGA_BALANCE': '0.3'},
              {'BLP_OMEGA_THETA': '0', 'BLP_OMEGA_BALANCE': '0.1'}, {'BLP_OMEGA_BALANCE': '0.3'},
              {'BLP_OMEGA_THETA': '0.02'}]
+if os.environ.get('SWEEP_BALANCE') == '2':  # dead zone of the feedback
+    cases = [{'BLP_OMEGA_DEADZONE': '0'}, {'BLP_OMEGA_DEADZONE': '0.5'}, {'BLP_OMEGA_DEADZONE': '0.25'}]
 if os.environ.get('SWEEP_COLD'):
     x0 = y0 = None
 for env in cases:

@@ -8,9 +8,11 @@ cost GPU minutes. Uses the oracle's scaling and the bench fixtures; never import
     python tests/tools/cpu_pdhg_lab.py c4 0:8 base frozen tb0.3      # nodes 0..7, three variants
     python tests/tools/cpu_pdhg_lab.py c5 1:2 trace                  # convergence trace of node 1
 
-Variants: base | frozen (theta=0) | theta<v> | tb<k> (theta .05 + residual balance k) |
-bal<k> (theta 0 + balance k) | dz<d>_<k> (balance k with dead zone d) | rho<v> (reflection) | ex<b> (balance .3 + restart point extrapolated by b) |
-art<v> (artificial restart constant) | om<f> (frozen weight f x omega0) | cold | trace
+Variants: base (the shipped rule: smoothing .05, balance .3, dead zone .25) | nobal (balance off) |
+frozen (weight never moves) | theta<v> (smoothing v, no balance) | tb<k> (balance k, no dead zone) |
+bal<k> (same with theta 0) | dz<d>_<k> (balance k, dead zone d) | rho<v> (reflection) |
+ex<b> (restart point extrapolated by b) | art<v> (artificial restart constant) |
+om<f> (frozen weight f x omega0) | cold (no warm start) | trace (base, with the convergence trace)
 
 Findings of round 1: on the C4/C5 frontiers the iteration is in its
 sublinear O(1/k) regime — the primal objective is right to 1e-8 after ~3 k iterations, the other
@@ -20,6 +22,8 @@ scalings; reflection 1.0 and the artificial-restart constant 0.36 are at their o
 bound tightening shrinks the gap by 30 % at a fixed y but does not shorten the run (the primal
 residual binds); a primal weight that is pushed towards the lagging criterion at restarts
 (``BLP_OMEGA_BALANCE``) leaves the mean iteration count alone and cuts the slowest nodes by 12-20 %.
+Iteration counts of this model match the device's (config 3, 128 children: mean 11 504 / max 30 976
+without balancing on both; 11 056 / 34 816 here against 11 052 / 34 816 on the GPU with balance .3).
 """
 import os
 import sys
@@ -37,8 +41,8 @@ INF = float('inf')
 
 
 def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=0.05, omega_init=None,
-           art=0.36, suff=0.2, nec=0.8, trace=False, long_after=32, balance=0.0, bal_clip=1.0,
-           bal_dead=0.0, rho=1.0, extrap=0.0):
+           art=0.36, suff=0.2, nec=0.8, trace=False, long_after=32, balance=0.3, bal_clip=1.0,
+           bal_dead=0.25, rho=1.0, extrap=0.0):
     """One node, the device algorithm: reflected Halpern PDHG, evaluation every K (4K after
     ``long_after`` periods) iterations, restart to T(z), primal weight updated at restarts."""
     n, m = P.n, P.m
@@ -115,18 +119,21 @@ def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=
 
 
 def variant_kwargs(v, P):
+    off = dict(balance=0.0, bal_dead=0.0)
     if v in ('base', 'trace', 'cold'):
         return {}
+    if v == 'nobal':
+        return off
     if v == 'frozen':
-        return dict(theta=0.0)
-    for prefix, make in (('theta', lambda s: dict(theta=float(s))),
-                         ('tb', lambda s: dict(balance=float(s))),
-                         ('bal', lambda s: dict(theta=0.0, balance=float(s))),
+        return dict(off, theta=0.0)
+    for prefix, make in (('theta', lambda s: dict(off, theta=float(s))),
+                         ('tb', lambda s: dict(balance=float(s), bal_dead=0.0)),
+                         ('bal', lambda s: dict(theta=0.0, balance=float(s), bal_dead=0.0)),
                          ('dz', lambda s: dict(bal_dead=float(s.split('_')[0]), balance=float(s.split('_')[1]))),
                          ('rho', lambda s: dict(rho=float(s))),
-                         ('ex', lambda s: dict(balance=0.3, extrap=float(s))),
+                         ('ex', lambda s: dict(extrap=float(s))),
                          ('art', lambda s: dict(art=float(s))),
-                         ('om', lambda s: dict(theta=0.0, omega_init=P.omega0 * float(s)))):
+                         ('om', lambda s: dict(off, theta=0.0, omega_init=P.omega0 * float(s)))):
         if v.startswith(prefix):
             return make(v[len(prefix):])
     raise SystemExit(f'unknown variant {v}')

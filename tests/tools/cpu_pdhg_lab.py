@@ -11,7 +11,7 @@ cost GPU minutes. Uses the oracle's scaling and the bench fixtures; never import
 Variants: base (the shipped rule: smoothing .05, balance .3, dead zone .25) | nobal (balance off) |
 frozen (weight never moves) | theta<v> (smoothing v, no balance) | tb<k> (balance k, no dead zone) |
 bal<k> (same with theta 0) | dz<d>_<k> (balance k, dead zone d) | rho<v> (reflection) |
-ex<b> (restart point extrapolated by b) | art<v> (artificial restart constant) |
+ex<b> (restart point extrapolated by b) | eta<f> (per-node step up to f/||A||) | art<v> (artificial restart constant) |
 om<f> (frozen weight f x omega0) | cold (no warm start) | trace (base, with the convergence trace)
 
 Findings of round 1: on the C4/C5 frontiers the iteration is in its
@@ -42,7 +42,7 @@ INF = float('inf')
 
 def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=0.05, omega_init=None,
            art=0.36, suff=0.2, nec=0.8, trace=False, long_after=32, balance=0.3, bal_clip=1.0,
-           bal_dead=0.25, rho=1.0, extrap=0.0):
+           bal_dead=0.25, rho=1.0, extrap=0.0, eta_max=1.0, eta_safety=0.9):
     """One node, the device algorithm: reflected Halpern PDHG, evaluation every K (4K after
     ``long_after`` periods) iterations, restart to T(z), primal weight updated at restarts."""
     n, m = P.n, P.m
@@ -53,7 +53,8 @@ def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=
     y = np.zeros(m) if y0 is None else np.maximum(y0 / P.dr * P.sc, 0)
     xa, ya = x.copy(), y.copy()
     omega = P.omega0 if omega_init is None else omega_init
-    eta = P.eta
+    eta = eta0 = P.eta
+    eta_resets = 0
     t = 0
     fpe0 = fpe_prev = INF
     rowscale = 1.0 / (P.dr * P.sb)
@@ -85,8 +86,13 @@ def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=
                 if trace:
                     hist.append([tot_it, rp, rg, pobj, dobj, fpe, omega, t + 1, ''])
                 if rp <= eps and rg <= eps:
-                    return dict(iters=tot_it, obj=pobj, dobj=dobj, hist=hist, omega=omega,
+                    return dict(iters=tot_it, obj=pobj, dobj=dobj, hist=hist, omega=omega, eta=eta / eta0,
+                                eta_resets=eta_resets,
                                 x=xp * P.dc / P.sb, y=yp * P.dr / P.sc)
+                cross = dx @ (gp - g)
+                if eta_max > 1.0 and eta > eta0 and fpe > 1.5 * min(fpe_prev, fpe0):
+                    eta, eta_resets = eta0, eta_resets + 1      # the larger step lost contraction: back to 1/||A||
+                    fpe0 = INF                                   # ... and restart from here
                 why = 's' if fpe <= suff * fpe0 else 'n' if (fpe <= nec * fpe0 and fpe > fpe_prev) \
                     else 'a' if t + 1 >= art * tot_it else 'i' if not np.isfinite(fpe0) else ''
                 if why:
@@ -98,6 +104,11 @@ def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=
                             lr = np.log(rp / rg)
                             lr = np.sign(lr) * max(abs(lr) - bal_dead, 0.0)
                             omega *= np.exp(balance * np.clip(lr, -bal_clip, bal_clip))
+                    if eta_max > 1.0 and np.isfinite(fpe0) and abs(cross) > 0:
+                        # per-node step: PDLP's bound ||dz||^2_omega / (2 |dx.A'dy|) >= 1/||A||,
+                        # evaluated on the last step of the phase; the iteration only feels the active block
+                        lim = eta_safety * (omega * (dx @ dx) + (dy @ dy) / omega) / (2 * abs(cross))
+                        eta = float(np.clip(lim, eta0, eta_max * eta0))
                     if extrap > 0 and np.isfinite(fpe0):       # extrapolated restart point (tried: see DESIGN)
                         zx = np.clip(xp + extrap * (xp - xa), l, u)
                         zy = np.maximum(yp + extrap * (yp - ya), 0)
@@ -114,7 +125,7 @@ def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=
             t += 1
         total += Kp
         periods += 1
-    return dict(iters=total, obj=pobj, dobj=dobj, hist=hist, omega=omega,
+    return dict(iters=total, obj=pobj, dobj=dobj, hist=hist, omega=omega, eta=eta / eta0, eta_resets=eta_resets,
                 x=xp * P.dc / P.sb, y=yp * P.dr / P.sc)
 
 
@@ -133,6 +144,7 @@ def variant_kwargs(v, P):
                          ('rho', lambda s: dict(rho=float(s))),
                          ('ex', lambda s: dict(extrap=float(s))),
                          ('art', lambda s: dict(art=float(s))),
+                         ('eta', lambda s: dict(eta_max=float(s))),
                          ('om', lambda s: dict(off, theta=0.0, omega_init=P.omega0 * float(s)))):
         if v.startswith(prefix):
             return make(v[len(prefix):])
@@ -150,7 +162,7 @@ def main():
             warm = {} if v == 'cold' else dict(x0=root['x'], y0=root['y'])
             t0 = time.time()
             r = solve1(P, lb[0], ub[0], trace=v == 'trace', **warm, **variant_kwargs(v, P))
-            print(v, 'node', k, 'iters', r['iters'], 'obj %.6f' % r['obj'], 'omega0 %.3f end %.3f' % (P.omega0, r['omega']),
+            print(v, 'node', k, 'iters', r['iters'], 'obj %.6f' % r['obj'], 'omega0 %.3f end %.3f' % (P.omega0, r['omega']), 'eta x%.2f resets %d' % (r['eta'], r['eta_resets']),
                   'time %.0f' % (time.time() - t0), flush=True)
             for h in r['hist']:
                 if h[-1] or h[0] % 2048 == 0:

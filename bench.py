@@ -39,7 +39,7 @@ WORKLOADS = {
     # name: (n, m, density, max dive depth, fixture)
     'c5': (50000, 20000, 2e-4, 32, 'c5_root.npz'),
     'c4': (10000, 5000, 2e-3, 16, 'c4_root.npz'),
-    'c3': (500, 300, 0.1, 8, None),
+    'c3': (500, 300, 0.1, 8, 'c3_root.npz'),
 }
 METRIC = 'node_lp_solves_per_sec'
 UNIT = 'node-LPs/s'
@@ -261,8 +261,9 @@ def main():
 
     from simple_mip_solver_b200.instances import frontier_nodes
     n, m, B = d.n, d.m, args.batch
-    if root is None:
-        root = root_by_oracle(d)
+    if root is None:      # the product arm never runs the oracle, not even to define its workload
+        raise SystemExit(f'bench_data/{WORKLOADS[args.workload][4]} is missing: make it with '
+                         f'tests/tools/make_bench_fixture.py')
 
     # ---- CPU baseline first (fork pool before CUDA is initialised), rank 0 at N=1 only ----
     cpu = None

@@ -294,7 +294,19 @@ def main():
         dist.barrier()
 
     lp = engine.BatchLP(d.A, d.b, d.c, device=local_rank)
-    use_comm = lp.comm_init()                 # blp_allreduce_min over NCCL when world > 1
+    # blp_allreduce_min over the library's own NCCL communicator when world > 1. If any rank cannot
+    # build it (no libnccl to bind), ALL ranks drop to torch.distributed for the 16-byte exchange:
+    # the node LPs, which are what is timed, do not depend on it.
+    use_comm = False
+    if world > 1:
+        try:
+            use_comm = lp.comm_init()
+        except Exception as e:           # noqa: BLE001 - reported, then agreed on by all ranks
+            print(f'[rank {rank}] blp_comm_init failed ({e}); using torch.distributed', file=sys.stderr)
+        agreed = parallel.allreduce_sum([1.0 if use_comm else 0.0], device=dev)[0]
+        if use_comm and agreed < world:
+            lp.comm_destroy()
+        use_comm = agreed == world
     ld = engine.leading_dim(B)
     W = min(args.slots, B) if args.slots > 0 else B           # resident node slots
     ldW = engine.leading_dim(W)
@@ -471,6 +483,9 @@ def main():
         cfg = workload_config(args, d, B)
         cfg['state_mb'] = round(state_mb, 1)
         cfg['timing'] = 'value: CUDA events on the library stream around the K timed steps, max over ranks'
+        if world > 1:
+            cfg['bound_exchange'] = ('blp_allreduce_min (library NCCL communicator), 16 bytes per step' if use_comm
+                                     else 'torch.distributed all_reduce (library communicator unavailable)')
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / max(args.steps, 1), 'higher_is_better': True,

@@ -363,12 +363,19 @@ class BatchLP:
             return False
         rank, world = dist.get_rank(), dist.get_world_size()
         buf = C.create_string_buffer(128)
-        if rank == 0:
-            _check(self._lib.blp_comm_unique_id(buf), 'blp_comm_unique_id')
-        box = [buf.raw]
+        box = [None]
+        if rank == 0:       # a failure here must still reach the broadcast, or the other ranks wait forever
+            rc = self._lib.blp_comm_unique_id(buf)
+            box = [buf.raw if rc == 0 else (self._lib.blp_last_error() or b'?').decode(errors='replace')]
         dist.broadcast_object_list(box, src=0)
+        if not isinstance(box[0], bytes):
+            raise RuntimeError(f'blp_comm_unique_id failed on rank 0: {box[0]}')
         _check(self._lib.blp_comm_init(self._h, world, rank, box[0]), 'blp_comm_init')
         return True
+
+    def comm_destroy(self):
+        """Leave the library's communicator (blp_comm_destroy); ``close()`` does it as well."""
+        _check(self._lib.blp_comm_destroy(self._h), 'blp_comm_destroy')
 
     def allreduce_min(self, incumbent: float, dual_bound: float):
         """Global (min incumbent, min open lower bound) through blp_allreduce_min."""

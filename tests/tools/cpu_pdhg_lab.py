@@ -11,7 +11,7 @@ cost GPU minutes. Uses the oracle's scaling and the bench fixtures; never import
 Variants: base (the shipped rule: smoothing .05, balance .3, dead zone .25) | nobal (balance off) |
 frozen (weight never moves) | theta<v> (smoothing v, no balance) | tb<k> (balance k, no dead zone) |
 bal<k> (same with theta 0) | dz<d>_<k> (balance k, dead zone d) | rho<v> (reflection) |
-ex<b> (restart point extrapolated by b) | eta<f> (per-node step up to f/||A||) | art<v> (artificial restart constant) |
+ex<b> (restart point extrapolated by b) | eta<f> (per-node step up to f/||A||) | hs<c> (Halpern weight (k+c)/(k+c+1)) | art<v> (artificial restart constant) |
 om<f> (frozen weight f x omega0) | cold (no warm start) | trace (base, with the convergence trace)
 
 Findings of round 1: on the C4/C5 frontiers the iteration is in its
@@ -42,7 +42,7 @@ INF = float('inf')
 
 def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=0.05, omega_init=None,
            art=0.36, suff=0.2, nec=0.8, trace=False, long_after=32, balance=0.3, bal_clip=1.0,
-           bal_dead=0.25, rho=1.0, extrap=0.0, eta_max=1.0, eta_safety=0.9):
+           bal_dead=0.25, rho=1.0, extrap=0.0, eta_max=1.0, eta_safety=0.9, hshift=1.0):
     """One node, the device algorithm: reflected Halpern PDHG, evaluation every K (4K after
     ``long_after`` periods) iterations, restart to T(z), primal weight updated at restarts."""
     n, m = P.n, P.m
@@ -66,7 +66,7 @@ def solve1(P, lb, ub, x0=None, y0=None, eps=1e-7, max_iters=150000, K=64, theta=
         Kp = K if periods < long_after else 4 * K
         for it in range(Kp):
             tau, sig = eta / omega, eta * omega
-            w = (t + 1) / (t + 2)
+            w = (t + hshift) / (t + hshift + 1)          # Halpern weight; hshift 1 is the device's
             g = AT @ y
             xp = np.clip(x - tau * (c - g), l, u)
             xbar = 2 * xp - x
@@ -145,6 +145,7 @@ def variant_kwargs(v, P):
                          ('ex', lambda s: dict(extrap=float(s))),
                          ('art', lambda s: dict(art=float(s))),
                          ('eta', lambda s: dict(eta_max=float(s))),
+                         ('hs', lambda s: dict(hshift=float(s))),
                          ('om', lambda s: dict(off, theta=0.0, omega_init=P.omega0 * float(s)))):
         if v.startswith(prefix):
             return make(v[len(prefix):])

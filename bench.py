@@ -294,19 +294,9 @@ def main():
         dist.barrier()
 
     lp = engine.BatchLP(d.A, d.b, d.c, device=local_rank)
-    # blp_allreduce_min over the library's own NCCL communicator when world > 1. If any rank cannot
-    # build it (no libnccl to bind), ALL ranks drop to torch.distributed for the 16-byte exchange:
-    # the node LPs, which are what is timed, do not depend on it.
-    use_comm = False
-    if world > 1:
-        try:
-            use_comm = lp.comm_init()
-        except Exception as e:           # noqa: BLE001 - reported, then agreed on by all ranks
-            print(f'[rank {rank}] blp_comm_init failed ({e}); using torch.distributed', file=sys.stderr)
-        agreed = parallel.allreduce_sum([1.0 if use_comm else 0.0], device=dev)[0]
-        if use_comm and agreed < world:
-            lp.comm_destroy()
-        use_comm = agreed == world
+    # blp_allreduce_min over the library's own NCCL communicator when world > 1; all ranks or none
+    # (parallel.join_library_comm): the node LPs, which are what is timed, do not depend on it
+    use_comm = parallel.join_library_comm(lp, device=dev, log=lambda msg: print(msg, file=sys.stderr))
     ld = engine.leading_dim(B)
     W = min(args.slots, B) if args.slots > 0 else B           # resident node slots
     ldW = engine.leading_dim(W)

@@ -49,6 +49,30 @@ def allreduce_bounds(incumbent: float, dual_bound: float, device=None, lp=None) 
     return float(a), float(b)
 
 
+def join_library_comm(lp, device=None, log=None) -> bool:
+    """Give ``lp`` (an ``engine.BatchLP``) the library's own NCCL communicator on every rank, or on none.
+
+    Each rank tries ``lp.comm_init()``; the ranks then agree (one all-reduce through the process
+    group) on whether ALL of them succeeded. If any failed — libnccl could not be bound, say — the
+    ranks that did succeed leave the communicator again and everybody uses ``torch.distributed`` for
+    the 16-byte exchange, so that no rank ever waits in a collective its peers do not enter.
+    Returns True when ``allreduce_bounds(..., lp=lp)`` may be used. Single rank: False, no-op."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return False
+    ok = False
+    try:
+        ok = bool(lp.comm_init())
+    except Exception as e:           # noqa: BLE001 - reported, then agreed on by all ranks
+        if log:
+            log(f'[rank {dist.get_rank()}] blp_comm_init failed ({e}); using torch.distributed')
+    world = dist.get_world_size()
+    agreed = allreduce_sum([1.0 if ok else 0.0], device=device)[0]
+    if ok and agreed < world:
+        lp.comm_destroy()
+    return agreed == world
+
+
 def allreduce_max(value: float, device=None) -> float:
     import torch
     import torch.distributed as dist

@@ -55,3 +55,55 @@ def test_two_rank_exchange():
     assert got[0][1] == [0, 1, 2, 3, 4] and got[1][1] == [5, 6, 7, 8, 9]
     for _, _, g_inc, g_low, t, s in got:
         assert g_inc == 3.5 and g_low == 0.25 and t == 2.0 and s == [10.0, 2.0]
+
+
+class _FakeLP:
+    """Stands in for engine.BatchLP: comm_init fails on the ranks listed in ``bad``."""
+    def __init__(self, rank, bad):
+        self.rank, self.bad, self.joined, self.left = rank, bad, False, False
+
+    def comm_init(self):
+        if self.rank in self.bad:
+            raise RuntimeError('libnccl.so.2 not found')
+        self.joined = True
+        return True
+
+    def comm_destroy(self):
+        self.left = True
+
+
+def _comm_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    res = []
+    for bad in ((), (1,), (0, 1)):
+        lp = _FakeLP(rank, bad)
+        msgs = []
+        use = parallel.join_library_comm(lp, log=msgs.append)
+        res.append((use, lp.joined, lp.left, len(msgs)))
+    out.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_all_ranks_or_none_use_the_library_communicator():
+    assert parallel.join_library_comm(_FakeLP(0, ())) is False        # no process group: nothing to join
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_comm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # every rank succeeds: both use it, nobody leaves
+    assert got[0][0] == (True, True, False, 0) and got[1][0] == (True, True, False, 0)
+    # rank 1 fails: rank 0 joined and must leave again, both fall back
+    assert got[0][1] == (False, True, True, 0) and got[1][1] == (False, False, False, 1)
+    # both fail
+    assert got[0][2] == (False, False, False, 1) and got[1][2] == (False, False, False, 1)

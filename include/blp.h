@@ -176,6 +176,52 @@ int blp_solve_children_host(blp_handle h, int B, const double* parent_lb, const 
                             double* obj, double* lower_bound, int32_t* status, int32_t* iters,
                             double* x, double* y, int32_t* frac_idx, blp_stats* stats);
 
+/*
+ * Dual simplex path for SMALL node LPs (at most blp_simplex_max_rows() rows incl. appended cut rows):
+ * one CTA per node runs a bounded dual simplex with a dense basis inverse (dual steepest edge pricing,
+ * bound flipping ratio test; csrc/blp_simplex.cuh, restated in numpy in oracle/dual_simplex.py). It
+ * returns what the reference reads from CLP after lp.dual(): a VERTEX and its BASIS, so that the
+ * integrality test (base_node.py:281-283), the most fractional index (:544-562), the tableau
+ * (:513-530) and get/setBasisStatus (:589, 608) mean what they mean in the reference, and max_pivots is
+ * literally lp.maxNumIteration (:645, the 5 pivots of strong branching, pseudo_cost.py:22).
+ * All arrays are HOST arrays, node major (one contiguous vector per node):
+ *   lb, ub            [B][n]
+ *   row_mask          [B][m-m_base] uint8 or NULL (all appended rows present)
+ *   col_status,       [B][n], [B][m] int8 in CLP's coding (1 basic, 2 at upper, 3 at lower; anything else
+ *   row_status        counts as "at lower") = lp.setBasisStatus of the parent's basis; both NULL = slack
+ *                     basis. A status that is not a basis is repaired (rows without a pivot keep their slack).
+ *   parent_slot       [B] or NULL: node k starts from the FACTORISED basis node parent_slot[k] of the
+ *                     previous blp_simplex_* call on this handle ended with (-1: factorise from the status).
+ *                     The store is dropped when rows are appended or truncated.
+ * outputs (each may be NULL): obj [B] (c.x of the final basic solution: the dual objective when status
+ * is 3, which is a valid lower bound as in pseudo_cost.py:86-92), status [B] CLP codes, pivots [B],
+ * x [B][n], y [B][m] row duals, rc [B][n] reduced costs, col_status_out [B][n], row_status_out [B][m].
+ * stats (may be NULL): iterations = max pivots of a node, node_iterations = sum of pivots, total_ms,
+ * step_kernel_ms = the simplex kernel, kernel_launches, refills = bound flips of the ratio tests.
+ */
+int blp_simplex_max_rows(void);
+int blp_simplex_batch_host(blp_handle h, int B, const double* lb, const double* ub, const uint8_t* row_mask,
+                           const int8_t* col_status, const int8_t* row_status, const int32_t* parent_slot,
+                           int max_pivots, double* obj, int32_t* status, int32_t* pivots, double* x,
+                           double* y, double* rc, int8_t* col_status_out, int8_t* row_status_out,
+                           blp_stats* stats);
+
+/* Children of ONE parent (pseudo_cost.py:57-62, base_node.py:592-608): bounds as deltas against the
+ * parent's (as in blp_solve_children_host), ONE row_mask [m-m_base], ONE parent basis col_status [n] /
+ * row_status [m] (or NULL) and ONE parent_slot (or -1) shared by all B children. */
+int blp_simplex_children_host(blp_handle h, int B, const double* parent_lb, const double* parent_ub,
+                              const int32_t* delta_ptr, const int32_t* delta_var, const double* delta_lb,
+                              const double* delta_ub, const uint8_t* row_mask, const int8_t* col_status,
+                              const int8_t* row_status, int parent_slot, int max_pivots, double* obj,
+                              int32_t* status, int32_t* pivots, double* x, double* y, double* rc,
+                              int8_t* col_status_out, int8_t* row_status_out, blp_stats* stats);
+
+/* Rows of the simplex tableau inv(B) [A, -I] of node `slot` of the previous blp_simplex_* call:
+ * out[t][0..n+m) is the row of the basic variable vars[t] (structural j < n, slack of row i = n + i),
+ * zeros if vars[t] is not basic. Replaces the dense inverse of BaseNode.tableau (base_node.py:513-526)
+ * for the rows _find_gomory_cuts needs (:468-511). */
+int blp_simplex_tableau_rows_host(blp_handle h, int slot, int nrows, const int32_t* vars, double* out);
+
 /* Batched SpMV on the handle's (unscaled) matrix, device pointers, node-fastest layout:
  * transpose == 0: Y[m][ld] = A X[n][ld];  transpose == 1: Y[n][ld] = A' X[m][ld].
  * Exposed for parity tests and for the SpMV roofline measurement. */

@@ -21,13 +21,17 @@ from typing import Dict, List, Optional
 import numpy as np
 import scipy.sparse as sp
 
+from oracle.dual_simplex import dual_simplex
 from oracle.highs_lp import HIGHS_INF, HighsLP
-from simple_mip_solver_b200.compat.binary_tree import BinaryTree as _Tree
-from simple_mip_solver_b200.compat.cylp_like import (COIN_INFINITY, CyLPArray, CyLPBounds,
-                                                     CyLPConstraint, CyLPExpr, CyLPVar)
-from simple_mip_solver_b200.compat.mps import read_mps
+from oracle.mps_py import read_mps
+from oracle.ref_lookalikes import BinaryTree as _Tree
+from oracle.ref_lookalikes import (COIN_INFINITY, CyLPArray, CyLPBounds, CyLPConstraint, CyLPExpr,
+                                   CyLPVar)
 
 WARM_START = True      # False: every solve is cold, a deterministic function of the LP data
+# which exact simplex answers lp.dual(): 'highs' (HiGHS 1.12 dual simplex) or 'dual_simplex' (the
+# textbook dual simplex of oracle/dual_simplex.py, the restatement of what the device runs)
+LP_BACKEND = 'highs'
 
 
 class _DenseCoefConstraint(CyLPConstraint):
@@ -166,7 +170,27 @@ class CyClpSimplex:
         pass
 
     # -- solving
+    def _solve_ds(self):
+        n = self.nVariables
+        c = np.zeros(n) if self._objective is None else np.asarray(self._objective)
+        A = self.coefMatrix.toarray()
+        assert (np.asarray(self.constraintsUpper) >= 1e300).all(), 'rows must read a.x >= b'
+        cs = rs = None
+        if WARM_START and self._basis is not None and len(self._basis[0]) == n \
+                and len(self._basis[1]) == A.shape[0]:
+            cs, rs = self._basis
+        r = dual_simplex(A, np.asarray(self.constraintsLower), c, np.asarray(self._l), np.asarray(self._u),
+                         col_status=cs, row_status=rs, max_pivots=self.maxNumIteration)
+        self._status, self.iteration = r.status, r.pivots
+        self._obj = r.objective if r.status != 1 else float('inf')
+        self._x = None if r.status == 1 else CyLPArray(r.x)
+        self._y, self._rc = r.y, r.rc
+        self._basis = (r.col_status.astype(np.int32), r.row_status.astype(np.int32))
+        return r.status
+
     def _solve(self):
+        if LP_BACKEND == 'dual_simplex':
+            return self._solve_ds()
         n = self.nVariables
         c = np.zeros(n) if self._objective is None else np.asarray(self._objective)
         A = self.coefMatrix

@@ -29,6 +29,11 @@ COIN_INFINITY = 1.7976931348623157e308      # what CyClpSimplex.getCoinInfinity(
 # pivots, base_node.py:645; a first-order iteration is far cheaper than a pivot)
 PDHG_ITERS_PER_PIVOT = 512
 
+# device memory the dense basis inverses of one simplex call may take ('auto' method selection)
+SIMPLEX_MEMORY_BUDGET = 16 << 30
+
+BASIC, AT_UPPER, AT_LOWER = 1, 2, 3      # CLP's getBasisStatus coding
+
 
 class CyLPArray(np.ndarray):
     """ndarray subclass with the name the reference imports from cylp.py.modeling.CyLPModel."""
@@ -139,6 +144,7 @@ class SharedLP:
     Owns the GPU handle. Cut rows are appended to the device matrix the first time an LP that
     contains them is solved and are switched on per node through the row mask of the batched call.
     """
+    default_method = 'auto'         # 'auto' | 'simplex' | 'pdhg' for models created from now on
 
     def __init__(self, A, b, c, device: int = 0):
         self.A = sp.csr_matrix(A, dtype=np.float64)
@@ -148,12 +154,17 @@ class SharedLP:
         self.device = device
         self._engine = None
         self.cut_names: List[str] = []                     # pool order = device row order
-        self.cut_index: Dict[str, int] = {}
+        self.cut_index: Dict[Tuple[str, int], int] = {}     # (name, content digest) -> pool row
         self.cut_rows: List[Tuple[np.ndarray, float]] = []
         self._on_device = 0                                # how many pool rows the device has
         self.solve_calls = 0
         self.lps_solved = 0
         self.kernel_launches = 0
+        # which device path solves the node LPs: 'auto' = the dual simplex (a vertex and a basis, as
+        # the reference gets from CLP) while the LP is small enough for it, PDHG beyond
+        self.method = SharedLP.default_method
+        self.simplex_calls = 0          # id of the last simplex call (its factors are the engine's store)
+        self.simplex_pivots = 0
 
     @property
     def engine(self):
@@ -162,14 +173,32 @@ class SharedLP:
             self._engine = BatchLP(self.A, self.b, self.c, device=self.device)
         return self._engine
 
-    def register_cut(self, name: str, pi: np.ndarray, pi0: float) -> int:
-        k = self.cut_index.get(name)
+    def register_cut(self, key: Tuple[str, int], pi: np.ndarray, pi0: float) -> int:
+        """Pool row of the cut ``key = (name, digest of its coefficients)``. Two runs on one model can
+        produce the same NAME for different rows (cut_gomory_<node>_<round>_<row>): the content is
+        part of the identity, so a re-used name never resolves to a stale device row."""
+        k = self.cut_index.get(key)
         if k is None:
             k = len(self.cut_names)
-            self.cut_names.append(name)
-            self.cut_index[name] = k
+            self.cut_names.append(key[0])
+            self.cut_index[key] = k
             self.cut_rows.append((np.asarray(pi, dtype=np.float64).copy(), float(pi0)))
         return k
+
+    def pool_row(self, lp: 'CyClpSimplex', name: str) -> int:
+        return self.cut_index[lp._cut_keys[name]]
+
+    def use_simplex(self, n_lps: int = 1) -> bool:
+        if self.method == 'pdhg':
+            return False
+        eng = self.engine
+        ok = bool(getattr(eng, 'simplex_capable', False))
+        if ok and self.method == 'auto':
+            m = self.m + len(self.cut_rows)
+            ok = n_lps * m * m * 8 <= SIMPLEX_MEMORY_BUDGET
+        if not ok and self.method == 'simplex':
+            raise RuntimeError('the LP is too large for the dual simplex path')
+        return ok
 
     def sync_cuts(self):
         if self._on_device < len(self.cut_rows):
@@ -193,6 +222,7 @@ class CyClpSimplex:
         self._l = None if lower is None else CyLPArray(lower)
         self._u = None if upper is None else CyLPArray(upper)
         self._cuts: Dict[str, Tuple[np.ndarray, float]] = {}      # cut rows present in this LP
+        self._cut_keys: Dict[str, Tuple[str, int]] = {}            # their pool identities
         self._pending_rows = []                                    # rows added before `shared` exists
         self._objective = None
         self.logLevel = 0
@@ -206,7 +236,12 @@ class CyClpSimplex:
         self._lower_bound = -np.inf
         self._solved_key = None
         self._warm: Optional[Tuple[np.ndarray, Dict[str, float], np.ndarray]] = None
-        self._basis = None
+        self._basis = None              # (cols, rows) handed over by setBasisStatus, rows in this LP's order
+        self._basis_out = None          # (cols, base rows, {cut name: status}) of the last simplex solve
+        self._factor_ref = None         # (simplex call id, slot, cut names) of the last simplex solve
+        self._parent_ref = None         # the parent's _factor_ref (copy_for_child)
+        self._parent_bounds = (None, None)   # the parent's bound arrays (children of one parent share them)
+        self._basis_start = None        # setBasisStatus by row NAME: (cols, base rows, {cut name: status})
         self.integer_indices_hint: Optional[Sequence[int]] = None
         self.solver_opts: Dict[str, float] = {}
         if shared is not None:
@@ -257,13 +292,16 @@ class CyClpSimplex:
         assert (np.asarray(cons.upper) >= 1e300).all(), 'rows must be one sided: a.x >= b'
         for r in range(M.shape[0]):
             nm = cons.name if M.shape[0] == 1 else f'{cons.name}_{r}'
-            self._cuts[nm] = (np.asarray(M.getrow(r).todense()).ravel(), float(cons.lower[r]))
+            pi, pi0 = np.asarray(M.getrow(r).todense()).ravel(), float(cons.lower[r])
+            self._cuts[nm] = (pi, pi0)
+            self._cut_keys[nm] = (nm, hash((pi.tobytes(), pi0)))
         self._solved_key = None
 
     def removeConstraint(self, name: str):
         if name not in self._cuts:
             raise KeyError(f'no removable constraint named {name!r}')
         del self._cuts[name]
+        del self._cut_keys[name]
         self._solved_key = None
 
     def _finalize(self, device: int = 0):
@@ -400,11 +438,16 @@ class CyClpSimplex:
         return self._lower_bound
 
     def getBasisStatus(self):
-        """Active-set image of the last primal-dual pair in CLP's coding (1 basic, 2 at upper,
-        3 at lower): a column strictly inside its bounds, or a row with slack, counts as basic.
-        At a non-degenerate vertex this is the simplex basis; elsewhere the count differs from the
-        number of rows and ``BaseNode.tableau`` returns None exactly as the reference does when
-        CLP reports an inconsistent basis (base_node.py:518-519)."""
+        """(column status, row status) in CLP's coding (1 basic, 2 at upper, 3 at lower), rows in this
+        LP's order (base rows, then its cut rows). After a dual simplex solve this is the optimal
+        BASIS, as in the reference (base_node.py:589). After a PDHG solve (large LPs) it is the active
+        set of the primal-dual pair: a column strictly inside its bounds, or a row with slack, counts
+        as basic; away from a non-degenerate vertex that is not a basis and ``BaseNode.tableau``
+        returns None as the reference does for an inconsistent basis (base_node.py:518-519)."""
+        if self._basis_out is not None and self._solved_key == self._state_key():
+            cols, base, cuts = self._basis_out
+            rows = np.concatenate([base, [cuts.get(nm, BASIC) for nm in self._cuts]]).astype(np.int32)
+            return cols.astype(np.int32), rows
         if self._x is None:
             n, m = self.nVariables, self.nConstraints
             return np.full(n, 3, dtype=np.int32), np.full(m, 1, dtype=np.int32)
@@ -418,8 +461,37 @@ class CyClpSimplex:
         rows = np.where(slack > tol * (1.0 + np.abs(self.constraintsLower)), 1, 3).astype(np.int32)
         return cols, rows
 
+    @property
+    def has_exact_basis(self) -> bool:
+        """True when getBasisStatus() is the basis of a dual simplex solve of the current LP."""
+        return self._basis_out is not None and self._solved_key == self._state_key()
+
     def setBasisStatus(self, cols, rows):
-        self._basis = (np.asarray(cols).copy(), np.asarray(rows).copy())
+        """Starting basis of the next dual simplex solve (base_node.py:608); rows in this LP's
+        current order, remembered by row name so that later cut rounds cannot shift them."""
+        cols, rows = np.asarray(cols).copy(), np.asarray(rows).copy()
+        self._basis = (cols, rows)
+        m = self._need_shared().m
+        if len(cols) == self.nVariables and len(rows) == m + len(self._cuts):
+            self._basis_start = (cols.astype(np.int8), rows[:m].astype(np.int8),
+                                 {nm: int(rows[m + t]) for t, nm in enumerate(self._cuts)})
+        else:
+            self._basis_start = None
+
+    def tableau_rows(self, variables) -> Optional[np.ndarray]:
+        """Rows of the simplex tableau inv(B) [A, -I] for the given basic variables (LP numbering:
+        structurals, then the slack of every row in this LP's order), computed on the device from the
+        factorised basis of the last simplex solve; None when that factor is gone (another batch was
+        solved since) or the LP was not solved by the simplex path."""
+        sh = self._need_shared()
+        ref = self._factor_ref
+        if ref is None or self._solved_key != self._state_key() or ref[0] != sh.simplex_calls:
+            return None
+        n, m = sh.n, sh.m
+        pool = [m + sh.pool_row(self, nm) for nm in self._cuts]      # pool row of every cut row of this LP
+        to_pool = np.concatenate([np.arange(n + m), n + np.asarray(pool, dtype=int)]).astype(int)
+        rows = sh.engine.simplex_tableau_rows(ref[1], to_pool[np.asarray(variables, dtype=int)])
+        return rows[:, to_pool]
 
     def set_warm_start(self, x, duals_by_row: Dict[str, float], y_base):
         """Parent's primal vector and row duals; the analogue of handing the parent's basis to
@@ -434,7 +506,7 @@ class CyClpSimplex:
         return self._shared
 
     def _state_key(self):
-        return (self._l.tobytes(), self._u.tobytes(), tuple(self._cuts), int(self.maxNumIteration))
+        return (self._l.tobytes(), self._u.tobytes(), tuple(self._cut_keys.values()), int(self.maxNumIteration))
 
     def dual(self):
         if self._solved_key is None or self._solved_key != self._state_key():
@@ -448,9 +520,13 @@ class CyClpSimplex:
         (what the per-child rebuild of base_node.py:592-608 amounts to)."""
         child = CyClpSimplex(self._need_shared(), self._l.copy(), self._u.copy())
         child._cuts = dict(self._cuts)
+        child._cut_keys = dict(self._cut_keys)
         child._objective = self._objective
         child.integer_indices_hint = self.integer_indices_hint
         child.solver_opts = self.solver_opts
+        if self._factor_ref is not None and self._solved_key == self._state_key():
+            child._parent_ref = self._factor_ref
+        child._parent_bounds = (self._l, self._u)
         if self._x is not None and self._y is not None:
             sh = self._shared
             child.set_warm_start(self._x, {nm: self._y[sh.m + k] for k, nm in enumerate(self._cuts)},
@@ -486,8 +562,129 @@ def solve_lps(lps: Iterable[CyClpSimplex], force: bool = False) -> int:
 def _solve_group(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_opts):
     for lp in batch:
         for nm, (pi, pi0) in lp._cuts.items():
-            sh.register_cut(nm, pi, pi0)
+            sh.register_cut(lp._cut_keys[nm], pi, pi0)
     sh.sync_cuts()
+    if sh.use_simplex(len(batch)):
+        _solve_group_simplex(sh, batch, budget)
+    else:
+        _solve_group_pdhg(sh, batch, budget, default_opts)
+    for lp in batch:
+        lp._solved_key = lp._state_key()
+
+
+def _child_deltas(batch: List[CyClpSimplex]):
+    """If every LP of the batch differs from the first one's PARENT bounds in a few entries only
+    — the children of one strong-branching round (base_node.py:592-608) — return those parent
+    bounds and the per-LP ``(var, lb, ub)`` changes; else None."""
+    first = batch[0]
+    pl, pu = getattr(first, '_parent_bounds', (None, None))
+    if pl is None or len(batch) < 2:
+        return None
+    deltas = []
+    for lp in batch:
+        if getattr(lp, '_parent_bounds', (None, None))[0] is not pl:
+            return None
+        idx = np.flatnonzero((lp._l != pl) | (lp._u != pu))
+        if len(idx) > 8:
+            return None
+        deltas.append([(int(j), float(lp._l[j]), float(lp._u[j])) for j in idx])
+    return pl, pu, deltas
+
+
+def _solve_group_simplex(sh: SharedLP, batch: List[CyClpSimplex], budget: int):
+    """One batched dual simplex call: vertex, duals, reduced costs and the optimal basis per node LP."""
+    eng = sh.engine
+    B, n, m, mc = len(batch), sh.n, sh.m, len(sh.cut_names)
+    use_cache = bool(batch[0].solver_opts.get('factor_cache', False))
+    same_cuts = all(lp._cut_keys == batch[0]._cut_keys for lp in batch)
+
+    def start_of(lp):
+        # a re-solve continues from the LP's own last basis (CLP keeps it inside the object), a first
+        # solve from what setBasisStatus handed over (base_node.py:608)
+        return lp._basis_out if lp._basis_out is not None else lp._basis_start
+
+    def status_rows(lp):
+        """starting status of the pool rows: base rows and this LP's cuts from the starting basis,
+        everything else basic (new cut rows enter with their slack basic)"""
+        rows = np.full(m + mc, BASIC, dtype=np.int8)
+        cols = np.full(n, AT_LOWER, dtype=np.int8)
+        start = start_of(lp)
+        if start is not None:
+            cols = np.asarray(start[0], dtype=np.int8)
+            rows[:m] = start[1]
+            for nm in lp._cuts:
+                rows[m + sh.pool_row(lp, nm)] = start[2].get(nm, BASIC)
+        return cols, rows
+
+    def parent_slot(lp):
+        keys = tuple(lp._cut_keys.values())
+        for ref in (lp._factor_ref, lp._parent_ref):
+            if use_cache and ref is not None and ref[0] == sh.simplex_calls and ref[2] == keys:
+                return ref[1]
+        return -1
+
+    def same_start(a, b):
+        sa, sb = start_of(a), start_of(b)
+        if sa is None or sb is None:
+            return sa is sb
+        return sa is sb or (np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1]) and sa[2] == sb[2])
+
+    same_basis = all(same_start(lp, batch[0]) and parent_slot(lp) == parent_slot(batch[0]) for lp in batch)
+
+    kids = _child_deltas(batch) if (same_cuts and same_basis) else None
+    if kids is not None:
+        pl, pu, deltas = kids
+        lp0 = batch[0]
+        mask = None
+        if mc:
+            mask = np.zeros(mc, dtype=np.uint8)
+            for nm in lp0._cuts:
+                mask[sh.pool_row(lp0, nm)] = 1
+        cols, rows = status_rows(lp0)
+        slot = parent_slot(lp0)
+        res = eng.simplex_children(np.where(pl <= -1e30, -np.inf, pl), np.where(pu >= 1e30, np.inf, pu), deltas,
+                                   row_mask=mask, col_status=cols, row_status=rows, parent_slot=slot,
+                                   max_pivots=budget)
+    else:
+        lb = np.empty((B, n))
+        ub = np.empty((B, n))
+        mask = np.zeros((B, mc), dtype=np.uint8) if mc else None
+        cs = np.empty((B, n), dtype=np.int8)
+        rs = np.empty((B, m + mc), dtype=np.int8)
+        par = np.full(B, -1, dtype=np.int32)
+        for k, lp in enumerate(batch):
+            lb[k] = np.where(lp._l <= -1e30, -np.inf, lp._l)
+            ub[k] = np.where(lp._u >= 1e30, np.inf, lp._u)
+            for nm in lp._cuts:
+                mask[k, sh.pool_row(lp, nm)] = 1
+            cs[k], rs[k] = status_rows(lp)
+            par[k] = parent_slot(lp)
+        res = eng.simplex_batch(lb, ub, row_mask=mask, col_status=cs, row_status=rs,
+                                parent_slot=par if (par >= 0).any() else None, max_pivots=budget)
+    sh.solve_calls += 1
+    sh.simplex_calls += 1
+    sh.lps_solved += B
+    sh.kernel_launches += int(res.stats.get('kernel_launches', 1))
+    sh.simplex_pivots += int(res.pivots.sum())
+    for k, lp in enumerate(batch):
+        st = int(res.status[k])
+        lp._status = st
+        lp.iteration = int(res.pivots[k])
+        rows = [m + sh.pool_row(lp, nm) for nm in lp._cuts]
+        lp._basis_out = (res.col_status[k].copy(), res.row_status[k, :m].copy(),
+                         {nm: int(res.row_status[k, r]) for nm, r in zip(lp._cuts, rows)})
+        lp._factor_ref = (sh.simplex_calls, k, tuple(lp._cut_keys.values()))
+        if st == 1:
+            lp._obj, lp._x, lp._y, lp._rc, lp._lower_bound = float('inf'), None, None, None, float('inf')
+            continue
+        lp._x = CyLPArray(res.x[k])
+        lp._y = np.concatenate([res.y[k, :m], res.y[k, rows]]) if rows else res.y[k, :m].copy()
+        lp._rc = CyLPArray(res.reduced_costs[k])
+        lp._obj = float(res.objective[k])
+        lp._lower_bound = lp._obj          # a dual feasible basis: c.x of the basic solution is the dual objective
+
+
+def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_opts):
     eng = sh.engine
     B, n, m, mc = len(batch), sh.n, sh.m, len(sh.cut_names)
     lb = np.empty((B, n))
@@ -500,16 +697,15 @@ def _solve_group(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_o
         lb[k] = np.where(lp._l <= -1e30, -np.inf, lp._l)
         ub[k] = np.where(lp._u >= 1e30, np.inf, lp._u)
         for nm in lp._cuts:
-            mask[k, sh.cut_index[nm]] = 1
+            mask[k, sh.pool_row(lp, nm)] = 1
         if lp._warm is not None:
             wx, wcuts, wy = lp._warm
             x0[k] = wx
             y0[k, :m] = wy
             for nm, v in wcuts.items():
-                j = sh.cut_index.get(nm)
-                if j is not None and nm in lp._cuts:
-                    y0[k, m + j] = v
-    okw = dict(batch[0].solver_opts)
+                if nm in lp._cuts:
+                    y0[k, m + sh.pool_row(lp, nm)] = v
+    okw = {k: v for k, v in batch[0].solver_opts.items() if k not in ('factor_cache', 'method')}
     if budget < 2147483647:
         okw['max_iters'] = int(min(budget * PDHG_ITERS_PER_PIVOT, 2_000_000_000))
     opts = default_opts(**okw)
@@ -523,7 +719,9 @@ def _solve_group(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_o
         lp._status = st
         lp.iteration = int(res.iterations[k])
         lp._lower_bound = float(res.lower_bound[k])
-        rows = [sh.cut_index[nm] + m for nm in lp._cuts]
+        lp._basis_out = None
+        lp._factor_ref = None
+        rows = [sh.pool_row(lp, nm) + m for nm in lp._cuts]
         ysel = np.concatenate([res.y[k, :m], res.y[k, rows]]) if rows else res.y[k, :m].copy()
         if st == 1:
             lp._obj, lp._x, lp._y, lp._rc = float('inf'), None, None, None
@@ -537,4 +735,3 @@ def _solve_group(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_o
             # status 3 = budget exhausted: report the Lagrangian bound, the analogue of the
             # dual-feasible objective an iteration-limited dual simplex returns
             lp._obj = float(res.objective[k]) if st != 3 else float(res.lower_bound[k])
-        lp._solved_key = lp._state_key()

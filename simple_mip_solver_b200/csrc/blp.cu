@@ -19,6 +19,7 @@
 
 #include "blp_kernels.cuh"
 #include "blp_prep.hpp"
+#include "blp_simplex.cuh"
 
 using namespace blp;
 
@@ -204,6 +205,11 @@ struct blp_handle_s {
     // device copies
     DevBuf rowptr, ent, cptr, cent, c, b, rowscale, colscale, d_dr, d_dc;
     DevBuf uent, ucent;                // unscaled entries, same patterns (blp_spmv)
+    DevBuf uc, ub;                     // unscaled objective / row lower bounds (simplex path)
+    // dual simplex path (blp_simplex_*): factor stores of the current and the previous call, staging
+    DevBuf sx_binv[2], sx_head[2], sx_stat[2], sx_wts[2], sx_work, sx_in, sx_out;
+    int sx_cur = 0;                    // store the NEXT call writes; the other one holds the last call
+    int sx_last_B = 0, sx_last_m = -1; // nodes / rows of the last call's store (-1: none)
     DevBuf chunkC, chunkR;             // row ranges of the step-kernel CTAs (primal / dual)
     std::vector<int32_t> h_chunkC, h_chunkR;
     DevProb P{};
@@ -320,6 +326,9 @@ int prepare(blp_handle h) {
     CK(upload(h->cent, eAt, s));
     CK(upload(h->uent, eA0, s));
     CK(upload(h->ucent, eA0t, s));
+    CK(upload(h->uc, h->c0, s));
+    CK(upload(h->ub, h->b0, s));
+    h->sx_last_m = -1;                 // the rows changed: stored factors are void
     CK(upload(h->c, cs, s));
     CK(upload(h->b, bs, s));
     CK(upload(h->rowscale, rowscale, s));
@@ -1283,6 +1292,305 @@ int blp_spmv(blp_handle h, int B, int transpose, const double* X, double* Y) {
     return BLP_OK;
 }
 
+// ---- dual simplex path for small node LPs (blp_simplex.cuh) ---------------------------------------
+namespace {
+
+__global__ void k_sx_expand_children(const int B, const int n, const int m, const double* __restrict__ plb,
+                                     const double* __restrict__ pub, const int8_t* __restrict__ pcs,
+                                     const int8_t* __restrict__ prs, const uint8_t* __restrict__ pmask, const int mc,
+                                     double* __restrict__ lb, double* __restrict__ ub, int8_t* __restrict__ cs,
+                                     int8_t* __restrict__ rs, uint8_t* __restrict__ mask) {
+    const size_t tot = (size_t)B * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e % n);
+        lb[e] = plb[j];
+        ub[e] = pub[j];
+        if (cs) cs[e] = pcs[j];
+    }
+    if (rs)
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)B * m; e += (size_t)gridDim.x * blockDim.x)
+            rs[e] = prs[e % m];
+    if (mask)
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)B * mc; e += (size_t)gridDim.x * blockDim.x)
+            mask[e] = pmask[e % mc];
+}
+
+__global__ void k_sx_patch_children(const int B, const int n, const int32_t* __restrict__ dptr,
+                                    const int32_t* __restrict__ dvar, const double* __restrict__ dlb,
+                                    const double* __restrict__ dub, double* __restrict__ lb, double* __restrict__ ub) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= B) return;
+    for (int p = dptr[k]; p < dptr[k + 1]; ++p) {
+        lb[(size_t)k * n + dvar[p]] = dlb[p];
+        ub[(size_t)k * n + dvar[p]] = dub[p];
+    }
+}
+
+struct SxStage {           // device pointers carved from h->sx_in / h->sx_out
+    double *lb, *ub;
+    uint8_t* mask;
+    int8_t *cs, *rs;
+    int32_t* parent;
+    double *obj, *x, *y, *rc;
+    int32_t *status, *pivots, *flips;
+    int8_t *cso, *rso;
+};
+
+int sx_carve(blp_handle h, int B, bool want_mask, bool want_status, bool want_parent, SxStage* S) {
+    const size_t n = h->n, m = h->A0.rows, mc = m - h->m_base;
+    {
+        size_t need = 2 * B * n * sizeof(double) + 256 * 8 + B * mc + B * n + B * m + B * sizeof(int32_t);
+        CK(h->sx_in.ensure(need));
+        Carve cv{h->sx_in.as<char>()};
+        S->lb = cv.take<double>(B * n);
+        S->ub = cv.take<double>(B * n);
+        S->mask = (want_mask && mc > 0) ? cv.take<uint8_t>(B * mc) : nullptr;
+        S->cs = want_status ? cv.take<int8_t>(B * n) : nullptr;
+        S->rs = want_status ? cv.take<int8_t>(B * m) : nullptr;
+        S->parent = want_parent ? cv.take<int32_t>(B) : nullptr;
+    }
+    {
+        size_t need = (size_t)B * (1 + 2 * n + m) * sizeof(double) + 256 * 10 + 3 * B * sizeof(int32_t) + B * (n + m);
+        CK(h->sx_out.ensure(need));
+        Carve cv{h->sx_out.as<char>()};
+        S->obj = cv.take<double>(B);
+        S->x = cv.take<double>(B * n);
+        S->y = cv.take<double>(B * m);
+        S->rc = cv.take<double>(B * n);
+        S->status = cv.take<int32_t>(B);
+        S->pivots = cv.take<int32_t>(B);
+        S->flips = cv.take<int32_t>(B);
+        S->cso = cv.take<int8_t>(B * n);
+        S->rso = cv.take<int8_t>(B * m);
+    }
+    return BLP_OK;
+}
+
+// launch the simplex kernel on staged inputs, copy the results back to the host
+int sx_run(blp_handle h, int B, const SxStage& S, bool use_parent, int max_pivots, double* obj,
+           int32_t* status, int32_t* pivots, double* x, double* y, double* rc, int8_t* cso, int8_t* rso,
+           blp_stats* stats) {
+    cudaStream_t st = h->stream;
+    const int n = h->n, m = h->A0.rows, N = n + m;
+    const int ldm = (m + 31) / 32 * 32;
+    const int cur = h->sx_cur, prev = cur ^ 1;
+    CK(h->sx_binv[cur].ensure((size_t)B * m * ldm * sizeof(double)));
+    CK(h->sx_head[cur].ensure((size_t)B * m * sizeof(int32_t)));
+    CK(h->sx_stat[cur].ensure((size_t)B * N));
+    CK(h->sx_wts[cur].ensure((size_t)B * m * sizeof(double)));
+    const size_t stride = (size_t)6 * N + 6 * m + (4 * (size_t)N + 7) / 8 + 2;
+    CK(h->sx_work.ensure((size_t)B * stride * sizeof(double)));
+    SxProb P{m, h->m_base, n, ldm, h->P.rowptr, h->uent.as<Ent>(), h->P.cptr, h->ucent.as<Ent>(),
+             h->uc.as<double>(), h->ub.as<double>()};
+    SxBatch Q{};
+    Q.B = B;
+    Q.max_pivots = max_pivots;
+    Q.lb = S.lb; Q.ub = S.ub; Q.rowon = S.mask; Q.cstat_in = S.cs; Q.rstat_in = S.rs;
+    Q.parent = use_parent ? S.parent : nullptr;
+    Q.Binv = h->sx_binv[cur].as<double>(); Q.head = h->sx_head[cur].as<int32_t>();
+    Q.stat = h->sx_stat[cur].as<int8_t>(); Q.wts = h->sx_wts[cur].as<double>();
+    Q.pBinv = h->sx_binv[prev].as<double>(); Q.phead = h->sx_head[prev].as<int32_t>();
+    Q.pstat = h->sx_stat[prev].as<int8_t>(); Q.pwts = h->sx_wts[prev].as<double>();
+    Q.work = h->sx_work.as<double>(); Q.work_stride = stride;
+    Q.obj = S.obj; Q.status = S.status; Q.pivots = S.pivots; Q.flips = S.flips;
+    Q.x = S.x; Q.y = S.y; Q.rc = S.rc; Q.cstat_out = S.cso; Q.rstat_out = S.rso;
+    const int threads = m <= 128 ? 128 : 512;
+    const size_t smem = (size_t)kSxWeightLanes * m * sizeof(double);
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_simplex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaEventRecord(h->ev[2], st));
+    k_simplex<<<B, threads, smem, st>>>(P, Q);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[3], st));
+    if (obj) CK(cudaMemcpyAsync(obj, S.obj, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, S.status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (pivots) CK(cudaMemcpyAsync(pivots, S.pivots, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (x) CK(cudaMemcpyAsync(x, S.x, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (y) CK(cudaMemcpyAsync(y, S.y, (size_t)B * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (rc) CK(cudaMemcpyAsync(rc, S.rc, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (cso) CK(cudaMemcpyAsync(cso, S.cso, (size_t)B * n, cudaMemcpyDeviceToHost, st));
+    if (rso) CK(cudaMemcpyAsync(rso, S.rso, (size_t)B * m, cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> hp;
+    if (stats) {
+        hp.resize(2 * (size_t)B);
+        CK(cudaMemcpyAsync(hp.data(), S.pivots, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hp.data() + B, S.flips, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(h->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    h->sx_cur = prev;                  // the store just written becomes "the last call"
+    h->sx_last_B = B;
+    h->sx_last_m = m;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        stats->total_ms = ms;
+        CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+        stats->step_kernel_ms = ms;
+        double tot = 0.0;
+        int mx = 0;
+        for (int k = 0; k < B; ++k) { tot += hp[k]; mx = std::max(mx, hp[k]); }
+        stats->iterations = mx;
+        stats->node_iterations = tot;
+        stats->kernel_launches = 1;
+        int fl = 0;
+        for (int k = 0; k < B; ++k) fl += hp[B + k];
+        stats->refills = fl;           // bound flips of the ratio test (reported, not a refill count)
+    }
+    return BLP_OK;
+}
+
+int sx_check(blp_handle h, int B, const char* who) {
+    if (!h) return fail(BLP_ERR_ARG, "%s: NULL handle", who);
+    if (B < 1) return fail(BLP_ERR_ARG, "%s: need B >= 1", who);
+    if (h->A0.rows > kSxMaxRows)
+        return fail(BLP_ERR_STATE, "%s: %d rows, the dense-inverse simplex takes at most %d (use blp_solve_batch)",
+                    who, h->A0.rows, kSxMaxRows);
+    return BLP_OK;
+}
+
+}  // namespace
+
+int blp_simplex_max_rows(void) { return kSxMaxRows; }
+
+int blp_simplex_batch_host(blp_handle h, int B, const double* lb, const double* ub, const uint8_t* row_mask,
+                           const int8_t* col_status, const int8_t* row_status, const int32_t* parent_slot,
+                           int max_pivots, double* obj, int32_t* status, int32_t* pivots, double* x,
+                           double* y, double* rc, int8_t* col_status_out, int8_t* row_status_out,
+                           blp_stats* stats) {
+    int rcode = sx_check(h, B, "blp_simplex_batch_host");
+    if (rcode) return rcode;
+    if (!lb || !ub) return fail(BLP_ERR_ARG, "blp_simplex_batch_host: lb/ub are NULL");
+    if ((col_status == nullptr) != (row_status == nullptr))
+        return fail(BLP_ERR_ARG, "blp_simplex_batch_host: col_status and row_status come together");
+    if (max_pivots < 0) return fail(BLP_ERR_ARG, "blp_simplex_batch_host: max_pivots < 0");
+    const size_t n = h->n, m = h->A0.rows, mc = m - h->m_base;
+    bool use_parent = false;
+    if (parent_slot) {
+        for (int k = 0; k < B; ++k) {
+            if (parent_slot[k] >= 0) use_parent = true;
+            if (parent_slot[k] >= 0 && ((int)m != h->sx_last_m || parent_slot[k] >= h->sx_last_B))
+                return fail(BLP_ERR_STATE, "blp_simplex_batch_host: parent_slot[%d] = %d does not name a node of the "
+                                           "previous simplex call on this matrix", k, parent_slot[k]);
+        }
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    CK(cudaEventRecord(h->ev[0], st));
+    SxStage S;
+    if ((rcode = sx_carve(h, B, row_mask != nullptr, col_status != nullptr, use_parent, &S))) return rcode;
+    CK(cudaMemcpyAsync(S.lb, lb, B * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.ub, ub, B * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (S.mask) CK(cudaMemcpyAsync(S.mask, row_mask, B * mc, cudaMemcpyHostToDevice, st));
+    if (S.cs) {
+        CK(cudaMemcpyAsync(S.cs, col_status, B * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(S.rs, row_status, B * m, cudaMemcpyHostToDevice, st));
+    }
+    if (use_parent) CK(cudaMemcpyAsync(S.parent, parent_slot, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    return sx_run(h, B, S, use_parent, max_pivots, obj, status, pivots, x, y, rc, col_status_out, row_status_out, stats);
+}
+
+int blp_simplex_children_host(blp_handle h, int B, const double* parent_lb, const double* parent_ub,
+                              const int32_t* delta_ptr, const int32_t* delta_var, const double* delta_lb,
+                              const double* delta_ub, const uint8_t* row_mask, const int8_t* col_status,
+                              const int8_t* row_status, int parent_slot, int max_pivots, double* obj,
+                              int32_t* status, int32_t* pivots, double* x, double* y, double* rc,
+                              int8_t* col_status_out, int8_t* row_status_out, blp_stats* stats) {
+    int rcode = sx_check(h, B, "blp_simplex_children_host");
+    if (rcode) return rcode;
+    if (!parent_lb || !parent_ub || !delta_ptr)
+        return fail(BLP_ERR_ARG, "blp_simplex_children_host: need parent bounds and delta_ptr");
+    if ((col_status == nullptr) != (row_status == nullptr))
+        return fail(BLP_ERR_ARG, "blp_simplex_children_host: col_status and row_status come together");
+    const int nd = delta_ptr[B];
+    if (delta_ptr[0] != 0 || nd < 0 || (nd > 0 && (!delta_var || !delta_lb || !delta_ub)))
+        return fail(BLP_ERR_ARG, "blp_simplex_children_host: bad delta arrays");
+    for (int k = 0; k < B; ++k)
+        if (delta_ptr[k + 1] < delta_ptr[k]) return fail(BLP_ERR_ARG, "blp_simplex_children_host: delta_ptr not monotone");
+    for (int p = 0; p < nd; ++p)
+        if (delta_var[p] < 0 || delta_var[p] >= h->n)
+            return fail(BLP_ERR_ARG, "blp_simplex_children_host: delta_var[%d] = %d out of range", p, delta_var[p]);
+    if (max_pivots < 0) return fail(BLP_ERR_ARG, "blp_simplex_children_host: max_pivots < 0");
+    const size_t n = h->n, m = h->A0.rows, mc = m - h->m_base;
+    const bool use_parent = parent_slot >= 0;
+    if (use_parent && ((int)m != h->sx_last_m || parent_slot >= h->sx_last_B))
+        return fail(BLP_ERR_STATE, "blp_simplex_children_host: parent_slot %d does not name a node of the previous "
+                                   "simplex call on this matrix", parent_slot);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    CK(cudaEventRecord(h->ev[0], st));
+    SxStage S;
+    if ((rcode = sx_carve(h, B, row_mask != nullptr, col_status != nullptr, use_parent, &S))) return rcode;
+    // parent vectors [lb | ub | cs | rs | mask] and deltas go up once, the per-node arrays are built on the device
+    const size_t pbytes = 2 * n * sizeof(double) + n + m + mc + 64;
+    const size_t ip = align_up((size_t)(B + 1) * sizeof(int32_t), 8), iv = align_up((size_t)nd * sizeof(int32_t), 8);
+    CK(h->s_par.ensure(pbytes));
+    CK(h->s_delta.ensure(ip + iv + 2 * (size_t)nd * sizeof(double) + 64));
+    char* pp = h->s_par.as<char>();
+    double* d_plb = reinterpret_cast<double*>(pp);
+    double* d_pub = d_plb + n;
+    int8_t* d_pcs = reinterpret_cast<int8_t*>(d_pub + n);
+    int8_t* d_prs = d_pcs + n;
+    uint8_t* d_pmask = reinterpret_cast<uint8_t*>(d_prs + m);
+    CK(cudaMemcpyAsync(d_plb, parent_lb, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_pub, parent_ub, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (col_status) {
+        CK(cudaMemcpyAsync(d_pcs, col_status, n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_prs, row_status, m, cudaMemcpyHostToDevice, st));
+    }
+    if (S.mask) CK(cudaMemcpyAsync(d_pmask, row_mask, mc, cudaMemcpyHostToDevice, st));
+    k_sx_expand_children<<<elementwise_grid((size_t)B * n), kCtaThreads, 0, st>>>(
+        B, (int)n, (int)m, d_plb, d_pub, d_pcs, d_prs, d_pmask, (int)mc, S.lb, S.ub, S.cs, S.rs, S.mask);
+    if (nd > 0) {
+        char* d = h->s_delta.as<char>();
+        CK(cudaMemcpyAsync(d, delta_ptr, (B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + ip, delta_var, nd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + ip + iv, delta_lb, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d + ip + iv + nd * sizeof(double), delta_ub, nd * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_sx_patch_children<<<(B + 127) / 128, 128, 0, st>>>(
+            B, (int)n, reinterpret_cast<int32_t*>(d), reinterpret_cast<int32_t*>(d + ip),
+            reinterpret_cast<double*>(d + ip + iv), reinterpret_cast<double*>(d + ip + iv + nd * sizeof(double)),
+            S.lb, S.ub);
+    }
+    if (use_parent) {
+        std::vector<int32_t> par(B, parent_slot);
+        CK(cudaMemcpyAsync(S.parent, par.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));      // `par` goes out of scope
+    }
+    CK(cudaGetLastError());
+    rcode = sx_run(h, B, S, use_parent, max_pivots, obj, status, pivots, x, y, rc, col_status_out, row_status_out, stats);
+    if (rcode == BLP_OK && stats) stats->kernel_launches += nd > 0 ? 2 : 1;
+    return rcode;
+}
+
+int blp_simplex_tableau_rows_host(blp_handle h, int slot, int nrows, const int32_t* vars, double* out) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_simplex_tableau_rows_host: NULL handle");
+    if (nrows < 1 || !vars || !out) return fail(BLP_ERR_ARG, "blp_simplex_tableau_rows_host: need nrows >= 1, vars, out");
+    const int n = h->n, m = h->A0.rows, N = n + m;
+    if (h->sx_last_m != m || slot < 0 || slot >= h->sx_last_B)
+        return fail(BLP_ERR_STATE, "blp_simplex_tableau_rows_host: slot %d does not name a node of the previous simplex "
+                                   "call on this matrix", slot);
+    for (int t = 0; t < nrows; ++t)
+        if (vars[t] < 0 || vars[t] >= N) return fail(BLP_ERR_ARG, "blp_simplex_tableau_rows_host: vars[%d] out of range", t);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int ldm = (m + 31) / 32 * 32;
+    const int last = h->sx_cur ^ 1;
+    CK(h->s_int.ensure((size_t)nrows * sizeof(int32_t)));
+    CK(h->s_tmp.ensure((size_t)nrows * N * sizeof(double)));
+    CK(cudaMemcpyAsync(h->s_int.p, vars, (size_t)nrows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SxProb P{m, h->m_base, n, ldm, h->P.rowptr, h->uent.as<Ent>(), h->P.cptr, h->ucent.as<Ent>(),
+             h->uc.as<double>(), h->ub.as<double>()};
+    k_simplex_tableau_rows<<<nrows, 256, 0, st>>>(P, h->sx_binv[last].as<double>() + (size_t)slot * m * ldm,
+                                                  h->sx_head[last].as<int32_t>() + (size_t)slot * m, nrows,
+                                                  h->s_int.as<int32_t>(), h->s_tmp.as<double>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->s_tmp.p, (size_t)nrows * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BLP_OK;
+}
+
 int blp_stream_sync(blp_handle h) {
     if (!h) return fail(BLP_ERR_ARG, "blp_stream_sync: NULL handle");
     CK(cudaSetDevice(h->device));
@@ -1356,7 +1664,9 @@ int blp_destroy(blp_handle h) {
     DevBuf* bufs[] = {&h->rowptr, &h->ent, &h->cptr, &h->cent, &h->c, &h->b,
                       &h->rowscale, &h->colscale, &h->d_dr, &h->d_dc, &h->uent, &h->ucent, &h->chunkC, &h->chunkR, &h->s_lb,
                       &h->s_ub, &h->s_x0, &h->s_y0, &h->s_mask, &h->s_x, &h->s_y, &h->s_tmp,
-                      &h->s_ws, &h->s_node, &h->s_int, &h->s_delta, &h->s_par};
+                      &h->s_ws, &h->s_node, &h->s_int, &h->s_delta, &h->s_par, &h->uc, &h->ub,
+                      &h->sx_binv[0], &h->sx_binv[1], &h->sx_head[0], &h->sx_head[1], &h->sx_stat[0],
+                      &h->sx_stat[1], &h->sx_wts[0], &h->sx_wts[1], &h->sx_work, &h->sx_in, &h->sx_out};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_join) if (e) cudaEventDestroy(e);

@@ -1,0 +1,729 @@
+// Batched bounded dual simplex for SMALL node LPs (rows <= kSxMaxRows): one CTA per node LP.
+//
+// Why it exists next to the PDHG kernels: the reference's Node API reads a simplex VERTEX and a
+// BASIS (integrality test base_node.py:281-283, most fractional index :544-562, tableau :513-530,
+// getBasisStatus/setBasisStatus :589, 608, "maxNumIteration pivots" :645-646). A first-order method
+// converges to a point of the optimal face; for the LP sizes of configs 1-3 a dense-inverse dual
+// simplex per node is both exact and faster. A batch (frontier, strong-branching children) is one
+// launch: blockIdx.x = node, the CTA's threads share the node's O(m^2) work.
+//
+// LP of a node:  min c.x,  A x - s = b,  l <= x <= u,  s >= 0  (s free where the row is masked off).
+// State per node in global memory (L2 resident): Binv (m x m, column major, leading dimension ldm),
+// x_B, reduced costs d, basis head, status, DSE weights. Pivoting rules, tolerances and the ORDER OF
+// EVERY FLOATING-POINT OPERATION are those of oracle/dual_simplex.py (the numpy restatement the tests
+// compare against pivot for pivot): single rounded operations only (__dmul_rn/__dadd_rn, no FMA
+// contraction), sums in ascending index order, row norms in 16 interleaved partial sums.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "blp_kernels.cuh"
+
+namespace blp {
+
+constexpr int kSxMaxRows = 1024;
+constexpr int kSxWeightLanes = 16;
+constexpr int SX_BASIC = 1, SX_UPPER = 2, SX_LOWER = 3;
+constexpr double kSxPrimalTol = 1e-9, kSxDualTol = 1e-9, kSxPivTol = 1e-9, kSxTieRel = 1e-12;
+constexpr double kSxRatioBin = 68719476736.0;      // 2^36
+constexpr double kSxBig = 1e8;
+constexpr int kSxRefactorEvery = 1000;
+
+struct SxProb {
+    int m, m_base, n, ldm;
+    const int32_t* rowptr; const Ent* ent;     // unscaled A, CSR (entries ascending by column)
+    const int32_t* cptr;   const Ent* cent;    // unscaled A', CSR (entries ascending by row)
+    const double* c; const double* b;          // unscaled objective / row lower bounds
+};
+
+// per-call arrays; node k uses slice k of each
+struct SxBatch {
+    int B, max_pivots;
+    const double* lb; const double* ub;        // [B][n] node major
+    const uint8_t* rowon;                      // [B][m - m_base] or null (all pool rows on)
+    const int8_t* cstat_in; const int8_t* rstat_in;   // [B][n], [B][m] CLP codes, or null = slack basis
+    const int32_t* parent;                     // [B] slot of the source store to start from (-1: from status), or null
+    // factor stores: this call's (written) and the previous call's (read when parent >= 0)
+    double* Binv; int32_t* head; int8_t* stat; double* wts;
+    const double* pBinv; const int32_t* phead; const int8_t* pstat; const double* pwts;
+    double* work;                              // [B][work_stride] doubles
+    size_t work_stride;
+    // outputs
+    double* obj; int32_t* status; int32_t* pivots; int32_t* flips;
+    double* x; double* y; double* rc;          // [B][n], [B][m], [B][n]
+    int8_t* cstat_out; int8_t* rstat_out;      // [B][n], [B][m]
+};
+
+__device__ __forceinline__ double sx_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double sx_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sx_sub(double a, double b) { return __dsub_rn(a, b); }
+
+// ---- block reductions (deterministic: max / min are order independent) ---------------------------
+struct SxRed {
+    double d[32];
+    int i[32];
+    double bd;
+    int bi;
+};
+
+__device__ __forceinline__ double sx_block_max(double v, SxRed& s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) s.d[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < nw ? s.d[lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (lane == 0) s.bd = t;
+    }
+    __syncthreads();
+    return s.bd;
+}
+
+__device__ __forceinline__ int sx_block_min_int(int v, SxRed& s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) s.i[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < nw ? s.i[lane] : 2147483647;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = min(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (lane == 0) s.bi = t;
+    }
+    __syncthreads();
+    return s.bi;
+}
+
+// lexicographic minimum of (key ascending, |alpha| descending, index ascending)
+struct SxCand {
+    double key, mag;
+    int j;
+};
+__device__ __forceinline__ bool sx_better(const SxCand& a, const SxCand& b) {
+    if (a.key != b.key) return a.key < b.key;
+    if (a.mag != b.mag) return a.mag > b.mag;
+    return a.j < b.j;
+}
+__device__ __forceinline__ SxCand sx_shfl(const SxCand& c, int o) {
+    SxCand r;
+    r.key = __shfl_xor_sync(0xffffffffu, c.key, o);
+    r.mag = __shfl_xor_sync(0xffffffffu, c.mag, o);
+    r.j = __shfl_xor_sync(0xffffffffu, c.j, o);
+    return r;
+}
+struct SxCandRed {
+    SxCand w[32];
+    SxCand best;
+};
+__device__ __forceinline__ SxCand sx_block_best(SxCand c, SxCandRed& s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const SxCand t = sx_shfl(c, o);
+        if (sx_better(t, c)) c = t;
+    }
+    __syncthreads();
+    if (lane == 0) s.w[warp] = c;
+    __syncthreads();
+    if (warp == 0) {
+        SxCand t;
+        t.key = INFINITY; t.mag = 0.0; t.j = 2147483647;
+        if (lane < nw) t = s.w[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const SxCand q = sx_shfl(t, o);
+            if (sx_better(q, t)) t = q;
+        }
+        if (lane == 0) s.best = t;
+    }
+    __syncthreads();
+    return s.best;
+}
+
+// ---- the node's view ---------------------------------------------------------------------------
+struct SxNode {
+    int m, n, N, ldm;
+    double* Binv;        // [m][ldm] column major: (i, k) at k * ldm + i
+    int32_t* head;       // [m]
+    int8_t* stat;        // [N]
+    double* w;           // [m] DSE weights
+    double *lo, *hi, *d, *ar, *key;      // [N]
+    double *xB, *rho, *aq, *col, *y, *rhs;   // [m]
+    double* xfull;       // [N]
+    int8_t *artlo, *arthi, *want, *flip; // [N]
+};
+
+__device__ __forceinline__ double sx_binv(const SxNode& nd, int i, int k) { return nd.Binv[(size_t)k * nd.ldm + i]; }
+
+// acc_i = sum_k Binv(i,k) v[k], ascending k, zeros of v skipped (thread per row)
+__device__ __forceinline__ void sx_matvec(const SxNode& nd, const double* __restrict__ v, double* __restrict__ out) {
+    for (int i = threadIdx.x; i < nd.m; i += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < nd.m; ++k) {
+            const double vk = v[k];
+            if (vk != 0.0) acc = sx_add(acc, sx_mul(nd.Binv[(size_t)k * nd.ldm + i], vk));
+        }
+        out[i] = acc;
+    }
+}
+
+// alpha = Binv a_j for column j of [A, -I] (thread per row; entries of a_j ascending by row)
+__device__ __forceinline__ void sx_ftran_col(const SxProb& P, const SxNode& nd, int j, double* __restrict__ out) {
+    if (j < nd.n) {
+        const int p0 = P.cptr[j], p1 = P.cptr[j + 1];
+        for (int i = threadIdx.x; i < nd.m; i += blockDim.x) {
+            double acc = 0.0;
+            for (int p = p0; p < p1; ++p) {
+                const Ent e = P.cent[p];
+                if (e.val != 0.0) acc = sx_add(acc, sx_mul(nd.Binv[(size_t)e.idx * nd.ldm + i], e.val));
+            }
+            out[i] = acc;
+        }
+    } else {
+        const int k = j - nd.n;
+        for (int i = threadIdx.x; i < nd.m; i += blockDim.x)
+            out[i] = sx_add(0.0, sx_mul(nd.Binv[(size_t)k * nd.ldm + i], -1.0));
+    }
+}
+
+// Binv <- E Binv for a basis change in row position r; rowr[k] = old Binv(r,k) / pivot must be ready.
+// With WEIGHTS the row norms are rebuilt in the same sweep: warp group g sums the squares of the
+// columns k = g, g + 16, ... in ascending order into part[g][i]; w_i = sum_g part[g][i], g ascending.
+template <bool WEIGHTS>
+__device__ __forceinline__ void sx_update_inverse(const SxNode& nd, const double* __restrict__ alpha,
+                                                  const double* __restrict__ rowr, const int r, double* part) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int m = nd.m;
+    for (int g = warp; g < kSxWeightLanes; g += nw) {
+        for (int i = lane; i < m; i += 32) {
+            const double ai = alpha[i];
+            double acc = 0.0;
+            for (int k = g; k < m; k += kSxWeightLanes) {
+                double* p = nd.Binv + (size_t)k * nd.ldm + i;
+                const double rk = rowr[k];
+                const double v = (i == r) ? rk : sx_sub(*p, sx_mul(ai, rk));
+                *p = v;
+                if (WEIGHTS) acc = sx_add(acc, sx_mul(v, v));
+            }
+            if (WEIGHTS) part[g * m + i] = acc;
+        }
+    }
+    __syncthreads();
+    if (WEIGHTS) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            double wsum = 0.0;
+#pragma unroll
+            for (int g = 0; g < kSxWeightLanes; ++g) wsum = sx_add(wsum, part[g * m + i]);
+            nd.w[i] = wsum;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void sx_weights(const SxNode& nd, double* part) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int m = nd.m;
+    for (int g = warp; g < kSxWeightLanes; g += nw)
+        for (int i = lane; i < m; i += 32) {
+            double acc = 0.0;
+            for (int k = g; k < m; k += kSxWeightLanes) {
+                const double v = nd.Binv[(size_t)k * nd.ldm + i];
+                acc = sx_add(acc, sx_mul(v, v));
+            }
+            part[g * m + i] = acc;
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double wsum = 0.0;
+#pragma unroll
+        for (int g = 0; g < kSxWeightLanes; ++g) wsum = sx_add(wsum, part[g * m + i]);
+        nd.w[i] = wsum;
+    }
+    __syncthreads();
+}
+
+// Slack basis, then the wanted structurals pivoted in one by one (start and refactorisation).
+// nd.want[j] != 0 marks the columns that should be basic; nd.stat holds the nonbasic sides.
+__device__ void sx_factor(const SxProb& P, const SxNode& nd, SxRed& red) {
+    const int m = nd.m, n = nd.n, N = nd.N;
+    for (size_t e = threadIdx.x; e < (size_t)m * nd.ldm; e += blockDim.x) {
+        const int k = (int)(e / nd.ldm), i = (int)(e % nd.ldm);
+        nd.Binv[e] = (i == k) ? -1.0 : 0.0;
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) nd.head[i] = n + i;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const int8_t s = nd.stat[j];
+        nd.key[j] = (double)s;                              // "keep": the status before this factorisation
+        if (j >= n) nd.stat[j] = SX_BASIC;
+        else if (s == SX_BASIC) nd.stat[j] = SX_LOWER;
+    }
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        if (!nd.want[j]) continue;                          // uniform: same data for every thread
+        sx_ftran_col(P, nd, j, nd.aq);
+        __syncthreads();
+        double best = kSxPivTol;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            const int hv = nd.head[i];
+            if (hv >= n && !nd.want[hv]) best = fmax(best, fabs(nd.aq[i]));
+        }
+        best = sx_block_max(best, red);
+        int r = 2147483647;
+        if (best > kSxPivTol)
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int hv = nd.head[i];
+                if (hv >= n && !nd.want[hv] && fabs(nd.aq[i]) == best) r = min(r, i);
+            }
+        r = sx_block_min_int(r, red);
+        if (r == 2147483647) continue;
+        const double piv = nd.aq[r];
+        for (int k = threadIdx.x; k < m; k += blockDim.x) nd.rho[k] = nd.Binv[(size_t)k * nd.ldm + r] / piv;
+        __syncthreads();
+        sx_update_inverse<false>(nd, nd.aq, nd.rho, r, nullptr);
+        if (threadIdx.x == 0) {
+            const int s = nd.head[r];
+            const int keep = (int)nd.key[s];
+            nd.stat[s] = keep != SX_BASIC ? (int8_t)keep : (int8_t)SX_LOWER;
+            nd.head[r] = j;
+            nd.stat[j] = SX_BASIC;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ double sx_nonbasic_value(const SxNode& nd, int j) {
+    const int8_t s = nd.stat[j];
+    return s == SX_BASIC ? 0.0 : (s == SX_UPPER ? nd.hi[j] : nd.lo[j]);
+}
+
+// y = c_B Binv (ascending row position, zeros of c_B skipped); d = c - A'y, d_slack = y, d_basic = 0
+__device__ void sx_duals(const SxProb& P, const SxNode& nd) {
+    const int m = nd.m, n = nd.n;
+    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+        double acc = 0.0;
+        const double* colk = nd.Binv + (size_t)k * nd.ldm;
+        for (int p = 0; p < m; ++p) {
+            const int hv = nd.head[p];
+            const double cb = hv < n ? P.c[hv] : 0.0;
+            if (cb != 0.0) acc = sx_add(acc, sx_mul(cb, colk[p]));
+        }
+        nd.y[k] = acc;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < nd.N; j += blockDim.x) {
+        double dj;
+        if (j < n) {
+            double acc = 0.0;
+            for (int p = P.cptr[j]; p < P.cptr[j + 1]; ++p) {
+                const Ent e = P.cent[p];
+                const double yi = nd.y[e.idx];
+                if (yi != 0.0) acc = sx_add(acc, sx_mul(yi, e.val));
+            }
+            dj = sx_sub(P.c[j], acc);
+        } else {
+            dj = nd.y[j - n];
+        }
+        nd.d[j] = nd.stat[j] == SX_BASIC ? 0.0 : dj;
+    }
+    __syncthreads();
+}
+
+// rhs = b - A x_N + x_N(slack);  x_B = Binv rhs
+__device__ void sx_primal(const SxProb& P, const SxNode& nd) {
+    const int m = nd.m, n = nd.n;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double acc = 0.0;
+        for (int p = P.rowptr[i]; p < P.rowptr[i + 1]; ++p) {
+            const Ent e = P.ent[p];
+            const double xj = sx_nonbasic_value(nd, e.idx);
+            if (xj != 0.0) acc = sx_add(acc, sx_mul(e.val, xj));
+        }
+        nd.rhs[i] = sx_add(sx_sub(P.b[i], acc), sx_nonbasic_value(nd, n + i));
+    }
+    __syncthreads();
+    sx_matvec(nd, nd.rhs, nd.xB);
+    __syncthreads();
+}
+
+__device__ void sx_make_dual_feasible(const SxNode& nd) {
+    for (int j = threadIdx.x; j < nd.N; j += blockDim.x) {
+        int8_t s = nd.stat[j];
+        if (s == SX_BASIC) continue;
+        double lo = nd.lo[j], hi = nd.hi[j];
+        if (lo == hi) { nd.stat[j] = SX_LOWER; continue; }
+        const double dj = nd.d[j];
+        if (dj < -kSxDualTol) s = SX_UPPER;
+        else if (dj > kSxDualTol) s = SX_LOWER;
+        else if (s == SX_LOWER && isinf(lo)) s = SX_UPPER;
+        else if (s == SX_UPPER && isinf(hi)) s = SX_LOWER;
+        if (s == SX_UPPER && isinf(hi)) { nd.hi[j] = kSxBig; nd.arthi[j] = 1; }
+        if (s == SX_LOWER && isinf(lo)) { nd.lo[j] = -kSxBig; nd.artlo[j] = 1; }
+        nd.stat[j] = s;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1)
+k_simplex(const SxProb P, const SxBatch Q) {
+    extern __shared__ double sx_part[];                    // [16][m] partial row norms
+    __shared__ SxRed red;
+    __shared__ SxCandRed cred;
+    __shared__ int s_r, s_q, s_nflip, s_status, s_par_ok;
+    __shared__ double s_slope;
+    const int node = blockIdx.x;
+    const int m = P.m, n = P.n, N = n + m;
+    SxNode nd;
+    nd.m = m; nd.n = n; nd.N = N; nd.ldm = P.ldm;
+    nd.Binv = Q.Binv + (size_t)node * m * P.ldm;
+    nd.head = Q.head + (size_t)node * m;
+    nd.stat = Q.stat + (size_t)node * N;
+    nd.w = Q.wts + (size_t)node * m;
+    {
+        double* wk = Q.work + (size_t)node * Q.work_stride;
+        nd.lo = wk; wk += N; nd.hi = wk; wk += N; nd.d = wk; wk += N; nd.ar = wk; wk += N; nd.key = wk; wk += N;
+        nd.xfull = wk; wk += N;
+        nd.xB = wk; wk += m; nd.rho = wk; wk += m; nd.aq = wk; wk += m; nd.col = wk; wk += m;
+        nd.y = wk; wk += m; nd.rhs = wk; wk += m;
+        int8_t* fl = reinterpret_cast<int8_t*>(wk);
+        nd.artlo = fl; nd.arthi = fl + N; nd.want = fl + 2 * N; nd.flip = fl + 3 * N;
+    }
+    const double* lbk = Q.lb + (size_t)node * n;
+    const double* ubk = Q.ub + (size_t)node * n;
+    const int mc = m - P.m_base;
+    const uint8_t* onk = Q.rowon ? Q.rowon + (size_t)node * mc : nullptr;
+    const int par = Q.parent ? Q.parent[node] : -1;
+    const bool from_status = Q.cstat_in != nullptr && Q.rstat_in != nullptr;
+    if (threadIdx.x == 0) s_par_ok = 1;
+    __syncthreads();
+
+    // ---- bounds, starting status ------------------------------------------------------------
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        double lo, hi;
+        bool on = true;
+        if (j < n) {
+            lo = lbk[j]; hi = ubk[j];
+            lo = (lo <= -1e30) ? -INFINITY : lo;
+            hi = (hi >= 1e30) ? INFINITY : hi;
+        } else {
+            const int i = j - n;
+            on = !(i >= P.m_base && onk && onk[i - P.m_base] == 0);
+            lo = on ? 0.0 : -INFINITY;
+            hi = INFINITY;
+        }
+        nd.lo[j] = lo; nd.hi[j] = hi;
+        nd.artlo[j] = 0; nd.arthi[j] = 0; nd.flip[j] = 0;
+        int8_t st = SX_LOWER, want = 0;
+        if (par >= 0) {
+            st = Q.pstat[(size_t)par * N + j];
+            want = st == SX_BASIC || !on;
+            if (!on && st != SX_BASIC) s_par_ok = 0;     // the parent's factor has this slack nonbasic
+        } else if (from_status) {
+            if (j < n) {
+                const int8_t cs = Q.cstat_in[(size_t)node * n + j];
+                st = cs == SX_UPPER ? SX_UPPER : SX_LOWER;
+                want = cs == SX_BASIC;
+            } else {
+                want = (Q.rstat_in[(size_t)node * m + (j - n)] == SX_BASIC) || !on;
+            }
+        } else {
+            want = j >= n;
+        }
+        nd.stat[j] = st;
+        nd.want[j] = want;
+    }
+    __syncthreads();
+    const bool use_parent = par >= 0 && s_par_ok != 0;
+    if (par >= 0 && !use_parent) {                       // fall back: factorise from the parent's status
+        for (int j = threadIdx.x; j < N; j += blockDim.x)
+            if (nd.stat[j] == SX_BASIC) nd.stat[j] = SX_LOWER;
+        __syncthreads();
+    }
+    if (use_parent) {
+        const double* src = Q.pBinv + (size_t)par * m * P.ldm;
+        for (size_t e = threadIdx.x; e < (size_t)m * P.ldm; e += blockDim.x) nd.Binv[e] = src[e];
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            nd.head[i] = Q.phead[(size_t)par * m + i];
+            nd.w[i] = Q.pwts[(size_t)par * m + i];
+        }
+        __syncthreads();
+    } else {
+        sx_factor(P, nd, red);
+    }
+    sx_duals(P, nd);
+    sx_make_dual_feasible(nd);
+    sx_primal(P, nd);
+    if (!use_parent) sx_weights(nd, sx_part);
+
+    int pivots = 0, flips_total = 0, since_factor = 0, status = 0;
+    while (true) {
+        // ---- leaving row: dual steepest edge ---------------------------------------------------
+        double sc[2] = {-1.0, -1.0};
+        double local = -1.0;
+        {
+            int t = 0;
+            for (int i = threadIdx.x; i < m; i += blockDim.x, ++t) {
+                const int hv = nd.head[i];
+                const double xb = nd.xB[i];
+                const double inf = fmax(sx_sub(nd.lo[hv], xb), sx_sub(xb, nd.hi[hv]));
+                double s = -1.0;
+                if (inf > sx_mul(kSxPrimalTol, sx_add(1.0, fabs(xb)))) s = sx_mul(inf, inf) / nd.w[i];
+                sc[t] = s;
+                local = fmax(local, s);
+            }
+        }
+        const double best = sx_block_max(local, red);
+        if (best < 0.0) { status = 0; break; }
+        if (pivots >= Q.max_pivots) { status = 3; break; }
+        if (since_factor >= kSxRefactorEvery) {
+            for (int j = threadIdx.x; j < N; j += blockDim.x) nd.want[j] = nd.stat[j] == SX_BASIC;
+            __syncthreads();
+            sx_factor(P, nd, red);
+            sx_duals(P, nd);
+            sx_primal(P, nd);
+            sx_weights(nd, sx_part);
+            since_factor = 0;
+            continue;
+        }
+        {
+            const double thr = sx_mul(best, sx_sub(1.0, kSxTieRel));
+            int hmin = 2147483647, t = 0;
+            for (int i = threadIdx.x; i < m; i += blockDim.x, ++t)
+                if (sc[t] >= thr) hmin = min(hmin, nd.head[i]);
+            hmin = sx_block_min_int(hmin, red);
+            for (int i = threadIdx.x; i < m; i += blockDim.x)
+                if (nd.head[i] == hmin) s_r = i;
+            __syncthreads();
+        }
+        const int r = s_r;
+        const int leaving = nd.head[r];
+        const double xbr = nd.xB[r];
+        const bool below = xbr < nd.lo[leaving];
+        const double infr = fmax(sx_sub(nd.lo[leaving], xbr), sx_sub(xbr, nd.hi[leaving]));
+        // ---- row r of the tableau, eligibility and ratio keys ---------------------------------
+        for (int k = threadIdx.x; k < m; k += blockDim.x) nd.rho[k] = nd.Binv[(size_t)k * nd.ldm + r];
+        __syncthreads();
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            double a;
+            if (j < n) {
+                double acc = 0.0;
+                for (int p = P.cptr[j]; p < P.cptr[j + 1]; ++p) {
+                    const Ent e = P.cent[p];
+                    const double ri = nd.rho[e.idx];
+                    if (ri != 0.0) acc = sx_add(acc, sx_mul(ri, e.val));
+                }
+                a = acc;
+            } else {
+                a = -nd.rho[j - n];
+            }
+            nd.ar[j] = a;
+            const int8_t st = nd.stat[j];
+            const double sa = below ? -a : a;
+            const bool elig = st != SX_BASIC && nd.lo[j] < nd.hi[j] &&
+                              ((st == SX_LOWER && sa > kSxPivTol) || (st == SX_UPPER && sa < -kSxPivTol));
+            nd.key[j] = elig ? rint(sx_mul(fabs(nd.d[j]) / fabs(a), kSxRatioBin)) : INFINITY;
+        }
+        if (threadIdx.x == 0) { s_slope = infr; s_nflip = 0; s_q = -1; }
+        __syncthreads();
+        // ---- bound flipping ratio test -------------------------------------------------------
+        const double flip_tol = sx_mul(kSxPrimalTol, sx_add(1.0, fabs(xbr)));
+        while (true) {
+            SxCand c;
+            c.key = INFINITY; c.mag = 0.0; c.j = 2147483647;
+            for (int j = threadIdx.x; j < N; j += blockDim.x) {
+                SxCand t;
+                t.key = nd.key[j]; t.mag = fabs(nd.ar[j]); t.j = j;
+                if (t.key < INFINITY && sx_better(t, c)) c = t;
+            }
+            c = sx_block_best(c, cred);
+            if (!(c.key < INFINITY)) break;                  // no candidate left: s_q stays -1
+            const int j = c.j;
+            const double rng = sx_sub(nd.hi[j], nd.lo[j]);
+            bool flipped = false;
+            if (isfinite(rng)) {
+                const double rest = sx_sub(s_slope, sx_mul(c.mag, rng));
+                if (rest > flip_tol) {
+                    flipped = true;
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        s_slope = rest;
+                        s_nflip += 1;
+                        nd.flip[j] = 1;
+                        nd.key[j] = INFINITY;
+                    }
+                    __syncthreads();
+                }
+            }
+            if (!flipped) {
+                if (threadIdx.x == 0) s_q = j;
+                __syncthreads();
+                break;
+            }
+        }
+        __syncthreads();
+        const int q = s_q;
+        if (q < 0) { status = 1; break; }
+        const int nflip = s_nflip;
+        if (nflip > 0) {
+            // xfull <- bound moves of the flipped columns; col = A delta - delta_slack; x_B -= Binv col
+            for (int j = threadIdx.x; j < N; j += blockDim.x) {
+                double dl = 0.0;
+                if (nd.flip[j]) {
+                    const bool atlo = nd.stat[j] == SX_LOWER;
+                    dl = atlo ? sx_sub(nd.hi[j], nd.lo[j]) : sx_sub(nd.lo[j], nd.hi[j]);
+                    nd.stat[j] = atlo ? SX_UPPER : SX_LOWER;
+                    nd.flip[j] = 0;
+                }
+                nd.xfull[j] = dl;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                double acc = 0.0;
+                for (int p = P.rowptr[i]; p < P.rowptr[i + 1]; ++p) {
+                    const Ent e = P.ent[p];
+                    const double dl = nd.xfull[e.idx];
+                    if (dl != 0.0) acc = sx_add(acc, sx_mul(e.val, dl));
+                }
+                nd.col[i] = sx_sub(acc, nd.xfull[n + i]);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                double acc = 0.0;
+                for (int k = 0; k < m; ++k) {
+                    const double ck = nd.col[k];
+                    if (ck != 0.0) acc = sx_add(acc, sx_mul(nd.Binv[(size_t)k * nd.ldm + i], ck));
+                }
+                nd.xB[i] = sx_sub(nd.xB[i], acc);
+            }
+            flips_total += nflip;
+            __syncthreads();
+        }
+        // ---- entering column, step lengths, updates -------------------------------------------
+        sx_ftran_col(P, nd, q, nd.aq);
+        __syncthreads();
+        const double piv = nd.aq[r];
+        const double target = below ? nd.lo[leaving] : nd.hi[leaving];
+        const double theta_p = sx_sub(nd.xB[r], target) / piv;
+        const double xq_new = sx_add(nd.stat[q] == SX_UPPER ? nd.hi[q] : nd.lo[q], theta_p);
+        const double theta_d = nd.d[q] / nd.ar[q];
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x)
+            nd.xB[i] = (i == r) ? xq_new : sx_sub(nd.xB[i], sx_mul(theta_p, nd.aq[i]));
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            double dj = sx_sub(nd.d[j], sx_mul(theta_d, nd.ar[j]));
+            if (j == leaving) dj = -theta_d;
+            if (j == q) dj = 0.0;
+            nd.d[j] = dj;
+        }
+        for (int k = threadIdx.x; k < m; k += blockDim.x) nd.rho[k] = nd.rho[k] / piv;
+        __syncthreads();
+        sx_update_inverse<true>(nd, nd.aq, nd.rho, r, sx_part);
+        if (threadIdx.x == 0) {
+            nd.stat[leaving] = below ? SX_LOWER : SX_UPPER;
+            nd.stat[q] = SX_BASIC;
+            nd.head[r] = q;
+        }
+        __syncthreads();
+        ++pivots;
+        ++since_factor;
+    }
+
+    // ---- finish: fresh x_B with one refinement step, duals, outputs ----------------------------
+    __syncthreads();
+    sx_primal(P, nd);
+    for (int j = threadIdx.x; j < N; j += blockDim.x) nd.xfull[j] = sx_nonbasic_value(nd, j);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) nd.xfull[nd.head[i]] = nd.xB[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {     // resid = rhs - B x_B
+        double res = nd.rhs[i];
+        for (int p = P.rowptr[i]; p < P.rowptr[i + 1]; ++p) {
+            const Ent e = P.ent[p];
+            if (nd.stat[e.idx] == SX_BASIC) res = sx_sub(res, sx_mul(e.val, nd.xfull[e.idx]));
+        }
+        if (nd.stat[n + i] == SX_BASIC) res = sx_add(res, nd.xfull[n + i]);
+        nd.col[i] = res;
+    }
+    __syncthreads();
+    sx_matvec(nd, nd.col, nd.aq);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double v = sx_add(nd.xB[i], nd.aq[i]);
+        nd.xB[i] = v;
+        nd.xfull[nd.head[i]] = v;
+    }
+    __syncthreads();
+    sx_duals(P, nd);
+    if (threadIdx.x == 0) s_status = status;
+    __syncthreads();
+    if (status == 0) {
+        bool bad = false;
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            const int8_t st = nd.stat[j];
+            if ((st == SX_UPPER && nd.arthi[j]) || (st == SX_LOWER && nd.artlo[j])) bad = true;
+            if (fabs(nd.xfull[j]) >= 0.5 * kSxBig) bad = true;
+        }
+        if (bad) s_status = 2;                              // benign race: every writer stores 2
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        if (Q.x) Q.x[(size_t)node * n + j] = nd.xfull[j];
+        if (Q.rc) Q.rc[(size_t)node * n + j] = nd.d[j];
+        if (Q.cstat_out) Q.cstat_out[(size_t)node * n + j] = nd.stat[j];
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        if (Q.y) Q.y[(size_t)node * m + i] = nd.y[i];
+        if (Q.rstat_out) Q.rstat_out[(size_t)node * m + i] = nd.stat[n + i];
+    }
+    if (threadIdx.x == 0) {
+        double obj = 0.0;
+        for (int j = 0; j < n; ++j) obj = sx_add(obj, sx_mul(P.c[j], nd.xfull[j]));
+        if (Q.obj) Q.obj[node] = obj;
+        if (Q.status) Q.status[node] = s_status;
+        if (Q.pivots) Q.pivots[node] = pivots;
+        if (Q.flips) Q.flips[node] = flips_total;
+    }
+}
+
+// Rows of the simplex tableau Binv [A, -I] of a node whose factor is in a store (device-side GMI
+// input, base_node.py:513-530): out[t][:] = row of the basic variable vars[t] (or zeros if not basic).
+// grid = (rows requested), block = 256.
+__global__ void k_simplex_tableau_rows(const SxProb P, const double* __restrict__ Binv,
+                                       const int32_t* __restrict__ head, const int nrows,
+                                       const int32_t* __restrict__ vars, double* __restrict__ out) {
+    __shared__ int s_pos;
+    const int t = blockIdx.x;
+    const int m = P.m, n = P.n, N = n + m;
+    if (threadIdx.x == 0) s_pos = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+        if (head[i] == vars[t]) s_pos = i;
+    __syncthreads();
+    const int r = s_pos;
+    double* o = out + (size_t)t * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        double a = 0.0;
+        if (r >= 0) {
+            if (j < n) {
+                double acc = 0.0;
+                for (int p = P.cptr[j]; p < P.cptr[j + 1]; ++p) {
+                    const Ent e = P.cent[p];
+                    const double ri = Binv[(size_t)e.idx * P.ldm + r];
+                    if (ri != 0.0) acc = sx_add(acc, sx_mul(ri, e.val));
+                }
+                a = acc;
+            } else {
+                a = -Binv[(size_t)(j - n) * P.ldm + r];
+            }
+        }
+        o[j] = a;
+    }
+}
+
+}  // namespace blp

@@ -66,6 +66,12 @@ _SIGNATURES = {
     'blp_solve_children_host': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                           C.c_int, C.POINTER(BlpOpts), _P, _P, _P, _P, _P, _P, _P,
                                           C.POINTER(BlpStats)]),
+    'blp_simplex_max_rows': (C.c_int, []),
+    'blp_simplex_batch_host': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P,
+                                         _P, _P, C.POINTER(BlpStats)]),
+    'blp_simplex_children_host': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int,
+                                            _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(BlpStats)]),
+    'blp_simplex_tableau_rows_host': (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     'blp_spmv': (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     'blp_stream': (_P, [_P]),
     'blp_stream_sync': (C.c_int, [_P]),
@@ -146,6 +152,20 @@ class BatchResult:
     frac_idx: np.ndarray          # [B] most fractional integer column or -1
     x: Optional[np.ndarray]       # [B, n]
     y: Optional[np.ndarray]       # [B, m] row duals (>= 0)
+    stats: dict
+
+
+@dataclass
+class SimplexBatchResult:
+    """Per-node results of one batched dual simplex call (host arrays)."""
+    objective: np.ndarray         # [B] c.x of the final basic solution
+    status: np.ndarray            # [B] CLP codes
+    pivots: np.ndarray            # [B]
+    x: np.ndarray                 # [B, n] the vertex
+    y: np.ndarray                 # [B, m] row duals
+    reduced_costs: np.ndarray     # [B, n]
+    col_status: np.ndarray        # [B, n] int8, CLP coding: 1 basic, 2 at upper, 3 at lower
+    row_status: np.ndarray        # [B, m]
     stats: dict
 
 
@@ -292,6 +312,103 @@ class BatchLP:
         return BatchResult(objective=out['obj'], lower_bound=out['lower'], status=out['status'],
                            iterations=out['iters'], frac_idx=out['frac'], x=out['x'], y=out['y'],
                            stats=st.as_dict())
+
+    # -- dual simplex path for small LPs: a vertex and a basis per node ----------------------------
+    @property
+    def simplex_capable(self) -> bool:
+        """True when the LP (with its appended rows) is small enough for blp_simplex_*."""
+        return self.m <= self._lib.blp_simplex_max_rows()
+
+    def _simplex_out(self, B, m):
+        return dict(obj=np.empty(B), status=np.empty(B, dtype=np.int32), pivots=np.empty(B, dtype=np.int32),
+                    x=np.empty((B, self.n)), y=np.empty((B, m)), rc=np.empty((B, self.n)),
+                    cs=np.empty((B, self.n), dtype=np.int8), rs=np.empty((B, m), dtype=np.int8))
+
+    @staticmethod
+    def _simplex_result(out, st) -> 'SimplexBatchResult':
+        return SimplexBatchResult(objective=out['obj'], status=out['status'], pivots=out['pivots'], x=out['x'],
+                                  y=out['y'], reduced_costs=out['rc'], col_status=out['cs'],
+                                  row_status=out['rs'], stats=st.as_dict())
+
+    def _mask_arg(self, row_mask, shape):
+        if row_mask is None or self.num_cut_rows == 0:
+            return None
+        mask = np.ascontiguousarray(row_mask, dtype=np.uint8)
+        if mask.shape != shape:
+            raise ValueError(f'row_mask must have shape {shape}, got {mask.shape}')
+        return mask
+
+    def simplex_batch(self, lb, ub, row_mask=None, col_status=None, row_status=None, parent_slot=None,
+                      max_pivots: int = 2147483647) -> 'SimplexBatchResult':
+        """Dual simplex for B node LPs (blp_simplex_batch_host): per-node bounds [B, n], optional
+        per-node starting basis in CLP's coding (lp.setBasisStatus, base_node.py:608) or the slot of
+        the previous simplex call whose factorised basis to continue from."""
+        lb = np.ascontiguousarray(np.atleast_2d(lb), dtype=np.float64)
+        B = lb.shape[0]
+        lb = _f64(lb, (B, self.n))
+        ub = _f64(np.atleast_2d(ub), (B, self.n))
+        m = self.m
+        mask = self._mask_arg(None if row_mask is None else np.atleast_2d(row_mask), (B, self.num_cut_rows))
+        cs = rs = None
+        if col_status is not None:
+            cs = np.ascontiguousarray(np.atleast_2d(col_status), dtype=np.int8)
+            rs = np.ascontiguousarray(np.atleast_2d(row_status), dtype=np.int8)
+            if cs.shape != (B, self.n) or rs.shape != (B, m):
+                raise ValueError(f'basis status must have shapes {(B, self.n)} and {(B, m)}')
+        par = None if parent_slot is None else np.ascontiguousarray(parent_slot, dtype=np.int32).reshape(B)
+        out = self._simplex_out(B, m)
+        st = BlpStats()
+        _check(self._lib.blp_simplex_batch_host(
+            self._h, B, _np_ptr(lb), _np_ptr(ub), _np_ptr(mask), _np_ptr(cs), _np_ptr(rs), _np_ptr(par),
+            int(min(max_pivots, 2147483647)), _np_ptr(out['obj']), _np_ptr(out['status']), _np_ptr(out['pivots']),
+            _np_ptr(out['x']), _np_ptr(out['y']), _np_ptr(out['rc']), _np_ptr(out['cs']), _np_ptr(out['rs']),
+            C.byref(st)), 'blp_simplex_batch_host')
+        return self._simplex_result(out, st)
+
+    def simplex_children(self, parent_lb, parent_ub, deltas, row_mask=None, col_status=None,
+                         row_status=None, parent_slot: int = -1,
+                         max_pivots: int = 2147483647) -> 'SimplexBatchResult':
+        """Dual simplex for B children of one parent (blp_simplex_children_host): ``deltas[k]`` lists the
+        ``(var, lb, ub)`` bound changes of child k (base_node.py:595-600); the parent's basis comes as
+        CLP status arrays or as the slot it had in the previous simplex call."""
+        B = len(deltas)
+        if B < 1:
+            raise ValueError('need at least one child')
+        parent_lb = _f64(parent_lb, (self.n,))
+        parent_ub = _f64(parent_ub, (self.n,))
+        m = self.m
+        dptr = np.zeros(B + 1, dtype=np.int32)
+        for k, d in enumerate(deltas):
+            dptr[k + 1] = dptr[k] + len(d)
+        flat = [t for d in deltas for t in d]
+        dvar = np.ascontiguousarray([t[0] for t in flat], dtype=np.int32)
+        dlb = np.ascontiguousarray([t[1] for t in flat], dtype=np.float64)
+        dub = np.ascontiguousarray([t[2] for t in flat], dtype=np.float64)
+        mask = self._mask_arg(row_mask, (self.num_cut_rows,))
+        cs = rs = None
+        if col_status is not None:
+            cs = np.ascontiguousarray(col_status, dtype=np.int8)
+            rs = np.ascontiguousarray(row_status, dtype=np.int8)
+            if cs.shape != (self.n,) or rs.shape != (m,):
+                raise ValueError(f'basis status must have shapes {(self.n,)} and {(m,)}')
+        out = self._simplex_out(B, m)
+        st = BlpStats()
+        _check(self._lib.blp_simplex_children_host(
+            self._h, B, _np_ptr(parent_lb), _np_ptr(parent_ub), _np_ptr(dptr), _np_ptr(dvar), _np_ptr(dlb),
+            _np_ptr(dub), _np_ptr(mask), _np_ptr(cs), _np_ptr(rs), int(parent_slot),
+            int(min(max_pivots, 2147483647)), _np_ptr(out['obj']), _np_ptr(out['status']), _np_ptr(out['pivots']),
+            _np_ptr(out['x']), _np_ptr(out['y']), _np_ptr(out['rc']), _np_ptr(out['cs']), _np_ptr(out['rs']),
+            C.byref(st)), 'blp_simplex_children_host')
+        return self._simplex_result(out, st)
+
+    def simplex_tableau_rows(self, slot: int, variables) -> np.ndarray:
+        """Rows of inv(B) [A, -I] that belong to the basic ``variables`` of node ``slot`` of the
+        previous simplex call (blp_simplex_tableau_rows_host; base_node.py:513-526)."""
+        v = np.ascontiguousarray(variables, dtype=np.int32).ravel()
+        out = np.empty((len(v), self.n + self.m))
+        _check(self._lib.blp_simplex_tableau_rows_host(self._h, int(slot), len(v), _np_ptr(v), _np_ptr(out)),
+               'blp_simplex_tableau_rows_host')
+        return out
 
     # -- device-buffer calls (torch tensors own the memory) --------------------------------------
     def solve_batch_device(self, lb, ub, row_mask=None, x0=None, y0=None, int_idx=None,

@@ -339,21 +339,21 @@ class BaseNode:
         """Gomory mixed integer cuts from the rows of the LP tableau that belong to fractional
         basic integer variables (reference :468-511; Conforti et al. 5.31), vectorised.
 
-        Two things differ from the reference, both because the LP solution here is a first-order
-        one and not a simplex vertex. (1) The basis is the active set of the solution; it is only
-        used if the basic solution it defines (computed exactly from the basis matrix) reproduces
-        the solver's x, and the right-hand side of a tableau row is taken from that basic solution,
-        not from the approximate x. (2) Nonbasic variables sitting at a nonzero bound (a branching
-        bound, an upper bound) are shifted/complemented to zero first; the reference's formula
-        assumes nonbasics at zero and is the special case without shifts (its pinned ``cut3``
-        example, test_base_node.py:654-684, gives the same cut)."""
+        The tableau rows come from the device: ``lp.tableau_rows`` multiplies the rows of the
+        factorised basis inverse the dual simplex kernel left behind into ``[A, -I]`` (only the rows
+        that are needed; the reference inverts the whole dense basis matrix, :513-526). Nonbasic
+        variables sitting at a nonzero bound (a branching bound, an upper bound) are
+        shifted/complemented to zero first; the reference's formula assumes nonbasics at zero and is
+        the special case without shifts (its pinned ``cut3`` example, test_base_node.py:654-684,
+        gives the same cut). When the LP was solved by the first-order path (LPs too large for the
+        simplex kernels) the basis is the active set of the solution and is used only if the basic
+        solution it defines reproduces the solver's x."""
         cuts = {}
-        tableau = self.tableau
-        if tableau is None:
-            return cuts
         n, m = self.lp.nVariables, self.lp.nConstraints
         col_stat, row_stat = self.lp.getBasisStatus()
         basic = self.basic_variable_indices
+        if len(basic) != m:
+            return cuts
         is_basic = np.zeros(n + m, dtype=bool)
         is_basic[basic] = True
         is_int = np.zeros(n + m, dtype=bool)
@@ -369,24 +369,36 @@ class BaseNode:
         if not np.isfinite(offset).all():
             return cuts
         sign = np.where(at_upper, -1.0, 1.0)
-        full = np.concatenate((A.toarray(), -np.identity(m)), axis=1)
-        try:
-            x_basic = np.linalg.solve(full[:, basic], b - full @ offset)
-        except np.linalg.LinAlgError:
-            return cuts
-        z = offset.copy()
-        z[basic] = x_basic
-        if np.max(np.abs(z[:n] - self.solution) / (1.0 + np.abs(self.solution))) > 1e-5:
-            return cuts                      # the active set is not the basis of this solution
+        x = np.asarray(self.solution, dtype=float)
+        if self.lp.has_exact_basis:
+            x_basic = np.concatenate([x, A @ x - b])[basic]
+        else:
+            full = np.concatenate((A.toarray(), -np.identity(m)), axis=1)
+            try:
+                x_basic = np.linalg.solve(full[:, basic], b - full @ offset)
+            except np.linalg.LinAlgError:
+                return cuts
+            z = offset.copy()
+            z[basic] = x_basic
+            if np.max(np.abs(z[:n] - x) / (1.0 + np.abs(x))) > 1e-5:
+                return cuts                      # the active set is not the basis of this solution
         is_int &= np.abs(offset - np.round(offset)) <= 1e-9          # shifted variable stays integer
         eps = good_coefficient_approximation_epsilon
+        wanted = []
         for row_idx, j in enumerate(basic):
             if j >= n or j not in self._integer_indices or not self._is_fractional(float(x_basic[row_idx])):
                 continue
             f0 = self._get_fraction(float(x_basic[row_idx]))
             if f0 < eps or f0 + eps > 1:
                 continue
-            row = np.where(is_basic, 0.0, tableau[row_idx] * sign)   # coefficients of the shifted nonbasics
+            wanted.append((row_idx, f0))
+        if not wanted:
+            return cuts
+        rows = self._tableau_rows([int(basic[r]) for r, _ in wanted])
+        if rows is None:
+            return cuts
+        for (row_idx, f0), trow in zip(wanted, rows):
+            row = np.where(is_basic, 0.0, trow * sign)               # coefficients of the shifted nonbasics
             f = row - np.floor(row)
             pi_int = np.where(f <= f0, f / f0, (1 - f) / (1 - f0))
             pi_cont = np.where(row > 0, row / f0, -row / (1 - f0))
@@ -399,19 +411,33 @@ class BaseNode:
             cuts[row_idx] = (CyLPArray(coefs), rhs)
         return cuts
 
-    @property
-    def tableau(self):
-        """Dense simplex tableau inv([A, -I]_B) [A, -I] of ``A x - s = b`` (reference :513-526),
-        or None when the active set of the solution is not a basis."""
+    def _tableau_rows(self, variables: Sequence[int]):
+        """Rows of inv([A, -I]_B) [A, -I] for the given basic variables: from the device when the
+        factorised basis of this LP's solve is still in the engine's store, else from a dense solve on
+        the host (what the reference does for every row, :513-526)."""
+        rows = self.lp.tableau_rows(variables)
+        if rows is not None:
+            return rows
         basic = self.basic_variable_indices
         m = self.lp.nConstraints
         if len(basic) != m:
             return None
         full = np.concatenate((self.lp.coefMatrix.toarray(), -np.identity(m)), axis=1)
+        pos = {int(j): p for p, j in enumerate(basic)}
         try:
-            return np.linalg.solve(full[:, basic], full)
+            T_ = np.linalg.solve(full[:, basic], full)
         except np.linalg.LinAlgError:
             return None
+        return np.array([T_[pos[int(v)]] if int(v) in pos else np.zeros(full.shape[1]) for v in variables])
+
+    @property
+    def tableau(self):
+        """Simplex tableau inv([A, -I]_B) [A, -I] of ``A x - s = b``, one row per basic variable in
+        ascending variable order (reference :513-526), or None when the status is not a basis."""
+        basic = self.basic_variable_indices
+        if len(basic) != self.lp.nConstraints:
+            return None
+        return self._tableau_rows([int(j) for j in basic])
 
     @property
     def basic_variable_indices(self):

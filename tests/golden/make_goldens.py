@@ -33,8 +33,8 @@ import simple_mip_solver as ref  # noqa: E402
 from coinor.cuppy.milpInstance import MILPInstance  # noqa: E402  (the stand-in)
 from simple_mip_solver.utils.floating_point import get_fraction, numerically_safe_cut  # noqa: E402
 from simple_mip_solver.algorithms.base_algorithm import BaseAlgorithm  # noqa: E402
-from simple_mip_solver_b200.compat.cylp_like import CyLPArray  # noqa: E402
-from simple_mip_solver_b200.compat.mps import read_mps  # noqa: E402
+from oracle.ref_lookalikes import CyLPArray  # noqa: E402
+from oracle.mps_py import read_mps  # noqa: E402
 
 REF_TESTS = '/root/reference/test_simple_mip_solver'
 NODE_CASES = {
@@ -54,10 +54,13 @@ def fl(v):
     return v if np.isfinite(v) else ('inf' if v > 0 else '-inf')
 
 
-def run_bb(make_model, Node, kwargs):
+def run_bb(make_model, Node, kwargs, backend='highs'):
     # strong branching is only meaningful from the parent's basis (5 warm pivots, base_node.py:
-    # 608, 645), so pseudo-cost runs use the warm-started stand-in; the others solve cold
-    ref_stubs.WARM_START = 'pseudo_costs' in kwargs
+    # 608, 645), so pseudo-cost runs use the warm-started stand-in; the others solve cold.
+    # The textbook dual simplex (backend 'dual_simplex') is deterministic, so there every LP starts
+    # from the basis the reference hands it, exactly as with CLP (base_node.py:589, 608).
+    ref_stubs.LP_BACKEND = backend
+    ref_stubs.WARM_START = 'pseudo_costs' in kwargs or backend == 'dual_simplex'
     kw = {k: (dict(v) if isinstance(v, dict) else v) for k, v in kwargs.items()}
     bb = ref.BranchAndBound(make_model(), Node, **kw)
     bb.solve()
@@ -74,6 +77,7 @@ def run_bb(make_model, Node, kwargs):
     if 'pseudo_costs' in bb._kwargs:
         out['pseudo_costs'] = {str(i): {d: dict(cost=float(e['cost']), times=int(e['times']))
                                         for d, e in v.items()} for i, v in bb._kwargs['pseudo_costs'].items()}
+    ref_stubs.LP_BACKEND = 'highs'
     return out
 
 
@@ -103,8 +107,10 @@ def scale_1():
                               mip_feasible=bool(root.mip_feasible))
         rec['mip_optimum'] = mip_optimum(A, b, mdl.c, mdl.l, mdl.u, mdl.integer_indices)
         rec['reference'] = {}
+        rec['reference_ds'] = {}       # the same runs with oracle/dual_simplex.py answering lp.dual()
         for label, (Node, kw) in NODE_CASES.items():
             rec['reference'][label] = run_bb(lambda: MILPInstance(file_name=path), Node, kw)
+            rec['reference_ds'][label] = run_bb(lambda: MILPInstance(file_name=path), Node, kw, 'dual_simplex')
         out[name[:-4]] = rec
     return out
 
@@ -140,12 +146,14 @@ def example_models():
                               mip_feasible=bool(node.mip_feasible),
                               most_fractional_index=node._most_fractional_index)
         rec['reference'] = {}
+        rec['reference_ds'] = {}
         if name != 'unbounded':
             for label, (Node, kw) in NODE_CASES.items():
-                try:
-                    rec['reference'][label] = run_bb(fresh, Node, kw)
-                except Exception as e:       # a reference failure on this model is recorded, not hidden
-                    rec['reference'][label] = dict(error=f'{type(e).__name__}: {e}')
+                for key, backend in (('reference', 'highs'), ('reference_ds', 'dual_simplex')):
+                    try:
+                        rec[key][label] = run_bb(fresh, Node, kw, backend)
+                    except Exception as e:       # a reference failure on this model is recorded, not hidden
+                        rec[key][label] = dict(error=f'{type(e).__name__}: {e}')
         out[name] = rec
     return out
 

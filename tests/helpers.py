@@ -9,6 +9,7 @@ from __future__ import annotations
 import numpy as np
 import scipy.sparse as sp
 
+from oracle.dual_simplex import dual_simplex
 from oracle.highs_lp import HIGHS_INF, HighsLP
 
 
@@ -40,6 +41,76 @@ class OracleBatchLP:
 
     def close(self):
         pass
+
+    # -- dual simplex path: the numpy restatement of the device kernel (oracle/dual_simplex.py), with
+    #    the engine's two-call factor store emulated so that parent_slot means the same thing
+    simplex_capable = True
+    _store = ()
+
+    def _full(self):
+        A = self.A.toarray()
+        if self.cut_rows:
+            A = np.vstack([A] + [r[None, :] for r in self.cut_rows])
+        return A, np.concatenate([self.b, self.cut_rhs])
+
+    def _simplex(self, lbs, ubs, masks, css, rss, parents, max_pivots):
+        from simple_mip_solver_b200.engine import SimplexBatchResult
+        A, b = self._full()
+        m, B = A.shape[0], len(lbs)
+        type(self).calls += 1
+        type(self).lps += B
+        type(self).batch_sizes.append(B)
+        out, pivots = [], 0
+        for k in range(B):
+            on = np.ones(m, bool)
+            if masks is not None:
+                on[self.m_base:] = np.asarray(masks[k], bool)
+            start = None
+            if parents is not None and parents[k] >= 0:
+                start = self._store[parents[k]]
+                assert start.Binv.shape[0] == m, 'the factor store was dropped when rows changed'
+            r = dual_simplex(A, b, self.c, lbs[k], ubs[k], row_on=on,
+                             col_status=None if css is None else css[k],
+                             row_status=None if rss is None else rss[k], max_pivots=max_pivots, start=start)
+            out.append(r)
+            pivots += r.pivots
+        self._store = tuple(out)
+        return SimplexBatchResult(
+            objective=np.array([r.objective for r in out]), status=np.array([r.status for r in out], np.int32),
+            pivots=np.array([r.pivots for r in out], np.int32), x=np.array([r.x for r in out]),
+            y=np.array([r.y for r in out]), reduced_costs=np.array([r.rc for r in out]),
+            col_status=np.array([r.col_status for r in out], np.int8),
+            row_status=np.array([r.row_status for r in out], np.int8),
+            stats=dict(kernel_launches=0, iterations=max(r.pivots for r in out), node_iterations=pivots))
+
+    def simplex_batch(self, lb, ub, row_mask=None, col_status=None, row_status=None, parent_slot=None,
+                      max_pivots=2147483647):
+        lb, ub = np.atleast_2d(lb), np.atleast_2d(ub)
+        return self._simplex(lb, ub, row_mask, col_status, row_status, parent_slot, max_pivots)
+
+    def simplex_children(self, parent_lb, parent_ub, deltas, row_mask=None, col_status=None, row_status=None,
+                         parent_slot=-1, max_pivots=2147483647):
+        B = len(deltas)
+        lb = np.tile(np.asarray(parent_lb, float), (B, 1))
+        ub = np.tile(np.asarray(parent_ub, float), (B, 1))
+        for k, d in enumerate(deltas):
+            for j, lo, hi in d:
+                lb[k, j], ub[k, j] = lo, hi
+        rep = lambda a: None if a is None else np.tile(np.asarray(a), (B, 1))
+        return self._simplex(lb, ub, rep(row_mask), rep(col_status), rep(row_status),
+                             None if parent_slot < 0 else np.full(B, parent_slot), max_pivots)
+
+    def simplex_tableau_rows(self, slot, variables):
+        r = self._store[slot]
+        A, _ = self._full()
+        m = A.shape[0]
+        full = np.concatenate([A, -np.eye(m)], axis=1)
+        pos = {int(v): i for i, v in enumerate(r.head)}
+        out = np.zeros((len(variables), full.shape[1]))
+        for t, v in enumerate(np.asarray(variables).ravel()):
+            if int(v) in pos:
+                out[t] = r.Binv[pos[int(v)]] @ full
+        return out
 
     def solve_batch(self, lb, ub, row_mask=None, x0=None, y0=None, integer_indices=None, opts=None,
                     want_x=True, want_y=True):
@@ -79,9 +150,12 @@ class OracleBatchLP:
                            frac_idx=frac, x=x, y=y, stats=dict(kernel_launches=0))
 
 
-def use_oracle_engine(monkeypatch):
-    """Route SharedLP's engine to the HiGHS stand-in (CPU tests of host logic)."""
+def use_oracle_engine(monkeypatch, method='auto'):
+    """Route SharedLP's engine to the CPU stand-in (tests of host logic): the numpy dual simplex for
+    the simplex path, HiGHS for the path that goes to the PDHG kernels (``method='pdhg'``)."""
     import simple_mip_solver_b200.engine as engine
+    from simple_mip_solver_b200.compat.cylp_like import SharedLP
+    monkeypatch.setattr(SharedLP, 'default_method', method)
     OracleBatchLP.calls = 0
     OracleBatchLP.lps = 0
     OracleBatchLP.batch_sizes = []

@@ -1,10 +1,12 @@
 """CPU tests of the host-side logic (Node classes, BranchAndBound, batched LP plumbing).
 
-The LP arithmetic comes from the HiGHS oracle through tests/helpers.OracleBatchLP (no GPU in this
-suite); what is under test is the Python that the product ships: that it takes the same decisions
-as the UNMODIFIED reference did when it was run here on the HiGHS stand-in
-(tests/golden/make_goldens.py) — same status, optimum, number of evaluated nodes and, node by node,
-the same tree (parent, branching variable, direction, LP value).
+The LP arithmetic comes from the oracle through tests/helpers.OracleBatchLP (no GPU in this suite):
+the numpy dual simplex (oracle/dual_simplex.py) where the product would call blp_simplex_*, HiGHS
+where it would call the PDHG kernels. What is under test is the Python that the product ships: that
+it takes the same decisions as the UNMODIFIED reference did when it was run here on the same exact
+simplex (tests/golden/make_goldens.py: ``reference_ds`` for the dual simplex, ``reference`` for
+HiGHS) — same status, optimum, number of evaluated nodes and, node by node, the same tree (parent,
+branching variable, direction, LP value).
 """
 import json
 import os
@@ -58,16 +60,20 @@ def check_against_reference(bb, gold, tree=True):
             assert n.objective_value == pytest.approx(unfl(obj), rel=1e-9, abs=1e-9)
 
 
+GOLD_KEY = {'auto': 'reference_ds', 'pdhg': 'reference'}
+
+
 @pytest.mark.parametrize('label', list(CASES))
 @pytest.mark.parametrize('frontier', [1, 8])
-def test_scale_1_models_same_tree_as_reference(monkeypatch, label, frontier):
-    use_oracle_engine(monkeypatch)
+@pytest.mark.parametrize('method', ['auto', 'pdhg'])
+def test_scale_1_models_same_tree_as_reference(monkeypatch, label, frontier, method):
+    use_oracle_engine(monkeypatch, method)
     Node, kw = CASES[label]
     for name, rec in SCALE1.items():
         kwargs = {k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()}
         bb = BranchAndBound(model_from(rec), Node, frontier_batch=frontier, **kwargs)
         bb.solve()
-        check_against_reference(bb, rec['reference'][label])
+        check_against_reference(bb, rec[GOLD_KEY[method]][label])
         assert bb.objective_value == pytest.approx(unfl(rec['mip_optimum']), abs=1e-6), name
 
 
@@ -75,17 +81,18 @@ def test_scale_1_models_same_tree_as_reference(monkeypatch, label, frontier):
 @pytest.mark.parametrize('name', ['no_branch', 'small_branch', 'infeasible', 'infeasible2', 'random', 'cut1',
                                   'cut2', 'cut3', 'square', 'h3p1', 'h3p1_0', 'h3p1_1', 'h3p1_2', 'h3p1_3',
                                   'h3p1_4', 'h3p1_5', 'lift_project'])
-def test_example_models_same_tree_as_reference(monkeypatch, name, label):
-    use_oracle_engine(monkeypatch)
+@pytest.mark.parametrize('method', ['auto', 'pdhg'])
+def test_example_models_same_tree_as_reference(monkeypatch, name, label, method):
+    use_oracle_engine(monkeypatch, method)
     rec = EXAMPLES[name]
     Node, kw = CASES[label]
     kwargs = {k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()}
     bb = BranchAndBound(model_from(rec), Node, **kwargs)
     bb.solve()
-    check_against_reference(bb, rec['reference'][label])
-    if 'pseudo_costs' in rec['reference'][label]:
+    check_against_reference(bb, rec[GOLD_KEY[method]][label])
+    if 'pseudo_costs' in rec[GOLD_KEY[method]][label]:
         pc = bb._kwargs['pseudo_costs']
-        gold = rec['reference'][label]['pseudo_costs']
+        gold = rec[GOLD_KEY[method]][label]['pseudo_costs']
         assert set(map(str, pc)) == set(gold)
         for i, v in gold.items():
             for d, e in v.items():
@@ -100,7 +107,7 @@ def test_frontier_prefetch_batches_lps(monkeypatch):
     rec = EXAMPLES['random']
     bb = BranchAndBound(model_from(rec), BaseNode, frontier_batch=16, gomory_cuts=False)
     bb.solve()
-    check_against_reference(bb, rec['reference']['BaseNode'])
+    check_against_reference(bb, rec['reference_ds']['BaseNode'])
     assert max(eng.batch_sizes) > 1 and eng.calls < eng.lps
     batched = eng.calls
     eng2 = use_oracle_engine(monkeypatch)

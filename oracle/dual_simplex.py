@@ -221,7 +221,7 @@ def dual_simplex(A, b, c, l, u, row_on=None, col_status=None, row_status=None,
         if not cand.any():
             status = 0
             break
-        if pivots >= max_pivots:
+        if pivots >= min(max_pivots, 50 * N + 1000):     # the cap ends a cycling node (no anti-cycling rule)
             status = 3
             break
         if since_factor >= REFACTOR_EVERY:

@@ -11,8 +11,10 @@ and the only collective is the 16-byte all-reduce(min) of [incumbent, dual bound
 
   value   device-resident inputs (bounds and warm start already in HBM), CUDA-event time on the
           library's stream, max over ranks;
-  e2e     same metric through the host-buffer plugin call (``BatchLP.solve_batch``): pinned host
-          arrays in, H2D + solve + D2H of objective/status/x/y inside the timed region;
+  e2e     same metric through the host-buffer plugin call (``BatchLP.solve_children`` =
+          blp_solve_children_host: the root's bounds, per node its changed bounds, the root's primal/dual
+          pair as warm start): host arrays in, H2D + solve + D2H of objective/status/x/y of every node
+          inside the timed region;
   roofline  k_primal / k_dual per-launch time from CUDA events around every launch of the timed
           steps (blp_opts.profile) against the measured HBM copy peak;
   cpu_baseline  the HiGHS dual-simplex stand-in for the reference's CLP path (oracle/highs_lp.py),
@@ -40,6 +42,8 @@ WORKLOADS = {
     'c5': (50000, 20000, 2e-4, 32, 'c5_root.npz'),
     'c4': (10000, 5000, 2e-3, 16, 'c4_root.npz'),
     'c3': (500, 300, 0.1, 8, 'c3_root.npz'),
+    # C5 stress variant of SURVEY 8d: density 1e-3 (~50 nonzeros per row, ~1.0 M in all)
+    'c5s': (50000, 20000, 1e-3, 32, 'c5s_root.npz'),
 }
 METRIC = 'node_lp_solves_per_sec'
 UNIT = 'node-LPs/s'
@@ -64,6 +68,57 @@ def load_instance(name):
     return d, depth, root
 
 
+def load_child_goldens(name):
+    """Committed HiGHS answers for the frontier nodes GOLD_FIRST.. (tests/tools/make_child_goldens.py)."""
+    path = os.path.join(ROOT, 'bench_data', f'{name}_children.npz')
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    return dict(node_ids=z['node_ids'], status=z['status'], objective=z['objective'])
+
+
+GOLD_PER_STEP = 8          # nodes with committed golden answers that ride in every step
+
+
+def step_nodes(d, root, depth, seed, slice_index, B, gold):
+    """Nodes of one step: B - 8 nodes of the frontier slice plus 8 of the 64 nodes whose HiGHS answers
+    are committed (the same generator, ids from the reserved range), rotating with the slice. They are
+    solved and timed like every other node; bench.py compares them with the goldens afterwards.
+    A node is its list of ``(var, lb, ub)`` changes against the root bounds (base_node.py:595-600)."""
+    from simple_mip_solver_b200.instances import GOLD_COUNT, GOLD_FIRST, frontier_nodes
+    g = GOLD_PER_STEP if (gold is not None and B > GOLD_PER_STEP) else 0
+    _, _, deltas = frontier_nodes(d, root['x'], slice_index * B, B - g, depth, seed=seed, dense=False)
+    gold_ids = []
+    if g:
+        gold_ids = [(slice_index * g + t) % GOLD_COUNT for t in range(g)]
+        for i in gold_ids:
+            deltas = deltas + frontier_nodes(d, root['x'], GOLD_FIRST + i, 1, depth, seed=0, dense=False)[2]
+    return deltas, gold_ids
+
+
+class Validator:
+    """Collects (golden id, status, objective) of the golden nodes of every timed step."""
+
+    def __init__(self, gold):
+        self.gold, self.rows = gold, []
+
+    def add(self, gold_ids, status, objective):
+        for i, st, ob in zip(gold_ids, status, objective):
+            self.rows.append((int(i), int(st), float(ob)))
+
+    def report(self, tol=1e-6):
+        if self.gold is None:
+            return {'checked': 0, 'ok': 0, 'note': 'no committed child goldens for this workload'}
+        ok, worst = 0, 0.0
+        for i, st, ob in self.rows:
+            gs, go = int(self.gold['status'][i]), float(self.gold['objective'][i])
+            err = abs(ob - go) / max(1.0, abs(go)) if (gs == 0 and st == 0) else 0.0
+            worst = max(worst, err)
+            ok += int(st == gs and err <= tol)
+        return {'checked': len(self.rows), 'ok': ok, 'max_rel_objective_error': worst, 'tolerance': tol,
+                'against': 'bench_data/*_children.npz (HiGHS dual simplex, made offline), compared after the timed region'}
+
+
 def root_by_oracle(d):
     """Root vertex/basis from the HiGHS oracle (only when no fixture is committed)."""
     from oracle.highs_lp import HIGHS_INF, HighsLP
@@ -76,9 +131,9 @@ def root_by_oracle(d):
 _W = {}
 
 
-def _cpu_init(A, b, c, l, u, col_basis, row_basis):
+def _cpu_init(A, b, c, l, u, col_basis, row_basis, tol=1e-9):
     from oracle.highs_lp import HIGHS_INF, HighsLP
-    _W['lp'] = HighsLP(A, c, b, np.full(A.shape[0], HIGHS_INF), l, u)
+    _W['lp'] = HighsLP(A, c, b, np.full(A.shape[0], HIGHS_INF), l, u, tol=tol)
     _W['basis'] = (col_basis, row_basis)
     _W['l'], _W['u'] = l, u
 
@@ -105,12 +160,12 @@ def host_cores():
 
 
 class CpuArm:
-    def __init__(self, d, root, cores):
+    def __init__(self, d, root, cores, tol=1e-9):
         import multiprocessing as mp
         self.cores = cores
         ctx = mp.get_context('fork')
         self.pool = ctx.Pool(cores, initializer=_cpu_init,
-                             initargs=(d.A, d.b, d.c, d.l, d.u, root['col_basis'], root['row_basis']))
+                             initargs=(d.A, d.b, d.c, d.l, d.u, root['col_basis'], root['row_basis'], tol))
 
     def run(self, deltas_list):
         t = time.perf_counter()
@@ -194,7 +249,7 @@ def run_reference(args, d, depth, root, rank):
     if root is None:
         root = root_by_oracle(d)
     per_step = args.cpu_nodes or cores
-    arm = CpuArm(d, root, cores)
+    arm = CpuArm(d, root, cores, tol=args.eps)
     steps = args.warmup + args.steps
     times, solved = [], 0
     for s in range(steps):
@@ -209,12 +264,12 @@ def run_reference(args, d, depth, root, rank):
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / max(args.steps, 1),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': workload_config(args, d, per_step),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': f'{per_step} frontier nodes per step on {cores} processes, HiGHS 1.12 dual '
-                                   'simplex (stand-in for CLP), presolve off, warm start from the root basis'},
+                                   f'simplex (stand-in for CLP), presolve off, feasibility tolerances {args.eps:g} (the GPU arm\'s eps_rel), warm start from the root basis'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -225,7 +280,8 @@ def workload_config(args, d, batch):
     n, m, dens, depth, _ = WORKLOADS[args.workload]
     return {'workload': f'{args.workload}: frontier of open-node LPs of a synthetic sparse MILP, {n} vars x {m} rows, '
                         f'{d.A.nnz} nonzeros, dive depth U{{1..{depth}}}, solved to rel. KKT {args.eps:g}; '
-                        f'{batch} nodes per step per GPU (the 4096-node frontier is swept in slices), '
+                        f'{batch} nodes per step per GPU ({args.scaling} scaling; the 4096-node frontier of the named config '
+                        f'is swept in slices), '
                         f'{min(args.slots, batch) if args.slots > 0 else batch} of them resident at a time '
                         f'(finished nodes hand their slot to pending ones)',
             'batch_per_gpu': batch, 'resident_slots': min(args.slots, batch) if args.slots > 0 else batch,
@@ -240,7 +296,12 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='blp', choices=['blp', 'reference'])
     ap.add_argument('--workload', default='c5', choices=list(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=1024, help='open nodes per step per GPU')
+    ap.add_argument('--batch', type=int, default=1024,
+                    help='open nodes per step: per GPU with --scaling weak, in total with --scaling strong')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: every GPU solves --batch nodes per step; strong: --batch nodes per step are '
+                         'split over the GPUs (BASELINE.json config 5 as named: --batch 4096 --scaling strong)')
+    ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--slots', type=int, default=512,
                     help='nodes resident at a time (blp_opts.max_active); 0 = the whole batch')
     ap.add_argument('--eps', type=float, default=1e-7)
@@ -259,8 +320,15 @@ def main():
         run_reference(args, d, depth, root, rank)
         return
 
+    if args.scaling == 'strong':
+        if args.batch % world:
+            raise SystemExit(f'--scaling strong: --batch {args.batch} is not a multiple of {world} GPUs')
+        args.batch //= world
     from simple_mip_solver_b200.instances import frontier_nodes
     n, m, B = d.n, d.m, args.batch
+    gold = load_child_goldens(args.workload)
+    checker = Validator(gold)
+    checker_e2e = Validator(gold)
     if root is None:      # the product arm never runs the oracle, not even to define its workload
         raise SystemExit(f'bench_data/{WORKLOADS[args.workload][4]} is missing: make it with '
                          f'tests/tools/make_bench_fixture.py')
@@ -271,14 +339,14 @@ def main():
         cores = host_cores()
         k = args.cpu_nodes or cores
         _, _, deltas = frontier_nodes(d, root['x'], 10_000_000, k, depth, seed=args.seed)
-        arm = CpuArm(d, root, cores)
+        arm = CpuArm(d, root, cores, tol=args.eps)
         out, dt = arm.run(deltas)
         arm.close()
         ok = sum(1 for st, _, _ in out if st in (0, 1, 2))
         cpu = {'value': ok / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                'sample': f'{k} frontier nodes of the same workload, one LP per process on {cores} processes, '
-                         f'HiGHS 1.12 dual simplex (stand-in for CLP), presolve off, warm start from the root '
-                         f'basis; {dt:.1f} s wall, mean {np.mean([t for _, _, t in out]):.2f} s per LP per core'}
+                         f'HiGHS 1.12 dual simplex (stand-in for CLP), presolve off, feasibility tolerances {args.eps:g}, '
+                         f'warm start from the root basis; {dt:.1f} s wall, mean {np.mean([t for _, _, t in out]):.2f} s per LP per core'}
         log('cpu_baseline', cpu)
 
     import torch
@@ -306,16 +374,29 @@ def main():
     int_idx = torch.arange(n, dtype=torch.int32, device=dev)
 
     def node_slice(step):
-        first = (step * world + rank) * B
-        return frontier_nodes(d, root['x'], first, B, depth, seed=args.seed)
+        return step_nodes(d, root, depth, args.seed, step * world + rank, B, gold)
 
-    def to_device(lbs, ubs, count=B):
+    root_l = torch.from_numpy(d.l).to(dev)
+    root_u = torch.from_numpy(d.u).to(dev)
+
+    def pack(deltas):
+        """host side of a slice: (node, var, lb, ub) of every bound change, pinned"""
+        node = np.concatenate([np.full(len(dl), k, dtype=np.int64) for k, dl in enumerate(deltas)])
+        flat = [t for dl in deltas for t in dl]
+        arr = lambda v, dt: torch.from_numpy(np.asarray(v, dtype=dt)).pin_memory()
+        return (arr(node, np.int64), arr([t[0] for t in flat], np.int64), arr([t[1] for t in flat], np.float64),
+                arr([t[2] for t in flat], np.float64))
+
+    def to_device(packed, count=B):
+        """root bounds broadcast over the node columns, then the slice's bound changes scattered in"""
         ldc = engine.leading_dim(count)
-        lb = torch.zeros((n, ldc), dtype=torch.float64, device=dev)
-        ub = torch.zeros((n, ldc), dtype=torch.float64, device=dev)
-        lb[:, :count] = torch.from_numpy(lbs[:count]).to(dev).T
-        ub[:, :count] = torch.from_numpy(ubs[:count]).to(dev).T
-        return lb.contiguous(), ub.contiguous()
+        lb = root_l[:, None].expand(n, ldc).contiguous()
+        ub = root_u[:, None].expand(n, ldc).contiguous()
+        node, var, lo, hi = (t.to(dev, non_blocking=True) for t in packed)
+        keep = node < count
+        lb[var[keep], node[keep]] = lo[keep]
+        ub[var[keep], node[keep]] = hi[keep]
+        return lb, ub
 
     x0 = torch.from_numpy(root['x']).to(dev)[:, None].expand(n, ld).contiguous()
     y0 = torch.from_numpy(root['y']).to(dev)[:, None].expand(m, ld).contiguous()
@@ -331,6 +412,7 @@ def main():
 
     total_steps = args.warmup + args.steps
     slices = [node_slice(s) for s in range(total_steps)]
+    packed = [pack(sl[0]) for sl in slices]
 
     def barrier():
         if world > 1:
@@ -345,7 +427,7 @@ def main():
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for s in range(total_steps):
-        lb, ub = to_device(slices[s][0], slices[s][1])
+        lb, ub = to_device(packed[s])
         if s == args.warmup:
             barrier()
             if rank == 0:
@@ -359,6 +441,9 @@ def main():
             agg['unsolved'] += int((st == 3).sum().item())
             agg['infeasible'] += int((st == 1).sum().item())
             iters_all.append(r['iters'][:B].cpu().numpy())
+            g = len(slices[s][1])
+            if g:
+                checker.add(slices[s][1], st[B - g:B].cpu().numpy(), r['obj'][B - g:B].cpu().numpy())
             sdict = r['stats']
             agg['launches'] += sdict['kernel_launches']
             agg['node_iters'] += sdict['node_iterations']
@@ -378,7 +463,7 @@ def main():
     # (blp_opts.profile: no CUDA graph; not part of `value`)
     prof = None
     if rank == 0:
-        lb, ub = to_device(slices[-1][0], slices[-1][1], W)
+        lb, ub = to_device(packed[-1], W)
         prof = lp.solve_batch_device(lb, ub, x0=x0[:, :ldW].contiguous(), y0=y0[:, :ldW].contiguous(),
                                      int_idx=int_idx, opts=opts_prof, want_x=False, want_y=False)['stats']
         del lb, ub
@@ -407,30 +492,36 @@ def main():
     value = sums[0] / (dev_ms * 1e-3)
 
     # ---- end-to-end arm: pinned host buffers through the plugin call ----
-    e2e_steps = 1
+    e2e_steps = max(1, args.e2e_steps)
     e2e_slices = [node_slice(total_steps + s) for s in range(1 + e2e_steps)]
+    # The nodes of a frontier are children of the root: the plugin call takes them as the reference
+    # creates them (base_node.py:592-608) — the parent's bounds, per node the changed bounds, the
+    # parent's primal/dual pair as the common warm start (blp_solve_children_host).
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    hx0 = pin(np.tile(root['x'], (B, 1)))
-    hy0 = pin(np.tile(root['y'], (B, 1)))
+    hl, hu, hx0, hy0 = pin(d.l), pin(d.u), pin(root['x']), pin(root['y'])
     opts_e = engine.default_opts(eps_rel=args.eps, max_iters=args.max_iters, max_active=W)
     ints = list(range(n))
     h2d = d2h = 0
     e2e_solved = 0
     t0 = None
     for s in range(1 + e2e_steps):
-        hlb, hub = pin(e2e_slices[s][0]), pin(e2e_slices[s][1])
+        deltas_s = e2e_slices[s][0]
         if s == 1:
             barrier()
             t0 = time.perf_counter()
-        rr = lp.solve_batch(hlb, hub, x0=hx0, y0=hy0, integer_indices=ints, opts=opts_e)
+        rr = lp.solve_children(hl, hu, deltas_s, x0=hx0, y0=hy0, integer_indices=ints, opts=opts_e)
         integral = (rr.status == 0) & (rr.frac_idx < 0)
         inc = float(rr.objective[integral].min()) if integral.any() else float('inf')
         open_ = (rr.status == 0) & ~integral
         lowb = float(rr.lower_bound[open_].min()) if open_.any() else float('inf')
         parallel.allreduce_bounds(inc, lowb, device=dev, lp=lp if use_comm else None)
         if s >= 1:
+            g = len(e2e_slices[s][1])
+            if g:
+                checker_e2e.add(e2e_slices[s][1], rr.status[B - g:], rr.objective[B - g:])
             e2e_solved += int(np.isin(rr.status, (0, 1, 2)).sum())
-            h2d = hlb.nbytes + hub.nbytes + hx0.nbytes + hy0.nbytes + 4 * n
+            nd = sum(len(dl) for dl in deltas_s)
+            h2d = hl.nbytes + hu.nbytes + hx0.nbytes + hy0.nbytes + 4 * n + 4 * (B + 1) + 20 * nd
             d2h = rr.x.nbytes + rr.y.nbytes + rr.objective.nbytes + rr.lower_bound.nbytes + \
                 rr.status.nbytes + rr.iterations.nbytes + rr.frac_idx.nbytes
     barrier()
@@ -479,7 +570,8 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / max(args.steps, 1), 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'validated': {'device_arm': checker.report(), 'e2e_arm': checker_e2e.report()},
             'e2e': {'value': e2e_total / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h), 'steps': e2e_steps},
             'gpu_launches': int(sums[2]),

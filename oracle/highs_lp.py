@@ -56,7 +56,7 @@ def _inf(v):
 class HighsLP:
     """One LP ``min c.x, row_lb <= A x <= row_ub, l <= x <= u`` held in a HiGHS instance."""
 
-    def __init__(self, A, c, row_lb, row_ub, l, u, threads: int = 1):
+    def __init__(self, A, c, row_lb, row_ub, l, u, threads: int = 1, tol: float = 1e-9):
         A = sp.csc_matrix(A, dtype=float)
         m, n = A.shape
         self.m, self.n = m, n
@@ -66,8 +66,8 @@ class HighsLP:
         h.setOptionValue('solver', 'simplex')
         h.setOptionValue('simplex_strategy', 1)          # serial dual simplex, as CLP's dual()
         h.setOptionValue('threads', threads)
-        h.setOptionValue('primal_feasibility_tolerance', 1e-9)
-        h.setOptionValue('dual_feasibility_tolerance', 1e-9)
+        h.setOptionValue('primal_feasibility_tolerance', float(tol))
+        h.setOptionValue('dual_feasibility_tolerance', float(tol))
         lp = _hc.HighsLp()
         lp.num_col_, lp.num_row_ = n, m
         lp.col_cost_ = np.asarray(c, dtype=float)

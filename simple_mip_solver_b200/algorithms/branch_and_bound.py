@@ -127,6 +127,7 @@ class BranchAndBound(BaseAlgorithm):
         self.frontier_batch = frontier_batch
         self.prefetch_calls = 0
         self.prefetched_lps = 0
+        self.unsolved_nodes = 0         # nodes whose LP stopped on the solver's iteration budget
 
     @property
     def dual_bound(self):
@@ -164,9 +165,9 @@ class BranchAndBound(BaseAlgorithm):
         self.solve_time += time.process_time() - start
         if self._unbounded:
             self.status = 'unbounded'
-        elif self._node_queue.empty() and self.primal_bound == float('inf'):
+        elif self._node_queue.empty() and self.primal_bound == float('inf') and not self.unsolved_nodes:
             self.status = 'infeasible'
-        elif self.primal_bound < float('inf') and self.current_gap <= self.mip_gap:
+        elif self.primal_bound < float('inf') and self.current_gap is not None and self.current_gap <= self.mip_gap:
             self.status = 'optimal'
         else:
             self.status = 'stopped on iterations or time'
@@ -200,6 +201,11 @@ class BranchAndBound(BaseAlgorithm):
         self._process_bound_rtn(node.bound(**self._kwargs))
         if node.unbounded:
             self._unbounded = True
+        if getattr(node, 'lp_unsolved', False):
+            # the LP hit the solver's iteration budget: the node stays an open leaf carrying the dual
+            # bound it reached (never dropped as infeasible, never branched on an unconverged point)
+            self.unsolved_nodes += 1
+            return
         if node.lp_feasible and node.objective_value < self.primal_bound:
             if node.mip_feasible:
                 self._best_solution = node.solution

@@ -124,8 +124,14 @@ def random_dive_bounds(data: MipData, x_root: np.ndarray, batch: int, max_depth:
     return lb, ub, deltas
 
 
+# Frontier nodes with committed golden answers (bench_data/<workload>_children.npz, made by
+# tests/tools/make_child_goldens.py): ids GOLD_FIRST .. GOLD_FIRST + GOLD_COUNT - 1 of frontier_nodes(seed=0).
+GOLD_FIRST = 20_000_000
+GOLD_COUNT = 64
+
+
 def frontier_nodes(data: MipData, x_root: np.ndarray, first: int, count: int, max_depth: int,
-                   seed: int = 0, p_down: float = 0.75):
+                   seed: int = 0, p_down: float = 0.75, dense: bool = True):
     """Bounds of open nodes ``first .. first+count-1`` of a synthetic frontier.
 
     Node k is reached from the root by depth_k ~ U{1..max_depth} branching decisions on integer
@@ -135,7 +141,8 @@ def frontier_nodes(data: MipData, x_root: np.ndarray, first: int, count: int, ma
     would make a row unsatisfiable even with every other variable at its lower bound is turned
     into a down-branch, so every node passes the row-activity screen and needs a real LP solve.
     Each node has its own generator seeded by (seed, k): the frontier does not depend on how it
-    is split into batches or over GPUs. Returns (lb, ub) of shape [count, n] and the deltas."""
+    is split into batches or over GPUs. Returns (lb, ub) of shape [count, n] and the deltas: per node the
+    list of ``(var, lb, ub)`` changes against the root bounds; with ``dense=False`` lb and ub are None."""
     n = data.n
     ints = np.asarray(data.integer_indices)
     vals = x_root[ints]
@@ -144,12 +151,13 @@ def frontier_nodes(data: MipData, x_root: np.ndarray, first: int, count: int, ma
     n_frac = int((frac > 1e-4).sum())
     A = data.A.tocsc()
     base_act = data.A @ data.l              # activity with everything at its lower bound
-    lb = np.tile(data.l, (count, 1))
-    ub = np.tile(data.u, (count, 1))
+    lb = np.tile(data.l, (count, 1)) if dense else None
+    ub = np.tile(data.u, (count, 1)) if dense else None
     deltas = []
     for t in range(count):
         k = first + t
         rng = np.random.Generator(np.random.PCG64([seed, k]))
+        cur = {}                                  # bounds this node has moved so far
         depth = int(rng.integers(1, max_depth + 1))
         pool = order[:max(n_frac, depth)]
         picks = rng.choice(pool, size=min(depth, pool.size), replace=False)
@@ -157,7 +165,7 @@ def frontier_nodes(data: MipData, x_root: np.ndarray, first: int, count: int, ma
         node = []
         for j in picks:
             v = x_root[j]
-            lo, hi = lb[t, j], ub[t, j]
+            lo, hi = cur.get(int(j), (data.l[j], data.u[j]))
             up = rng.random() >= p_down and np.ceil(v) <= hi and np.ceil(v) > lo
             if up:
                 col = A.getcol(j)
@@ -166,9 +174,12 @@ def frontier_nodes(data: MipData, x_root: np.ndarray, first: int, count: int, ma
                     up = False
                 else:
                     act[col.indices] = trial
-                    lb[t, j] = np.ceil(v)
+                    lo = np.ceil(v)
             if not up:
-                ub[t, j] = max(min(hi, np.floor(v)), lo)
-            node.append((int(j), float(lb[t, j]), float(ub[t, j])))
+                hi = max(min(hi, np.floor(v)), lo)
+            cur[int(j)] = (float(lo), float(hi))
+            if dense:
+                lb[t, j], ub[t, j] = lo, hi
+            node.append((int(j), float(lo), float(hi)))
         deltas.append(node)
     return lb, ub, deltas

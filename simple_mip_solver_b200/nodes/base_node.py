@@ -71,6 +71,7 @@ class BaseNode:
         self.objective_value = None
         self.solution = None
         self.lp_feasible = None
+        self.lp_unsolved = False
         self.unbounded = None
         self.mip_feasible = None
         self._b_dir, self._b_idx, self._b_val = b_dir, b_idx, b_val
@@ -157,7 +158,7 @@ class BaseNode:
         def out_of_time():
             return time.process_time() - start >= max_cut_generation_run_time
 
-        while self.lp_feasible and not self.mip_feasible and not self.cut_generation_stalled \
+        while self.lp_feasible and not self.lp_unsolved and not self.mip_feasible and not self.cut_generation_stalled \
                 and self.cut_generation_iterations < max_cut_generation_iterations \
                 and not out_of_time() and self.objective_value < max_dual_bound:
             self._cut_generation_iteration(**kwargs)
@@ -211,9 +212,19 @@ class BaseNode:
 
     def _read_lp(self: T) -> None:
         code = self.lp.getStatusCode()
-        self.lp_feasible = code in [0, 2]          # optimal or dual infeasible (:274)
+        # CLP never stops a normal bound on an iteration count; the device solvers can (PDHG's
+        # iteration budget on a degenerate LP, the simplex kernel's anti-cycling cap). Such a node
+        # is NOT infeasible: it stays an open leaf whose value is the dual bound the solve reached,
+        # and the search reports 'stopped on iterations or time' unless the incumbent closes it.
+        self.lp_unsolved = code == 3 and self.lp.maxNumIteration >= 2147483647
+        self.lp_feasible = code in [0, 2] or self.lp_unsolved     # optimal or dual infeasible (:274)
         self.unbounded = code == 2
         self.objective_value = self.lp.objectiveValue if self.lp_feasible else float('inf')
+        if self.lp_unsolved:
+            self.objective_value = float(self.lp.lagrangianBound)
+            self.solution = self.lp.primalVariableSolution['x']
+            self.mip_feasible = False
+            return
         sol = self.lp.primalVariableSolution
         self.solution = None if not self.lp_feasible else sol['x'] if isinstance(sol, dict) else sol
         if self.lp_feasible and len(self._integer_indices):

@@ -91,3 +91,29 @@ def test_config4_full_size_root_golden_and_properties(blp_lib):
     lp.close()
     assert abs(r.objective[0] - gobj) <= REL * abs(gobj), (r.objective[0], gobj)
     _check_properties(d, lbs, ubs, r, gobj, ints)
+
+
+@pytest.mark.parametrize('name,shape', [('c4', (10000, 5000, 2e-3, 16)), ('c5', (50000, 20000, 2e-4, 32))])
+def test_children_against_committed_highs_goldens(blp_lib, name, shape):
+    """64 frontier children of the C4 / C5 root against HiGHS answers made offline
+    (tests/tools/make_child_goldens.py -> bench_data/<name>_children.npz): equal status and objective
+    within 1e-6 relative, through the children form of the C ABI (bounds as deltas against the root,
+    the root's primal/dual pair as warm start, continuous batching with 48 resident slots)."""
+    from simple_mip_solver_b200 import engine as eng
+    from simple_mip_solver_b200.instances import GOLD_COUNT, GOLD_FIRST
+    n, m, dens, depth = shape
+    d = numpy_random_mip(n, m, density=dens, seed=2)
+    gx, gy, gobj = _golden(name)
+    z = np.load(os.path.join(ROOT, 'bench_data', f'{name}_children.npz'))
+    assert z['node_ids'][0] == GOLD_FIRST and len(z['node_ids']) == GOLD_COUNT
+    _, _, deltas = frontier_nodes(d, gx, GOLD_FIRST, GOLD_COUNT, depth, seed=0, dense=False)
+    lp = eng.BatchLP(d.A, d.b, d.c)
+    r = lp.solve_children(d.l, d.u, deltas, x0=gx, y0=gy, opts=eng.default_opts(max_active=48), want_x=False,
+                          want_y=False)
+    lp.close()
+    assert np.array_equal(r.status, z['status']), (r.status, z['status'])
+    ok = z['status'] == 0
+    err = np.abs(r.objective[ok] - z['objective'][ok]) / np.maximum(1.0, np.abs(z['objective'][ok]))
+    print(f'{name}: 64 children, max rel. objective error vs HiGHS {err.max():.2e}, '
+          f'mean {int(r.iterations.mean())} PDHG iterations')
+    assert err.max() <= REL

@@ -207,3 +207,29 @@ def test_assertion_messages():
         BranchAndBound(m, BaseNode, mip_gap=2)
     with pytest.raises(AssertionError, match='next_node_idx is reserved'):
         BranchAndBound(m, BaseNode, next_node_idx=3)
+
+
+def test_iteration_limited_full_solve_is_not_infeasible(monkeypatch):
+    """A full (not strong-branching) LP solve that stops on the solver's iteration budget must not be
+    dropped as infeasible: the node stays an open leaf with the bound it reached and the run ends
+    'stopped on iterations or time' (the reference's CLP never stops a bound early)."""
+    eng = use_oracle_engine(monkeypatch, 'pdhg')
+    real = eng.solve_batch
+    calls = {'n': 0}
+
+    def limited(self, lb, ub, **kw):
+        res = real(self, lb, ub, **kw)
+        calls['n'] += 1
+        if calls['n'] == 2:                       # the second LP call of the search runs out of budget
+            res.status[:] = 3
+            res.lower_bound[:] = res.objective - 0.25
+        return res
+    monkeypatch.setattr(eng, 'solve_batch', limited)
+    bb = BranchAndBound(model_from(EXAMPLES['small_branch']), BaseNode, frontier_batch=1, gomory_cuts=False)
+    bb.solve()
+    assert bb.unsolved_nodes == 1
+    assert bb.status == 'stopped on iterations or time'
+    leaf = [v.attr['node'] for v in bb.tree.nodes.values() if getattr(v.attr['node'], 'lp_unsolved', False)]
+    assert len(leaf) == 1 and leaf[0].is_leaf and leaf[0].lp_feasible
+    assert bb.dual_bound <= leaf[0].objective_value         # its bound still counts in the global dual bound
+    assert bb.dual_bound < bb.primal_bound or bb.primal_bound == float('inf')

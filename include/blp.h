@@ -244,10 +244,14 @@ const char* blp_last_error(void);
  *   two_vals[1] = smallest lower bound of the nodes still open (BranchAndBound.dual_bound, :199-201)
  * with one 16-byte ncclAllReduce(min) over NVLink on the handle's stream. NCCL is bound at run time
  * (dlopen of libnccl.so.2, or $BLP_NCCL_LIB).
+ *   blp_comm_probe      0 when blp_comm_init can be entered on this rank (libnccl bound, the handle has no
+ *                       communicator yet, its device can be selected). ncclCommInitRank is itself a
+ *                       collective: the ranks agree on their probes BEFORE any of them enters it
  *   blp_comm_unique_id  rank 0 creates the 128-byte NCCL id; the host distributes it to all ranks
  *   blp_comm_init       every rank joins with (nranks, rank, id); collective
  *   blp_allreduce_min   two_vals: HOST pointer, in/out; identity on a handle without communicator
  */
+int blp_comm_probe(blp_handle h);
 int blp_comm_unique_id(char id[128]);
 int blp_comm_init(blp_handle h, int nranks, int rank, const char id[128]);
 int blp_allreduce_min(blp_handle h, double* two_vals);

@@ -128,6 +128,7 @@ class BranchAndBound(BaseAlgorithm):
         self.prefetch_calls = 0
         self.prefetched_lps = 0
         self.unsolved_nodes = 0         # nodes whose LP stopped on the solver's iteration budget
+        self.frontier_bounds = (None, None)
 
     @property
     def dual_bound(self):
@@ -191,6 +192,9 @@ class BranchAndBound(BaseAlgorithm):
         sent = type(node).prefetch(batch)
         self.prefetch_calls += 1
         self.prefetched_lps += sent
+        # with several GPUs the shards of the batch agree on [incumbent, dual bound] through
+        # blp_allreduce_min; kept for monitoring — pruning stays in the reference's node order
+        self.frontier_bounds = getattr(getattr(node.lp, '_shared', None), 'last_global_bounds', (None, None))
 
     def _evaluate_node(self, node: BaseNode) -> None:
         """Bound the node unless the incumbent prunes it; then record a new incumbent or branch

@@ -145,6 +145,7 @@ class SharedLP:
     contains them is solved and are switched on per node through the row mask of the batched call.
     """
     default_method = 'auto'         # 'auto' | 'simplex' | 'pdhg' for models created from now on
+    default_devices = None          # e.g. [0, 1, 2, 3]: shard every batch of node LPs over these GPUs
 
     def __init__(self, A, b, c, device: int = 0):
         self.A = sp.csr_matrix(A, dtype=np.float64)
@@ -152,6 +153,7 @@ class SharedLP:
         self.b = np.asarray(b, dtype=np.float64).reshape(self.m).copy()
         self.c = np.asarray(c, dtype=np.float64).reshape(self.n).copy()
         self.device = device
+        self.devices = None             # set to a list of GPU ids before the first solve to use several
         self._engine = None
         self.cut_names: List[str] = []                     # pool order = device row order
         self.cut_index: Dict[Tuple[str, int], int] = {}     # (name, content digest) -> pool row
@@ -165,12 +167,22 @@ class SharedLP:
         self.method = SharedLP.default_method
         self.simplex_calls = 0          # id of the last simplex call (its factors are the engine's store)
         self.simplex_pivots = 0
+        self.pool_cap = 256             # appended cut rows the device matrix may hold before it is rebuilt
+        self.pool_rebuilds = 0
+        # [best integral objective, smallest open lower bound] of the last batch, reduced over the GPUs
+        # that shared it (blp_allreduce_min); (None, None) on a single device
+        self.last_global_bounds = (None, None)
 
     @property
     def engine(self):
         if self._engine is None:
-            from simple_mip_solver_b200.engine import BatchLP
-            self._engine = BatchLP(self.A, self.b, self.c, device=self.device)
+            from simple_mip_solver_b200 import engine as _engine
+            devices = self.devices if self.devices is not None else SharedLP.default_devices
+            if devices is not None and len(devices) > 1:
+                self._engine = _engine.MultiGpuBatchLP(self.A, self.b, self.c, devices=devices)
+            else:
+                self._engine = _engine.BatchLP(self.A, self.b, self.c,
+                                               device=self.device if not devices else devices[0])
         return self._engine
 
     def register_cut(self, key: Tuple[str, int], pi: np.ndarray, pi0: float) -> int:
@@ -184,6 +196,22 @@ class SharedLP:
             self.cut_index[key] = k
             self.cut_rows.append((np.asarray(pi, dtype=np.float64).copy(), float(pi0)))
         return k
+
+    def make_room(self, needed) -> None:
+        """Garbage collection of the device cut pool. Rows stay in the pool after the node that
+        added them is done (another open node may hold the same cut); when the pool would outgrow
+        ``pool_cap`` rows (and twice what the batch about to be solved needs) it is emptied
+        (blp_truncate_rows) and the batch re-appends what it uses. Stored simplex factors refer to the
+        old row numbering and are dropped with it."""
+        new = sum(1 for key in needed if key not in self.cut_index)
+        if len(self.cut_names) + new <= max(self.pool_cap, 2 * len(needed)):
+            return
+        self.cut_names, self.cut_index, self.cut_rows = [], {}, []
+        self._on_device = 0
+        self.pool_rebuilds += 1
+        self.simplex_calls += 1
+        if self._engine is not None:
+            self._engine.truncate_rows(self.m)
 
     def pool_row(self, lp: 'CyClpSimplex', name: str) -> int:
         return self.cut_index[lp._cut_keys[name]]
@@ -485,7 +513,8 @@ class CyClpSimplex:
         solved since) or the LP was not solved by the simplex path."""
         sh = self._need_shared()
         ref = self._factor_ref
-        if ref is None or self._solved_key != self._state_key() or ref[0] != sh.simplex_calls:
+        if ref is None or self._solved_key != self._state_key() or ref[0] != sh.simplex_calls \
+                or hasattr(sh.engine, 'parts'):          # several GPUs: the factor lives on one of them
             return None
         n, m = sh.n, sh.m
         pool = [m + sh.pool_row(self, nm) for nm in self._cuts]      # pool row of every cut row of this LP
@@ -560,6 +589,7 @@ def solve_lps(lps: Iterable[CyClpSimplex], force: bool = False) -> int:
 
 
 def _solve_group(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_opts):
+    sh.make_room({lp._cut_keys[nm] for lp in batch for nm in lp._cuts})
     for lp in batch:
         for nm, (pi, pi0) in lp._cuts.items():
             sh.register_cut(lp._cut_keys[nm], pi, pi0)
@@ -595,7 +625,7 @@ def _solve_group_simplex(sh: SharedLP, batch: List[CyClpSimplex], budget: int):
     """One batched dual simplex call: vertex, duals, reduced costs and the optimal basis per node LP."""
     eng = sh.engine
     B, n, m, mc = len(batch), sh.n, sh.m, len(sh.cut_names)
-    use_cache = bool(batch[0].solver_opts.get('factor_cache', False))
+    use_cache = bool(batch[0].solver_opts.get('factor_cache', False)) and not hasattr(eng, 'parts')
     same_cuts = all(lp._cut_keys == batch[0]._cut_keys for lp in batch)
 
     def start_of(lp):
@@ -663,6 +693,7 @@ def _solve_group_simplex(sh: SharedLP, batch: List[CyClpSimplex], budget: int):
                                 parent_slot=par if (par >= 0).any() else None, max_pivots=budget)
     sh.solve_calls += 1
     sh.simplex_calls += 1
+    sh.last_global_bounds = (res.stats.get('global_incumbent'), res.stats.get('global_lower_bound'))
     sh.lps_solved += B
     sh.kernel_launches += int(res.stats.get('kernel_launches', 1))
     sh.simplex_pivots += int(res.pivots.sum())
@@ -712,6 +743,7 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
     ints = batch[0].integer_indices_hint
     res = eng.solve_batch(lb, ub, row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
     sh.solve_calls += 1
+    sh.last_global_bounds = (res.stats.get('global_incumbent'), res.stats.get('global_lower_bound'))
     sh.lps_solved += B
     sh.kernel_launches += int(res.stats['kernel_launches'])
     for k, lp in enumerate(batch):

@@ -202,6 +202,7 @@ struct blp_handle_s {
     std::vector<int32_t> hptrA, hptrAT; // host copies of the row pointers of A and A' (slab sizing)
     std::vector<double> c0, b0;
     std::vector<double> dr, dc;
+    std::vector<double> dr_base, dc_base;   // scaling of the base problem (computed once)
     // device copies
     DevBuf rowptr, ent, cptr, cent, c, b, rowscale, colscale, d_dr, d_dc;
     DevBuf uent, ucent;                // unscaled entries, same patterns (blp_spmv)
@@ -289,15 +290,33 @@ int nccl_fail(const NcclApi* a, const char* what, int rc) {
 
 // (re)build scaling, transpose, step size and the device copies of the shared LP data
 int prepare(blp_handle h) {
-    const int m = h->A0.rows, n = h->n;
+    const int m = h->A0.rows, n = h->n, mb = h->m_base;
     HostCsr As = h->A0;
+    // The scaling of the BASE rows, the column scaling and the scalar scalings of b and c are a
+    // function of the base problem only, computed once: appended cut rows are then equilibrated
+    // against that fixed column scaling. A node's step size ratio, termination tolerance
+    // (relative to ||b_base||) and warm start therefore do not depend on the cuts other nodes hold.
+    if ((int)h->dr_base.size() != mb) {
+        HostCsr Ab = h->A0;
+        Ab.rows = mb;
+        Ab.ptr.resize(mb + 1);
+        Ab.idx.resize(Ab.ptr.back());
+        Ab.val.resize(Ab.ptr.back());
+        h->dr_base.assign(mb, 1.0);
+        h->dc_base.assign(n, 1.0);
+        ruiz_pc(Ab, h->dr_base, h->dc_base, 10, 0);
+    }
     h->dr.assign(m, 1.0);
-    h->dc.assign(n, 1.0);
-    ruiz_pc(As, h->dr, h->dc, 10, 0);
+    h->dc = h->dc_base;
+    std::copy(h->dr_base.begin(), h->dr_base.end(), h->dr.begin());
+    for (int i = 0; i < m; ++i)
+        for (int32_t p = As.ptr[i]; p < As.ptr[i + 1]; ++p) As.val[p] *= h->dr[i] * h->dc[As.idx[p]];
+    if (m > mb) ruiz_pc(As, h->dr, h->dc, 10, mb);
     std::vector<double> bs(m), cs(n), rowscale(m), colscale(n);
     for (int i = 0; i < m; ++i) bs[i] = h->b0[i] * h->dr[i];
     for (int j = 0; j < n; ++j) cs[j] = h->c0[j] * h->dc[j];
-    const double sb = 1.0 / (norm2(bs) + 1.0), sc = 1.0 / (norm2(cs) + 1.0);
+    const std::vector<double> bs_base(bs.begin(), bs.begin() + mb), b0_base(h->b0.begin(), h->b0.begin() + mb);
+    const double sb = 1.0 / (norm2(bs_base) + 1.0), sc = 1.0 / (norm2(cs) + 1.0);
     double cinf = 0.0;
     for (int i = 0; i < m; ++i) bs[i] *= sb;
     for (int j = 0; j < n; ++j) {
@@ -311,7 +330,7 @@ int prepare(blp_handle h) {
     const double eta = 0.998 / sigma_max(As, At);
     h->hptrA = As.ptr;
     h->hptrAT = At.ptr;
-    const double nb = norm2(bs), nc = norm2(cs);
+    const double nb = norm2(bs_base) * sb, nc = norm2(cs);
 
     cudaStream_t s = h->stream;
     auto pack = [](const HostCsr& a) {
@@ -355,7 +374,7 @@ int prepare(blp_handle h) {
     P.sb = sb;
     P.sc = sc;
     P.objscale = 1.0 / (sb * sc);
-    P.bnorm0 = norm2(h->b0);
+    P.bnorm0 = norm2(b0_base);
     P.cnorm0 = norm2(h->c0);
     P.cinf_s = cinf;
     P.omega0 = ((nb > 1e-12 && nc > 1e-12) ? nc / nb : 1.0) * env_dbl("BLP_OMEGA0_SCALE", 1.0);
@@ -1606,6 +1625,14 @@ int blp_comm_unique_id(char id[128]) {
     const int rc = a->GetUniqueId(&u);
     if (rc) return nccl_fail(a, "ncclGetUniqueId", rc);
     memcpy(id, u.internal, 128);
+    return BLP_OK;
+}
+
+int blp_comm_probe(blp_handle h) {
+    if (!h) return fail(BLP_ERR_ARG, "blp_comm_probe: NULL handle");
+    if (h->comm) return fail(BLP_ERR_STATE, "blp_comm_probe: the handle already has a communicator");
+    if (!nccl_api()) return fail(BLP_ERR_STATE, "blp_comm_probe: libnccl.so.2 not found (set BLP_NCCL_LIB)");
+    CK(cudaSetDevice(h->device));
     return BLP_OK;
 }
 

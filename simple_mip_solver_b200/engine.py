@@ -78,6 +78,7 @@ _SIGNATURES = {
     'blp_destroy': (C.c_int, [_P]),
     'blp_last_error': (C.c_char_p, []),
     'blp_version': (C.c_char_p, []),
+    'blp_comm_probe': (C.c_int, [_P]),
     'blp_comm_unique_id': (C.c_int, [C.c_char_p]),
     'blp_comm_init': (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),
     'blp_allreduce_min': (C.c_int, [_P, C.POINTER(C.c_double)]),
@@ -490,6 +491,10 @@ class BatchLP:
         _check(self._lib.blp_comm_init(self._h, world, rank, box[0]), 'blp_comm_init')
         return True
 
+    def comm_probe(self) -> bool:
+        """True when this rank can enter blp_comm_init (libnccl bound, no communicator yet)."""
+        return self._lib.blp_comm_probe(self._h) == 0
+
     def comm_destroy(self):
         """Leave the library's communicator (blp_comm_destroy); ``close()`` does it as well."""
         _check(self._lib.blp_comm_destroy(self._h), 'blp_comm_destroy')
@@ -506,3 +511,194 @@ class BatchLP:
     @property
     def stream_ptr(self) -> int:
         return int(self._lib.blp_stream(self._h) or 0)
+
+
+class MultiGpuBatchLP:
+    """The same node LPs on several GPUs of one box from ONE process: one ``BatchLP`` handle (its own
+    replica of the matrix, its own CUDA stream) per device, one host thread per handle — ctypes
+    releases the GIL for the duration of a C call, so the devices run concurrently.
+
+    Node LPs are independent, so a batch is split by node into contiguous shards
+    (``parallel.shard_bounds``) and the data path has no collective. The one exchange of the path —
+    the all-reduce(min) of ``[best integral objective, smallest open lower bound]`` — runs over the
+    library's NCCL communicator between the handles (``blp_allreduce_min``, NVLink) when the devices
+    are distinct; every result carries it in ``stats['global_incumbent'/'global_lower_bound']``.
+
+    Same call surface as ``BatchLP`` (the part the Node layer uses). The stored simplex factors of a
+    call live on the device that solved the node, so ``parent_slot`` is not offered here: children
+    start from the parent's basis status, as with ``lp.setBasisStatus`` in the reference.
+    The reference is single process, single device; the callers that form the
+    batches are BranchAndBound.solve (branch_and_bound.py:226-232) and
+    PseudoCostBranchNode._update_pseudo_costs (pseudo_cost.py:57-62)."""
+
+    def __init__(self, A, b, c, devices: Sequence[int]):
+        from concurrent.futures import ThreadPoolExecutor
+        if len(devices) < 1:
+            raise ValueError('need at least one device')
+        self.devices = [int(dv) for dv in devices]
+        self.parts = [BatchLP(A, b, c, device=dv) for dv in self.devices]
+        self.n, self.m_base = self.parts[0].n, self.parts[0].m_base
+        self._pool = ThreadPoolExecutor(max_workers=len(self.parts))
+        self._comm = False
+        if len(set(self.devices)) == len(self.devices) and len(self.devices) > 1:
+            self._comm = self._comm_init()
+
+    # -- bookkeeping ---------------------------------------------------------------------------------
+    @property
+    def m(self) -> int:
+        return self.parts[0].m
+
+    @property
+    def num_cut_rows(self) -> int:
+        return self.parts[0].num_cut_rows
+
+    @property
+    def simplex_capable(self) -> bool:
+        return self.parts[0].simplex_capable
+
+    @property
+    def uses_nccl(self) -> bool:
+        return self._comm
+
+    def _comm_init(self) -> bool:
+        """All handles join one NCCL communicator (rank = position in ``devices``); ncclCommInitRank is
+        collective, so every handle enters it from its own thread. All or none."""
+        lib = self.parts[0]._lib
+        if not all(p.comm_probe() for p in self.parts):
+            return False
+        buf = C.create_string_buffer(128)
+        if lib.blp_comm_unique_id(buf) != 0:
+            return False
+        ident = buf.raw
+        world = len(self.parts)
+        rcs = list(self._pool.map(lambda rp: lib.blp_comm_init(rp[1]._h, world, rp[0], ident), enumerate(self.parts)))
+        if any(rcs):
+            for p, rc in zip(self.parts, rcs):
+                if rc == 0:
+                    p.comm_destroy()
+            return False
+        return True
+
+    def append_rows(self, rows, rhs) -> int:
+        first = [p.append_rows(rows, rhs) for p in self.parts]
+        return first[0]
+
+    def truncate_rows(self, m_keep: int):
+        for p in self.parts:
+            p.truncate_rows(m_keep)
+
+    def close(self):
+        for p in self.parts:
+            p.close()
+        self._pool.shutdown(wait=True)
+
+    # -- sharded calls -------------------------------------------------------------------------------
+    def _shards(self, B: int):
+        from .parallel import shard_bounds
+        world = min(len(self.parts), B)
+        return [shard_bounds(B, r, world) for r in range(world)]
+
+    def _run(self, B, call):
+        """``call(part, begin, end)`` on every shard concurrently; then the bound exchange."""
+        shards = self._shards(B)
+        futs = [self._pool.submit(call, self.parts[r], b, e) for r, (b, e) in enumerate(shards)]
+        return [f.result() for f in futs]
+
+    def _exchange(self, pairs):
+        """Global (incumbent, lower bound): over NCCL between the handles, else a host min."""
+        if self._comm and len(pairs) == len(self.parts):
+            got = list(self._pool.map(lambda pp: pp[0].allreduce_min(*pp[1]), zip(self.parts, pairs)))
+            return got[0]
+        return min(p[0] for p in pairs), min(p[1] for p in pairs)
+
+    @staticmethod
+    def _pair(obj, lower, status, frac):
+        integral = (status == 0) & (frac < 0)
+        open_ = (status == 0) & ~integral
+        inc = float(obj[integral].min()) if integral.any() else float('inf')
+        low = float(lower[open_].min()) if open_.any() else float('inf')
+        return inc, low
+
+    @staticmethod
+    def _cat(parts, name):
+        vals = [getattr(p, name) for p in parts]
+        return None if vals[0] is None else np.concatenate(vals)
+
+    def _merge_stats(self, parts, pairs):
+        st = dict(parts[0].stats)
+        for k in ('kernel_launches', 'node_iterations', 'refills', 'compactions', 'evaluations'):
+            st[k] = sum(p.stats.get(k, 0) for p in parts)
+        for k in ('iterations', 'total_ms', 'step_kernel_ms'):
+            st[k] = max(p.stats.get(k, 0) for p in parts)
+        st['devices'] = self.devices[:len(parts)]
+        st['global_incumbent'], st['global_lower_bound'] = self._exchange(pairs)
+        st['bound_exchange'] = 'blp_allreduce_min (NCCL)' if self._comm and len(pairs) == len(self.parts) else 'host'
+        return st
+
+    def _merge(self, parts):
+        pairs = [self._pair(p.objective, p.lower_bound, p.status, p.frac_idx) for p in parts]
+        return BatchResult(objective=self._cat(parts, 'objective'), lower_bound=self._cat(parts, 'lower_bound'),
+                           status=self._cat(parts, 'status'), iterations=self._cat(parts, 'iterations'),
+                           frac_idx=self._cat(parts, 'frac_idx'), x=self._cat(parts, 'x'), y=self._cat(parts, 'y'),
+                           stats=self._merge_stats(parts, pairs))
+
+    def _merge_simplex(self, parts, integer_indices=None):
+        pairs = []
+        for p in parts:
+            ok = p.status == 0
+            inc = low = float('inf')
+            if ok.any():
+                if integer_indices is not None and len(integer_indices):
+                    xi = p.x[:, list(integer_indices)]
+                    integral = ok & (np.max(np.abs(xi - np.round(xi)), axis=1) <= 1e-4)
+                else:
+                    integral = ok
+                inc = float(p.objective[integral].min()) if integral.any() else float('inf')
+                low = float(p.objective[ok & ~integral].min()) if (ok & ~integral).any() else float('inf')
+            pairs.append((inc, low))
+        return SimplexBatchResult(objective=self._cat(parts, 'objective'), status=self._cat(parts, 'status'),
+                                  pivots=self._cat(parts, 'pivots'), x=self._cat(parts, 'x'), y=self._cat(parts, 'y'),
+                                  reduced_costs=self._cat(parts, 'reduced_costs'),
+                                  col_status=self._cat(parts, 'col_status'), row_status=self._cat(parts, 'row_status'),
+                                  stats=self._merge_stats(parts, pairs))
+
+    @staticmethod
+    def _rows(a, b, e):
+        return None if a is None else np.atleast_2d(a)[b:e]
+
+    def solve_batch(self, lb, ub, row_mask=None, x0=None, y0=None, integer_indices=None, opts=None,
+                    want_x=True, want_y=True) -> BatchResult:
+        lb, ub = np.atleast_2d(lb), np.atleast_2d(ub)
+        R = self._rows
+        return self._merge(self._run(lb.shape[0], lambda p, b, e: p.solve_batch(
+            lb[b:e], ub[b:e], row_mask=R(row_mask, b, e), x0=R(x0, b, e), y0=R(y0, b, e),
+            integer_indices=integer_indices, opts=opts, want_x=want_x, want_y=want_y)))
+
+    def solve_children(self, parent_lb, parent_ub, deltas, row_mask=None, x0=None, y0=None,
+                       integer_indices=None, opts=None, want_x=True, want_y=True) -> BatchResult:
+        R = self._rows
+        return self._merge(self._run(len(deltas), lambda p, b, e: p.solve_children(
+            parent_lb, parent_ub, deltas[b:e], row_mask=R(row_mask, b, e), x0=x0, y0=y0,
+            integer_indices=integer_indices, opts=opts, want_x=want_x, want_y=want_y)))
+
+    def simplex_batch(self, lb, ub, row_mask=None, col_status=None, row_status=None, parent_slot=None,
+                      max_pivots: int = 2147483647, integer_indices=None) -> SimplexBatchResult:
+        if parent_slot is not None and (np.asarray(parent_slot) >= 0).any():
+            raise BlpError('stored simplex factors are per device: MultiGpuBatchLP takes no parent_slot')
+        lb, ub = np.atleast_2d(lb), np.atleast_2d(ub)
+        R = self._rows
+        return self._merge_simplex(self._run(lb.shape[0], lambda p, b, e: p.simplex_batch(
+            lb[b:e], ub[b:e], row_mask=R(row_mask, b, e), col_status=R(col_status, b, e),
+            row_status=R(row_status, b, e), max_pivots=max_pivots)), integer_indices)
+
+    def simplex_children(self, parent_lb, parent_ub, deltas, row_mask=None, col_status=None, row_status=None,
+                         parent_slot: int = -1, max_pivots: int = 2147483647,
+                         integer_indices=None) -> SimplexBatchResult:
+        if parent_slot >= 0:
+            raise BlpError('stored simplex factors are per device: MultiGpuBatchLP takes no parent_slot')
+        return self._merge_simplex(self._run(len(deltas), lambda p, b, e: p.simplex_children(
+            parent_lb, parent_ub, deltas[b:e], row_mask=row_mask, col_status=col_status, row_status=row_status,
+            max_pivots=max_pivots)), integer_indices)
+
+    def simplex_tableau_rows(self, slot: int, variables):
+        raise BlpError('stored simplex factors are per device: MultiGpuBatchLP offers no tableau rows')

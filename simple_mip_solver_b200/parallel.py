@@ -52,13 +52,26 @@ def allreduce_bounds(incumbent: float, dual_bound: float, device=None, lp=None) 
 def join_library_comm(lp, device=None, log=None) -> bool:
     """Give ``lp`` (an ``engine.BatchLP``) the library's own NCCL communicator on every rank, or on none.
 
-    Each rank tries ``lp.comm_init()``; the ranks then agree (one all-reduce through the process
-    group) on whether ALL of them succeeded. If any failed — libnccl could not be bound, say — the
-    ranks that did succeed leave the communicator again and everybody uses ``torch.distributed`` for
-    the 16-byte exchange, so that no rank ever waits in a collective its peers do not enter.
+    ``ncclCommInitRank`` is itself a collective, so the ranks first agree — one all-reduce through the
+    process group — that EVERY rank can enter it (``lp.comm_probe()``: libnccl bound, no communicator
+    yet, device selectable); a rank whose precondition fails never leaves its peers waiting inside the
+    initialisation. Then each rank calls ``lp.comm_init()`` and the ranks agree once more on whether
+    all of them succeeded; if not, those that did leave the communicator again and everybody uses
+    ``torch.distributed`` for the 16-byte exchange.
     Returns True when ``allreduce_bounds(..., lp=lp)`` may be used. Single rank: False, no-op."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return False
+    world = dist.get_world_size()
+    can = False
+    try:
+        can = bool(lp.comm_probe())
+    except Exception as e:           # noqa: BLE001
+        if log:
+            log(f'[rank {dist.get_rank()}] blp_comm_probe failed ({e})')
+    if allreduce_sum([1.0 if can else 0.0], device=device)[0] < world:
+        if log and not can:
+            log(f'[rank {dist.get_rank()}] cannot join the library communicator; all ranks use torch.distributed')
         return False
     ok = False
     try:
@@ -66,7 +79,6 @@ def join_library_comm(lp, device=None, log=None) -> bool:
     except Exception as e:           # noqa: BLE001 - reported, then agreed on by all ranks
         if log:
             log(f'[rank {dist.get_rank()}] blp_comm_init failed ({e}); using torch.distributed')
-    world = dist.get_world_size()
     agreed = allreduce_sum([1.0 if ok else 0.0], device=device)[0]
     if ok and agreed < world:
         lp.comm_destroy()

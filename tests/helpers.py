@@ -39,6 +39,12 @@ class OracleBatchLP:
             self.cut_rhs.append(float(v))
         return first
 
+    def truncate_rows(self, m_keep):
+        keep = m_keep - self.m_base
+        del self.cut_rows[keep:]
+        del self.cut_rhs[keep:]
+        self._store = ()
+
     def close(self):
         pass
 

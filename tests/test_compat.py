@@ -129,3 +129,27 @@ def test_binary_tree():
         t.add_left_child(3, 0)
     with pytest.raises(AssertionError):
         t.add_left_child(2, 1)
+
+
+def test_cut_pool_is_garbage_collected_and_cut_names_are_content_keyed(monkeypatch):
+    """Cut rows of finished nodes do not pile up in the device matrix for ever, and a cut NAME that is
+    re-used with other coefficients (a second run on the same model) never resolves to the old row."""
+    from helpers import use_oracle_engine
+    from simple_mip_solver_b200 import CyLPArray, MILPInstance
+    from simple_mip_solver_b200.compat import solve_lps
+    use_oracle_engine(monkeypatch)
+    m = MILPInstance(A=np.array([[-1.0, -1.0]]), b=CyLPArray([-3.5]), c=CyLPArray([-1.0, -1.0]),
+                     l=CyLPArray([0, 0]), u=CyLPArray([10, 10]), sense=['Min', '>='], integerIndices=[0, 1], numVars=2)
+    sh = m.lp._need_shared()
+    sh.pool_cap = 4
+    x = m.lp.getVarByName('x')
+    vals = []
+    for k in range(12):
+        lp = m.lp.copy_for_child()
+        lp.addConstraint(CyLPArray([-1.0, 0.0]) * x >= -float(k % 3), 'cut_same_name')      # same name, new content
+        lp.addConstraint(CyLPArray([0.0, -1.0]) * x >= -(0.5 + k), f'cut_{k}')
+        solve_lps([lp])
+        vals.append(lp.objectiveValue)
+        assert lp.objectiveValue == -min(3.5, float(k % 3) + min(10.0, 0.5 + k))
+        assert len(sh.cut_names) <= 6
+    assert sh.pool_rebuilds >= 2

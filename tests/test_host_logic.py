@@ -233,3 +233,24 @@ def test_iteration_limited_full_solve_is_not_infeasible(monkeypatch):
     assert len(leaf) == 1 and leaf[0].is_leaf and leaf[0].lp_feasible
     assert bb.dual_bound <= leaf[0].objective_value         # its bound still counts in the global dual bound
     assert bb.dual_bound < bb.primal_bound or bb.primal_bound == float('inf')
+
+
+@pytest.mark.parametrize('method', ['auto', 'pdhg'])
+def test_batches_sharded_over_several_handles_build_the_same_tree(monkeypatch, method):
+    """MultiGpuBatchLP (one handle and one host thread per device, batches split by node): the search is
+    the one a single handle produces. Here three CPU stand-in handles; on the GPU box
+    tests/test_gpu_multi.py does the same with real devices."""
+    from simple_mip_solver_b200.compat.cylp_like import SharedLP
+    eng = use_oracle_engine(monkeypatch, method)
+    monkeypatch.setattr(SharedLP, 'default_devices', [0, 0, 0])
+    for name in ('random', 'small_branch'):
+        rec = EXAMPLES[name]
+        for label in ('BaseNode', 'PseudoCostBranchNode'):
+            Node, kw = CASES[label]
+            kwargs = {k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()}
+            bb = BranchAndBound(model_from(rec), Node, frontier_batch=8, **kwargs)
+            bb.solve()
+            check_against_reference(bb, rec[GOLD_KEY[method]][label])
+            sh = bb.model.lp._shared
+            assert len(sh.engine.parts) == 3 and not sh.engine.uses_nccl
+    assert max(eng.batch_sizes) >= 1 and eng.calls > 3

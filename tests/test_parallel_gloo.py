@@ -58,11 +58,17 @@ def test_two_rank_exchange():
 
 
 class _FakeLP:
-    """Stands in for engine.BatchLP: comm_init fails on the ranks listed in ``bad``."""
-    def __init__(self, rank, bad):
-        self.rank, self.bad, self.joined, self.left = rank, bad, False, False
+    """Stands in for engine.BatchLP: comm_init fails on the ranks listed in ``bad``, the
+    precondition probe on the ranks listed in ``unready``."""
+    def __init__(self, rank, bad, unready=()):
+        self.rank, self.bad, self.unready, self.joined, self.left = rank, bad, unready, False, False
+        self.entered_init = False
+
+    def comm_probe(self):
+        return self.rank not in self.unready
 
     def comm_init(self):
+        self.entered_init = True
         if self.rank in self.bad:
             raise RuntimeError('libnccl.so.2 not found')
         self.joined = True
@@ -83,6 +89,10 @@ def _comm_worker(rank, world, port, out):
         msgs = []
         use = parallel.join_library_comm(lp, log=msgs.append)
         res.append((use, lp.joined, lp.left, len(msgs)))
+    # a rank > 0 whose precondition fails (libnccl missing there): NOBODY may enter ncclCommInitRank
+    lp = _FakeLP(rank, (), unready=(1,))
+    use = parallel.join_library_comm(lp)
+    res.append((use, lp.entered_init))
     out.put((rank, res))
     dist.destroy_process_group()
 
@@ -107,3 +117,5 @@ def test_all_ranks_or_none_use_the_library_communicator():
     assert got[0][1] == (False, True, True, 0) and got[1][1] == (False, False, False, 1)
     # both fail
     assert got[0][2] == (False, False, False, 1) and got[1][2] == (False, False, False, 1)
+    # rank 1 is not ready: no rank enters the collective initialisation
+    assert got[0][3] == (False, False) and got[1][3] == (False, False)

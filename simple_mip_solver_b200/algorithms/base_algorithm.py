@@ -40,7 +40,7 @@ class BaseAlgorithm:
         """``A x <= b`` becomes ``-A x >= -b``; the objective is already a minimisation."""
         if model.sense != '<=':
             return model
-        A = model.A.toarray() if sp.issparse(model.A) else model.A
+        A = model.A        # negated as it is: a sparse matrix stays sparse
         return MILPInstance(A=-A, b=-model.b, c=model.lp.objective, l=model.l, u=model.u,
                             integerIndices=model.integerIndices, sense=['Min', '>='],
                             numVars=len(model.c))

@@ -172,6 +172,10 @@ class SharedLP:
         # [best integral objective, smallest open lower bound] of the last batch, reduced over the GPUs
         # that shared it (blp_allreduce_min); (None, None) on a single device
         self.last_global_bounds = (None, None)
+        # root of the model: its bounds (every node is the root plus a few changed bounds,
+        # base_node.py:595-600) and, once solved, its primal/dual pair (the common warm start of a frontier)
+        self.root_bounds = None
+        self.root_xy = None
 
     @property
     def engine(self):
@@ -266,6 +270,7 @@ class CyClpSimplex:
         self._warm: Optional[Tuple[np.ndarray, Dict[str, float], np.ndarray]] = None
         self._basis = None              # (cols, rows) handed over by setBasisStatus, rows in this LP's order
         self._basis_out = None          # (cols, base rows, {cut name: status}) of the last simplex solve
+        self._basis_exact = False       # _basis_out is a basis of the LP as it is now
         self._factor_ref = None         # (simplex call id, slot, cut names) of the last simplex solve
         self._parent_ref = None         # the parent's _factor_ref (copy_for_child)
         self._parent_bounds = (None, None)   # the parent's bound arrays (children of one parent share them)
@@ -302,6 +307,7 @@ class CyClpSimplex:
             if stmt.upper is not None:
                 self._u = CyLPArray(stmt.upper)
             self._solved_key = None
+            self._basis_exact = False
         elif isinstance(stmt, CyLPConstraint):
             self.addConstraint(stmt)
         else:
@@ -324,6 +330,7 @@ class CyClpSimplex:
             self._cuts[nm] = (pi, pi0)
             self._cut_keys[nm] = (nm, hash((pi.tobytes(), pi0)))
         self._solved_key = None
+        self._basis_exact = False
 
     def removeConstraint(self, name: str):
         if name not in self._cuts:
@@ -331,6 +338,7 @@ class CyClpSimplex:
         del self._cuts[name]
         del self._cut_keys[name]
         self._solved_key = None
+        self._basis_exact = False
 
     def _finalize(self, device: int = 0):
         """Turn a model built with addVariable/addConstraint/objective into a shared LP."""
@@ -382,6 +390,7 @@ class CyClpSimplex:
     def variablesLower(self, v):
         self._l = CyLPArray(v)
         self._solved_key = None
+        self._basis_exact = False
 
     @property
     def variablesUpper(self):
@@ -391,6 +400,7 @@ class CyClpSimplex:
     def variablesUpper(self, v):
         self._u = CyLPArray(v)
         self._solved_key = None
+        self._basis_exact = False
 
     @property
     def constraintsLower(self):
@@ -472,7 +482,7 @@ class CyClpSimplex:
         set of the primal-dual pair: a column strictly inside its bounds, or a row with slack, counts
         as basic; away from a non-degenerate vertex that is not a basis and ``BaseNode.tableau``
         returns None as the reference does for an inconsistent basis (base_node.py:518-519)."""
-        if self._basis_out is not None and self._solved_key == self._state_key():
+        if self._basis_out is not None and self._basis_exact:
             cols, base, cuts = self._basis_out
             rows = np.concatenate([base, [cuts.get(nm, BASIC) for nm in self._cuts]]).astype(np.int32)
             return cols.astype(np.int32), rows
@@ -492,7 +502,7 @@ class CyClpSimplex:
     @property
     def has_exact_basis(self) -> bool:
         """True when getBasisStatus() is the basis of a dual simplex solve of the current LP."""
-        return self._basis_out is not None and self._solved_key == self._state_key()
+        return self._basis_out is not None and self._basis_exact
 
     def setBasisStatus(self, cols, rows):
         """Starting basis of the next dual simplex solve (base_node.py:608); rows in this LP's
@@ -705,6 +715,7 @@ def _solve_group_simplex(sh: SharedLP, batch: List[CyClpSimplex], budget: int):
         lp._basis_out = (res.col_status[k].copy(), res.row_status[k, :m].copy(),
                          {nm: int(res.row_status[k, r]) for nm, r in zip(lp._cuts, rows)})
         lp._factor_ref = (sh.simplex_calls, k, tuple(lp._cut_keys.values()))
+        lp._basis_exact = True
         if st == 1:
             lp._obj, lp._x, lp._y, lp._rc, lp._lower_bound = float('inf'), None, None, None, float('inf')
             continue
@@ -715,33 +726,81 @@ def _solve_group_simplex(sh: SharedLP, batch: List[CyClpSimplex], budget: int):
         lp._lower_bound = lp._obj          # a dual feasible basis: c.x of the basic solution is the dual objective
 
 
+def _deltas_against(lp: CyClpSimplex, l0, u0, limit: int):
+    idx = np.flatnonzero((lp._l != l0) | (lp._u != u0))
+    if len(idx) > limit:
+        return None
+    fin = lambda v, s: float(np.inf * s) if abs(v) >= 1e30 else float(v)
+    return [(int(j), fin(lp._l[j], -1), fin(lp._u[j], 1)) for j in idx]
+
+
 def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_opts):
+    """One batched PDHG call. Nodes go to the device as the reference creates them
+    (base_node.py:592-608): a parent's bounds plus the few bounds each node has moved, with ONE
+    primal/dual pair as the common warm start (blp_solve_children_host) — the parent's for the
+    children of a strong-branching round, the root's for a frontier of open nodes. No per-node dense
+    vector is built on the host. (The first solve of a model, and a node that has moved more than
+    256 bounds, take the dense form blp_solve_batch_host.)"""
     eng = sh.engine
     B, n, m, mc = len(batch), sh.n, sh.m, len(sh.cut_names)
-    lb = np.empty((B, n))
-    ub = np.empty((B, n))
-    mask = np.zeros((B, mc), dtype=np.uint8) if mc else None
-    any_warm = any(lp._warm is not None for lp in batch)
-    x0 = np.zeros((B, n)) if any_warm else None
-    y0 = np.zeros((B, m + mc)) if any_warm else None
-    for k, lp in enumerate(batch):
-        lb[k] = np.where(lp._l <= -1e30, -np.inf, lp._l)
-        ub[k] = np.where(lp._u >= 1e30, np.inf, lp._u)
-        for nm in lp._cuts:
-            mask[k, sh.pool_row(lp, nm)] = 1
-        if lp._warm is not None:
-            wx, wcuts, wy = lp._warm
-            x0[k] = wx
-            y0[k, :m] = wy
-            for nm, v in wcuts.items():
-                if nm in lp._cuts:
-                    y0[k, m + sh.pool_row(lp, nm)] = v
     okw = {k: v for k, v in batch[0].solver_opts.items() if k not in ('factor_cache', 'method')}
     if budget < 2147483647:
         okw['max_iters'] = int(min(budget * PDHG_ITERS_PER_PIVOT, 2_000_000_000))
     opts = default_opts(**okw)
     ints = batch[0].integer_indices_hint
-    res = eng.solve_batch(lb, ub, row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
+    mask = None
+    if mc:
+        mask = np.zeros((B, mc), dtype=np.uint8)
+        for k, lp in enumerate(batch):
+            for nm in lp._cuts:
+                mask[k, sh.pool_row(lp, nm)] = 1
+
+    def warm_vectors(lp):
+        wx, wcuts, wy = lp._warm
+        y0 = np.zeros(m + mc)
+        y0[:m] = wy
+        for nm, v in wcuts.items():
+            if nm in lp._cuts:
+                y0[m + sh.pool_row(lp, nm)] = v
+        return wx, y0
+
+    res = None
+    kids = _child_deltas(batch)
+    same_warm = all(lp._warm is batch[0]._warm or
+                    (lp._warm is not None and batch[0]._warm is not None and lp._warm[0] is batch[0]._warm[0])
+                    for lp in batch)
+    if kids is not None and same_warm:                    # children of one parent
+        pl, pu, deltas = kids
+        x0 = y0 = None
+        if batch[0]._warm is not None:
+            x0, y0 = warm_vectors(batch[0])
+        res = eng.solve_children(np.where(pl <= -1e30, -np.inf, pl), np.where(pu >= 1e30, np.inf, pu), deltas,
+                                 row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
+    elif sh.root_bounds is not None and sh.root_xy is not None and B > 1:      # a frontier of open nodes
+        l0, u0 = sh.root_bounds
+        deltas = [_deltas_against(lp, l0, u0, 256) for lp in batch]
+        if all(dl is not None for dl in deltas):
+            x0, ybase = sh.root_xy
+            y0 = np.concatenate([ybase, np.zeros(mc)])
+            res = eng.solve_children(np.where(l0 <= -1e30, -np.inf, l0), np.where(u0 >= 1e30, np.inf, u0), deltas,
+                                     row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
+    if res is None:
+        lb = np.empty((B, n))
+        ub = np.empty((B, n))
+        any_warm = any(lp._warm is not None for lp in batch)
+        x0 = np.zeros((B, n)) if any_warm else None
+        y0 = np.zeros((B, m + mc)) if any_warm else None
+        for k, lp in enumerate(batch):
+            lb[k] = np.where(lp._l <= -1e30, -np.inf, lp._l)
+            ub[k] = np.where(lp._u >= 1e30, np.inf, lp._u)
+            if lp._warm is not None:
+                x0[k], y0[k] = warm_vectors(lp)
+        res = eng.solve_batch(lb, ub, row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
+    if sh.root_bounds is None:
+        sh.root_bounds = (np.asarray(batch[0]._l).copy(), np.asarray(batch[0]._u).copy())
+    if sh.root_xy is None and B == 1 and not batch[0]._cuts and int(res.status[0]) == 0 and \
+            np.array_equal(batch[0]._l, sh.root_bounds[0]) and np.array_equal(batch[0]._u, sh.root_bounds[1]):
+        sh.root_xy = (res.x[0].copy(), res.y[0, :m].copy())
     sh.solve_calls += 1
     sh.last_global_bounds = (res.stats.get('global_incumbent'), res.stats.get('global_lower_bound'))
     sh.lps_solved += B
@@ -752,6 +811,7 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
         lp.iteration = int(res.iterations[k])
         lp._lower_bound = float(res.lower_bound[k])
         lp._basis_out = None
+        lp._basis_exact = False
         lp._factor_ref = None
         rows = [sh.pool_row(lp, nm) + m for nm in lp._cuts]
         ysel = np.concatenate([res.y[k, :m], res.y[k, rows]]) if rows else res.y[k, :m].copy()

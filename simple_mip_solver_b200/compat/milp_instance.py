@@ -57,7 +57,9 @@ class MILPInstance:
         senses = set(mdl.row_senses)
         assert senses <= {'L'} or senses <= {'G'}, 'all rows must have the same sense'
         self.sense = '>=' if senses == {'G'} else '<='
-        self.A = mdl.A.toarray()
+        # the matrix stays sparse (the reference's cuppy hands out a csc_matrixPlus for MPS input,
+        # base_algorithm.py:55-56): a 50 000 x 20 000 model is 8 GB dense
+        self.A = mdl.A.tocsc()
         self.numCons, self.numVars = mdl.A.shape
         self.b = CyLPArray(mdl.rhs)
         self.c = CyLPArray(mdl.c)

@@ -18,6 +18,8 @@ from statistics import median
 from typing import Any, Dict, Iterable, List, Sequence, Set, Tuple, TypeVar, Union
 
 import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
 
 from simple_mip_solver_b200.compat.cylp_like import CyClpSimplex, CyLPArray, solve_lps
 from simple_mip_solver_b200.utils.floating_point import numerically_safe_cut
@@ -383,12 +385,19 @@ class BaseNode:
         x = np.asarray(self.solution, dtype=float)
         if self.lp.has_exact_basis:
             x_basic = np.concatenate([x, A @ x - b])[basic]
-        else:
+        elif m <= 512:
             full = np.concatenate((A.toarray(), -np.identity(m)), axis=1)
             try:
                 x_basic = np.linalg.solve(full[:, basic], b - full @ offset)
             except np.linalg.LinAlgError:
                 return cuts
+        else:
+            lu = self._sparse_basis_factor(basic)
+            if lu is None:
+                return cuts
+            A_full = sp.hstack([sp.csr_matrix(A), -sp.identity(m, format='csr')], format='csr')
+            x_basic = lu.solve(b - A_full @ offset)
+        if not self.lp.has_exact_basis:
             z = offset.copy()
             z[basic] = x_basic
             if np.max(np.abs(z[:n] - x) / (1.0 + np.abs(x))) > 1e-5:
@@ -433,13 +442,42 @@ class BaseNode:
         m = self.lp.nConstraints
         if len(basic) != m:
             return None
-        full = np.concatenate((self.lp.coefMatrix.toarray(), -np.identity(m)), axis=1)
         pos = {int(j): p for p, j in enumerate(basic)}
-        try:
-            T_ = np.linalg.solve(full[:, basic], full)
-        except np.linalg.LinAlgError:
+        if m <= 512:
+            # small LPs: the reference's own dense computation (:513-526); its round-off is what the
+            # reference's pinned cut rounds (test_base_node.py:316-337) were recorded with
+            full = np.concatenate((self.lp.coefMatrix.toarray(), -np.identity(m)), axis=1)
+            try:
+                T_ = np.linalg.solve(full[:, basic], full)
+            except np.linalg.LinAlgError:
+                return None
+            return np.array([T_[pos[int(v)]] if int(v) in pos else np.zeros(full.shape[1]) for v in variables])
+        lu = self._sparse_basis_factor(basic)
+        if lu is None:
             return None
-        return np.array([T_[pos[int(v)]] if int(v) in pos else np.zeros(full.shape[1]) for v in variables])
+        # row of basic variable at position p: z' [A, -I] with B' z = e_p (one sparse solve per row,
+        # SURVEY 8f #1) — never the dense m x (n+m) tableau
+        A_full = sp.hstack([sp.csr_matrix(self.lp.coefMatrix), -sp.identity(m, format='csr')], format='csc')
+        out = np.zeros((len(variables), A_full.shape[1]))
+        for t, v in enumerate(variables):
+            if int(v) in pos:
+                e = np.zeros(m)
+                e[pos[int(v)]] = 1.0
+                out[t] = A_full.T @ lu.solve(e, trans='T')
+        return out
+
+    def _sparse_basis_factor(self, basic):
+        """Sparse LU of the basis matrix [A, -I]_B (host; used when the factor is not on the device)."""
+        m = self.lp.nConstraints
+        A_full = sp.hstack([sp.csr_matrix(self.lp.coefMatrix), -sp.identity(m, format='csr')], format='csc')
+        try:
+            with np.errstate(all='ignore'):
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter('error')
+                    return spla.splu(A_full[:, basic].tocsc())
+        except Exception:          # singular (RuntimeError) or near-singular (MatrixRankWarning)
+            return None
 
     @property
     def tableau(self):

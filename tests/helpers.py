@@ -156,6 +156,21 @@ class OracleBatchLP:
                            frac_idx=frac, x=x, y=y, stats=dict(kernel_launches=0))
 
 
+def _solve_children(self, parent_lb, parent_ub, deltas, row_mask=None, x0=None, y0=None, integer_indices=None,
+                    opts=None, want_x=True, want_y=True):
+    B = len(deltas)
+    lb = np.tile(np.asarray(parent_lb, float), (B, 1))
+    ub = np.tile(np.asarray(parent_ub, float), (B, 1))
+    for k, d in enumerate(deltas):
+        for j, lo, hi in d:
+            lb[k, j], ub[k, j] = lo, hi
+    type(self).children_calls = getattr(type(self), 'children_calls', 0) + 1
+    return self.solve_batch(lb, ub, row_mask=row_mask, integer_indices=integer_indices, opts=opts)
+
+
+OracleBatchLP.solve_children = _solve_children
+
+
 def use_oracle_engine(monkeypatch, method='auto'):
     """Route SharedLP's engine to the CPU stand-in (tests of host logic): the numpy dual simplex for
     the simplex path, HiGHS for the path that goes to the PDHG kernels (``method='pdhg'``)."""
@@ -165,6 +180,7 @@ def use_oracle_engine(monkeypatch, method='auto'):
     OracleBatchLP.calls = 0
     OracleBatchLP.lps = 0
     OracleBatchLP.batch_sizes = []
+    OracleBatchLP.children_calls = 0
     monkeypatch.setattr(engine, 'BatchLP', OracleBatchLP)
     monkeypatch.setattr(engine, 'default_opts', lambda **kw: kw)
     return OracleBatchLP

@@ -254,3 +254,26 @@ def test_batches_sharded_over_several_handles_build_the_same_tree(monkeypatch, m
             sh = bb.model.lp._shared
             assert len(sh.engine.parts) == 3 and not sh.engine.uses_nccl
     assert max(eng.batch_sizes) >= 1 and eng.calls > 3
+
+
+def test_pdhg_path_sends_nodes_as_deltas(monkeypatch):
+    """strong-branching children and frontier nodes reach the engine through the children
+    form (parent/root bounds + changed bounds, one warm start), not as dense [B, n] arrays."""
+    eng = use_oracle_engine(monkeypatch, 'pdhg')
+    dense_batches = []
+    real = eng.solve_batch
+
+    def spy(self, lb, ub, **kw):
+        dense_batches.append(np.atleast_2d(lb).shape[0])
+        return real(self, lb, ub, **kw)
+    rec = EXAMPLES['random']
+    bb = BranchAndBound(model_from(rec), PseudoCostBranchNode, frontier_batch=8, pseudo_costs={}, gomory_cuts=False)
+    bb.solve()
+    check_against_reference(bb, rec['reference']['PseudoCostBranchNode'])
+    assert eng.children_calls > 5
+    monkeypatch.setattr(eng, 'solve_batch', spy)
+    eng.children_calls = 0
+    bb = BranchAndBound(model_from(rec), BaseNode, frontier_batch=8, gomory_cuts=False)
+    bb.solve()
+    check_against_reference(bb, rec['reference']['BaseNode'])
+    assert eng.children_calls > 0

@@ -764,6 +764,9 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
                 y0[m + sh.pool_row(lp, nm)] = v
         return wx, y0
 
+    # a large iteration-limited batch is a strong-branching round: only status and objective of the
+    # children are read (pseudo_cost.py:68-100), so their primal/dual vectors stay on the device
+    want_xy = budget >= 2147483647 or B * (n + m) <= (1 << 22)
     res = None
     kids = _child_deltas(batch)
     same_warm = all(lp._warm is batch[0]._warm or
@@ -775,7 +778,8 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
         if batch[0]._warm is not None:
             x0, y0 = warm_vectors(batch[0])
         res = eng.solve_children(np.where(pl <= -1e30, -np.inf, pl), np.where(pu >= 1e30, np.inf, pu), deltas,
-                                 row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
+                                 row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts,
+                                 want_x=want_xy, want_y=want_xy)
     elif sh.root_bounds is not None and sh.root_xy is not None and B > 1:      # a frontier of open nodes
         l0, u0 = sh.root_bounds
         deltas = [_deltas_against(lp, l0, u0, 256) for lp in batch]
@@ -783,7 +787,8 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
             x0, ybase = sh.root_xy
             y0 = np.concatenate([ybase, np.zeros(mc)])
             res = eng.solve_children(np.where(l0 <= -1e30, -np.inf, l0), np.where(u0 >= 1e30, np.inf, u0), deltas,
-                                     row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
+                                     row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts,
+                                     want_x=want_xy, want_y=want_xy)
     if res is None:
         lb = np.empty((B, n))
         ub = np.empty((B, n))
@@ -795,7 +800,8 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
             ub[k] = np.where(lp._u >= 1e30, np.inf, lp._u)
             if lp._warm is not None:
                 x0[k], y0[k] = warm_vectors(lp)
-        res = eng.solve_batch(lb, ub, row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts)
+        res = eng.solve_batch(lb, ub, row_mask=mask, x0=x0, y0=y0, integer_indices=ints, opts=opts,
+                              want_x=want_xy, want_y=want_xy)
     if sh.root_bounds is None:
         sh.root_bounds = (np.asarray(batch[0]._l).copy(), np.asarray(batch[0]._u).copy())
     if sh.root_xy is None and B == 1 and not batch[0]._cuts and int(res.status[0]) == 0 and \
@@ -814,10 +820,13 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
         lp._basis_exact = False
         lp._factor_ref = None
         rows = [sh.pool_row(lp, nm) + m for nm in lp._cuts]
-        ysel = np.concatenate([res.y[k, :m], res.y[k, rows]]) if rows else res.y[k, :m].copy()
         if st == 1:
             lp._obj, lp._x, lp._y, lp._rc = float('inf'), None, None, None
+        elif not want_xy:
+            lp._x = lp._y = lp._rc = None
+            lp._obj = float(res.objective[k]) if st != 3 else float(res.lower_bound[k])
         else:
+            ysel = np.concatenate([res.y[k, :m], res.y[k, rows]]) if rows else res.y[k, :m].copy()
             x = res.x[k].copy()
             lp._x = CyLPArray(x)
             lp._y = ysel

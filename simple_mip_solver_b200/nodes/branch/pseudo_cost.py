@@ -17,6 +17,7 @@ pseudo_costs_hint = Dict[int, Dict[str, Dict[str, Union[float, int]]]]
 
 
 class PseudoCostBranchNode(BaseNode):
+    strong_branch_chunk = 256
 
     def __init__(self: T, *args: Any, **kwargs: Any):
         super().__init__(*args, **kwargs)
@@ -41,9 +42,13 @@ class PseudoCostBranchNode(BaseNode):
         batch), then update the cost of the variable this node was branched on (reference :46-66)."""
         sb_indices = [idx for idx in self._integer_indices
                       if self._is_fractional(float(self.solution[idx])) and idx not in self.pseudo_costs]
-        if sb_indices:
-            children = self._strong_branch_batch(sb_indices, self.strong_branch_iters)
-            for idx in sb_indices:
+        # up to 256 candidates (512 child LPs) per GPU call: wide enough for the kernels, and the child
+        # LP objects of a chunk (each holds its own bound vectors, as in the reference :592-608) are
+        # dropped before the next chunk is built, so a root with thousands of candidates stays small
+        for first in range(0, len(sb_indices), self.strong_branch_chunk):
+            chunk = sb_indices[first:first + self.strong_branch_chunk]
+            children = self._strong_branch_batch(chunk, self.strong_branch_iters)
+            for idx in chunk:
                 for child in children[idx].values():
                     self._calculate_costs(child)
         if self._b_idx is not None and self._b_idx not in sb_indices:

@@ -101,3 +101,115 @@ def test_config4_cut_rounds_with_row_masks(blp_lib):
     lp.truncate_rows(d.m)
     assert lp.m == d.m
     lp.close()
+
+
+def test_config3_default_five_pivot_strong_branching(blp_lib):
+    """Config 3 with the reference's DEFAULT budget, strong_branch_iters=5 (pseudo_cost.py:22): on the
+    dual simplex path that is literally 5 dual simplex pivots per child from the parent's basis, the
+    objective of an unfinished child being the dual objective of its last basis (a valid lower bound,
+    pseudo_cost.py:86-92). Checked against the numpy restatement pivot for pivot, and the branching
+    variable the costs select (:118-133) against the one the restatement's costs select."""
+    from oracle.dual_simplex import dual_simplex
+    d = grumpy_random_mip(500, 300, density=0.1, maxObjCoeff=10, maxConsCoeff=10, tightness=2, rand_seed=2)
+    model = MILPInstance(A=d.A.toarray(), b=CyLPArray(d.b), c=CyLPArray(d.c), l=CyLPArray(d.l), u=CyLPArray(d.u),
+                         sense=['Min', '>='], integerIndices=d.integer_indices, numVars=d.n)
+    node = PseudoCostBranchNode(model.lp, model.integerIndices, idx=0)
+    rtn = node.bound(pseudo_costs={}, gomory_cuts=False)            # strong_branch_iters defaults to 5
+    pcs = rtn['pseudo_costs']
+    sh = model.lp._shared
+    assert sh.solve_calls == 2 and sh.lps_solved == 1 + 2 * len(pcs) and len(pcs) >= 100
+    A = d.A.toarray()
+    root = dual_simplex(A, d.b, d.c, d.l, d.u)
+    assert np.array_equal(np.asarray(node.solution), root.x) and node.objective_value == root.objective
+    x = root.x
+    want = {}
+    limited = 0
+    for j in pcs:
+        want[j] = {}
+        for direction in ('left', 'right'):
+            l, u = d.l.copy(), d.u.copy()
+            if direction == 'left':
+                u[j] = np.floor(x[j]); change = x[j] - u[j]
+            else:
+                l[j] = np.ceil(x[j]); change = l[j] - x[j]
+            r = dual_simplex(A, d.b, d.c, l, u, col_status=root.col_status, row_status=root.row_status, max_pivots=5)
+            limited += r.status == 3
+            cost = max(r.objective - root.objective, 0) / change if r.status in (0, 3) else 0.0
+            want[j][direction] = cost
+            assert pcs[j][direction]['cost'] == cost, (j, direction)          # exact: same pivots, same arithmetic
+    assert limited > len(pcs)                    # most children do stop at the 5-pivot budget
+    gold = {j: {dr: dict(cost=c, times=1) for dr, c in v.items()} for j, v in want.items()}
+    assert node._best_pseudo_costs_index(pcs) == node._best_pseudo_costs_index(gold)
+    # against HiGHS under the same 5-iteration limit: a different simplex takes different 5 pivots, so
+    # the costs are not comparable one by one; report how the selected variable ranks there
+    h = HighsLP(d.A, d.c, d.b, np.full(d.m, HIGHS_INF), d.l, d.u)
+    hr = h.solve()
+    hcost = {}
+    for j in pcs:
+        hcost[j] = {}
+        for direction in ('left', 'right'):
+            h.set_col_bounds(d.l, d.u)
+            if direction == 'left':
+                h.set_one_col_bound(j, d.l[j], np.floor(x[j])); change = x[j] - np.floor(x[j])
+            else:
+                h.set_one_col_bound(j, np.ceil(x[j]), d.u[j]); change = np.ceil(x[j]) - x[j]
+            h.set_basis(hr.col_basis, hr.row_basis)
+            r = h.solve(iteration_limit=5)
+            hcost[j][direction] = dict(cost=max(r.objective - hr.objective, 0) / change if r.status in (0, 3) else 0.0, times=1)
+    pick, hpick = node._best_pseudo_costs_index(pcs), node._best_pseudo_costs_index(hcost)
+
+    def score(costs, j):
+        return min(costs[j]['right']['cost'] * (np.ceil(x[j]) - x[j]), costs[j]['left']['cost'] * (x[j] - np.floor(x[j])))
+    rank = sorted(hcost, key=lambda j: -score(hcost, j)).index(pick)
+    print(f'5-pivot strong branching, {len(pcs)} candidates: device picks x{pick}, HiGHS-5-iteration costs pick x{hpick}; '
+          f'the device pick ranks {rank + 1} of {len(pcs)} under the HiGHS costs')
+
+
+def _write_mps(path, d):
+    """Free-format MPS of ``min c.x, A x >= b, l <= x <= u`` with integer columns (what CLP writes)."""
+    A = d.A.tocsc()
+    with open(path, 'w') as f:
+        f.write('NAME bench\nROWS\n N OBJ\n')
+        for i in range(d.m):
+            f.write(f' G R{i}\n')
+        f.write('COLUMNS\n')
+        for j in range(d.n):
+            f.write(f' C{j} OBJ {d.c[j]:.17g}\n')
+            for p in range(A.indptr[j], A.indptr[j + 1]):
+                f.write(f' C{j} R{A.indices[p]} {A.data[p]:.17g}\n')
+        f.write('RHS\n')
+        for i in range(d.m):
+            f.write(f' RHS R{i} {d.b[i]:.17g}\n')
+        f.write('BOUNDS\n')
+        for j in range(d.n):
+            f.write(f' UI BND C{j} {d.u[j]:.17g}\n')
+        f.write('ENDATA\n')
+
+
+def test_config4_shape_through_the_node_api(blp_lib, tmp_path):
+    """The Node API at the C4 shape (10 000 x 5 000), from an MPS file, in a fresh process so that its
+    peak resident set is its own: BaseNode.bound() with the reference's default cut loop, and
+    BranchAndBound(PseudoCostBranchNode) for a few nodes — the root's strong-branching round hands
+    thousands of children to the GPU in one call. The model stays sparse on the host (no dense A, no
+    dense [B, n] bound arrays): resident set under 2 GB."""
+    import json
+    import os
+    import subprocess
+    import sys
+    d = numpy_random_mip(10000, 5000, density=2e-3, seed=2)
+    path = str(tmp_path / 'c4.mps')
+    _write_mps(path, d)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'tests', 'tools', 'c4_node_api.py'), path],
+                         capture_output=True, text=True, timeout=1500, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith('{')][-1])
+    print(r)
+    gold = float(np.load(os.path.join(root, 'bench_data', 'c4_root.npz'))['objective'])
+    assert r['sparse_model'] and r['n'] == 10000 and r['n_int'] == 10000
+    assert r['bound_feasible'] and r['bound_objective'] >= gold - 1e-6 * abs(gold)      # cut rounds only raise it
+    assert r['bb_status'] == 'stopped on iterations or time' and r['bb_nodes'] == 3
+    assert rel(r['bb_root_objective'], gold) <= 1e-6
+    assert r['bb_dual_bound'] >= gold - 1e-6 * abs(gold)
+    assert r['pseudo_costs'] > 1000 and r['lps_solved'] > 2000
+    assert r['peak_rss_gb'] < 2.0, r['peak_rss_gb']

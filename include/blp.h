@@ -16,7 +16,7 @@
  *   - return value 0 = ok, negative = blp_status error; text via blp_last_error() (thread local).
  *   - per-node solver outcomes are DATA (status[]), not errors. CLP codes are kept
  *     (base_node.py:274-275, pseudo_cost.py:86): 0 optimal, 1 primal infeasible,
- *     2 dual infeasible (unbounded), 3 iteration limit.
+ *     2 dual infeasible (unbounded), 3 iteration limit; 5 = stopped by blp_opts.obj_cutoff (opt-in).
  *   - "device" pointers are CUDA device pointers owned by the caller (torch tensors in the Python
  *     host layer) and borrowed for the duration of the call. Batched vectors are stored
  *     node-fastest: element (j, k) of an [rows][ld] array lives at j*ld + k, ld = blp_ld(B)
@@ -63,6 +63,13 @@ typedef struct blp_opts {
                               time) is swept at constant batch width with state for max_active nodes
                               only. max_iters then counts per node from its own start and may be
                               overshot by less than one evaluation period. default 0 */
+    double obj_cutoff;     /* objective limit (the analogue of CLP's dual objective limit): a node whose dual
+                              objective b.y + sum_j min(r_j l_j, r_j u_j) — a valid lower bound of its LP at
+                              every evaluation — reaches obj_cutoff is retired with status 5, its lower_bound
+                              being that bound. The reference prunes such a node after the full solve
+                              (branch_and_bound.py:251, 261): with the incumbent's value as the cutoff the
+                              search tree is the same, only the node's LP value is a bound instead of the
+                              optimum, which is why this is opt-in. default +inf (off) */
 } blp_opts;
 
 typedef struct blp_stats {

@@ -91,9 +91,12 @@ class BranchAndBound(BaseAlgorithm):
     def __init__(self, model: MILPInstance, Node: Type[BaseNode] = BaseNode, node_queue: Any = None,
                  node_limit: int = float('inf'), mip_gap: float = .0001, logging: bool = False,
                  max_run_time: float = float('inf'), initial_primal_bound: float = float('inf'),
-                 frontier_batch: int = 32, **kwargs: Any):
+                 frontier_batch: int = 32, lp_cutoff: bool = False, **kwargs: Any):
         """``frontier_batch``: how many open nodes have their LP relaxation solved per GPU call
-        (1 = one LP per call, as the reference). All other arguments as in the reference."""
+        (1 = one LP per call, as the reference). ``lp_cutoff``: hand the incumbent's value to the LP solver as
+        an objective limit, so that a node whose dual bound already reaches it stops iterating (the
+        reference solves it to the end and prunes it then, :251, :261; the tree is the same, the node's
+        recorded LP value is a bound). All other arguments as in the reference."""
         node_queue = node_queue or PriorityQueue()
         super().__init__(model=model, Node=Node, node_attributes=self._node_attributes,
                          node_funcs=self._node_funcs, **kwargs)
@@ -125,6 +128,7 @@ class BranchAndBound(BaseAlgorithm):
         self.logging = logging
         self.max_run_time = max_run_time
         self.frontier_batch = frontier_batch
+        self.lp_cutoff = bool(lp_cutoff)
         self.prefetch_calls = 0
         self.prefetched_lps = 0
         self.unsolved_nodes = 0         # nodes whose LP stopped on the solver's iteration budget
@@ -160,6 +164,8 @@ class BranchAndBound(BaseAlgorithm):
             if self.logging and self.evaluated_nodes % 100 == 0:
                 print(f'{self.evaluated_nodes} nodes evaluated gap: {self.current_gap}')
             node = self._node_queue.get()
+            if self.lp_cutoff and self.primal_bound < float('inf') and hasattr(node.lp, 'solver_opts'):
+                node.lp.solver_opts['obj_cutoff'] = float(self.primal_bound)     # shared by the model's LPs
             self._prefetch_frontier(node)
             self._evaluate_node(node)
 

@@ -824,7 +824,7 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
             lp._obj, lp._x, lp._y, lp._rc = float('inf'), None, None, None
         elif not want_xy:
             lp._x = lp._y = lp._rc = None
-            lp._obj = float(res.objective[k]) if st != 3 else float(res.lower_bound[k])
+            lp._obj = float(res.objective[k]) if st not in (3, 5) else float(res.lower_bound[k])
         else:
             ysel = np.concatenate([res.y[k, :m], res.y[k, rows]]) if rows else res.y[k, :m].copy()
             x = res.x[k].copy()
@@ -835,4 +835,4 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
                                (np.vstack([sh.cut_rows[j - m][0] for j in rows]).T @ full_y[rows] if rows else 0.0))
             # status 3 = budget exhausted: report the Lagrangian bound, the analogue of the
             # dual-feasible objective an iteration-limited dual simplex returns
-            lp._obj = float(res.objective[k]) if st != 3 else float(res.lower_bound[k])
+            lp._obj = float(res.objective[k]) if st not in (3, 5) else float(res.lower_bound[k])

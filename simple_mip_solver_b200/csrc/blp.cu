@@ -597,7 +597,7 @@ int check_opts(const blp_opts* in, blp_opts* o) {
     blp_default_opts(o);
     if (in) *o = *in;
     if (!(o->eps_rel > 0.0) || !(o->eps_infeas > 0.0) || o->max_iters < 1 || o->eval_every < 1 ||
-        o->max_active < 0)
+        o->max_active < 0 || std::isnan(o->obj_cutoff))
         return fail(BLP_ERR_ARG, "blp_opts: eps_rel/eps_infeas must be > 0, max_iters/eval_every >= 1, "
                                  "max_active >= 0");
     return BLP_OK;
@@ -619,6 +619,7 @@ void blp_default_opts(blp_opts* o) {
     o->verbose = 0;
     o->profile = 0;
     o->max_active = 0;
+    o->obj_cutoff = INFINITY;
 }
 
 int blp_slots(int B, const blp_opts* o) {
@@ -784,7 +785,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     DecideArgs D{0, 0, K, o.max_iters, o.eps_rel, o.eps_infeas,
                  env_dbl("BLP_BETA_SUFF", 0.2), env_dbl("BLP_BETA_NEC", 0.8), env_dbl("BLP_BETA_ART", 0.36),
                  env_dbl("BLP_OMEGA_THETA", 0.05), env_dbl("BLP_OMEGA_BALANCE", 0.3),
-                 env_dbl("BLP_OMEGA_DEADZONE", 0.25)};
+                 env_dbl("BLP_OMEGA_DEADZONE", 0.25), o.obj_cutoff};
     int launches = 0;
 
     CK(cudaEventRecord(h->ev[0], st));

@@ -997,6 +997,7 @@ struct DecideArgs {
     double eps, eps_inf;
     double beta_suff, beta_nec, beta_art, theta;    // restart thresholds, primal-weight smoothing
     double balance, balance_dead;   // primal-weight feedback on the lagging criterion (0 = off), see k_decide
+    double cutoff;                  // blp_opts.obj_cutoff: retire a node whose dual bound reaches it (status 5)
 };
 
 // counters: [0] nodes still running after the evaluation, [1] nodes restarting,
@@ -1070,6 +1071,9 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
             r[R_ADNEG] <= 1e-8 * dmax && c[C_DVIOL] <= 1e-8 * dmax)
             st = 2;
     }
+    // objective limit: the dual objective is a valid lower bound of the node LP whenever the dual
+    // iterate is feasible (rd: the part of the reduced costs no finite bound can absorb)
+    if (st < 0 && rd <= D.eps && dobj >= D.cutoff) st = 5;
     if (st < 0 && last) st = 3;
     if (st >= 0) {
         S.status[node] = st;

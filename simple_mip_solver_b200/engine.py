@@ -33,7 +33,7 @@ class BlpError(RuntimeError):
 class BlpOpts(C.Structure):
     _fields_ = [('eps_rel', C.c_double), ('eps_infeas', C.c_double), ('max_iters', C.c_int),
                 ('eval_every', C.c_int), ('use_graph', C.c_int), ('compact', C.c_int),
-                ('verbose', C.c_int), ('profile', C.c_int), ('max_active', C.c_int)]
+                ('verbose', C.c_int), ('profile', C.c_int), ('max_active', C.c_int), ('obj_cutoff', C.c_double)]
 
 
 class BlpStats(C.Structure):

@@ -74,6 +74,7 @@ class BaseNode:
         self.solution = None
         self.lp_feasible = None
         self.lp_unsolved = False
+        self.lp_cut_off = False
         self.unbounded = None
         self.mip_feasible = None
         self._b_dir, self._b_idx, self._b_val = b_dir, b_idx, b_val
@@ -160,7 +161,7 @@ class BaseNode:
         def out_of_time():
             return time.process_time() - start >= max_cut_generation_run_time
 
-        while self.lp_feasible and not self.lp_unsolved and not self.mip_feasible and not self.cut_generation_stalled \
+        while self.lp_feasible and not self.lp_unsolved and not self.lp_cut_off and not self.mip_feasible and not self.cut_generation_stalled \
                 and self.cut_generation_iterations < max_cut_generation_iterations \
                 and not out_of_time() and self.objective_value < max_dual_bound:
             self._cut_generation_iteration(**kwargs)
@@ -222,7 +223,13 @@ class BaseNode:
         self.lp_feasible = code in [0, 2] or self.lp_unsolved     # optimal or dual infeasible (:274)
         self.unbounded = code == 2
         self.objective_value = self.lp.objectiveValue if self.lp_feasible else float('inf')
-        if self.lp_unsolved:
+        # status 5: the solve was stopped by the objective limit (blp_opts.obj_cutoff, opt-in through
+        # BranchAndBound(lp_cutoff=True)): the node's value is a lower bound that already reaches the
+        # incumbent, so the search prunes it exactly where the reference would (branch_and_bound.py:261)
+        self.lp_cut_off = code == 5
+        if self.lp_cut_off:
+            self.lp_feasible = True
+        if self.lp_unsolved or self.lp_cut_off:
             self.objective_value = float(self.lp.lagrangianBound)
             self.solution = self.lp.primalVariableSolution['x']
             self.mip_feasible = False

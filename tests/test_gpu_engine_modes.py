@@ -177,3 +177,51 @@ def test_continuous_batching_carries_row_masks_and_warm_starts(blp_lib):
             assert abs(res.objective[k] - ref.objective) <= 1e-6 * max(1.0, abs(ref.objective)), k
     ok = res.status == 0
     assert (res.y[ok][:, d.m:][masks[ok] == 0] == 0).all()
+
+
+def test_objective_cutoff_retires_nodes_early_with_a_valid_bound(blp_lib):
+    """blp_opts.obj_cutoff: a node whose dual bound reaches the limit stops with status 5; its
+    lower_bound is >= the cutoff and <= its true LP value; nodes below the limit are not affected."""
+    from simple_mip_solver_b200.instances import frontier_nodes, numpy_random_mip
+    d = numpy_random_mip(2000, 1000, density=5e-3, seed=3)
+    lp = engine.BatchLP(d.A, d.b, d.c)
+    root = lp.solve_batch(d.l[None], d.u[None])
+    _, _, deltas = frontier_nodes(d, root.x[0], 0, 64, 8, seed=1, dense=False)
+    full = lp.solve_children(d.l, d.u, deltas, x0=root.x[0], y0=root.y[0])
+    assert (full.status == 0).all()
+    cutoff = float(np.median(full.objective))
+    cut = lp.solve_children(d.l, d.u, deltas, x0=root.x[0], y0=root.y[0], opts=engine.default_opts(obj_cutoff=cutoff))
+    above = full.objective > cutoff + 1e-6 * abs(cutoff)
+    below = full.objective < cutoff - 1e-6 * abs(cutoff)
+    assert above.sum() >= 16 and below.sum() >= 16
+    assert (cut.status[above] == 5).all() and (cut.status[below] == 0).all()
+    assert (cut.lower_bound[above] >= cutoff).all()
+    assert (cut.lower_bound[above] <= full.objective[above] + 1e-7 * np.abs(full.objective[above])).all()
+    assert np.allclose(cut.objective[below], full.objective[below], rtol=1e-7)
+    assert cut.iterations[above].mean() < 0.8 * full.iterations[above].mean()
+    print(f'cutoff at the median: {int(above.sum())} nodes retired after {int(cut.iterations[above].mean())} '
+          f'instead of {int(full.iterations[above].mean())} iterations')
+    lp.close()
+
+
+def test_branch_and_bound_with_lp_cutoff_builds_the_same_tree(blp_lib, monkeypatch):
+    import json, os
+    from simple_mip_solver_b200 import BaseNode, BranchAndBound, CyLPArray, MILPInstance
+    from simple_mip_solver_b200.compat.cylp_like import SharedLP
+    monkeypatch.setattr(SharedLP, 'default_method', 'pdhg')
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'example_models.json')))
+    rec = gold['random']
+
+    def run(cut):
+        m = MILPInstance(A=np.array(rec['A']), b=CyLPArray(rec['b']), c=CyLPArray(rec['c']), l=CyLPArray(rec['l']),
+                         u=CyLPArray(rec['u']), sense=['Min', '>='], integerIndices=list(rec['integer_indices']),
+                         numVars=len(rec['c']))
+        bb = BranchAndBound(m, BaseNode, frontier_batch=8, gomory_cuts=False, lp_cutoff=cut)
+        bb.solve()
+        tree = {i: (bb.tree.get_parent(i), v.attr['node']._b_idx, v.attr['node']._b_dir) for i, v in bb.tree.nodes.items()}
+        cut_nodes = sum(1 for v in bb.tree.nodes.values() if getattr(v.attr['node'], 'lp_cut_off', False))
+        m.lp._shared.close()
+        return bb.status, bb.objective_value, tree, cut_nodes
+    a, b = run(False), run(True)
+    assert a[0] == b[0] == 'optimal' and abs(a[1] - b[1]) <= 1e-6 * abs(a[1]) and a[2] == b[2]
+    print('nodes stopped by the objective limit:', b[3], 'of', len(b[2]))

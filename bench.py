@@ -42,8 +42,6 @@ WORKLOADS = {
     'c5': (50000, 20000, 2e-4, 32, 'c5_root.npz'),
     'c4': (10000, 5000, 2e-3, 16, 'c4_root.npz'),
     'c3': (500, 300, 0.1, 8, 'c3_root.npz'),
-    # C5 stress variant of SURVEY 8d: density 1e-3 (~50 nonzeros per row, ~1.0 M in all)
-    'c5s': (50000, 20000, 1e-3, 32, 'c5s_root.npz'),
 }
 METRIC = 'node_lp_solves_per_sec'
 UNIT = 'node-LPs/s'

@@ -182,7 +182,7 @@ def test_continuous_batching_carries_row_masks_and_warm_starts(blp_lib):
 def test_objective_cutoff_retires_nodes_early_with_a_valid_bound(blp_lib):
     """blp_opts.obj_cutoff: a node whose dual bound reaches the limit stops with status 5; its
     lower_bound is >= the cutoff and <= its true LP value; nodes below the limit are not affected."""
-    from simple_mip_solver_b200.instances import frontier_nodes, numpy_random_mip
+    from simple_mip_solver_b200 import engine
     d = numpy_random_mip(2000, 1000, density=5e-3, seed=3)
     lp = engine.BatchLP(d.A, d.b, d.c)
     root = lp.solve_batch(d.l[None], d.u[None])

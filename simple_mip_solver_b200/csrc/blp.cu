@@ -463,32 +463,6 @@ void launch_steps(const DevProb& P, const DevState& S, const Plan& pc, const Pla
                   bool major, cudaStream_t st, int which = 2, int tile0 = 0, int ntiles = -1) {
     if (pc.V == 2) {
         const int nt = ntiles < 0 ? pc.tiles : ntiles;
-#if BLP_TILES2
-        {   // two node tiles per warp
-            const int mode = BLP_TILES2;      // 1: both kernels, 2: primal only, 3: dual only
-            const dim3 gcw(pc.chunks, (nt + 1) / 2), grw(pr.chunks, (nt + 1) / 2);
-            const dim3 gc1(pc.chunks, nt), gr1(pr.chunks, nt);
-            if (which != 1) {
-                if (mode == 1 || mode == 2) {
-                    if (major) k_primal2w<true><<<gcw, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr, tile0, nt);
-                    else k_primal2w<false><<<gcw, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr, tile0, nt);
-                } else {
-                    if (major) k_primal2<true><<<gc1, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr, tile0);
-                    else k_primal2<false><<<gc1, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr, tile0);
-                }
-            }
-            if (which != 0) {
-                if (mode == 1 || mode == 3) {
-                    if (major) k_dual2w<true><<<grw, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr, tile0, nt);
-                    else k_dual2w<false><<<grw, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr, tile0, nt);
-                } else {
-                    if (major) k_dual2<true><<<gr1, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr, tile0);
-                    else k_dual2<false><<<gr1, kCtaThreads, pr.smem, st>>>(P, S, it, pr.rows_per_cta, pr.cap, pr.chunk_ptr, tile0);
-                }
-            }
-            return;
-        }
-#endif
         const dim3 gc(pc.chunks, nt), gr(pr.chunks, nt);
         if (which != 1) {
             if (major) k_primal2<true><<<gc, kCtaThreads, pc.smem, st>>>(P, S, it, pc.rows_per_cta, pc.cap, pc.chunk_ptr, tile0);

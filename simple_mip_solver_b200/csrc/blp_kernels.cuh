@@ -861,215 +861,14 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// TWO node tiles per warp (BLP_TILES2=1): a warp owns one matrix row for 128 nodes, lane l holding nodes
-// 2l, 2l+1 of tile A and of tile B. Row pointers, entry reads, address arithmetic and loop control are
-// spent once per 128 nodes, and every entry issues two 128-bit gathers. Same arithmetic per node as
-// k_primal2 / k_dual2 (bit-identical results). Long-row chunks stay with the one-tile kernels' path.
-#ifndef BLP_TILES2
-#define BLP_TILES2 0
-#endif
-#ifndef BLP_MINB2W
-#define BLP_MINB2W 3
-#endif
-
-template <bool SHARED>
-__device__ __forceinline__ void dot4_entries(const int4* __restrict__ E, const int p0, const int p1,
-                                             const double* __restrict__ Va, const double* __restrict__ Vb,
-                                             double (&g)[4]) {
-    constexpr int kU = BLP_U;
-    for (int p = p0; p < p1; p += kU) {
-        double2 va[kU], vb[kU];
-#pragma unroll
-        for (int q = 0; q < kU; ++q) {
-            va[q] = make_double2(0.0, 0.0);
-            vb[q] = make_double2(0.0, 0.0);
-            if (p + q < p1) {
-                const int col = SHARED ? E[p + q].x : __ldg(&E[p + q].x);
-                va[q] = ld2(Va + (size_t)col * kBlk);
-                vb[q] = ld2(Vb + (size_t)col * kBlk);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < kU; ++q)
-            if (p + q < p1) {
-                const int2 c = SHARED ? *reinterpret_cast<const int2*>(&E[p + q].z)
-                                      : __ldg(reinterpret_cast<const int2*>(&E[p + q].z));
-                const double cf = __hiloint2double(c.y, c.x);
-                g[0] = fma(cf, va[q].x, g[0]);
-                g[1] = fma(cf, va[q].y, g[1]);
-                g[2] = fma(cf, vb[q].x, g[2]);
-                g[3] = fma(cf, vb[q].y, g[3]);
-            }
-    }
-}
-
-template <bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads, BLP_MINB2W)
-k_primal2w(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-           const int* __restrict__ chunk_ptr, const int tile0, const int ntiles) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tA = tile0 + 2 * blockIdx.y, tB = tA + 1;
-    const bool hasB = tB < tile0 + ntiles;
-    int node[2] = {tA * kBlk + lane * 2, (hasB ? tB : tA) * kBlk + lane * 2};
-    bool k[4];
-    double w[4], tau[4];
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int nd = node[t] + h;
-            const bool ok = (t == 0 || hasB) && nd < S.B && S.fin[nd] == 0;
-            k[2 * t + h] = ok;
-            w[2 * t + h] = 0.0;
-            tau[2 * t + h] = 0.0;
-            if (ok) {
-                const int s = S.sbase[nd] + it;
-                w[2 * t + h] = (double)s / (double)(s + 1);
-                tau[2 * t + h] = P.eta / S.omega[nd];
-            }
-        }
-    if (__ballot_sync(0xffffffffu, k[0] || k[1] || k[2] || k[3]) == 0) return;
-    const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
-    const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
-    size_t base[2], fblk[2];
-    const double* yn[2];
-    unsigned bit[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        base[t] = tix(0, node[t], P.n);
-        yn[t] = S.y + tix(0, node[t], P.m);
-        fblk[t] = (size_t)(node[t] >> 5) * P.n;
-        bit[t] = node[t] & 31;
-    }
-    const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
-    double cg[4] = {0.0, 0.0, 0.0, 0.0};
-    if (coop) {
-        coop_dot2(sl, P.cent, yn[0], warp, lane, cg[0], cg[1]);
-        __syncthreads();
-        coop_dot2(sl, P.cent, yn[1], warp, lane, cg[2], cg[3]);
-        if (warp != 0) return;
-    }
-    for (int j = r0 + warp; j < r1; j += kWarps) {
-        double2 xb[2], a[2];
-        double lo[4], hi[4];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const size_t e = base[t] + (size_t)j * kBlk;
-            xb[t] = ld2(S.xbar + e);
-            a[t] = ldcs2(S.xa + e);
-            const uint32_t mk = (__ldg(S.lumask + fblk[t] + j) >> bit[t]) & 3u;
-            lo[2 * t] = lo[2 * t + 1] = __ldg(S.lref + fblk[t] + j);
-            hi[2 * t] = hi[2 * t + 1] = __ldg(S.uref + fblk[t] + j);
-            if (mk) {
-                const double2 l2 = ldcs2(S.l + e), u2 = ldcs2(S.u + e);
-                if (mk & 1u) { lo[2 * t] = l2.x; hi[2 * t] = u2.x; }
-                if (mk & 2u) { lo[2 * t + 1] = l2.y; hi[2 * t + 1] = u2.y; }
-            }
-        }
-        double g[4] = {cg[0], cg[1], cg[2], cg[3]};
-        if (!coop) {
-            const int p0 = sl.sp[j - r0], p1 = sl.sp[j - r0 + 1];
-            if (sl.se) dot4_entries<true>(sl.se - sl.base, p0, p1, yn[0], yn[1], g);
-            else dot4_entries<false>(reinterpret_cast<const int4*>(P.cent), p0, p1, yn[0], yn[1], g);
-        }
-        const double cj = __ldg(P.c + j);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const size_t e = base[t] + (size_t)j * kBlk;
-            const double xc0 = fma(w[2 * t], xb[t].x - a[t].x, a[t].x), xc1 = fma(w[2 * t + 1], xb[t].y - a[t].y, a[t].y);
-            const double xp0 = fmin(fmax(xc0 - tau[2 * t] * (cj - g[2 * t]), lo[2 * t]), hi[2 * t]);
-            const double xp1 = fmin(fmax(xc1 - tau[2 * t + 1] * (cj - g[2 * t + 1]), lo[2 * t + 1]), hi[2 * t + 1]);
-            st2(S.xbar + e, make_double2(2.0 * xp0 - xc0, 2.0 * xp1 - xc1), k[2 * t], k[2 * t + 1]);
-            if constexpr (MAJOR) {
-                st2(S.X1 + e, make_double2(xp0, xp1), k[2 * t], k[2 * t + 1]);
-                st2(S.DX + e, make_double2(xp0 - xc0, xp1 - xc1), k[2 * t], k[2 * t + 1]);
-                st2(S.G + e, make_double2(g[2 * t], g[2 * t + 1]), k[2 * t], k[2 * t + 1]);
-            }
-        }
-    }
-}
-
-template <bool MAJOR>
-__global__ void __launch_bounds__(kCtaThreads, BLP_MINB2W)
-k_dual2w(const DevProb P, const DevState S, const int it, const int rows_per_cta, const int cap,
-         const int* __restrict__ chunk_ptr, const int tile0, const int ntiles) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tA = tile0 + 2 * blockIdx.y, tB = tA + 1;
-    const bool hasB = tB < tile0 + ntiles;
-    int node[2] = {tA * kBlk + lane * 2, (hasB ? tB : tA) * kBlk + lane * 2};
-    bool k[4];
-    double w[4], sig[4];
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int nd = node[t] + h;
-            const bool ok = (t == 0 || hasB) && nd < S.B && S.fin[nd] == 0;
-            k[2 * t + h] = ok;
-            w[2 * t + h] = 0.0;
-            sig[2 * t + h] = 0.0;
-            if (ok) {
-                const int s = S.sbase[nd] + it;
-                w[2 * t + h] = (double)(s + 1) / (double)(s + 2);
-                sig[2 * t + h] = P.eta * S.omega[nd];
-            }
-        }
-    if (__ballot_sync(0xffffffffu, k[0] || k[1] || k[2] || k[3]) == 0) return;
-    const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
-    const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
-    const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
-    size_t base[2];
-    const double* xn[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        base[t] = tix(0, node[t], P.m);
-        xn[t] = S.xbar + tix(0, node[t], P.n);
-    }
-    const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
-    double cg[4] = {0.0, 0.0, 0.0, 0.0};
-    if (coop) {
-        coop_dot2(sl, P.ent, xn[0], warp, lane, cg[0], cg[1]);
-        __syncthreads();
-        coop_dot2(sl, P.ent, xn[1], warp, lane, cg[2], cg[3]);
-        if (warp != 0) return;
-    }
-    for (int i = r0 + warp; i < r1; i += kWarps) {
-        double2 yc[2], a[2];
-        bool on[4] = {true, true, true, true};
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const size_t e = base[t] + (size_t)i * kBlk;
-            yc[t] = ld2(S.y + e);
-            a[t] = ldcs2(S.ya + e);
-            if (i >= P.m_base && S.rowmask) {
-                const uint8_t* mrow = S.rowmask + (size_t)(i - P.m_base) * S.ld + node[t];
-                on[2 * t] = mrow[0] != 0;
-                on[2 * t + 1] = mrow[1] != 0;
-            }
-        }
-        double ax[4] = {cg[0], cg[1], cg[2], cg[3]};
-        if (!coop) {
-            const int p0 = sl.sp[i - r0], p1 = sl.sp[i - r0 + 1];
-            if (sl.se) dot4_entries<true>(sl.se - sl.base, p0, p1, xn[0], xn[1], ax);
-            else dot4_entries<false>(reinterpret_cast<const int4*>(P.ent), p0, p1, xn[0], xn[1], ax);
-        }
-        const double bi = __ldg(P.b + i);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const size_t e = base[t] + (size_t)i * kBlk;
-            const double yp0 = on[2 * t] ? fmax(0.0, yc[t].x + sig[2 * t] * (bi - ax[2 * t])) : 0.0;
-            const double yp1 = on[2 * t + 1] ? fmax(0.0, yc[t].y + sig[2 * t + 1] * (bi - ax[2 * t + 1])) : 0.0;
-            st2(S.y + e, make_double2(fma(w[2 * t], (2.0 * yp0 - yc[t].x) - a[t].x, a[t].x),
-                                      fma(w[2 * t + 1], (2.0 * yp1 - yc[t].y) - a[t].y, a[t].y)), k[2 * t], k[2 * t + 1]);
-            if constexpr (MAJOR) {
-                st2(S.Y1 + e, make_double2(yp0, yp1), k[2 * t], k[2 * t + 1]);
-                st2(S.DY + e, make_double2(yp0 - yc[t].x, yp1 - yc[t].y), k[2 * t], k[2 * t + 1]);
-            }
-        }
-    }
-}
+// Two node tiles per warp (one matrix row x 128 nodes per warp trip, the "4 nodes per lane" layout the
+// round-1 review asked for) was built and measured in commit 8a72e5b (k_primal2w / k_dual2w): results
+// bit-identical, 0.637 us per node-iteration with the primal step alone widened, 0.649 the dual step
+// alone, 0.725 both at 3-4 CTAs/SM, 0.875 at 2 CTAs/SM without spills, against 0.560 for these kernels
+// (profiles/r2e_ab_tiles2.log). Like the two-rows-per-trip variant above it halves the per-node
+// instruction count and doubles the bytes a warp has in flight, and like it it loses: what these
+// kernels need is resident WARPS, and every variant that buys per-warp parallelism with registers pays
+// in warps. Removed again; the one-row, one-tile kernels stay.
 
 // ---------------------------------------------------------------------------------------------
 // CTA-level, order-fixed reduction of per-thread accumulators into the chunk's partial slot.

@@ -30,11 +30,16 @@ def is_stale() -> bool:
     return any(p.stat().st_mtime > t for p in SOURCES + DEPS)
 
 
-def build_extension(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not is_stale():
+def build_extension(force: bool = False, verbose: bool = False, tuning: bool = False, out: Path = None) -> Path:
+    """``tuning=True`` adds -DBLP_TUNING: the library then reads the BLP_* sweep variables (tools/).
+    ``out``: build to another path (e.g. a tuning library next to the production one; select it with
+    the BLP_LIB environment variable)."""
+    if out is None and not force and not is_stale():
         return LIB
     cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-           '-shared', '-Xcompiler', '-fPIC', '-o', str(LIB)] + [str(s) for s in SOURCES]
+           '-shared', '-Xcompiler', '-fPIC', '-o', str(out or LIB)] + [str(s) for s in SOURCES]
+    if tuning:
+        cmd.insert(1, '-DBLP_TUNING')
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')
@@ -43,8 +48,9 @@ def build_extension(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return Path(out) if out is not None else LIB
 
 
 if __name__ == '__main__':
-    print(build_extension(force=True, verbose=True))
+    import sys
+    print(build_extension(force=True, verbose=True, tuning='--tuning' in sys.argv))

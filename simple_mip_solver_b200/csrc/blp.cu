@@ -147,6 +147,11 @@ void plan_slab(Plan& p, const std::vector<int32_t>& ptr, int rows) {
     p.smem = 16 * ((size_t)ptr_slots + (size_t)p.cap);
 }
 
+// Tuning constants of the restart / primal-weight logic and of the launch plans. A production build
+// compiles the defaults in; only a library built with -DBLP_TUNING (python -m simple_mip_solver_b200._build
+// --tuning, used by the sweep tools under tools/) reads BLP_* environment variables, so that two values
+// can be A/B-ed in one process.
+#ifdef BLP_TUNING
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
@@ -156,6 +161,10 @@ double env_dbl(const char* name, double dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atof(s) : dflt;
 }
+#else
+constexpr int env_int(const char*, int dflt) { return dflt; }
+constexpr double env_dbl(const char*, double dflt) { return dflt; }
+#endif
 
 int pick_nt(int B) {
     int nt = 1;
@@ -630,7 +639,13 @@ int blp_ld(int B) { return B <= 0 ? 0 : (B + kBlk - 1) / kBlk * kBlk; }
 
 const char* blp_last_error(void) { return g_err.c_str(); }
 
-const char* blp_version(void) { return "blp 0.1 sm_100a"; }
+const char* blp_version(void) {
+#ifdef BLP_TUNING
+    return "blp 0.2 sm_100a (tuning build: BLP_* environment variables are read)";
+#else
+    return "blp 0.2 sm_100a";
+#endif
+}
 
 int blp_create(int device, int m, int n, int64_t nnz, const int32_t* rowptr, const int32_t* colidx,
                const double* val, const double* c, const double* row_lb, blp_handle* out) {

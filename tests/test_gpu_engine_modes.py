@@ -67,8 +67,11 @@ def test_batch_composition_does_not_change_a_node(blp_lib):
     assert one.status[0] == full.status[7] and one.iterations[0] == full.iterations[7]
 
 
-def test_one_and_two_nodes_per_lane_kernels_agree(blp_lib):
-    """BLP_V2=0 forces the one-node-per-lane step kernels for wide batches (env read per call)."""
+def test_one_and_two_nodes_per_lane_kernels_agree(blp_lib, tmp_path):
+    """BLP_V2=0 forces the one-node-per-lane step kernels for wide batches. The production library
+    ignores BLP_* variables; a tuning build (-DBLP_TUNING) of the same sources reads them."""
+    from simple_mip_solver_b200 import _build
+    tuning_lib = _build.build_extension(tuning=True, out=tmp_path / 'libblp_tuning.so')
     code = (
         "import sys, json, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')\n"
         "from test_gpu_engine_modes import _instance, _solve\n"
@@ -78,7 +81,7 @@ def test_one_and_two_nodes_per_lane_kernels_agree(blp_lib):
     ) % (ROOT, ROOT)
     outs = []
     for v2 in ('1', '0'):
-        env = dict(os.environ, BLP_V2=v2)
+        env = dict(os.environ, BLP_V2=v2, BLP_LIB=str(tuning_lib))
         res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
         assert res.returncode == 0, res.stderr[-2000:]
         import json

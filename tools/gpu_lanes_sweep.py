@@ -3,6 +3,8 @@ the period graph at the C5 shape for a few batch widths, and bit-equality of the
 import os, sys, hashlib
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _tuning  # noqa: F401  (tuning build of libblp.so: reads the BLP_* variables below)
 import torch
 import bench
 from simple_mip_solver_b200 import engine

@@ -2,6 +2,8 @@
 import os, sys, itertools
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _tuning  # noqa: F401  (tuning build of libblp.so: reads the BLP_* variables below)
 import bench
 from simple_mip_solver_b200 import engine
 from simple_mip_solver_b200.instances import frontier_nodes

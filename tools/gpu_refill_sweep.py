@@ -3,6 +3,8 @@ iterations for a few (nodes per call, resident slots, evaluation period) setting
 import os, sys, time, json
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _tuning  # noqa: F401  (tuning build of libblp.so: reads the BLP_* variables below)
 import torch
 import bench
 from simple_mip_solver_b200 import engine

@@ -31,6 +31,7 @@ PDHG_ITERS_PER_PIVOT = 512
 
 # device memory the dense basis inverses of one simplex call may take ('auto' method selection)
 SIMPLEX_MEMORY_BUDGET = 16 << 30
+SIMPLEX_WIDE_MAX_BATCH = 2
 
 BASIC, AT_UPPER, AT_LOWER = 1, 2, 3      # CLP's getBasisStatus coding
 
@@ -228,6 +229,10 @@ class SharedLP:
         if ok and self.method == 'auto':
             m = self.m + len(self.cut_rows)
             ok = n_lps * m * m * 8 <= SIMPLEX_MEMORY_BUDGET
+            # mid-size LPs (the whole GPU per node, one after the other): only where the vertex is what
+            # the caller is after — a single node's bound / cut round; batches go to PDHG
+            if ok and not getattr(eng, 'simplex_batched', True):
+                ok = n_lps <= SIMPLEX_WIDE_MAX_BATCH
         if not ok and self.method == 'simplex':
             raise RuntimeError('the LP is too large for the dual simplex path')
         return ok

@@ -217,7 +217,7 @@ struct blp_handle_s {
     DevBuf uent, ucent;                // unscaled entries, same patterns (blp_spmv)
     DevBuf uc, ub;                     // unscaled objective / row lower bounds (simplex path)
     // dual simplex path (blp_simplex_*): factor stores of the current and the previous call, staging
-    DevBuf sx_binv[2], sx_head[2], sx_stat[2], sx_wts[2], sx_work, sx_in, sx_out;
+    DevBuf sx_binv[2], sx_head[2], sx_stat[2], sx_wts[2], sx_work, sx_in, sx_out, sx_wide;
     int sx_cur = 0;                    // store the NEXT call writes; the other one holds the last call
     int sx_last_B = 0, sx_last_m = -1; // nodes / rows of the last call's store (-1: none)
     DevBuf chunkC, chunkR;             // row ranges of the step-kernel CTAs (primal / dual)
@@ -1429,12 +1429,35 @@ int sx_run(blp_handle h, int B, const SxStage& S, bool use_parent, int max_pivot
     Q.work = h->sx_work.as<double>(); Q.work_stride = stride;
     Q.obj = S.obj; Q.status = S.status; Q.pivots = S.pivots; Q.flips = S.flips;
     Q.x = S.x; Q.y = S.y; Q.rc = S.rc; Q.cstat_out = S.cso; Q.rstat_out = S.rso;
-    const int threads = m <= 128 ? 128 : 512;
-    const size_t smem = (size_t)kSxWeightLanes * m * sizeof(double);
-    if (smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_simplex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaEventRecord(h->ev[2], st));
-    k_simplex<<<B, threads, smem, st>>>(P, Q);
+    if (m <= kSxMaxRows) {
+        const int threads = m <= 128 ? 128 : 512;
+        const size_t smem = (size_t)kSxWeightLanes * m * sizeof(double);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(k_simplex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_simplex<<<B, threads, smem, st>>>(P, Q);
+    } else {
+        // the whole GPU on one node at a time: cooperative grid, one CTA per SM
+        if (!h->coop_ok) return fail(BLP_ERR_STATE, "blp_simplex: LPs of more than %d rows need cooperative launches", kSxMaxRows);
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_wide, 512, 0));
+        if (occ < 1) return fail(BLP_ERR_STATE, "blp_simplex: k_simplex_wide does not fit an SM");
+        const int grid = h->num_sms;
+        const size_t need = (size_t)kSxWeightLanes * m * sizeof(double) + 256 + sizeof(SxCtrl) + 256 +
+                            (size_t)grid * (sizeof(double) + sizeof(int) + sizeof(SxCand)) + 1024;
+        CK(h->sx_wide.ensure(need));
+        Carve cv{h->sx_wide.as<char>()};
+        SxWideScratch W;
+        W.part = cv.take<double>((size_t)kSxWeightLanes * m);
+        W.ctrl = cv.take<SxCtrl>(1);
+        W.gd = cv.take<double>(grid);
+        W.gi = cv.take<int>(grid);
+        W.gc = cv.take<SxCand>(grid);
+        for (int node = 0; node < B; ++node) {
+            void* args[] = {(void*)&P, (void*)&Q, (void*)&node, (void*)&W};
+            CK(cudaLaunchCooperativeKernel((const void*)k_simplex_wide, dim3(grid), dim3(512), args, 0, st));
+        }
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[3], st));
     if (obj) CK(cudaMemcpyAsync(obj, S.obj, B * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1479,15 +1502,16 @@ int sx_run(blp_handle h, int B, const SxStage& S, bool use_parent, int max_pivot
 int sx_check(blp_handle h, int B, const char* who) {
     if (!h) return fail(BLP_ERR_ARG, "%s: NULL handle", who);
     if (B < 1) return fail(BLP_ERR_ARG, "%s: need B >= 1", who);
-    if (h->A0.rows > kSxMaxRows)
+    if (h->A0.rows > kSxMaxRowsWide)
         return fail(BLP_ERR_STATE, "%s: %d rows, the dense-inverse simplex takes at most %d (use blp_solve_batch)",
-                    who, h->A0.rows, kSxMaxRows);
+                    who, h->A0.rows, kSxMaxRowsWide);
     return BLP_OK;
 }
 
 }  // namespace
 
-int blp_simplex_max_rows(void) { return kSxMaxRows; }
+int blp_simplex_max_rows(void) { return kSxMaxRowsWide; }
+int blp_simplex_batch_rows(void) { return kSxMaxRows; }
 
 int blp_simplex_batch_host(blp_handle h, int B, const double* lb, const double* ub, const uint8_t* row_mask,
                            const int8_t* col_status, const int8_t* row_status, const int32_t* parent_slot,
@@ -1709,7 +1733,7 @@ int blp_destroy(blp_handle h) {
                       &h->s_ub, &h->s_x0, &h->s_y0, &h->s_mask, &h->s_x, &h->s_y, &h->s_tmp,
                       &h->s_ws, &h->s_node, &h->s_int, &h->s_delta, &h->s_par, &h->uc, &h->ub,
                       &h->sx_binv[0], &h->sx_binv[1], &h->sx_head[0], &h->sx_head[1], &h->sx_stat[0],
-                      &h->sx_stat[1], &h->sx_wts[0], &h->sx_wts[1], &h->sx_work, &h->sx_in, &h->sx_out};
+                      &h->sx_stat[1], &h->sx_wts[0], &h->sx_wts[1], &h->sx_work, &h->sx_in, &h->sx_out, &h->sx_wide};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_join) if (e) cudaEventDestroy(e);

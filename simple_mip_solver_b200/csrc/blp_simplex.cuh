@@ -15,13 +15,15 @@
 // contraction), sums in ascending index order, row norms in 16 interleaved partial sums.
 #pragma once
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "blp_kernels.cuh"
 
 namespace blp {
 
-constexpr int kSxMaxRows = 1024;
+constexpr int kSxMaxRows = 1024;          // one CTA per node (k_simplex)
+constexpr int kSxMaxRowsWide = 8192;      // the whole GPU per node (k_simplex_wide, cooperative launch)
 constexpr int kSxWeightLanes = 16;
 constexpr int SX_BASIC = 1, SX_UPPER = 2, SX_LOWER = 3;
 constexpr double kSxPrimalTol = 1e-9, kSxDualTol = 1e-9, kSxPivTol = 1e-9, kSxTieRel = 1e-12;
@@ -146,6 +148,68 @@ __device__ __forceinline__ SxCand sx_block_best(SxCand c, SxCandRed& s) {
     return s.best;
 }
 
+
+// ---- the team that works on ONE node: a CTA (k_simplex) or the whole cooperative grid (k_simplex_wide) ----
+// Loops run over team threads, barriers and reductions are team wide. Reductions are max / min /
+// lexicographic min, i.e. order independent, so both teams compute bit-identical results.
+struct SxCtrl {            // scalars one thread decides and everybody reads after a team barrier
+    int r, q, nflip, status, par_ok, nlist;
+    double slope;
+};
+
+template <bool WIDE>
+struct SxTeam {
+    int tid, nth, lane, warp, nwarps;
+    SxRed* red;            // shared memory of this CTA
+    SxCandRed* cred;
+    SxCtrl* ctrl;          // shared (CTA team) or global (grid team)
+    double* gd;            // grid team: one slot per CTA for the partial results of a reduction
+    int* gi;
+    SxCand* gc;
+
+    __device__ __forceinline__ void sync() const {
+        if (WIDE) cooperative_groups::this_grid().sync();
+        else __syncthreads();
+    }
+    __device__ __forceinline__ double max(double v) const {
+        v = sx_block_max(v, *red);
+        if (!WIDE) return v;
+        if (threadIdx.x == 0) gd[blockIdx.x] = v;
+        sync();
+        double t = -INFINITY;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t = fmax(t, gd[b]);
+        t = sx_block_max(t, *red);
+        sync();                                            // gd may be reused by the next reduction
+        return t;
+    }
+    __device__ __forceinline__ int min_int(int v) const {
+        v = sx_block_min_int(v, *red);
+        if (!WIDE) return v;
+        if (threadIdx.x == 0) gi[blockIdx.x] = v;
+        sync();
+        int t = 2147483647;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t = min(t, gi[b]);
+        t = sx_block_min_int(t, *red);
+        sync();
+        return t;
+    }
+    __device__ __forceinline__ SxCand best(SxCand c) const {
+        c = sx_block_best(c, *cred);
+        if (!WIDE) return c;
+        if (threadIdx.x == 0) gc[blockIdx.x] = c;
+        sync();
+        SxCand t;
+        t.key = INFINITY; t.mag = 0.0; t.j = 2147483647;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            const SxCand o = gc[b];
+            if (sx_better(o, t)) t = o;
+        }
+        t = sx_block_best(t, *cred);
+        sync();
+        return t;
+    }
+};
+
 // ---- the node's view ---------------------------------------------------------------------------
 struct SxNode {
     int m, n, N, ldm;
@@ -192,8 +256,9 @@ __device__ __forceinline__ double sx_dot_entries(const Ent* __restrict__ ent, co
 }
 
 // acc_i = sum_k Binv(i,k) v[k], ascending k, zeros of v skipped (thread per row)
-__device__ __forceinline__ void sx_matvec(const SxNode& nd, const double* __restrict__ v, double* __restrict__ out) {
-    for (int i = threadIdx.x; i < nd.m; i += blockDim.x) {
+template <class Team>
+__device__ __forceinline__ void sx_matvec(const Team& T, const SxNode& nd, const double* v, double* out) {
+    for (int i = T.tid; i < nd.m; i += T.nth) {
         double acc = 0.0;
         for (int k0 = 0; k0 < nd.m; k0 += kSxDotBatch) {
             double bv[kSxDotBatch], vk[kSxDotBatch];
@@ -212,17 +277,18 @@ __device__ __forceinline__ void sx_matvec(const SxNode& nd, const double* __rest
 }
 
 // alpha = Binv a_j for column j of [A, -I] (thread per row; entries of a_j ascending by row)
-__device__ __forceinline__ void sx_ftran_col(const SxProb& P, const SxNode& nd, int j, double* __restrict__ out) {
+template <class Team>
+__device__ __forceinline__ void sx_ftran_col(const Team& T, const SxProb& P, const SxNode& nd, int j, double* out) {
     if (j < nd.n) {
         const int p0 = P.cptr[j], p1 = P.cptr[j + 1];
-        for (int i = threadIdx.x; i < nd.m; i += blockDim.x) {
-            const double* __restrict__ Bi = nd.Binv + i;
+        for (int i = T.tid; i < nd.m; i += T.nth) {
+            const double* Bi = nd.Binv + i;
             const size_t ldm = nd.ldm;
             out[i] = sx_dot_entries(P.cent, p0, p1, [&](int k) { return Bi[(size_t)k * ldm]; });
         }
     } else {
         const int k = j - nd.n;
-        for (int i = threadIdx.x; i < nd.m; i += blockDim.x)
+        for (int i = T.tid; i < nd.m; i += T.nth)
             out[i] = sx_add(0.0, sx_mul(nd.Binv[(size_t)k * nd.ldm + i], -1.0));
     }
 }
@@ -230,18 +296,20 @@ __device__ __forceinline__ void sx_ftran_col(const SxProb& P, const SxNode& nd, 
 // Binv <- E Binv for a basis change in row position r; rowr[k] = old Binv(r,k) / pivot must be ready.
 // With WEIGHTS the row norms are rebuilt in the same sweep: warp group g sums the squares of the
 // columns k = g, g + 16, ... in ascending order into part[g][i]; w_i = sum_g part[g][i], g ascending.
-template <bool WEIGHTS>
-__device__ __forceinline__ void sx_update_inverse(const SxNode& nd, const double* __restrict__ alpha,
-                                                  const double* __restrict__ rowr, const int r, double* part) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int m = nd.m;
+template <bool WEIGHTS, class Team>
+__device__ __forceinline__ void sx_update_inverse(const Team& T, const SxNode& nd, const double* alpha,
+                                                  const double* rowr, const int r, double* part) {
+    const int lane = T.lane;
+    const int m = nd.m, nchunk = (m + 31) / 32;
     // The loads of a batch of kSxBatchK columns are issued before the first store: the compiler cannot
     // prove that a store to Binv does not alias the next load, and one L2 round trip per element
     // (~190 dependent ones per warp at m = 300) was 70 of the 86 us a pivot took. The order of the
     // arithmetic (ascending k) is unchanged.
     constexpr int kSxBatchK = 8;
-    for (int g = warp; g < kSxWeightLanes; g += nw) {
-        for (int i = lane; i < m; i += 32) {
+    // work item = (column group g, chunk of 32 rows); a CTA team gives warp w the items of group w
+    for (int item = T.warp; item < kSxWeightLanes * nchunk; item += T.nwarps) {
+        const int g = item % kSxWeightLanes, i = (item / kSxWeightLanes) * 32 + lane;
+        if (i < m) {
             const double ai = alpha[i];
             double acc = 0.0;
             for (int k0 = g; k0 < m; k0 += kSxWeightLanes * kSxBatchK) {
@@ -265,23 +333,25 @@ __device__ __forceinline__ void sx_update_inverse(const SxNode& nd, const double
             if (WEIGHTS) part[g * m + i] = acc;
         }
     }
-    __syncthreads();
+    T.sync();
     if (WEIGHTS) {
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        for (int i = T.tid; i < m; i += T.nth) {
             double wsum = 0.0;
 #pragma unroll
             for (int g = 0; g < kSxWeightLanes; ++g) wsum = sx_add(wsum, part[g * m + i]);
             nd.w[i] = wsum;
         }
-        __syncthreads();
+        T.sync();
     }
 }
 
-__device__ __forceinline__ void sx_weights(const SxNode& nd, double* part) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int m = nd.m;
-    for (int g = warp; g < kSxWeightLanes; g += nw)
-        for (int i = lane; i < m; i += 32) {
+template <class Team>
+__device__ __forceinline__ void sx_weights(const Team& T, const SxNode& nd, double* part) {
+    const int lane = T.lane;
+    const int m = nd.m, nchunk = (m + 31) / 32;
+    for (int item = T.warp; item < kSxWeightLanes * nchunk; item += T.nwarps) {
+        const int g = item % kSxWeightLanes, i = (item / kSxWeightLanes) * 32 + lane;
+        if (i < m) {
             double acc = 0.0;
             for (int k = g; k < m; k += kSxWeightLanes) {
                 const double v = nd.Binv[(size_t)k * nd.ldm + i];
@@ -289,62 +359,64 @@ __device__ __forceinline__ void sx_weights(const SxNode& nd, double* part) {
             }
             part[g * m + i] = acc;
         }
-    __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    }
+    T.sync();
+    for (int i = T.tid; i < m; i += T.nth) {
         double wsum = 0.0;
 #pragma unroll
         for (int g = 0; g < kSxWeightLanes; ++g) wsum = sx_add(wsum, part[g * m + i]);
         nd.w[i] = wsum;
     }
-    __syncthreads();
+    T.sync();
 }
 
 // Slack basis, then the wanted structurals pivoted in one by one (start and refactorisation).
 // nd.want[j] != 0 marks the columns that should be basic; nd.stat holds the nonbasic sides.
-__device__ void sx_factor(const SxProb& P, const SxNode& nd, SxRed& red) {
+template <class Team>
+__device__ void sx_factor(const Team& T, const SxProb& P, const SxNode& nd) {
     const int m = nd.m, n = nd.n, N = nd.N;
-    for (size_t e = threadIdx.x; e < (size_t)m * nd.ldm; e += blockDim.x) {
+    for (size_t e = T.tid; e < (size_t)m * nd.ldm; e += T.nth) {
         const int k = (int)(e / nd.ldm), i = (int)(e % nd.ldm);
         nd.Binv[e] = (i == k) ? -1.0 : 0.0;
     }
-    for (int i = threadIdx.x; i < m; i += blockDim.x) nd.head[i] = n + i;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    for (int i = T.tid; i < m; i += T.nth) nd.head[i] = n + i;
+    for (int j = T.tid; j < N; j += T.nth) {
         const int8_t s = nd.stat[j];
         nd.key[j] = (double)s;                              // "keep": the status before this factorisation
         if (j >= n) nd.stat[j] = SX_BASIC;
         else if (s == SX_BASIC) nd.stat[j] = SX_LOWER;
     }
-    __syncthreads();
+    T.sync();
     for (int j = 0; j < n; ++j) {
         if (!nd.want[j]) continue;                          // uniform: same data for every thread
-        sx_ftran_col(P, nd, j, nd.aq);
-        __syncthreads();
+        sx_ftran_col(T, P, nd, j, nd.aq);
+        T.sync();
         double best = kSxPivTol;
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        for (int i = T.tid; i < m; i += T.nth) {
             const int hv = nd.head[i];
             if (hv >= n && !nd.want[hv]) best = fmax(best, fabs(nd.aq[i]));
         }
-        best = sx_block_max(best, red);
+        best = T.max(best);
         int r = 2147483647;
         if (best > kSxPivTol)
-            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            for (int i = T.tid; i < m; i += T.nth) {
                 const int hv = nd.head[i];
                 if (hv >= n && !nd.want[hv] && fabs(nd.aq[i]) == best) r = min(r, i);
             }
-        r = sx_block_min_int(r, red);
+        r = T.min_int(r);
         if (r == 2147483647) continue;
         const double piv = nd.aq[r];
-        for (int k = threadIdx.x; k < m; k += blockDim.x) nd.rho[k] = nd.Binv[(size_t)k * nd.ldm + r] / piv;
-        __syncthreads();
-        sx_update_inverse<false>(nd, nd.aq, nd.rho, r, nullptr);
-        if (threadIdx.x == 0) {
+        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)k * nd.ldm + r] / piv;
+        T.sync();
+        sx_update_inverse<false>(T, nd, nd.aq, nd.rho, r, nullptr);
+        if (T.tid == 0) {
             const int s = nd.head[r];
             const int keep = (int)nd.key[s];
             nd.stat[s] = keep != SX_BASIC ? (int8_t)keep : (int8_t)SX_LOWER;
             nd.head[r] = j;
             nd.stat[j] = SX_BASIC;
         }
-        __syncthreads();
+        T.sync();
     }
 }
 
@@ -354,17 +426,18 @@ __device__ __forceinline__ double sx_nonbasic_value(const SxNode& nd, int j) {
 }
 
 // y = c_B Binv (ascending row position, zeros of c_B skipped); d = c - A'y, d_slack = y, d_basic = 0
-__device__ void sx_duals(const SxProb& P, const SxNode& nd) {
+template <class Team>
+__device__ void sx_duals(const Team& T, const SxProb& P, const SxNode& nd) {
     const int m = nd.m, n = nd.n;
     // c_B is gathered once (xfull is free here); thread k then walks its own column of Binv
-    for (int p = threadIdx.x; p < m; p += blockDim.x) {
+    for (int p = T.tid; p < m; p += T.nth) {
         const int hv = nd.head[p];
         nd.col[p] = hv < n ? P.c[hv] : 0.0;
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+    T.sync();
+    for (int k = T.tid; k < m; k += T.nth) {
         double acc = 0.0;
-        const double* __restrict__ colk = nd.Binv + (size_t)k * nd.ldm;
+        const double* colk = nd.Binv + (size_t)k * nd.ldm;
         for (int p0 = 0; p0 < m; p0 += kSxDotBatch) {
             double cb[kSxDotBatch], bv[kSxDotBatch];
 #pragma unroll
@@ -379,35 +452,37 @@ __device__ void sx_duals(const SxProb& P, const SxNode& nd) {
         }
         nd.y[k] = acc;
     }
-    __syncthreads();
-    for (int j = threadIdx.x; j < nd.N; j += blockDim.x) {
+    T.sync();
+    for (int j = T.tid; j < nd.N; j += T.nth) {
         double dj;
         if (j < n) {
-            const double* __restrict__ yv = nd.y;
+            const double* yv = nd.y;
             dj = sx_sub(P.c[j], sx_dot_entries(P.cent, P.cptr[j], P.cptr[j + 1], [&](int i) { return yv[i]; }));
         } else {
             dj = nd.y[j - n];
         }
         nd.d[j] = nd.stat[j] == SX_BASIC ? 0.0 : dj;
     }
-    __syncthreads();
+    T.sync();
 }
 
 // rhs = b - A x_N + x_N(slack);  x_B = Binv rhs
-__device__ void sx_primal(const SxProb& P, const SxNode& nd) {
+template <class Team>
+__device__ void sx_primal(const Team& T, const SxProb& P, const SxNode& nd) {
     const int m = nd.m, n = nd.n;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    for (int i = T.tid; i < m; i += T.nth) {
         const double acc = sx_dot_entries(P.ent, P.rowptr[i], P.rowptr[i + 1],
                                           [&](int j) { return sx_nonbasic_value(nd, j); });
         nd.rhs[i] = sx_add(sx_sub(P.b[i], acc), sx_nonbasic_value(nd, n + i));
     }
-    __syncthreads();
-    sx_matvec(nd, nd.rhs, nd.xB);
-    __syncthreads();
+    T.sync();
+    sx_matvec(T, nd, nd.rhs, nd.xB);
+    T.sync();
 }
 
-__device__ void sx_make_dual_feasible(const SxNode& nd) {
-    for (int j = threadIdx.x; j < nd.N; j += blockDim.x) {
+template <class Team>
+__device__ void sx_make_dual_feasible(const Team& T, const SxNode& nd) {
+    for (int j = T.tid; j < nd.N; j += T.nth) {
         int8_t s = nd.stat[j];
         if (s == SX_BASIC) continue;
         double lo = nd.lo[j], hi = nd.hi[j];
@@ -421,18 +496,15 @@ __device__ void sx_make_dual_feasible(const SxNode& nd) {
         if (s == SX_LOWER && isinf(lo)) { nd.lo[j] = -kSxBig; nd.artlo[j] = 1; }
         nd.stat[j] = s;
     }
-    __syncthreads();
+    T.sync();
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1)
-k_simplex(const SxProb P, const SxBatch Q) {
-    extern __shared__ double sx_part[];                    // [16][m] partial row norms
-    __shared__ SxRed red;
-    __shared__ SxCandRed cred;
-    __shared__ int s_r, s_q, s_nflip, s_status, s_par_ok;
-    __shared__ double s_slope;
-    const int node = blockIdx.x;
+// The dual simplex of one node, run by a team (see SxTeam). sx_part: [16][m] partial row norms.
+template <bool WIDE>
+__device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node, const SxTeam<WIDE>& T,
+                              double* sx_part) {
+    SxCtrl& C = *T.ctrl;
     const int m = P.m, n = P.n, N = n + m;
     SxNode nd;
     nd.m = m; nd.n = n; nd.N = N; nd.ldm = P.ldm;
@@ -455,11 +527,11 @@ k_simplex(const SxProb P, const SxBatch Q) {
     const uint8_t* onk = Q.rowon ? Q.rowon + (size_t)node * mc : nullptr;
     const int par = Q.parent ? Q.parent[node] : -1;
     const bool from_status = Q.cstat_in != nullptr && Q.rstat_in != nullptr;
-    if (threadIdx.x == 0) s_par_ok = 1;
-    __syncthreads();
+    if (T.tid == 0) C.par_ok = 1;
+    T.sync();
 
     // ---- bounds, starting status ------------------------------------------------------------
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    for (int j = T.tid; j < N; j += T.nth) {
         double lo, hi;
         bool on = true;
         if (j < n) {
@@ -478,7 +550,7 @@ k_simplex(const SxProb P, const SxBatch Q) {
         if (par >= 0) {
             st = Q.pstat[(size_t)par * N + j];
             want = st == SX_BASIC || !on;
-            if (!on && st != SX_BASIC) s_par_ok = 0;     // the parent's factor has this slack nonbasic
+            if (!on && st != SX_BASIC) C.par_ok = 0;     // the parent's factor has this slack nonbasic
         } else if (from_status) {
             if (j < n) {
                 const int8_t cs = Q.cstat_in[(size_t)node * n + j];
@@ -493,28 +565,28 @@ k_simplex(const SxProb P, const SxBatch Q) {
         nd.stat[j] = st;
         nd.want[j] = want;
     }
-    __syncthreads();
-    const bool use_parent = par >= 0 && s_par_ok != 0;
+    T.sync();
+    const bool use_parent = par >= 0 && C.par_ok != 0;
     if (par >= 0 && !use_parent) {                       // fall back: factorise from the parent's status
-        for (int j = threadIdx.x; j < N; j += blockDim.x)
+        for (int j = T.tid; j < N; j += T.nth)
             if (nd.stat[j] == SX_BASIC) nd.stat[j] = SX_LOWER;
-        __syncthreads();
+        T.sync();
     }
     if (use_parent) {
         const double* src = Q.pBinv + (size_t)par * m * P.ldm;
-        for (size_t e = threadIdx.x; e < (size_t)m * P.ldm; e += blockDim.x) nd.Binv[e] = src[e];
-        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        for (size_t e = T.tid; e < (size_t)m * P.ldm; e += T.nth) nd.Binv[e] = src[e];
+        for (int i = T.tid; i < m; i += T.nth) {
             nd.head[i] = Q.phead[(size_t)par * m + i];
             nd.w[i] = Q.pwts[(size_t)par * m + i];
         }
-        __syncthreads();
+        T.sync();
     } else {
-        sx_factor(P, nd, red);
+        sx_factor(T, P, nd);
     }
-    sx_duals(P, nd);
-    sx_make_dual_feasible(nd);
-    sx_primal(P, nd);
-    if (!use_parent) sx_weights(nd, sx_part);
+    sx_duals(T, P, nd);
+    sx_make_dual_feasible(T, nd);
+    sx_primal(T, P, nd);
+    if (!use_parent) sx_weights(T, nd, sx_part);
 
     int pivots = 0, flips_total = 0, since_factor = 0, status = 0;
     // no anti-cycling rule: a hard cap far above any pivot count seen ends a cycling node with status 3
@@ -525,7 +597,7 @@ k_simplex(const SxProb P, const SxBatch Q) {
         double local = -1.0;
         {
             int t = 0;
-            for (int i = threadIdx.x; i < m; i += blockDim.x, ++t) {
+            for (int i = T.tid; i < m; i += T.nth, ++t) {
                 const int hv = nd.head[i];
                 const double xb = nd.xB[i];
                 const double inf = fmax(sx_sub(nd.lo[hv], xb), sx_sub(xb, nd.hi[hv]));
@@ -535,41 +607,41 @@ k_simplex(const SxProb P, const SxBatch Q) {
                 local = fmax(local, s);
             }
         }
-        const double best = sx_block_max(local, red);
+        const double best = T.max(local);
         if (best < 0.0) { status = 0; break; }
         if (pivots >= pivot_cap) { status = 3; break; }
         if (since_factor >= kSxRefactorEvery) {
-            for (int j = threadIdx.x; j < N; j += blockDim.x) nd.want[j] = nd.stat[j] == SX_BASIC;
-            __syncthreads();
-            sx_factor(P, nd, red);
-            sx_duals(P, nd);
-            sx_primal(P, nd);
-            sx_weights(nd, sx_part);
+            for (int j = T.tid; j < N; j += T.nth) nd.want[j] = nd.stat[j] == SX_BASIC;
+            T.sync();
+            sx_factor(T, P, nd);
+            sx_duals(T, P, nd);
+            sx_primal(T, P, nd);
+            sx_weights(T, nd, sx_part);
             since_factor = 0;
             continue;
         }
         {
             const double thr = sx_mul(best, sx_sub(1.0, kSxTieRel));
             int hmin = 2147483647, t = 0;
-            for (int i = threadIdx.x; i < m; i += blockDim.x, ++t)
+            for (int i = T.tid; i < m; i += T.nth, ++t)
                 if (sc[t] >= thr) hmin = min(hmin, nd.head[i]);
-            hmin = sx_block_min_int(hmin, red);
-            for (int i = threadIdx.x; i < m; i += blockDim.x)
-                if (nd.head[i] == hmin) s_r = i;
-            __syncthreads();
+            hmin = T.min_int(hmin);
+            for (int i = T.tid; i < m; i += T.nth)
+                if (nd.head[i] == hmin) C.r = i;
+            T.sync();
         }
-        const int r = s_r;
+        const int r = C.r;
         const int leaving = nd.head[r];
         const double xbr = nd.xB[r];
         const bool below = xbr < nd.lo[leaving];
         const double infr = fmax(sx_sub(nd.lo[leaving], xbr), sx_sub(xbr, nd.hi[leaving]));
         // ---- row r of the tableau, eligibility and ratio keys ---------------------------------
-        for (int k = threadIdx.x; k < m; k += blockDim.x) nd.rho[k] = nd.Binv[(size_t)k * nd.ldm + r];
-        __syncthreads();
-        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)k * nd.ldm + r];
+        T.sync();
+        for (int j = T.tid; j < N; j += T.nth) {
             double a;
             if (j < n) {
-                const double* __restrict__ rv = nd.rho;
+                const double* rv = nd.rho;
                 a = sx_dot_entries(P.cent, P.cptr[j], P.cptr[j + 1], [&](int i) { return rv[i]; });
             } else {
                 a = -nd.rho[j - n];
@@ -581,50 +653,50 @@ k_simplex(const SxProb P, const SxBatch Q) {
                               ((st == SX_LOWER && sa > kSxPivTol) || (st == SX_UPPER && sa < -kSxPivTol));
             nd.key[j] = elig ? rint(sx_mul(fabs(nd.d[j]) / fabs(a), kSxRatioBin)) : INFINITY;
         }
-        if (threadIdx.x == 0) { s_slope = infr; s_nflip = 0; s_q = -1; }
-        __syncthreads();
+        if (T.tid == 0) { C.slope = infr; C.nflip = 0; C.q = -1; }
+        T.sync();
         // ---- bound flipping ratio test -------------------------------------------------------
         const double flip_tol = sx_mul(kSxPrimalTol, sx_add(1.0, fabs(xbr)));
         while (true) {
             SxCand c;
             c.key = INFINITY; c.mag = 0.0; c.j = 2147483647;
-            for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            for (int j = T.tid; j < N; j += T.nth) {
                 SxCand t;
                 t.key = nd.key[j]; t.mag = fabs(nd.ar[j]); t.j = j;
                 if (t.key < INFINITY && sx_better(t, c)) c = t;
             }
-            c = sx_block_best(c, cred);
-            if (!(c.key < INFINITY)) break;                  // no candidate left: s_q stays -1
+            c = T.best(c);
+            if (!(c.key < INFINITY)) break;                  // no candidate left: C.q stays -1
             const int j = c.j;
             const double rng = sx_sub(nd.hi[j], nd.lo[j]);
             bool flipped = false;
             if (isfinite(rng)) {
-                const double rest = sx_sub(s_slope, sx_mul(c.mag, rng));
+                const double rest = sx_sub(C.slope, sx_mul(c.mag, rng));
                 if (rest > flip_tol) {
                     flipped = true;
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
-                        s_slope = rest;
-                        s_nflip += 1;
+                    T.sync();
+                    if (T.tid == 0) {
+                        C.slope = rest;
+                        C.nflip += 1;
                         nd.flip[j] = 1;
                         nd.key[j] = INFINITY;
                     }
-                    __syncthreads();
+                    T.sync();
                 }
             }
             if (!flipped) {
-                if (threadIdx.x == 0) s_q = j;
-                __syncthreads();
+                if (T.tid == 0) C.q = j;
+                T.sync();
                 break;
             }
         }
-        __syncthreads();
-        const int q = s_q;
+        T.sync();
+        const int q = C.q;
         if (q < 0) { status = 1; break; }
-        const int nflip = s_nflip;
+        const int nflip = C.nflip;
         if (nflip > 0) {
             // xfull <- bound moves of the flipped columns; col = A delta - delta_slack; x_B -= Binv col
-            for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            for (int j = T.tid; j < N; j += T.nth) {
                 double dl = 0.0;
                 if (nd.flip[j]) {
                     const bool atlo = nd.stat[j] == SX_LOWER;
@@ -634,57 +706,57 @@ k_simplex(const SxProb P, const SxBatch Q) {
                 }
                 nd.xfull[j] = dl;
             }
-            __syncthreads();
-            for (int i = threadIdx.x; i < m; i += blockDim.x) {
-                const double* __restrict__ dv = nd.xfull;
+            T.sync();
+            for (int i = T.tid; i < m; i += T.nth) {
+                const double* dv = nd.xfull;
                 const double acc = sx_dot_entries(P.ent, P.rowptr[i], P.rowptr[i + 1], [&](int j) { return dv[j]; });
                 nd.col[i] = sx_sub(acc, nd.xfull[n + i]);
             }
-            __syncthreads();
-            sx_matvec(nd, nd.col, nd.aq);
-            __syncthreads();
-            for (int i = threadIdx.x; i < m; i += blockDim.x) nd.xB[i] = sx_sub(nd.xB[i], nd.aq[i]);
+            T.sync();
+            sx_matvec(T, nd, nd.col, nd.aq);
+            T.sync();
+            for (int i = T.tid; i < m; i += T.nth) nd.xB[i] = sx_sub(nd.xB[i], nd.aq[i]);
             flips_total += nflip;
-            __syncthreads();
+            T.sync();
         }
         // ---- entering column, step lengths, updates -------------------------------------------
-        sx_ftran_col(P, nd, q, nd.aq);
-        __syncthreads();
+        sx_ftran_col(T, P, nd, q, nd.aq);
+        T.sync();
         const double piv = nd.aq[r];
         const double target = below ? nd.lo[leaving] : nd.hi[leaving];
         const double theta_p = sx_sub(nd.xB[r], target) / piv;
         const double xq_new = sx_add(nd.stat[q] == SX_UPPER ? nd.hi[q] : nd.lo[q], theta_p);
         const double theta_d = nd.d[q] / nd.ar[q];
-        __syncthreads();
-        for (int i = threadIdx.x; i < m; i += blockDim.x)
+        T.sync();
+        for (int i = T.tid; i < m; i += T.nth)
             nd.xB[i] = (i == r) ? xq_new : sx_sub(nd.xB[i], sx_mul(theta_p, nd.aq[i]));
-        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        for (int j = T.tid; j < N; j += T.nth) {
             double dj = sx_sub(nd.d[j], sx_mul(theta_d, nd.ar[j]));
             if (j == leaving) dj = -theta_d;
             if (j == q) dj = 0.0;
             nd.d[j] = dj;
         }
-        for (int k = threadIdx.x; k < m; k += blockDim.x) nd.rho[k] = nd.rho[k] / piv;
-        __syncthreads();
-        sx_update_inverse<true>(nd, nd.aq, nd.rho, r, sx_part);
-        if (threadIdx.x == 0) {
+        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.rho[k] / piv;
+        T.sync();
+        sx_update_inverse<true>(T, nd, nd.aq, nd.rho, r, sx_part);
+        if (T.tid == 0) {
             nd.stat[leaving] = below ? SX_LOWER : SX_UPPER;
             nd.stat[q] = SX_BASIC;
             nd.head[r] = q;
         }
-        __syncthreads();
+        T.sync();
         ++pivots;
         ++since_factor;
     }
 
     // ---- finish: fresh x_B with one refinement step, duals, outputs ----------------------------
-    __syncthreads();
-    sx_primal(P, nd);
-    for (int j = threadIdx.x; j < N; j += blockDim.x) nd.xfull[j] = sx_nonbasic_value(nd, j);
-    __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) nd.xfull[nd.head[i]] = nd.xB[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {     // resid = rhs - B x_B
+    T.sync();
+    sx_primal(T, P, nd);
+    for (int j = T.tid; j < N; j += T.nth) nd.xfull[j] = sx_nonbasic_value(nd, j);
+    T.sync();
+    for (int i = T.tid; i < m; i += T.nth) nd.xfull[nd.head[i]] = nd.xB[i];
+    T.sync();
+    for (int i = T.tid; i < m; i += T.nth) {     // resid = rhs - B x_B
         double res = nd.rhs[i];
         for (int p = P.rowptr[i]; p < P.rowptr[i + 1]; ++p) {
             const Ent e = P.ent[p];
@@ -693,45 +765,78 @@ k_simplex(const SxProb P, const SxBatch Q) {
         if (nd.stat[n + i] == SX_BASIC) res = sx_add(res, nd.xfull[n + i]);
         nd.col[i] = res;
     }
-    __syncthreads();
-    sx_matvec(nd, nd.col, nd.aq);
-    __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    T.sync();
+    sx_matvec(T, nd, nd.col, nd.aq);
+    T.sync();
+    for (int i = T.tid; i < m; i += T.nth) {
         const double v = sx_add(nd.xB[i], nd.aq[i]);
         nd.xB[i] = v;
         nd.xfull[nd.head[i]] = v;
     }
-    __syncthreads();
-    sx_duals(P, nd);
-    if (threadIdx.x == 0) s_status = status;
-    __syncthreads();
+    T.sync();
+    sx_duals(T, P, nd);
+    if (T.tid == 0) C.status = status;
+    T.sync();
     if (status == 0) {
         bool bad = false;
-        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        for (int j = T.tid; j < N; j += T.nth) {
             const int8_t st = nd.stat[j];
             if ((st == SX_UPPER && nd.arthi[j]) || (st == SX_LOWER && nd.artlo[j])) bad = true;
             if (fabs(nd.xfull[j]) >= 0.5 * kSxBig) bad = true;
         }
-        if (bad) s_status = 2;                              // benign race: every writer stores 2
-        __syncthreads();
+        if (bad) C.status = 2;                              // benign race: every writer stores 2
+        T.sync();
     }
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    for (int j = T.tid; j < n; j += T.nth) {
         if (Q.x) Q.x[(size_t)node * n + j] = nd.xfull[j];
         if (Q.rc) Q.rc[(size_t)node * n + j] = nd.d[j];
         if (Q.cstat_out) Q.cstat_out[(size_t)node * n + j] = nd.stat[j];
     }
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    for (int i = T.tid; i < m; i += T.nth) {
         if (Q.y) Q.y[(size_t)node * m + i] = nd.y[i];
         if (Q.rstat_out) Q.rstat_out[(size_t)node * m + i] = nd.stat[n + i];
     }
-    if (threadIdx.x == 0) {
+    if (T.tid == 0) {
         double obj = 0.0;
         for (int j = 0; j < n; ++j) obj = sx_add(obj, sx_mul(P.c[j], nd.xfull[j]));
         if (Q.obj) Q.obj[node] = obj;
-        if (Q.status) Q.status[node] = s_status;
+        if (Q.status) Q.status[node] = C.status;
         if (Q.pivots) Q.pivots[node] = pivots;
         if (Q.flips) Q.flips[node] = flips_total;
     }
+}
+
+// One CTA per node: blockIdx.x = node of the batch.
+__global__ void __launch_bounds__(512, 1)
+k_simplex(const SxProb P, const SxBatch Q) {
+    extern __shared__ double sx_part_smem[];               // [16][m] partial row norms
+    __shared__ SxRed red;
+    __shared__ SxCandRed cred;
+    __shared__ SxCtrl ctrl;
+    SxTeam<false> T;
+    T.tid = threadIdx.x; T.nth = blockDim.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
+    T.nwarps = blockDim.x >> 5;
+    T.red = &red; T.cred = &cred; T.ctrl = &ctrl; T.gd = nullptr; T.gi = nullptr; T.gc = nullptr;
+    sx_solve_node<false>(P, Q, blockIdx.x, T, sx_part_smem);
+}
+
+// The whole GPU on ONE node (cooperative launch, one CTA per SM): LPs of up to kSxMaxRowsWide rows, whose
+// dense inverse (m^2 doubles: 200 MB at m = 5000) is swept by all SMs at once. Same code, same results.
+struct SxWideScratch {
+    double* part;          // [16][m]
+    SxCtrl* ctrl;
+    double* gd; int* gi; SxCand* gc;   // [grid]
+};
+
+__global__ void __launch_bounds__(512, 1)
+k_simplex_wide(const SxProb P, const SxBatch Q, const int node, const SxWideScratch W) {
+    __shared__ SxRed red;
+    __shared__ SxCandRed cred;
+    SxTeam<true> T;
+    T.tid = blockIdx.x * blockDim.x + threadIdx.x; T.nth = gridDim.x * blockDim.x; T.lane = threadIdx.x & 31;
+    T.warp = T.tid >> 5; T.nwarps = T.nth >> 5;
+    T.red = &red; T.cred = &cred; T.ctrl = W.ctrl; T.gd = W.gd; T.gi = W.gi; T.gc = W.gc;
+    sx_solve_node<true>(P, Q, node, T, W.part);
 }
 
 // Rows of the simplex tableau Binv [A, -I] of a node whose factor is in a store (device-side GMI

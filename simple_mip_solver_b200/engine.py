@@ -67,6 +67,7 @@ _SIGNATURES = {
                                           C.c_int, C.POINTER(BlpOpts), _P, _P, _P, _P, _P, _P, _P,
                                           C.POINTER(BlpStats)]),
     'blp_simplex_max_rows': (C.c_int, []),
+    'blp_simplex_batch_rows': (C.c_int, []),
     'blp_simplex_batch_host': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P,
                                          _P, _P, C.POINTER(BlpStats)]),
     'blp_simplex_children_host': (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int,
@@ -320,6 +321,12 @@ class BatchLP:
         """True when the LP (with its appended rows) is small enough for blp_simplex_*."""
         return self.m <= self._lib.blp_simplex_max_rows()
 
+    @property
+    def simplex_batched(self) -> bool:
+        """True when a simplex batch is ONE launch (one CTA per node); beyond blp_simplex_batch_rows()
+        rows the whole GPU works on one node at a time."""
+        return self.m <= self._lib.blp_simplex_batch_rows()
+
     def _simplex_out(self, B, m):
         return dict(obj=np.empty(B), status=np.empty(B, dtype=np.int32), pivots=np.empty(B, dtype=np.int32),
                     x=np.empty((B, self.n)), y=np.empty((B, m)), rc=np.empty((B, self.n)),
@@ -555,6 +562,10 @@ class MultiGpuBatchLP:
     @property
     def simplex_capable(self) -> bool:
         return self.parts[0].simplex_capable
+
+    @property
+    def simplex_batched(self) -> bool:
+        return self.parts[0].simplex_batched
 
     @property
     def uses_nccl(self) -> bool:

@@ -298,11 +298,17 @@ class BaseNode:
                 getattr(self, f'iterations_gmic_{operation}') + (1 if hits else 0))
         setattr(self, f'number_gmic_{operation}', getattr(self, f'number_gmic_{operation}') + hits)
 
-    def _generate_cuts(self: T, gomory_cuts: bool = True, **kwargs) -> Dict[str, Tuple[CyLPArray, float]]:
+    def _generate_cuts(self: T, gomory_cuts: bool = True, max_gomory_cuts: int = None,
+                       **kwargs) -> Dict[str, Tuple[CyLPArray, float]]:
+        """``max_gomory_cuts`` (new; default None = one cut per fractional basic integer variable, as
+        the reference :365-385): only the rows of the most fractional ones — a root with thousands of
+        fractional variables would otherwise spend its time rounding thousands of dense cuts on the host."""
         assert isinstance(gomory_cuts, bool), 'gomory_cuts is boolean'
+        assert max_gomory_cuts is None or (isinstance(max_gomory_cuts, int) and max_gomory_cuts > 0), \
+            'max_gomory_cuts is a positive integer if provided'
         pool = {}
         if gomory_cuts:
-            for row_idx, (pi, pi0) in self._find_gomory_cuts().items():
+            for row_idx, (pi, pi0) in self._find_gomory_cuts(max_rows=max_gomory_cuts).items():
                 name = f'cut_gomory_{self.idx}_{self.cut_generation_iterations}_{row_idx}'
                 pool[name] = numerically_safe_cut(pi=pi, pi0=pi0, estimate='over')
             self._update_gmic_counts(cut_idxs=pool, operation='created')
@@ -355,7 +361,7 @@ class BaseNode:
         self._update_gmic_counts(cut_idxs=added, operation='added')
         return added
 
-    def _find_gomory_cuts(self: T) -> Dict[int, Tuple[CyLPArray, float]]:
+    def _find_gomory_cuts(self: T, max_rows: int = None) -> Dict[int, Tuple[CyLPArray, float]]:
         """Gomory mixed integer cuts from the rows of the LP tableau that belong to fractional
         basic integer variables (reference :468-511; Conforti et al. 5.31), vectorised.
 
@@ -421,6 +427,9 @@ class BaseNode:
             wanted.append((row_idx, f0))
         if not wanted:
             return cuts
+        if max_rows is not None and len(wanted) > max_rows:
+            keep = sorted(wanted, key=lambda t: -min(t[1], 1 - t[1]))[:max_rows]      # most fractional first (stable)
+            wanted = sorted(keep)
         rows = self._tableau_rows([int(basic[r]) for r, _ in wanted])
         if rows is None:
             return cuts

@@ -51,6 +51,7 @@ class OracleBatchLP:
     # -- dual simplex path: the numpy restatement of the device kernel (oracle/dual_simplex.py), with
     #    the engine's two-call factor store emulated so that parent_slot means the same thing
     simplex_capable = True
+    simplex_batched = True
     _store = ()
 
     def _full(self):

@@ -213,3 +213,41 @@ def test_config4_shape_through_the_node_api(blp_lib, tmp_path):
     assert r['bb_dual_bound'] >= gold - 1e-6 * abs(gold)
     assert r['pseudo_costs'] > 1000 and r['lps_solved'] > 2000
     assert r['peak_rss_gb'] < 2.0, r['peak_rss_gb']
+
+
+def test_config4_shape_exact_vertex_and_gomory_round(blp_lib):
+    """SURVEY 8f #1 at the C4 shape (10 000 x 5 000): a single node's LP goes to the wide dual simplex
+    (the whole GPU on one node), so BaseNode gets an exact vertex and basis, GMI cuts are generated from
+    tableau rows computed on the device, appended, and the LP is re-solved from the previous basis."""
+    import time
+    from simple_mip_solver_b200 import BaseNode
+    d = numpy_random_mip(10000, 5000, density=2e-3, seed=2)
+    gold = float(np.load('bench_data/c4_root.npz')['objective'])
+    model = MILPInstance(A=d.A, b=CyLPArray(d.b), c=CyLPArray(d.c), l=CyLPArray(d.l), u=CyLPArray(d.u),
+                         sense=['Min', '>='], integerIndices=d.integer_indices, numVars=d.n)
+    node = BaseNode(model.lp, model.integerIndices, idx=0)
+    t = time.perf_counter()
+    node._bound_lp()
+    t_root = time.perf_counter() - t
+    assert node.lp.has_exact_basis and rel(node.objective_value, gold) <= 1e-9
+    cols, rows = node.lp.getBasisStatus()
+    assert int((cols == 1).sum() + (rows == 1).sum()) == 5000                  # a basis: exactly m basics
+    x = np.asarray(node.solution)
+    assert (d.A @ x >= d.b - 1e-7).all() and (x >= d.l - 1e-9).all() and (x <= d.u + 1e-9).all()
+    frac = np.minimum(x - np.floor(x), np.ceil(x) - x)
+    n_frac = int((frac > 1e-4).sum())
+    assert n_frac <= 5000                                                       # a vertex: at most m fractional
+    before = node.objective_value
+    t = time.perf_counter()
+    node._cut_generation_iteration(max_gomory_cuts=16, track_dual_bound=False)
+    t_round = time.perf_counter() - t
+    assert node.number_gmic_created == 16 and node.number_gmic_added >= 1
+    assert node.lp.nConstraints == 5000 + node.number_gmic_added
+    assert node.objective_value >= before - 1e-9 * abs(before)
+    x2 = np.asarray(node.solution)
+    for name, (pi, pi0) in node.lp._cuts.items():
+        assert float(np.dot(pi, x2)) >= pi0 - 1e-7 * max(1.0, abs(pi0)), name    # the new vertex satisfies the cuts
+        assert float(np.dot(pi, x)) < pi0                                        # ... which cut off the old one
+    print(f'C4 root by the wide dual simplex: {node.lp.iteration if False else ""} {t_root:.2f} s, {n_frac} fractional; one GMI round '
+          f'(16 cuts created, {node.number_gmic_added} added): {t_round:.2f} s, bound {before:.6f} -> {node.objective_value:.6f}')
+    model.lp._shared.close()

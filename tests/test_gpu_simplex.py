@@ -183,10 +183,43 @@ def test_cut_rows_masks_and_tableau(blp_lib):
     lp.close()
 
 
+def test_wide_kernel_is_bit_identical_too(blp_lib):
+    """Above 1024 rows the whole GPU works on one node (k_simplex_wide, cooperative grid): same code
+    path per element, order-independent reductions, so the numpy restatement is matched exactly again —
+    root cold, children from the basis status and from the stored factor."""
+    d = grumpy_random_mip(500, 1100, density=0.02, maxObjCoeff=10, maxConsCoeff=10, tightness=2, rand_seed=7)
+    A = d.A.toarray()
+    lp = engine.BatchLP(d.A, d.b, d.c)
+    assert lp.simplex_capable and not lp.simplex_batched
+    root = lp.simplex_batch(d.l[None], d.u[None])
+    ref_root = dual_simplex(A, d.b, d.c, d.l, d.u)
+    same(root, 0, ref_root, 'wide root')
+    h = HighsLP(d.A, d.c, d.b, np.full(d.m, HIGHS_INF), d.l, d.u).solve()
+    assert abs(root.objective[0] - h.objective) <= 1e-9 * max(1.0, abs(h.objective))
+    deltas = _children(d, ref_root.x, 2)
+    for cached in (False, True):
+        if cached:
+            lp.simplex_batch(d.l[None], d.u[None])
+        res = lp.simplex_children(d.l, d.u, deltas, col_status=root.col_status[0], row_status=root.row_status[0],
+                                  parent_slot=0 if cached else -1, max_pivots=5)
+        for k, dl in enumerate(deltas):
+            l, u = d.l.copy(), d.u.copy()
+            for j, lo, hi in dl:
+                l[j], u[j] = lo, hi
+            ref = dual_simplex(A, d.b, d.c, l, u, col_status=ref_root.col_status, row_status=ref_root.row_status,
+                               max_pivots=5, start=ref_root if cached else None)
+            same(res, k, ref, ('wide child', cached, k))
+    basic = np.flatnonzero(np.concatenate([res.col_status[0], res.row_status[0]]) == 1)[:5]
+    rows = lp.simplex_tableau_rows(0, basic)
+    assert rows.shape == (5, d.n + d.m) and np.isfinite(rows).all()
+    print('wide simplex 500 x 1100: root', int(root.pivots[0]), 'pivots', root.stats['total_ms'], 'ms')
+    lp.close()
+
+
 def test_too_many_rows_is_refused(blp_lib):
     d = grumpy_random_mip(40, 20, density=0.2, rand_seed=2)
-    big = np.vstack([d.A.toarray()] * 60)           # 1200 rows
-    lp = engine.BatchLP(big, np.tile(d.b, 60), d.c)
+    big = np.vstack([d.A.toarray()] * 420)          # 8400 rows
+    lp = engine.BatchLP(big, np.tile(d.b, 420), d.c)
     assert not lp.simplex_capable
     with pytest.raises(engine.BlpError):
         lp.simplex_batch(d.l[None], d.u[None])

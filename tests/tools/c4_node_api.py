@@ -15,10 +15,11 @@ path = sys.argv[1]
 model = MILPInstance(file_name=path)
 out = dict(sparse_model=bool(sp.issparse(model.A)), n=model.numVars, n_int=len(model.integerIndices))
 node = BaseNode(model.lp, model.integerIndices, idx=0)
-node.bound(max_cut_generation_iterations=2)
+node.bound(max_cut_generation_iterations=2, max_gomory_cuts=16)
 out.update(bound_feasible=bool(node.lp_feasible), bound_objective=float(node.objective_value),
            cut_rounds=node.cut_generation_iterations, terminator=node.cut_generation_terminator,
-           rows_in_lp=int(node.lp.nConstraints))
+           rows_in_lp=int(node.lp.nConstraints), gmic_added=node.number_gmic_added,
+           exact_basis=bool(node.lp.has_exact_basis), first_lp_value=float(node.cut_generation_dual_bound.get(0, float('nan'))))
 model.lp._shared.close()
 model = MILPInstance(file_name=path)
 bb = BranchAndBound(model, PseudoCostBranchNode, node_limit=3, pseudo_costs={}, gomory_cuts=False,

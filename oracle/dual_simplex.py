@@ -49,7 +49,8 @@ RATIO_BIN = 2.0 ** 36
 BIG = 1e8
 INF = 1e30
 WEIGHT_LANES = 16            # the kernel sums a row's squares in 16 interleaved partial sums
-REFACTOR_EVERY = 1000
+REFACTOR_EVERY = 1000        # ... or 2 m pivots if that is more (a refactorisation costs about as many pivots as there are basic structurals)
+PIVOT_MISMATCH = 1e-7        # |alpha_q[r] - alpha_r[q]| relative: the inverse has drifted, refactorise before pivoting
 
 
 @dataclass
@@ -224,7 +225,7 @@ def dual_simplex(A, b, c, l, u, row_on=None, col_status=None, row_status=None,
         if pivots >= min(max_pivots, 50 * N + 1000):     # the cap ends a cycling node (no anti-cycling rule)
             status = 3
             break
-        if since_factor >= REFACTOR_EVERY:
+        if since_factor >= max(REFACTOR_EVERY, 2 * m):
             wb = np.zeros(N, bool)
             wb[head] = True
             factor(wb)
@@ -277,6 +278,9 @@ def dual_simplex(A, b, c, l, u, row_on=None, col_status=None, row_status=None,
             flips_total += len(flips)
         aq = A[:, q] if q < n else -np.eye(m)[:, q - n]
         alpha_q = _matvec_cols(Binv, aq)
+        if since_factor > 0 and abs(alpha_q[r] - alpha_r[q]) > PIVOT_MISMATCH * (1.0 + abs(alpha_r[q])):
+            since_factor = max(REFACTOR_EVERY, 2 * m)       # the two ways to the pivot element disagree
+            continue
         target = lo[head[r]] if below else hi[head[r]]
         theta_p = (xB[r] - target) / alpha_q[r]
         xB = xB - theta_p * alpha_q

@@ -610,7 +610,7 @@ def _solve_group(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_o
             sh.register_cut(lp._cut_keys[nm], pi, pi0)
     sh.sync_cuts()
     if sh.use_simplex(len(batch)):
-        _solve_group_simplex(sh, batch, budget)
+        _solve_group_simplex(sh, batch, budget, default_opts)
     else:
         _solve_group_pdhg(sh, batch, budget, default_opts)
     for lp in batch:
@@ -636,9 +636,23 @@ def _child_deltas(batch: List[CyClpSimplex]):
     return pl, pu, deltas
 
 
-def _solve_group_simplex(sh: SharedLP, batch: List[CyClpSimplex], budget: int):
+def _solve_group_simplex(sh: SharedLP, batch: List[CyClpSimplex], budget: int, default_opts=None):
     """One batched dual simplex call: vertex, duals, reduced costs and the optimal basis per node LP."""
     eng = sh.engine
+    if not getattr(eng, 'simplex_batched', True) and default_opts is not None and budget >= 2147483647:
+        # Mid-size LP (the whole GPU per node), no basis to start from: CROSSOVER. A cold dual simplex needs
+        # tens of thousands of pivots here (41 116 at the C4 root); the first-order solve finds the optimal
+        # face in a second or two, its active set is the starting status (repaired where it is not a
+        # basis, made dual feasible by bound flips) and the dual simplex only cleans up.
+        cold = [lp for lp in batch if lp._basis_out is None and lp._basis_start is None]
+        if cold:
+            _solve_group_pdhg(sh, cold, budget, default_opts)
+            m0 = sh.m
+            for lp in cold:
+                if lp._status == 0 and lp._x is not None:
+                    cols, rows = lp.getBasisStatus()
+                    lp._basis_start = (cols.astype(np.int8), rows[:m0].astype(np.int8),
+                                       {nm: int(rows[m0 + t]) for t, nm in enumerate(lp._cuts)})
     B, n, m, mc = len(batch), sh.n, sh.m, len(sh.cut_names)
     use_cache = bool(batch[0].solver_opts.get('factor_cache', False)) and not hasattr(eng, 'parts')
     same_cuts = all(lp._cut_keys == batch[0]._cut_keys for lp in batch)

@@ -1432,10 +1432,7 @@ int sx_run(blp_handle h, int B, const SxStage& S, bool use_parent, int max_pivot
     CK(cudaEventRecord(h->ev[2], st));
     if (m <= kSxMaxRows) {
         const int threads = m <= 128 ? 128 : 512;
-        const size_t smem = (size_t)kSxWeightLanes * m * sizeof(double);
-        if (smem > 48 * 1024)
-            CK(cudaFuncSetAttribute(k_simplex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_simplex<<<B, threads, smem, st>>>(P, Q);
+        k_simplex<<<B, threads, 0, st>>>(P, Q);
     } else {
         // the whole GPU on one node at a time: cooperative grid, one CTA per SM
         if (!h->coop_ok) return fail(BLP_ERR_STATE, "blp_simplex: LPs of more than %d rows need cooperative launches", kSxMaxRows);
@@ -1443,12 +1440,10 @@ int sx_run(blp_handle h, int B, const SxStage& S, bool use_parent, int max_pivot
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_wide, 512, 0));
         if (occ < 1) return fail(BLP_ERR_STATE, "blp_simplex: k_simplex_wide does not fit an SM");
         const int grid = h->num_sms;
-        const size_t need = (size_t)kSxWeightLanes * m * sizeof(double) + 256 + sizeof(SxCtrl) + 256 +
-                            (size_t)grid * (sizeof(double) + sizeof(int) + sizeof(SxCand)) + 1024;
+        const size_t need = sizeof(SxCtrl) + 256 + (size_t)grid * (sizeof(double) + sizeof(int) + sizeof(SxCand)) + 1024;
         CK(h->sx_wide.ensure(need));
         Carve cv{h->sx_wide.as<char>()};
         SxWideScratch W;
-        W.part = cv.take<double>((size_t)kSxWeightLanes * m);
         W.ctrl = cv.take<SxCtrl>(1);
         W.gd = cv.take<double>(grid);
         W.gi = cv.take<int>(grid);

@@ -8,7 +8,8 @@
 // launch: blockIdx.x = node, the CTA's threads share the node's O(m^2) work.
 //
 // LP of a node:  min c.x,  A x - s = b,  l <= x <= u,  s >= 0  (s free where the row is masked off).
-// State per node in global memory (L2 resident): Binv (m x m, column major, leading dimension ldm),
+// State per node in global memory: Binv (m x m, ROW major, leading dimension ldm: a warp streams a whole
+// row of it in the update sweep, and the row the ratio test needs is one contiguous read),
 // x_B, reduced costs d, basis head, status, DSE weights. Pivoting rules, tolerances and the ORDER OF
 // EVERY FLOATING-POINT OPERATION are those of oracle/dual_simplex.py (the numpy restatement the tests
 // compare against pivot for pivot): single rounded operations only (__dmul_rn/__dadd_rn, no FMA
@@ -29,7 +30,8 @@ constexpr int SX_BASIC = 1, SX_UPPER = 2, SX_LOWER = 3;
 constexpr double kSxPrimalTol = 1e-9, kSxDualTol = 1e-9, kSxPivTol = 1e-9, kSxTieRel = 1e-12;
 constexpr double kSxRatioBin = 68719476736.0;      // 2^36
 constexpr double kSxBig = 1e8;
-constexpr int kSxRefactorEvery = 1000;
+constexpr int kSxRefactorEvery = 1000;     // ... or 2 m pivots if that is more
+constexpr double kSxPivotMismatch = 1e-7; // |alpha_q[r] - alpha_r[q]| relative: refactorise before pivoting
 
 struct SxProb {
     int m, m_base, n, ldm;
@@ -213,7 +215,7 @@ struct SxTeam {
 // ---- the node's view ---------------------------------------------------------------------------
 struct SxNode {
     int m, n, N, ldm;
-    double* Binv;        // [m][ldm] column major: (i, k) at k * ldm + i
+    double* Binv;        // [m][ldm] row major: (i, k) at i * ldm + k
     int32_t* head;       // [m]
     int8_t* stat;        // [N]
     double* w;           // [m] DSE weights
@@ -223,7 +225,6 @@ struct SxNode {
     int8_t *artlo, *arthi, *want, *flip; // [N]
 };
 
-__device__ __forceinline__ double sx_binv(const SxNode& nd, int i, int k) { return nd.Binv[(size_t)k * nd.ldm + i]; }
 
 // Ordered sparse dot  sum_p val[p] * vec(idx[p])  over the CSR/CSC entries [p0, p1): the sum runs in
 // entry order with single rounded operations (oracle order), but the loads of 8 entries and of the 8
@@ -266,7 +267,7 @@ __device__ __forceinline__ void sx_matvec(const Team& T, const SxNode& nd, const
             for (int u = 0; u < kSxDotBatch; ++u) {
                 const int k = k0 + u;
                 vk[u] = k < nd.m ? v[k] : 0.0;
-                bv[u] = (k < nd.m && vk[u] != 0.0) ? nd.Binv[(size_t)k * nd.ldm + i] : 0.0;
+                bv[u] = (k < nd.m && vk[u] != 0.0) ? nd.Binv[(size_t)i * nd.ldm + k] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < kSxDotBatch; ++u)
@@ -282,90 +283,98 @@ __device__ __forceinline__ void sx_ftran_col(const Team& T, const SxProb& P, con
     if (j < nd.n) {
         const int p0 = P.cptr[j], p1 = P.cptr[j + 1];
         for (int i = T.tid; i < nd.m; i += T.nth) {
-            const double* Bi = nd.Binv + i;
-            const size_t ldm = nd.ldm;
-            out[i] = sx_dot_entries(P.cent, p0, p1, [&](int k) { return Bi[(size_t)k * ldm]; });
+            const double* Bi = nd.Binv + (size_t)i * nd.ldm;
+            out[i] = sx_dot_entries(P.cent, p0, p1, [&](int k) { return Bi[k]; });
         }
     } else {
         const int k = j - nd.n;
         for (int i = T.tid; i < nd.m; i += T.nth)
-            out[i] = sx_add(0.0, sx_mul(nd.Binv[(size_t)k * nd.ldm + i], -1.0));
+            out[i] = sx_add(0.0, sx_mul(nd.Binv[(size_t)i * nd.ldm + k], -1.0));
     }
+}
+
+// Ordered row norm while a warp walks row i of Binv 32 columns at a time: the oracle sums the squares of
+// the columns k = g, g + 16, g + 32, ... (ascending) into partial sum g, then adds the 16 partial sums in
+// order. In a chunk of 32 consecutive columns lane g < 16 holds column 32t + g and lane g + 16 holds column
+// 32t + g + 16, i.e. the next term of the same partial sum: lane g adds its own square, then the one its
+// partner hands over. sq = -1 marks a column beyond m (no term).
+__device__ __forceinline__ void sx_norm_step(double& acc, const double sq, const int lane) {
+    const double other = __shfl_down_sync(0xffffffffu, sq, 16);
+    if (lane < 16) {
+        if (sq >= 0.0) acc = sx_add(acc, sq);
+        if (other >= 0.0) acc = sx_add(acc, other);
+    }
+}
+__device__ __forceinline__ double sx_norm_finish(const double acc) {
+    double w = 0.0;
+#pragma unroll
+    for (int g = 0; g < kSxWeightLanes; ++g) w = sx_add(w, __shfl_sync(0xffffffffu, acc, g));
+    return w;
 }
 
 // Binv <- E Binv for a basis change in row position r; rowr[k] = old Binv(r,k) / pivot must be ready.
-// With WEIGHTS the row norms are rebuilt in the same sweep: warp group g sums the squares of the
-// columns k = g, g + 16, ... in ascending order into part[g][i]; w_i = sum_g part[g][i], g ascending.
+// A warp owns a row: Binv(i,k) <- Binv(i,k) - alpha_i rowr[k] (row r <- rowr), streamed 32 columns per
+// trip, 8 trips of loads issued before the first store (the compiler cannot prove that a store to Binv
+// does not alias the next load). With WEIGHTS the row norm is rebuilt in the same sweep.
 template <bool WEIGHTS, class Team>
 __device__ __forceinline__ void sx_update_inverse(const Team& T, const SxNode& nd, const double* alpha,
-                                                  const double* rowr, const int r, double* part) {
-    const int lane = T.lane;
-    const int m = nd.m, nchunk = (m + 31) / 32;
-    // The loads of a batch of kSxBatchK columns are issued before the first store: the compiler cannot
-    // prove that a store to Binv does not alias the next load, and one L2 round trip per element
-    // (~190 dependent ones per warp at m = 300) was 70 of the 86 us a pivot took. The order of the
-    // arithmetic (ascending k) is unchanged.
-    constexpr int kSxBatchK = 8;
-    // work item = (column group g, chunk of 32 rows); a CTA team gives warp w the items of group w
-    for (int item = T.warp; item < kSxWeightLanes * nchunk; item += T.nwarps) {
-        const int g = item % kSxWeightLanes, i = (item / kSxWeightLanes) * 32 + lane;
-        if (i < m) {
-            const double ai = alpha[i];
-            double acc = 0.0;
-            for (int k0 = g; k0 < m; k0 += kSxWeightLanes * kSxBatchK) {
-                double v[kSxBatchK];
+                                                  const double* rowr, const int r) {
+    constexpr int kTrips = 8;
+    const int lane = T.lane, m = nd.m;
+    for (int i = T.warp; i < m; i += T.nwarps) {
+        double* row = nd.Binv + (size_t)i * nd.ldm;
+        const double ai = alpha[i];
+        double acc = 0.0;
+        for (int k0 = 0; k0 < m; k0 += 32 * kTrips) {
+            double v[kTrips], rk[kTrips];
 #pragma unroll
-                for (int u = 0; u < kSxBatchK; ++u) {
-                    const int k = k0 + u * kSxWeightLanes;
-                    v[u] = (k < m) ? nd.Binv[(size_t)k * nd.ldm + i] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < kSxBatchK; ++u) {
-                    const int k = k0 + u * kSxWeightLanes;
-                    if (k < m) {
-                        const double rk = rowr[k];
-                        const double nv = (i == r) ? rk : sx_sub(v[u], sx_mul(ai, rk));
-                        nd.Binv[(size_t)k * nd.ldm + i] = nv;
-                        if (WEIGHTS) acc = sx_add(acc, sx_mul(nv, nv));
-                    }
-                }
+            for (int u = 0; u < kTrips; ++u) {
+                const int k = k0 + 32 * u + lane;
+                v[u] = (k < m) ? row[k] : 0.0;
+                rk[u] = (k < m) ? rowr[k] : 0.0;
             }
-            if (WEIGHTS) part[g * m + i] = acc;
+#pragma unroll
+            for (int u = 0; u < kTrips; ++u) {
+                const int k = k0 + 32 * u + lane;
+                double sq = -1.0;
+                if (k < m) {
+                    const double nv = (i == r) ? rk[u] : sx_sub(v[u], sx_mul(ai, rk[u]));
+                    row[k] = nv;
+                    sq = sx_mul(nv, nv);
+                }
+                if (WEIGHTS && k0 + 32 * u < m) sx_norm_step(acc, sq, lane);
+            }
+        }
+        if (WEIGHTS) {
+            const double w = sx_norm_finish(acc);
+            if (lane == 0) nd.w[i] = w;
         }
     }
     T.sync();
-    if (WEIGHTS) {
-        for (int i = T.tid; i < m; i += T.nth) {
-            double wsum = 0.0;
-#pragma unroll
-            for (int g = 0; g < kSxWeightLanes; ++g) wsum = sx_add(wsum, part[g * m + i]);
-            nd.w[i] = wsum;
-        }
-        T.sync();
-    }
 }
 
 template <class Team>
-__device__ __forceinline__ void sx_weights(const Team& T, const SxNode& nd, double* part) {
-    const int lane = T.lane;
-    const int m = nd.m, nchunk = (m + 31) / 32;
-    for (int item = T.warp; item < kSxWeightLanes * nchunk; item += T.nwarps) {
-        const int g = item % kSxWeightLanes, i = (item / kSxWeightLanes) * 32 + lane;
-        if (i < m) {
-            double acc = 0.0;
-            for (int k = g; k < m; k += kSxWeightLanes) {
-                const double v = nd.Binv[(size_t)k * nd.ldm + i];
-                acc = sx_add(acc, sx_mul(v, v));
-            }
-            part[g * m + i] = acc;
-        }
-    }
-    T.sync();
-    for (int i = T.tid; i < m; i += T.nth) {
-        double wsum = 0.0;
+__device__ __forceinline__ void sx_weights(const Team& T, const SxNode& nd) {
+    constexpr int kTrips = 8;
+    const int lane = T.lane, m = nd.m;
+    for (int i = T.warp; i < m; i += T.nwarps) {
+        const double* row = nd.Binv + (size_t)i * nd.ldm;
+        double acc = 0.0;
+        for (int k0 = 0; k0 < m; k0 += 32 * kTrips) {
+            double v[kTrips];
 #pragma unroll
-        for (int g = 0; g < kSxWeightLanes; ++g) wsum = sx_add(wsum, part[g * m + i]);
-        nd.w[i] = wsum;
+            for (int u = 0; u < kTrips; ++u) {
+                const int k = k0 + 32 * u + lane;
+                v[u] = (k < m) ? row[k] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kTrips; ++u) {
+                const int k = k0 + 32 * u + lane;
+                if (k0 + 32 * u < m) sx_norm_step(acc, (k < m) ? sx_mul(v[u], v[u]) : -1.0, lane);
+            }
+        }
+        const double w = sx_norm_finish(acc);
+        if (lane == 0) nd.w[i] = w;
     }
     T.sync();
 }
@@ -376,7 +385,7 @@ template <class Team>
 __device__ void sx_factor(const Team& T, const SxProb& P, const SxNode& nd) {
     const int m = nd.m, n = nd.n, N = nd.N;
     for (size_t e = T.tid; e < (size_t)m * nd.ldm; e += T.nth) {
-        const int k = (int)(e / nd.ldm), i = (int)(e % nd.ldm);
+        const int i = (int)(e / nd.ldm), k = (int)(e % nd.ldm);
         nd.Binv[e] = (i == k) ? -1.0 : 0.0;
     }
     for (int i = T.tid; i < m; i += T.nth) nd.head[i] = n + i;
@@ -406,9 +415,9 @@ __device__ void sx_factor(const Team& T, const SxProb& P, const SxNode& nd) {
         r = T.min_int(r);
         if (r == 2147483647) continue;
         const double piv = nd.aq[r];
-        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)k * nd.ldm + r] / piv;
+        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)r * nd.ldm + k] / piv;
         T.sync();
-        sx_update_inverse<false>(T, nd, nd.aq, nd.rho, r, nullptr);
+        sx_update_inverse<false>(T, nd, nd.aq, nd.rho, r);
         if (T.tid == 0) {
             const int s = nd.head[r];
             const int keep = (int)nd.key[s];
@@ -437,14 +446,15 @@ __device__ void sx_duals(const Team& T, const SxProb& P, const SxNode& nd) {
     T.sync();
     for (int k = T.tid; k < m; k += T.nth) {
         double acc = 0.0;
-        const double* colk = nd.Binv + (size_t)k * nd.ldm;
+        const double* colk = nd.Binv + k;                     // element (p, k) at p * ldm + k: coalesced over k
+        const size_t ldm = nd.ldm;
         for (int p0 = 0; p0 < m; p0 += kSxDotBatch) {
             double cb[kSxDotBatch], bv[kSxDotBatch];
 #pragma unroll
             for (int u = 0; u < kSxDotBatch; ++u) {
                 const int p = p0 + u;
                 cb[u] = p < m ? nd.col[p] : 0.0;
-                bv[u] = (p < m && cb[u] != 0.0) ? colk[p] : 0.0;
+                bv[u] = (p < m && cb[u] != 0.0) ? colk[(size_t)p * ldm] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < kSxDotBatch; ++u)
@@ -500,10 +510,9 @@ __device__ void sx_make_dual_feasible(const Team& T, const SxNode& nd) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The dual simplex of one node, run by a team (see SxTeam). sx_part: [16][m] partial row norms.
+// The dual simplex of one node, run by a team (see SxTeam).
 template <bool WIDE>
-__device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node, const SxTeam<WIDE>& T,
-                              double* sx_part) {
+__device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node, const SxTeam<WIDE>& T) {
     SxCtrl& C = *T.ctrl;
     const int m = P.m, n = P.n, N = n + m;
     SxNode nd;
@@ -586,11 +595,12 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
     sx_duals(T, P, nd);
     sx_make_dual_feasible(T, nd);
     sx_primal(T, P, nd);
-    if (!use_parent) sx_weights(T, nd, sx_part);
+    if (!use_parent) sx_weights(T, nd);
 
     int pivots = 0, flips_total = 0, since_factor = 0, status = 0;
     // no anti-cycling rule: a hard cap far above any pivot count seen ends a cycling node with status 3
     const int pivot_cap = min(Q.max_pivots, 50 * N + 1000);
+    const int refactor_every = max(kSxRefactorEvery, 2 * m);
     while (true) {
         // ---- leaving row: dual steepest edge ---------------------------------------------------
         double sc[2] = {-1.0, -1.0};
@@ -610,13 +620,13 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
         const double best = T.max(local);
         if (best < 0.0) { status = 0; break; }
         if (pivots >= pivot_cap) { status = 3; break; }
-        if (since_factor >= kSxRefactorEvery) {
+        if (since_factor >= refactor_every) {
             for (int j = T.tid; j < N; j += T.nth) nd.want[j] = nd.stat[j] == SX_BASIC;
             T.sync();
             sx_factor(T, P, nd);
             sx_duals(T, P, nd);
             sx_primal(T, P, nd);
-            sx_weights(T, nd, sx_part);
+            sx_weights(T, nd);
             since_factor = 0;
             continue;
         }
@@ -636,7 +646,7 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
         const bool below = xbr < nd.lo[leaving];
         const double infr = fmax(sx_sub(nd.lo[leaving], xbr), sx_sub(xbr, nd.hi[leaving]));
         // ---- row r of the tableau, eligibility and ratio keys ---------------------------------
-        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)k * nd.ldm + r];
+        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)r * nd.ldm + k];
         T.sync();
         for (int j = T.tid; j < N; j += T.nth) {
             double a;
@@ -723,6 +733,11 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
         sx_ftran_col(T, P, nd, q, nd.aq);
         T.sync();
         const double piv = nd.aq[r];
+        if (since_factor > 0 && fabs(sx_sub(piv, nd.ar[q])) > sx_mul(kSxPivotMismatch, sx_add(1.0, fabs(nd.ar[q])))) {
+            since_factor = refactor_every;                // the two ways to the pivot element disagree
+            T.sync();
+            continue;
+        }
         const double target = below ? nd.lo[leaving] : nd.hi[leaving];
         const double theta_p = sx_sub(nd.xB[r], target) / piv;
         const double xq_new = sx_add(nd.stat[q] == SX_UPPER ? nd.hi[q] : nd.lo[q], theta_p);
@@ -738,7 +753,7 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
         }
         for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.rho[k] / piv;
         T.sync();
-        sx_update_inverse<true>(T, nd, nd.aq, nd.rho, r, sx_part);
+        sx_update_inverse<true>(T, nd, nd.aq, nd.rho, r);
         if (T.tid == 0) {
             nd.stat[leaving] = below ? SX_LOWER : SX_UPPER;
             nd.stat[q] = SX_BASIC;
@@ -809,7 +824,6 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
 // One CTA per node: blockIdx.x = node of the batch.
 __global__ void __launch_bounds__(512, 1)
 k_simplex(const SxProb P, const SxBatch Q) {
-    extern __shared__ double sx_part_smem[];               // [16][m] partial row norms
     __shared__ SxRed red;
     __shared__ SxCandRed cred;
     __shared__ SxCtrl ctrl;
@@ -817,13 +831,12 @@ k_simplex(const SxProb P, const SxBatch Q) {
     T.tid = threadIdx.x; T.nth = blockDim.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
     T.nwarps = blockDim.x >> 5;
     T.red = &red; T.cred = &cred; T.ctrl = &ctrl; T.gd = nullptr; T.gi = nullptr; T.gc = nullptr;
-    sx_solve_node<false>(P, Q, blockIdx.x, T, sx_part_smem);
+    sx_solve_node<false>(P, Q, blockIdx.x, T);
 }
 
 // The whole GPU on ONE node (cooperative launch, one CTA per SM): LPs of up to kSxMaxRowsWide rows, whose
 // dense inverse (m^2 doubles: 200 MB at m = 5000) is swept by all SMs at once. Same code, same results.
 struct SxWideScratch {
-    double* part;          // [16][m]
     SxCtrl* ctrl;
     double* gd; int* gi; SxCand* gc;   // [grid]
 };
@@ -836,7 +849,7 @@ k_simplex_wide(const SxProb P, const SxBatch Q, const int node, const SxWideScra
     T.tid = blockIdx.x * blockDim.x + threadIdx.x; T.nth = gridDim.x * blockDim.x; T.lane = threadIdx.x & 31;
     T.warp = T.tid >> 5; T.nwarps = T.nth >> 5;
     T.red = &red; T.cred = &cred; T.ctrl = W.ctrl; T.gd = W.gd; T.gi = W.gi; T.gc = W.gc;
-    sx_solve_node<true>(P, Q, node, T, W.part);
+    sx_solve_node<true>(P, Q, node, T);
 }
 
 // Rows of the simplex tableau Binv [A, -I] of a node whose factor is in a store (device-side GMI
@@ -862,12 +875,12 @@ __global__ void k_simplex_tableau_rows(const SxProb P, const double* __restrict_
                 double acc = 0.0;
                 for (int p = P.cptr[j]; p < P.cptr[j + 1]; ++p) {
                     const Ent e = P.cent[p];
-                    const double ri = Binv[(size_t)e.idx * P.ldm + r];
+                    const double ri = Binv[(size_t)r * P.ldm + e.idx];
                     if (ri != 0.0) acc = sx_add(acc, sx_mul(ri, e.val));
                 }
                 a = acc;
             } else {
-                a = -Binv[(size_t)(j - n) * P.ldm + r];
+                a = -Binv[(size_t)r * P.ldm + (j - n)];
             }
         }
         o[j] = a;

@@ -1440,16 +1440,11 @@ int sx_run(blp_handle h, int B, const SxStage& S, bool use_parent, int max_pivot
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_simplex_wide, 512, 0));
         if (occ < 1) return fail(BLP_ERR_STATE, "blp_simplex: k_simplex_wide does not fit an SM");
         const int grid = h->num_sms;
-        const size_t need = sizeof(SxCtrl) + 256 + (size_t)grid * (sizeof(double) + sizeof(int) + sizeof(SxCand)) + 1024;
-        CK(h->sx_wide.ensure(need));
-        Carve cv{h->sx_wide.as<char>()};
-        SxWideScratch W;
-        W.ctrl = cv.take<SxCtrl>(1);
-        W.gd = cv.take<double>(grid);
-        W.gi = cv.take<int>(grid);
-        W.gc = cv.take<SxCand>(grid);
+        CK(h->sx_wide.ensure(256));
+        unsigned* counter = h->sx_wide.as<unsigned>();
         for (int node = 0; node < B; ++node) {
-            void* args[] = {(void*)&P, (void*)&Q, (void*)&node, (void*)&W};
+            CK(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));      // the grid barrier's arrival counter
+            void* args[] = {(void*)&P, (void*)&Q, (void*)&node, (void*)&counter};
             CK(cudaLaunchCooperativeKernel((const void*)k_simplex_wide, dim3(grid), dim3(512), args, 0, st));
         }
     }

@@ -152,10 +152,14 @@ __device__ __forceinline__ SxCand sx_block_best(SxCand c, SxCandRed& s) {
 
 
 // ---- the team that works on ONE node: a CTA (k_simplex) or the whole cooperative grid (k_simplex_wide) ----
-// Loops run over team threads, barriers and reductions are team wide. Reductions are max / min /
-// lexicographic min, i.e. order independent, so both teams compute bit-identical results.
-struct SxCtrl {            // scalars one thread decides and everybody reads after a team barrier
-    int r, q, nflip, status, par_ok, nlist;
+// Array work (the O(m^2) sweep, row / column dots, vector updates) is split over the team's threads and
+// followed by a team barrier. DECISIONS (pricing, ratio test, pivot row of a factorisation step) are
+// taken by every CTA for itself from the shared arrays: the reductions are max / min / lexicographic min
+// over all m or n+m elements — cheap, order independent, so every CTA reaches the same decision and the
+// scalars live in its own shared memory; no cross-CTA reduction, no barrier per decision. A grid team
+// therefore needs 5 barriers per pivot (8 with bound flips) and both teams compute bit-identical results.
+struct SxCtrl {            // per-CTA scalars: one thread decides, the CTA reads them after __syncthreads
+    int r, q, nflip, status, par_ok;
     double slope;
 };
 
@@ -164,52 +168,30 @@ struct SxTeam {
     int tid, nth, lane, warp, nwarps;
     SxRed* red;            // shared memory of this CTA
     SxCandRed* cred;
-    SxCtrl* ctrl;          // shared (CTA team) or global (grid team)
-    double* gd;            // grid team: one slot per CTA for the partial results of a reduction
-    int* gi;
-    SxCand* gc;
+    SxCtrl* ctrl;
+    unsigned* bar;         // grid team: arrival counter of the barrier (zeroed before the launch)
+    unsigned* gen;         // ... and this CTA's barrier generation (shared memory)
 
+    // Barrier over the team. Grid team: every CTA arrives once per generation on a global counter; thread 0
+    // spins until all have (the cooperative launch guarantees co-residency). The gpu-scope fences order
+    // the CTA's earlier global writes before the arrival and drop its stale L1 lines after it.
     __device__ __forceinline__ void sync() const {
-        if (WIDE) cooperative_groups::this_grid().sync();
-        else __syncthreads();
-    }
-    __device__ __forceinline__ double max(double v) const {
-        v = sx_block_max(v, *red);
-        if (!WIDE) return v;
-        if (threadIdx.x == 0) gd[blockIdx.x] = v;
-        sync();
-        double t = -INFINITY;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t = fmax(t, gd[b]);
-        t = sx_block_max(t, *red);
-        sync();                                            // gd may be reused by the next reduction
-        return t;
-    }
-    __device__ __forceinline__ int min_int(int v) const {
-        v = sx_block_min_int(v, *red);
-        if (!WIDE) return v;
-        if (threadIdx.x == 0) gi[blockIdx.x] = v;
-        sync();
-        int t = 2147483647;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) t = min(t, gi[b]);
-        t = sx_block_min_int(t, *red);
-        sync();
-        return t;
-    }
-    __device__ __forceinline__ SxCand best(SxCand c) const {
-        c = sx_block_best(c, *cred);
-        if (!WIDE) return c;
-        if (threadIdx.x == 0) gc[blockIdx.x] = c;
-        sync();
-        SxCand t;
-        t.key = INFINITY; t.mag = 0.0; t.j = 2147483647;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-            const SxCand o = gc[b];
-            if (sx_better(o, t)) t = o;
+        if (!WIDE) { __syncthreads(); return; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned target = (*gen + 1u) * gridDim.x;
+            __threadfence();
+            atomicAdd(bar, 1u);
+            while (*reinterpret_cast<volatile unsigned*>(bar) < target) __nanosleep(32);
+            __threadfence();
+            *gen += 1u;
         }
-        t = sx_block_best(t, *cred);
-        sync();
-        return t;
+        __syncthreads();
     }
+    // CTA-local reductions over values every CTA computes for ALL elements
+    __device__ __forceinline__ double max(double v) const { return sx_block_max(v, *red); }
+    __device__ __forceinline__ int min_int(int v) const { return sx_block_min_int(v, *red); }
+    __device__ __forceinline__ SxCand best(SxCand c) const { return sx_block_best(c, *cred); }
 };
 
 // ---- the node's view ---------------------------------------------------------------------------
@@ -400,28 +382,29 @@ __device__ void sx_factor(const Team& T, const SxProb& P, const SxNode& nd) {
         if (!nd.want[j]) continue;                          // uniform: same data for every thread
         sx_ftran_col(T, P, nd, j, nd.aq);
         T.sync();
+        // pivot row: every CTA for itself, over all rows
         double best = kSxPivTol;
-        for (int i = T.tid; i < m; i += T.nth) {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
             const int hv = nd.head[i];
             if (hv >= n && !nd.want[hv]) best = fmax(best, fabs(nd.aq[i]));
         }
         best = T.max(best);
         int r = 2147483647;
         if (best > kSxPivTol)
-            for (int i = T.tid; i < m; i += T.nth) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
                 const int hv = nd.head[i];
                 if (hv >= n && !nd.want[hv] && fabs(nd.aq[i]) == best) r = min(r, i);
             }
         r = T.min_int(r);
         if (r == 2147483647) continue;
         const double piv = nd.aq[r];
+        const int s_old = nd.head[r];
+        const int keep = (int)nd.key[s_old];
         for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)r * nd.ldm + k] / piv;
-        T.sync();
-        sx_update_inverse<false>(T, nd, nd.aq, nd.rho, r);
+        T.sync();                                           // rho staged, everybody has read head[r] / key
+        sx_update_inverse<false>(T, nd, nd.aq, nd.rho, r);  // ends with a team barrier
         if (T.tid == 0) {
-            const int s = nd.head[r];
-            const int keep = (int)nd.key[s];
-            nd.stat[s] = keep != SX_BASIC ? (int8_t)keep : (int8_t)SX_LOWER;
+            nd.stat[s_old] = keep != SX_BASIC ? (int8_t)keep : (int8_t)SX_LOWER;
             nd.head[r] = j;
             nd.stat[j] = SX_BASIC;
         }
@@ -536,8 +519,14 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
     const uint8_t* onk = Q.rowon ? Q.rowon + (size_t)node * mc : nullptr;
     const int par = Q.parent ? Q.parent[node] : -1;
     const bool from_status = Q.cstat_in != nullptr && Q.rstat_in != nullptr;
-    if (T.tid == 0) C.par_ok = 1;
-    T.sync();
+    // can the parent's factor be continued? Only if every row that is masked off here has its slack
+    // basic there (every CTA checks all pool rows for itself)
+    if (threadIdx.x == 0) C.par_ok = 1;
+    __syncthreads();
+    if (par >= 0 && onk)
+        for (int i = threadIdx.x; i < mc; i += blockDim.x)
+            if (onk[i] == 0 && Q.pstat[(size_t)par * N + n + P.m_base + i] != SX_BASIC) C.par_ok = 0;
+    __syncthreads();
 
     // ---- bounds, starting status ------------------------------------------------------------
     for (int j = T.tid; j < N; j += T.nth) {
@@ -559,7 +548,6 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
         if (par >= 0) {
             st = Q.pstat[(size_t)par * N + j];
             want = st == SX_BASIC || !on;
-            if (!on && st != SX_BASIC) C.par_ok = 0;     // the parent's factor has this slack nonbasic
         } else if (from_status) {
             if (j < n) {
                 const int8_t cs = Q.cstat_in[(size_t)node * n + j];
@@ -601,26 +589,21 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
     // no anti-cycling rule: a hard cap far above any pivot count seen ends a cycling node with status 3
     const int pivot_cap = min(Q.max_pivots, 50 * N + 1000);
     const int refactor_every = max(kSxRefactorEvery, 2 * m);
+    auto score_of = [&](const int i) {
+        const int hv = nd.head[i];
+        const double xb = nd.xB[i];
+        const double inf = fmax(sx_sub(nd.lo[hv], xb), sx_sub(xb, nd.hi[hv]));
+        return inf > sx_mul(kSxPrimalTol, sx_add(1.0, fabs(xb))) ? sx_mul(inf, inf) / nd.w[i] : -1.0;
+    };
     while (true) {
-        // ---- leaving row: dual steepest edge ---------------------------------------------------
-        double sc[2] = {-1.0, -1.0};
+        // ---- leaving row: dual steepest edge; every CTA decides for itself over all rows -----------
         double local = -1.0;
-        {
-            int t = 0;
-            for (int i = T.tid; i < m; i += T.nth, ++t) {
-                const int hv = nd.head[i];
-                const double xb = nd.xB[i];
-                const double inf = fmax(sx_sub(nd.lo[hv], xb), sx_sub(xb, nd.hi[hv]));
-                double s = -1.0;
-                if (inf > sx_mul(kSxPrimalTol, sx_add(1.0, fabs(xb)))) s = sx_mul(inf, inf) / nd.w[i];
-                sc[t] = s;
-                local = fmax(local, s);
-            }
-        }
+        for (int i = threadIdx.x; i < m; i += blockDim.x) local = fmax(local, score_of(i));
         const double best = T.max(local);
         if (best < 0.0) { status = 0; break; }
         if (pivots >= pivot_cap) { status = 3; break; }
         if (since_factor >= refactor_every) {
+            T.sync();                                      // nobody still reads the state being rebuilt
             for (int j = T.tid; j < N; j += T.nth) nd.want[j] = nd.stat[j] == SX_BASIC;
             T.sync();
             sx_factor(T, P, nd);
@@ -632,48 +615,47 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
         }
         {
             const double thr = sx_mul(best, sx_sub(1.0, kSxTieRel));
-            int hmin = 2147483647, t = 0;
-            for (int i = T.tid; i < m; i += T.nth, ++t)
-                if (sc[t] >= thr) hmin = min(hmin, nd.head[i]);
+            int hmin = 2147483647;
+            for (int i = threadIdx.x; i < m; i += blockDim.x)
+                if (score_of(i) >= thr) hmin = min(hmin, nd.head[i]);
             hmin = T.min_int(hmin);
-            for (int i = T.tid; i < m; i += T.nth)
+            for (int i = threadIdx.x; i < m; i += blockDim.x)
                 if (nd.head[i] == hmin) C.r = i;
-            T.sync();
+            __syncthreads();
         }
         const int r = C.r;
         const int leaving = nd.head[r];
         const double xbr = nd.xB[r];
         const bool below = xbr < nd.lo[leaving];
         const double infr = fmax(sx_sub(nd.lo[leaving], xbr), sx_sub(xbr, nd.hi[leaving]));
-        // ---- row r of the tableau, eligibility and ratio keys ---------------------------------
-        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)r * nd.ldm + k];
-        T.sync();
-        for (int j = T.tid; j < N; j += T.nth) {
-            double a;
-            if (j < n) {
-                const double* rv = nd.rho;
-                a = sx_dot_entries(P.cent, P.cptr[j], P.cptr[j + 1], [&](int i) { return rv[i]; });
-            } else {
-                a = -nd.rho[j - n];
+        // ---- row r of the tableau, eligibility and ratio keys (split over the team) ----------------
+        {
+            const double* rv = nd.Binv + (size_t)r * nd.ldm;      // row r of Binv, read in place
+            for (int j = T.tid; j < N; j += T.nth) {
+                double a;
+                if (j < n) a = sx_dot_entries(P.cent, P.cptr[j], P.cptr[j + 1], [&](int i) { return rv[i]; });
+                else a = -rv[j - n];
+                nd.ar[j] = a;
+                const int8_t st = nd.stat[j];
+                const double sa = below ? -a : a;
+                const bool elig = st != SX_BASIC && nd.lo[j] < nd.hi[j] &&
+                                  ((st == SX_LOWER && sa > kSxPivTol) || (st == SX_UPPER && sa < -kSxPivTol));
+                nd.key[j] = elig ? rint(sx_mul(fabs(nd.d[j]) / fabs(a), kSxRatioBin)) : INFINITY;
             }
-            nd.ar[j] = a;
-            const int8_t st = nd.stat[j];
-            const double sa = below ? -a : a;
-            const bool elig = st != SX_BASIC && nd.lo[j] < nd.hi[j] &&
-                              ((st == SX_LOWER && sa > kSxPivTol) || (st == SX_UPPER && sa < -kSxPivTol));
-            nd.key[j] = elig ? rint(sx_mul(fabs(nd.d[j]) / fabs(a), kSxRatioBin)) : INFINITY;
         }
-        if (T.tid == 0) { C.slope = infr; C.nflip = 0; C.q = -1; }
-        T.sync();
-        // ---- bound flipping ratio test -------------------------------------------------------
+        if (threadIdx.x == 0) { C.slope = infr; C.nflip = 0; C.q = -1; }
+        T.sync();                                          // barrier 1: ar, key complete
+        // ---- bound flipping ratio test: every CTA walks the candidates in order for itself ----------
         const double flip_tol = sx_mul(kSxPrimalTol, sx_add(1.0, fabs(xbr)));
+        SxCand prev;
+        prev.key = -1.0; prev.mag = INFINITY; prev.j = -1;  // before every candidate (keys are >= 0)
         while (true) {
             SxCand c;
             c.key = INFINITY; c.mag = 0.0; c.j = 2147483647;
-            for (int j = T.tid; j < N; j += T.nth) {
+            for (int j = threadIdx.x; j < N; j += blockDim.x) {
                 SxCand t;
                 t.key = nd.key[j]; t.mag = fabs(nd.ar[j]); t.j = j;
-                if (t.key < INFINITY && sx_better(t, c)) c = t;
+                if (t.key < INFINITY && sx_better(prev, t) && sx_better(t, c)) c = t;
             }
             c = T.best(c);
             if (!(c.key < INFINITY)) break;                  // no candidate left: C.q stays -1
@@ -684,27 +666,27 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
                 const double rest = sx_sub(C.slope, sx_mul(c.mag, rng));
                 if (rest > flip_tol) {
                     flipped = true;
-                    T.sync();
-                    if (T.tid == 0) {
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
                         C.slope = rest;
                         C.nflip += 1;
-                        nd.flip[j] = 1;
-                        nd.key[j] = INFINITY;
+                        nd.flip[j] = 1;                  // every CTA sets the same marks
                     }
-                    T.sync();
+                    __syncthreads();
+                    prev = c;
                 }
             }
             if (!flipped) {
-                if (T.tid == 0) C.q = j;
-                T.sync();
+                if (threadIdx.x == 0) C.q = j;
                 break;
             }
         }
-        T.sync();
+        __syncthreads();
         const int q = C.q;
         if (q < 0) { status = 1; break; }
         const int nflip = C.nflip;
         if (nflip > 0) {
+            T.sync();                                      // every CTA has set its marks before they are cleared
             // xfull <- bound moves of the flipped columns; col = A delta - delta_slack; x_B -= Binv col
             for (int j = T.tid; j < N; j += T.nth) {
                 double dl = 0.0;
@@ -723,26 +705,23 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
                 nd.col[i] = sx_sub(acc, nd.xfull[n + i]);
             }
             T.sync();
-            sx_matvec(T, nd, nd.col, nd.aq);
-            T.sync();
+            sx_matvec(T, nd, nd.col, nd.aq);               // thread i writes aq[i] and is the one to use it
             for (int i = T.tid; i < m; i += T.nth) nd.xB[i] = sx_sub(nd.xB[i], nd.aq[i]);
             flips_total += nflip;
-            T.sync();
         }
-        // ---- entering column, step lengths, updates -------------------------------------------
+        // ---- entering column, step lengths, updates -----------------------------------------------
         sx_ftran_col(T, P, nd, q, nd.aq);
-        T.sync();
+        T.sync();                                          // barrier 2: alpha_q (and the flipped x_B) complete
         const double piv = nd.aq[r];
         if (since_factor > 0 && fabs(sx_sub(piv, nd.ar[q])) > sx_mul(kSxPivotMismatch, sx_add(1.0, fabs(nd.ar[q])))) {
             since_factor = refactor_every;                // the two ways to the pivot element disagree
-            T.sync();
             continue;
         }
         const double target = below ? nd.lo[leaving] : nd.hi[leaving];
         const double theta_p = sx_sub(nd.xB[r], target) / piv;
         const double xq_new = sx_add(nd.stat[q] == SX_UPPER ? nd.hi[q] : nd.lo[q], theta_p);
         const double theta_d = nd.d[q] / nd.ar[q];
-        T.sync();
+        T.sync();                                          // barrier 3: everybody has read the old x_B, d
         for (int i = T.tid; i < m; i += T.nth)
             nd.xB[i] = (i == r) ? xq_new : sx_sub(nd.xB[i], sx_mul(theta_p, nd.aq[i]));
         for (int j = T.tid; j < N; j += T.nth) {
@@ -751,15 +730,15 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
             if (j == q) dj = 0.0;
             nd.d[j] = dj;
         }
-        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.rho[k] / piv;
-        T.sync();
-        sx_update_inverse<true>(T, nd, nd.aq, nd.rho, r);
-        if (T.tid == 0) {
+        for (int k = T.tid; k < m; k += T.nth) nd.rho[k] = nd.Binv[(size_t)r * nd.ldm + k] / piv;
+        T.sync();                                          // barrier 4: scaled pivot row staged
+        sx_update_inverse<true>(T, nd, nd.aq, nd.rho, r);  // ends with barrier 5
+        if (threadIdx.x == 0) {                            // every CTA writes the same three values
             nd.stat[leaving] = below ? SX_LOWER : SX_UPPER;
             nd.stat[q] = SX_BASIC;
             nd.head[r] = q;
         }
-        T.sync();
+        __syncthreads();
         ++pivots;
         ++since_factor;
     }
@@ -790,17 +769,17 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
     }
     T.sync();
     sx_duals(T, P, nd);
-    if (T.tid == 0) C.status = status;
-    T.sync();
-    if (status == 0) {
+    if (threadIdx.x == 0) C.status = status;
+    __syncthreads();
+    if (status == 0) {                                     // every CTA scans all variables for itself
         bool bad = false;
-        for (int j = T.tid; j < N; j += T.nth) {
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
             const int8_t st = nd.stat[j];
             if ((st == SX_UPPER && nd.arthi[j]) || (st == SX_LOWER && nd.artlo[j])) bad = true;
             if (fabs(nd.xfull[j]) >= 0.5 * kSxBig) bad = true;
         }
         if (bad) C.status = 2;                              // benign race: every writer stores 2
-        T.sync();
+        __syncthreads();
     }
     for (int j = T.tid; j < n; j += T.nth) {
         if (Q.x) Q.x[(size_t)node * n + j] = nd.xfull[j];
@@ -830,25 +809,24 @@ k_simplex(const SxProb P, const SxBatch Q) {
     SxTeam<false> T;
     T.tid = threadIdx.x; T.nth = blockDim.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
     T.nwarps = blockDim.x >> 5;
-    T.red = &red; T.cred = &cred; T.ctrl = &ctrl; T.gd = nullptr; T.gi = nullptr; T.gc = nullptr;
+    T.red = &red; T.cred = &cred; T.ctrl = &ctrl; T.bar = nullptr; T.gen = nullptr;
     sx_solve_node<false>(P, Q, blockIdx.x, T);
 }
 
 // The whole GPU on ONE node (cooperative launch, one CTA per SM): LPs of up to kSxMaxRowsWide rows, whose
 // dense inverse (m^2 doubles: 200 MB at m = 5000) is swept by all SMs at once. Same code, same results.
-struct SxWideScratch {
-    SxCtrl* ctrl;
-    double* gd; int* gi; SxCand* gc;   // [grid]
-};
-
 __global__ void __launch_bounds__(512, 1)
-k_simplex_wide(const SxProb P, const SxBatch Q, const int node, const SxWideScratch W) {
+k_simplex_wide(const SxProb P, const SxBatch Q, const int node, unsigned* const barrier_counter) {
     __shared__ SxRed red;
     __shared__ SxCandRed cred;
+    __shared__ SxCtrl ctrl;
+    __shared__ unsigned gen;
+    if (threadIdx.x == 0) gen = 0u;
+    __syncthreads();
     SxTeam<true> T;
     T.tid = blockIdx.x * blockDim.x + threadIdx.x; T.nth = gridDim.x * blockDim.x; T.lane = threadIdx.x & 31;
     T.warp = T.tid >> 5; T.nwarps = T.nth >> 5;
-    T.red = &red; T.cred = &cred; T.ctrl = W.ctrl; T.gd = W.gd; T.gi = W.gi; T.gc = W.gc;
+    T.red = &red; T.cred = &cred; T.ctrl = &ctrl; T.bar = barrier_counter; T.gen = &gen;
     sx_solve_node<true>(P, Q, node, T);
 }
 

@@ -384,6 +384,8 @@ int prepare(blp_handle h) {
     P.sc = sc;
     P.objscale = 1.0 / (sb * sc);
     P.bnorm0 = norm2(b0_base);
+    P.bcut2 = 0.0;
+    for (int i = mb; i < m; ++i) P.bcut2 += h->b0[i] * h->b0[i];
     P.cnorm0 = norm2(h->c0);
     P.cinf_s = cinf;
     P.omega0 = ((nb > 1e-12 && nc > 1e-12) ? nc / nb : 1.0) * env_dbl("BLP_OMEGA0_SCALE", 1.0);

@@ -68,6 +68,7 @@ struct DevProb {
     const double* rowscale; const double* colscale;   // scaled residual -> unscaled
     const double* dr; const double* dc;
     double eta, sb, sc, objscale, bnorm0, cnorm0, cinf_s, omega0;
+    double bcut2;          // sum of squares of the (unscaled) right-hand sides of ALL appended rows
 };
 
 struct DevState {
@@ -1047,7 +1048,21 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
     const double fpe = sqrt(fmax(c[C_DX2] / tau + r[R_DY2] / sig + 2.0 * c[C_CROSS], 0.0));
     const double pobj = c[C_CX] * P.objscale;
     const double dobj = (r[R_BY] + c[C_BND]) * P.objscale;
-    const double rp = sqrt(r[R_PRES2]) / (1.0 + P.bnorm0);
+    // the primal tolerance is relative to ||b|| over the rows of THIS node's LP: the base rows plus the
+    // appended rows its mask switches on — not over rows that only other nodes hold
+    double bn2 = P.bnorm0 * P.bnorm0;
+    if (P.m > P.m_base) {
+        if (S.rowmask) {
+            for (int i = P.m_base; i < P.m; ++i)
+                if (S.rowmask[(size_t)(i - P.m_base) * S.ld + node]) {
+                    const double b0 = P.b[i] * P.rowscale[i];
+                    bn2 = fma(b0, b0, bn2);
+                }
+        } else {
+            bn2 += P.bcut2;
+        }
+    }
+    const double rp = sqrt(r[R_PRES2]) / (1.0 + sqrt(bn2));
     const double rd = sqrt(c[C_DRES2]) / (1.0 + P.cnorm0);
     const double rg = fabs(pobj - dobj) / (1.0 + fabs(pobj) + fabs(dobj));
     S.pobj[node] = pobj;

@@ -211,7 +211,6 @@ struct blp_handle_s {
     std::vector<int32_t> hptrA, hptrAT; // host copies of the row pointers of A and A' (slab sizing)
     std::vector<double> c0, b0;
     std::vector<double> dr, dc;
-    std::vector<double> dr_base, dc_base;   // scaling of the base problem (computed once)
     // device copies
     DevBuf rowptr, ent, cptr, cent, c, b, rowscale, colscale, d_dr, d_dc;
     DevBuf uent, ucent;                // unscaled entries, same patterns (blp_spmv)
@@ -301,31 +300,20 @@ int nccl_fail(const NcclApi* a, const char* what, int rc) {
 int prepare(blp_handle h) {
     const int m = h->A0.rows, n = h->n, mb = h->m_base;
     HostCsr As = h->A0;
-    // The scaling of the BASE rows, the column scaling and the scalar scalings of b and c are a
-    // function of the base problem only, computed once: appended cut rows are then equilibrated
-    // against that fixed column scaling. A node's step size ratio, termination tolerance
-    // (relative to ||b_base||) and warm start therefore do not depend on the cuts other nodes hold.
-    if ((int)h->dr_base.size() != mb) {
-        HostCsr Ab = h->A0;
-        Ab.rows = mb;
-        Ab.ptr.resize(mb + 1);
-        Ab.idx.resize(Ab.ptr.back());
-        Ab.val.resize(Ab.ptr.back());
-        h->dr_base.assign(mb, 1.0);
-        h->dc_base.assign(n, 1.0);
-        ruiz_pc(Ab, h->dr_base, h->dc_base, 10, 0);
-    }
+    // Diagonal scaling over ALL rows currently in the matrix (base + appended cut rows). It only
+    // conditions the iteration: residuals, tolerances and certificates are evaluated in the unscaled
+    // problem, and the tolerance scale ||b|| is taken per node over the rows of ITS LP (k_decide), so what
+    // a node is held to does not depend on cuts only other nodes carry. (Equilibrating appended rows
+    // against a column scaling frozen at the base problem was measured: config 4's cut rounds needed
+    // 14-33 % more iterations, profiles/r2g_configs_3_4.json — dense cut rows want their say in dc.)
     h->dr.assign(m, 1.0);
-    h->dc = h->dc_base;
-    std::copy(h->dr_base.begin(), h->dr_base.end(), h->dr.begin());
-    for (int i = 0; i < m; ++i)
-        for (int32_t p = As.ptr[i]; p < As.ptr[i + 1]; ++p) As.val[p] *= h->dr[i] * h->dc[As.idx[p]];
-    if (m > mb) ruiz_pc(As, h->dr, h->dc, 10, mb);
+    h->dc.assign(n, 1.0);
+    ruiz_pc(As, h->dr, h->dc, 10, 0);
     std::vector<double> bs(m), cs(n), rowscale(m), colscale(n);
     for (int i = 0; i < m; ++i) bs[i] = h->b0[i] * h->dr[i];
     for (int j = 0; j < n; ++j) cs[j] = h->c0[j] * h->dc[j];
-    const std::vector<double> bs_base(bs.begin(), bs.begin() + mb), b0_base(h->b0.begin(), h->b0.begin() + mb);
-    const double sb = 1.0 / (norm2(bs_base) + 1.0), sc = 1.0 / (norm2(cs) + 1.0);
+    const std::vector<double> b0_base(h->b0.begin(), h->b0.begin() + mb);
+    const double sb = 1.0 / (norm2(bs) + 1.0), sc = 1.0 / (norm2(cs) + 1.0);
     double cinf = 0.0;
     for (int i = 0; i < m; ++i) bs[i] *= sb;
     for (int j = 0; j < n; ++j) {
@@ -339,7 +327,7 @@ int prepare(blp_handle h) {
     const double eta = 0.998 / sigma_max(As, At);
     h->hptrA = As.ptr;
     h->hptrAT = At.ptr;
-    const double nb = norm2(bs_base) * sb, nc = norm2(cs);
+    const double nb = norm2(bs), nc = norm2(cs);
 
     cudaStream_t s = h->stream;
     auto pack = [](const HostCsr& a) {

@@ -182,23 +182,30 @@ class BaseNode:
         return rtn
 
     def _good_cut_generation_dual_bound_dict(self, d) -> Tuple[bool, Union[str, None]]:
-        if not isinstance(d, dict):
-            return False, 'cut_generation_dual_bound_dict should be a dictionary'
-        for idx, per_round in d.items():
-            if not isinstance(idx, int):
-                return False, f'index {idx} should be integer'
-            if idx == self.idx:
-                return False, f'index {idx} has already been processed'
-            if not isinstance(per_round, dict):
-                return False, f'index {idx} should have dictionary value'
-            for cut_idx, value in per_round.items():
-                if not isinstance(cut_idx, int):
-                    return False, f'cut index {cut_idx} for node {idx} should be integer'
-                if not isinstance(value, (int, float)):
-                    return False, f'dual bound for node {idx} cut index {cut_idx} should be a number'
-            if set(per_round) != set(range(max(per_round) + 1)):
-                return False, f'index {idx} should have dictionary keyed by range of ints'
-        return True, None
+        """(ok, message) for a ``{node idx: {cut round: dual bound}}`` record travelling on the kwargs
+        bus. The messages are part of the reference's API contract (its tests match on them,
+        test_base_node.py:176-313); the checks are written as a first-failure search."""
+        def first_problem():
+            if not isinstance(d, dict):
+                yield 'cut_generation_dual_bound_dict should be a dictionary'
+                return
+            for idx, rounds in d.items():
+                problems = (
+                    (not isinstance(idx, int), f'index {idx} should be integer'),
+                    (idx == self.idx, f'index {idx} has already been processed'),
+                    (not isinstance(rounds, dict), f'index {idx} should have dictionary value'),
+                )
+                yield from (msg for bad, msg in problems if bad)
+                if not isinstance(rounds, dict):
+                    continue
+                yield from (f'cut index {k} for node {idx} should be integer'
+                            for k in rounds if not isinstance(k, int))
+                yield from (f'dual bound for node {idx} cut index {k} should be a number'
+                            for k, v in rounds.items() if not isinstance(v, (int, float)))
+                if sorted(rounds) != list(range(len(rounds))):          # rounds 0, 1, ..., no gaps
+                    yield f'index {idx} should have dictionary keyed by range of ints'
+        msg = next(first_problem(), None)
+        return msg is None, msg
 
     def _bound_lp(self: T, track_dual_bound: bool = False) -> None:
         """Solve this node's LP relaxation and record status, objective, solution and the

@@ -153,3 +153,25 @@ def test_cut_pool_is_garbage_collected_and_cut_names_are_content_keyed(monkeypat
         assert lp.objectiveValue == -min(3.5, float(k % 3) + min(10.0, 0.5 + k))
         assert len(sh.cut_names) <= 6
     assert sh.pool_rebuilds >= 2
+
+
+def test_cut_generation_dual_bound_dict_messages(monkeypatch):
+    """Message strings of the kwargs-bus validation (the reference's tests match on them,
+    test_base_node.py:176-313)."""
+    from helpers import use_oracle_engine
+    from simple_mip_solver_b200 import BaseNode, CyLPArray, MILPInstance
+    use_oracle_engine(monkeypatch)
+    m = MILPInstance(A=np.array([[-1.0, -1.0]]), b=CyLPArray([-3.5]), c=CyLPArray([-1.0, -1.0]),
+                     l=CyLPArray([0, 0]), u=CyLPArray([10, 10]), sense=['Min', '>='], integerIndices=[0, 1], numVars=2)
+    node = BaseNode(m.lp, m.integerIndices, idx=4)
+    good = node._good_cut_generation_dual_bound_dict
+    assert good({1: {0: -3.0, 1: -2.5}, 2: {0: 1}}) == (True, None)
+    assert good([]) == (False, 'cut_generation_dual_bound_dict should be a dictionary')
+    assert good({'a': {0: 1.0}}) == (False, 'index a should be integer')
+    assert good({4: {0: 1.0}}) == (False, 'index 4 has already been processed')
+    assert good({1: [1.0]}) == (False, 'index 1 should have dictionary value')
+    assert good({1: {'x': 1.0}}) == (False, 'cut index x for node 1 should be integer')
+    assert good({1: {0: 'v'}}) == (False, 'dual bound for node 1 cut index 0 should be a number')
+    assert good({1: {0: 1.0, 2: 2.0}}) == (False, 'index 1 should have dictionary keyed by range of ints')
+    with pytest.raises(AssertionError, match='index 4 has already been processed'):
+        node._base_bound(cut_generation_dual_bound_dict={4: {0: 1.0}})

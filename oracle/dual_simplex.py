@@ -119,6 +119,7 @@ def dual_simplex(A, b, c, l, u, row_on=None, col_status=None, row_status=None,
     cost = np.concatenate([np.asarray(c, dtype=float), np.zeros(m)])
     art_lo = np.zeros(N, bool)
     art_hi = np.zeros(N, bool)
+    art_done = np.zeros(N, bool)
     stat = np.full(N, AT_LOWER, dtype=np.int32)
     want_basic = np.zeros(N, bool)
     if col_status is None or row_status is None:
@@ -220,6 +221,18 @@ def dual_simplex(A, b, c, l, u, row_on=None, col_status=None, row_status=None,
         infeas = np.maximum(lo[head] - xB, xB - hi[head])
         cand = infeas > PRIMAL_TOL * (1.0 + np.abs(xB))
         if not cand.any():
+            # optimal for the bounded problem. A nonbasic variable resting on an ARTIFICIAL bound with a zero
+            # reduced cost does not make the LP unbounded (the objective does not care where it sits): move
+            # it to its real bound once and let the dual simplex repair what that breaks.
+            back = np.flatnonzero((stat != BASIC) & (np.abs(d) <= DUAL_TOL) & ~art_done &
+                                  (((stat == AT_UPPER) & art_hi & np.isfinite(lo)) |
+                                   ((stat == AT_LOWER) & art_lo & np.isfinite(hi))))
+            if len(back):
+                for j in back:
+                    stat[j] = AT_LOWER if stat[j] == AT_UPPER else AT_UPPER
+                    art_done[j] = True
+                xB, _ = primal()
+                continue
             status = 0
             break
         if pivots >= min(max_pivots, 50 * N + 1000):     # the cap ends a cycling node (no anti-cycling rule)

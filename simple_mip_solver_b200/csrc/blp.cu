@@ -1403,7 +1403,7 @@ int sx_run(blp_handle h, int B, const SxStage& S, bool use_parent, int max_pivot
     CK(h->sx_head[cur].ensure((size_t)B * m * sizeof(int32_t)));
     CK(h->sx_stat[cur].ensure((size_t)B * N));
     CK(h->sx_wts[cur].ensure((size_t)B * m * sizeof(double)));
-    const size_t stride = (size_t)6 * N + 6 * m + (4 * (size_t)N + 7) / 8 + 2;
+    const size_t stride = (size_t)6 * N + 6 * m + (5 * (size_t)N + 7) / 8 + 2;
     CK(h->sx_work.ensure((size_t)B * stride * sizeof(double)));
     SxProb P{m, h->m_base, n, ldm, h->P.rowptr, h->uent.as<Ent>(), h->P.cptr, h->ucent.as<Ent>(),
              h->uc.as<double>(), h->ub.as<double>()};

@@ -204,7 +204,7 @@ struct SxNode {
     double *lo, *hi, *d, *ar, *key;      // [N]
     double *xB, *rho, *aq, *col, *y, *rhs;   // [m]
     double* xfull;       // [N]
-    int8_t *artlo, *arthi, *want, *flip; // [N]
+    int8_t *artlo, *arthi, *want, *flip, *artdone; // [N]
 };
 
 
@@ -511,7 +511,7 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
         nd.xB = wk; wk += m; nd.rho = wk; wk += m; nd.aq = wk; wk += m; nd.col = wk; wk += m;
         nd.y = wk; wk += m; nd.rhs = wk; wk += m;
         int8_t* fl = reinterpret_cast<int8_t*>(wk);
-        nd.artlo = fl; nd.arthi = fl + N; nd.want = fl + 2 * N; nd.flip = fl + 3 * N;
+        nd.artlo = fl; nd.arthi = fl + N; nd.want = fl + 2 * N; nd.flip = fl + 3 * N; nd.artdone = fl + 4 * N;
     }
     const double* lbk = Q.lb + (size_t)node * n;
     const double* ubk = Q.ub + (size_t)node * n;
@@ -543,7 +543,7 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
             hi = INFINITY;
         }
         nd.lo[j] = lo; nd.hi[j] = hi;
-        nd.artlo[j] = 0; nd.arthi[j] = 0; nd.flip[j] = 0;
+        nd.artlo[j] = 0; nd.arthi[j] = 0; nd.flip[j] = 0; nd.artdone[j] = 0;
         int8_t st = SX_LOWER, want = 0;
         if (par >= 0) {
             st = Q.pstat[(size_t)par * N + j];
@@ -600,7 +600,30 @@ __device__ void sx_solve_node(const SxProb& P, const SxBatch& Q, const int node,
         double local = -1.0;
         for (int i = threadIdx.x; i < m; i += blockDim.x) local = fmax(local, score_of(i));
         const double best = T.max(local);
-        if (best < 0.0) { status = 0; break; }
+        if (best < 0.0) {
+            // optimal for the bounded problem. A nonbasic variable resting on an ARTIFICIAL bound with a
+            // zero reduced cost does not make the LP unbounded: move it to its real bound once and let
+            // the dual simplex repair what that breaks (every CTA scans all variables for itself)
+            auto goes_back = [&](const int j) {
+                const int8_t st = nd.stat[j];
+                return st != SX_BASIC && fabs(nd.d[j]) <= kSxDualTol && !nd.artdone[j] &&
+                       ((st == SX_UPPER && nd.arthi[j] && isfinite(nd.lo[j])) ||
+                        (st == SX_LOWER && nd.artlo[j] && isfinite(nd.hi[j])));
+            };
+            double any = -1.0;
+            for (int j = threadIdx.x; j < N; j += blockDim.x)
+                if (goes_back(j)) any = 1.0;
+            if (T.max(any) < 0.0) { status = 0; break; }
+            T.sync();                                      // everybody has scanned before anything moves
+            for (int j = T.tid; j < N; j += T.nth)
+                if (goes_back(j)) {
+                    nd.stat[j] = nd.stat[j] == SX_UPPER ? SX_LOWER : SX_UPPER;
+                    nd.artdone[j] = 1;
+                }
+            T.sync();
+            sx_primal(T, P, nd);
+            continue;
+        }
         if (pivots >= pivot_cap) { status = 3; break; }
         if (since_factor >= refactor_every) {
             T.sync();                                      // nobody still reads the state being rebuilt

@@ -224,3 +224,27 @@ def test_too_many_rows_is_refused(blp_lib):
     with pytest.raises(engine.BlpError):
         lp.simplex_batch(d.l[None], d.u[None])
     lp.close()
+
+
+def test_random_lps_bit_exact_and_against_highs(blp_lib):
+    """400 random small LPs (infeasible, unbounded through infinite bounds, degenerate, fixed variables):
+    the device's status, basis, pivot count and vertex equal the numpy restatement's exactly; status and
+    value equal HiGHS's."""
+    from test_oracle_pins import _random_lp
+    rng = np.random.default_rng(2024)
+    seen = {0: 0, 1: 0, 2: 0}
+    for t in range(400):
+        A, b, c, l, u = _random_lp(rng)
+        if not A.any():
+            continue
+        lp = engine.BatchLP(A, b, c)
+        res = lp.simplex_batch(l[None], np.minimum(u, 1e300)[None])
+        ref = dual_simplex(A, b, c, l, u)
+        same(res, 0, ref, t)
+        seen[ref.status] = seen.get(ref.status, 0) + 1
+        h = HighsLP(A, c, b, np.full(len(b), HIGHS_INF), l, u).solve()
+        assert ref.status == h.status or (h.status in (2, -1) and ref.status in (1, 2)), t
+        if ref.status == 0:
+            assert abs(res.objective[0] - h.objective) <= 1e-7 * max(1, abs(h.objective)), t
+        lp.close()
+    assert min(seen.values()) > 20

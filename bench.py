@@ -599,6 +599,9 @@ def main():
                       'pdhg_iterations_per_step': agg['iters'] / max(args.steps, 1),
                       'refills_per_step': agg['refills'] / max(args.steps, 1),
                       'mean_iterations_per_node': agg['node_iters'] / max(agg['solved'] + agg['unsolved'], 1),
+                      # how full the resident slots were over the timed steps: 1 - this is the tail of a step (slots
+                      # idle once nothing is pending and the slowest nodes finish), rank 0
+                      'slot_utilisation': agg['node_iters'] / max(agg['iters'] * W, 1),
                       'iterations_p50_p90_max': [float(np.percentile(np.concatenate(iters_all), q)) for q in (50, 90, 100)]},
         }
         print(json.dumps(line), flush=True)

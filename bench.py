@@ -421,7 +421,7 @@ def main():
     # ---- device-resident arm ----
     iters_all = []
     agg = dict(launches=0, solved=0, unsolved=0, infeasible=0, node_iters=0.0, iters=0,
-               primal_ms=0.0, dual_ms=0.0, step_ms=0.0, total_ms=0.0, refills=0)
+               primal_ms=0.0, dual_ms=0.0, step_ms=0.0, total_ms=0.0, refills=0, skipped_cols=0.0, skipped_rows=0.0)
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for s in range(total_steps):
@@ -451,6 +451,8 @@ def main():
             agg['step_ms'] += sdict['step_kernel_ms']
             agg['total_ms'] += sdict['total_ms']
             agg['refills'] += sdict['refills']
+            agg['skipped_cols'] += sdict['skipped_col_updates']
+            agg['skipped_rows'] += sdict['skipped_row_updates']
         log(f'[rank {rank}] step {s} iters {r["stats"]["iterations"]} total_ms {r["stats"]["total_ms"]:.0f}')
         del lb, ub
     ev1.record(ext)
@@ -539,13 +541,15 @@ def main():
         bytes_AT = 12 * d.A.nnz + 4 * (n + 1)
         # iteration pair over the TIMED steps (CUDA events around each period's step graph)
         it_timed = max(agg['iters'], 1)
-        pair_bytes = ((pb + db) * agg['node_iters'] + (bytes_A + bytes_AT) * it_timed) / it_timed
+        # coordinates the kernels skipped because they were frozen (blp_opts.freeze) cost no stream bytes
+        pair_bytes = ((pb + db) * agg['node_iters'] - 20 * (agg['skipped_cols'] + agg['skipped_rows'])
+                      + (bytes_A + bytes_AT) * it_timed) / it_timed
         pair_s = agg['step_ms'] * 1e-3 / it_timed
         pair_gbs = pair_bytes / pair_s / 1e9
         # per-kernel split from the profile step (same slice as the last timed step)
         it_prof = max(prof['iterations'], 1)
-        primal_bytes = (pb * prof['node_iterations'] + bytes_AT * it_prof) / it_prof
-        dual_bytes = (db * prof['node_iterations'] + bytes_A * it_prof) / it_prof
+        primal_bytes = (pb * prof['node_iterations'] - 20 * prof['skipped_col_updates'] + bytes_AT * it_prof) / it_prof
+        dual_bytes = (db * prof['node_iterations'] - 20 * prof['skipped_row_updates'] + bytes_A * it_prof) / it_prof
         primal_s = prof['primal_kernel_ms'] * 1e-3 / it_prof
         dual_s = prof['dual_kernel_ms'] * 1e-3 / it_prof
         prim_gbs = primal_bytes / primal_s / 1e9 if primal_s > 0 else 0.0
@@ -582,7 +586,8 @@ def main():
                          'peak_source': peak_src, 'bytes_per_launch': pair_bytes,
                          'ms_per_launch': pair_s * 1e3,
                          'measured': 'CUDA events around every period graph (64 iterations) of the timed steps; '
-                                     'bytes = 28(n+m) per running node and iteration + both matrices (bounds kept as block reference + mask, fp32 anchors)',
+                                     'bytes = 28(n+m) per running node and iteration, less 20 per coordinate update skipped as frozen, '
+                                     '+ both matrices (bounds kept as block reference + mask, fp32 anchors)',
                          'k_primal': {'achieved': prim_gbs, 'frac': prim_gbs / peak, 'bytes_per_launch': primal_bytes,
                                       'ms_per_launch': primal_s * 1e3},
                          'k_dual': {'achieved': dual_gbs, 'frac': dual_gbs / peak, 'bytes_per_launch': dual_bytes,
@@ -602,6 +607,9 @@ def main():
                       # how full the resident slots were over the timed steps: 1 - this is the tail of a step (slots
                       # idle once nothing is pending and the slowest nodes finish), rank 0
                       'slot_utilisation': agg['node_iters'] / max(agg['iters'] * W, 1),
+                      # share of the (column, node, iteration) / (row, node, iteration) updates skipped as frozen
+                      'frozen_col_share': agg['skipped_cols'] / max(agg['node_iters'] * n, 1),
+                      'frozen_row_share': agg['skipped_rows'] / max(agg['node_iters'] * m, 1),
                       'iterations_p50_p90_max': [float(np.percentile(np.concatenate(iters_all), q)) for q in (50, 90, 100)]},
         }
         print(json.dumps(line), flush=True)

@@ -70,6 +70,13 @@ typedef struct blp_opts {
                               (branch_and_bound.py:251, 261): with the incumbent's value as the cutoff the
                               search tree is the same, only the node's LP value is a bound instead of the
                               optimum, which is why this is opt-in. default +inf (off) */
+    int freeze;            /* 1: wide batches skip the update of coordinates that rest — a column on a bound with a
+                              reduced cost of the right sign, a row with zero multiplier and slack — for every node
+                              of a 64-node tile. The last iteration of every evaluation period updates everything
+                              and the KKT test is always the full problem's, so a status never depends on the
+                              frozen set; what is saved is HBM stream (blp_stats.skipped_*). default 1 */
+    double freeze_margin;  /* safety margin of that rule in units of the scaled problem's rms cost / right-hand
+                              side: freeze above it, release below a third of it. default 0.05 */
 } blp_opts;
 
 typedef struct blp_stats {
@@ -83,6 +90,8 @@ typedef struct blp_stats {
     double primal_kernel_ms;   /* profile mode: device time of all k_primal launches */
     double dual_kernel_ms;     /* profile mode: device time of all k_dual launches */
     int refills;               /* nodes that entered through a freed slot (max_active < B) */
+    double skipped_col_updates;/* (column, node, iteration) updates skipped because the column was frozen */
+    double skipped_row_updates;/* the same for rows; node_iterations * (n + m) is the total without freezing */
 } blp_stats;
 
 /* default options */

@@ -13,7 +13,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / 'csrc'
 LIB = CSRC / 'libblp.so'
 SOURCES = [CSRC / 'blp.cu', CSRC / 'blp_mps.cpp']
-DEPS = [CSRC / 'blp_kernels.cuh', CSRC / 'blp_prep.hpp', CSRC.parent.parent / 'include' / 'blp.h']
+DEPS = [CSRC / 'blp_kernels.cuh', CSRC / 'blp_simplex.cuh', CSRC / 'blp_prep.hpp', CSRC.parent.parent / 'include' / 'blp.h']
 
 
 def _nvcc() -> str:

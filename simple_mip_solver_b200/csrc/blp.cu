@@ -224,7 +224,8 @@ struct blp_handle_s {
     DevProb P{};
     // staging of the host-buffer entry points
     DevBuf s_lb, s_ub, s_x0, s_y0, s_mask, s_x, s_y, s_tmp, s_ws, s_node, s_int, s_delta, s_par;
-    int32_t* h_counters = nullptr;     // pinned
+    int32_t* h_counters = nullptr;     // pinned, 16 entries
+    double frz_c = 0.0, frz_r = 0.0;   // units of the freezing margins: rms of the scaled objective / right-hand side
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // node tiles are independent chains of launches: inside a period graph they run as up to
     // kLanes parallel branches, so the tail of one branch's kernel overlaps the next kernel of another
@@ -328,6 +329,8 @@ int prepare(blp_handle h) {
     h->hptrA = As.ptr;
     h->hptrAT = At.ptr;
     const double nb = norm2(bs), nc = norm2(cs);
+    h->frz_c = nc / std::sqrt((double)std::max(n, 1));
+    h->frz_r = nb / std::sqrt((double)std::max(m, 1));
 
     cudaStream_t s = h->stream;
     auto pack = [](const HostCsr& a) {
@@ -437,7 +440,9 @@ size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
     s.lref = cv.take<double>(n * (size_t)(ld / 32));
     s.uref = cv.take<double>(n * (size_t)(ld / 32));
     s.lumask = cv.take<uint32_t>(n * (size_t)(ld / 32));
-    s.counters = cv.take<int32_t>(8);
+    s.counters = cv.take<int32_t>(16);
+    s.cfrz = cv.take<uint8_t>(n * (size_t)(ld / 32));
+    s.rfrz = cv.take<uint8_t>(m * (size_t)(ld / 32));
     if (S) *S = s;
     return align_up(cv.off, 256);
 }
@@ -488,6 +493,21 @@ void launch_eval_nt(const DevProb& P, const DevState& S, const Plan& ec, const P
                     cudaStream_t st) {
     k_eval_cols<NT><<<dim3(ec.chunks, ec.tiles), kCtaThreads, 0, st>>>(P, S, ec.rows_per_cta);
     k_eval_rows<NT><<<dim3(er.chunks, er.tiles), kCtaThreads, 0, st>>>(P, S, er.rows_per_cta);
+}
+
+// Recompute the frozen-coordinate flags of every 32-node block (mode: see k_freeze_cols) and their count.
+constexpr int kFreezeLaunches = 3;
+void launch_freeze(const DevProb& P, const DevState& S, const FreezeArgs& F, int mode, cudaStream_t st) {
+    const int halves = (S.B + 31) / 32;
+    auto rows_per_cta = [&](int rows) {
+        const int want_chunks = std::max(1, 148 * 8 / halves);
+        const int r = (rows + want_chunks - 1) / want_chunks;
+        return std::max(kWarps, (r + kWarps - 1) / kWarps * kWarps);
+    };
+    const int rc = rows_per_cta(P.n), rr = rows_per_cta(P.m);
+    k_freeze_cols<<<dim3((P.n + rc - 1) / rc, halves), kCtaThreads, 0, st>>>(P, S, F, rc, mode);
+    k_freeze_rows<<<dim3((P.m + rr - 1) / rr, halves), kCtaThreads, 0, st>>>(P, S, F, rr, mode);
+    k_freeze_count<<<(S.B + kBlk - 1) / kBlk, kCtaThreads, 0, st>>>(P, S);
 }
 
 void launch_eval(const DevProb& P, const DevState& S, const Plan& ec, const Plan& er,
@@ -596,9 +616,9 @@ int check_opts(const blp_opts* in, blp_opts* o) {
     blp_default_opts(o);
     if (in) *o = *in;
     if (!(o->eps_rel > 0.0) || !(o->eps_infeas > 0.0) || o->max_iters < 1 || o->eval_every < 1 ||
-        o->max_active < 0 || std::isnan(o->obj_cutoff))
+        o->max_active < 0 || std::isnan(o->obj_cutoff) || !(o->freeze_margin >= 0.0))
         return fail(BLP_ERR_ARG, "blp_opts: eps_rel/eps_infeas must be > 0, max_iters/eval_every >= 1, "
-                                 "max_active >= 0");
+                                 "max_active >= 0, freeze_margin >= 0");
     return BLP_OK;
 }
 
@@ -619,6 +639,8 @@ void blp_default_opts(blp_opts* o) {
     o->profile = 0;
     o->max_active = 0;
     o->obj_cutoff = INFINITY;
+    o->freeze = 1;
+    o->freeze_margin = 0.05;
 }
 
 int blp_slots(int B, const blp_opts* o) {
@@ -675,7 +697,7 @@ int blp_create(int device, int m, int n, int64_t nnz, const int32_t* rowptr, con
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->coop_ok, cudaDevAttrCooperativeLaunch, device);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMallocHost(&h->h_counters, 8 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_counters, 16 * sizeof(int32_t));
     for (int q = 0; q < 4 && e == cudaSuccess; ++q) e = cudaEventCreate(&h->ev[q]);
     for (int q = 0; q < blp_handle_s::kLanes - 1 && e == cudaSuccess; ++q) {
         e = cudaStreamCreateWithFlags(&h->side[q], cudaStreamNonBlocking);
@@ -775,6 +797,14 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     const bool have_mask = (P.m > P.m_base) && row_mask != nullptr;
     uint8_t* mask_ws = S.rowmask;
     if (!have_mask) S.rowmask = nullptr;
+    // frozen coordinates (k_freeze_cols): margins in units of the scaled problem's rms cost / right-hand side
+    const bool freeze = o.freeze != 0 && o.freeze_margin > 0.0 && env_int("BLP_FREEZE", 1) != 0;
+    const double fm = env_dbl("BLP_FREEZE_MARGIN", o.freeze_margin), fl = env_dbl("BLP_FREEZE_RELEASE", 1.0 / 3.0);
+    const FreezeArgs F{h->frz_c > 0.0 ? fl * fm * h->frz_c : INFINITY, h->frz_c > 0.0 ? fm * h->frz_c : INFINITY,
+                       h->frz_r > 0.0 ? fl * fm * h->frz_r : INFINITY, h->frz_r > 0.0 ? fm * h->frz_r : INFINITY};
+    uint8_t* const cfrz_ws = S.cfrz;
+    const size_t frz_bytes = (size_t)(S.rfrz - S.cfrz) + (size_t)P.m * (S.ld / 32);
+    if (!freeze) S.cfrz = S.rfrz = nullptr;
     const bool want_frac = frac_idx != nullptr && int_idx != nullptr && n_int > 0;
     if (o.verbose < 2) S.dbg = nullptr;
     uint8_t* isint_ws = const_cast<uint8_t*>(S.isint);
@@ -794,7 +824,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     int launches = 0;
 
     CK(cudaEventRecord(h->ev[0], st));
-    CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(S.counters, 0, 16 * sizeof(int32_t), st));
+    if (freeze) CK(cudaMemsetAsync(cfrz_ws, 0, frz_bytes, st));
     if (have_mask)
         CK(cudaMemcpy2DAsync(mask_ws, S.ld, row_mask, ld_in, S.ld, P.m - P.m_base, cudaMemcpyDeviceToDevice, st));
     if (want_frac) {
@@ -820,7 +851,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     k_count_active<<<(W + 127) / 128, 128, 0, st>>>(S);
     launches += 6;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_counters, S.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_counters, S.counters, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     int active = h->h_counters[0];
 
@@ -845,8 +876,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     // nodes still spreads over all SMs (the per-iteration latency floor of the solve's tail)
     const bool allow_v2 = env_int("BLP_V2", 1) != 0;
     const int graph_lanes = env_int("BLP_GRAPH_LANES", 2);
-    const int rpw2 = env_int("BLP_ROWS_PER_WARP2", 16);   // two-nodes-per-lane kernels: 128 rows per CTA
-    const int rpw2p = env_int("BLP_ROWS_PER_WARP2P", rpw2);
+    const int rpw2 = std::min(env_int("BLP_ROWS_PER_WARP2", 16), kMaxChunkRows / kWarps);   // two-nodes-per-lane kernels: 128 rows per CTA
+    const int rpw2p = std::min(env_int("BLP_ROWS_PER_WARP2P", rpw2), kMaxChunkRows / kWarps);
     auto step_plan = [&](int rows, int width, bool primal = false) {
         // two nodes per lane pay off when a launch has real work; tiny LPs stay on the
         // one-node-per-lane kernels, which can run a whole period as one cooperative launch
@@ -898,7 +929,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
             k_count_active<<<(S.B + 127) / 128, 128, 0, st>>>(S);
             launches += 6;
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h->h_counters, S.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h->h_counters, S.counters, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             next += nnew;
             refills += nnew;
@@ -908,6 +939,13 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         return BLP_OK;
     };
     if ((rc = refill()) != BLP_OK) return rc;
+    // frozen coordinates exist for the two-nodes-per-lane step kernels only (wide batches)
+    auto refreeze = [&](int mode) {
+        if (!freeze || pc.V != 2) return;
+        launch_freeze(P, S, F, mode, st);
+        launches += kFreezeLaunches;
+    };
+    refreeze(2);
 
     const bool profile = o.profile == 1;
     const bool use_graph = o.use_graph && !profile;
@@ -970,7 +1008,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     };
 
     int total = 0, evals = 0, compactions = 0;
-    double step_ms = 0.0, primal_ms = 0.0, dual_ms = 0.0, node_iters = 0.0;
+    double step_ms = 0.0, primal_ms = 0.0, dual_ms = 0.0, node_iters = 0.0, skipped_cols = 0.0, skipped_rows = 0.0;
     while (active > 0 && (refill_mode || total < o.max_iters)) {
         // retire finished nodes: pack the running ones to the front when that frees node tiles
         // (while nodes are pending, freed slots are refilled instead)
@@ -984,6 +1022,10 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 CK(cudaGetLastError());
                 S.B = active;
                 k_build_lumask<<<elementwise_grid((size_t)P.n * ((S.B + 31) / 32) * 32), kCtaThreads, 0, st>>>(P, S);
+                if (freeze) {      // the slots moved and x', y' are stale until the next evaluation: release everything
+                    CK(cudaMemsetAsync(cfrz_ws, 0, frz_bytes, st));
+                    CK(cudaMemsetAsync(S.counters + 8, 0, 4 * sizeof(int32_t), st));
+                }
                 launches += 3;
                 ++compactions;
                 NT = pick_nt(S.B);
@@ -1041,7 +1083,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
             launch_eval(P, S, ec, er, D, K, st);
         }
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->h_counters, S.counters, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->h_counters, S.counters, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
@@ -1055,16 +1097,24 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 dual_ms += t;
             }
         node_iters += (double)active * K;
+        if (freeze && pc.V == 2) {      // counts of the flags that were in force during this period
+            unsigned long long fc[2];
+            memcpy(fc, h->h_counters + 8, sizeof fc);
+            skipped_cols += (double)fc[0] * (K - 1);
+            skipped_rows += (double)fc[1] * (K - 1);
+        }
         total += K;
         evals += 1;
         launches += (coop ? 1 : 2 * K) + 5;
         active = h->h_counters[0];
         const int finished_now = h->h_counters[3], restarting = h->h_counters[1];
+        const int refills_before = refills;
         if (finished_now > 0) {
             launch_harvest(P, S, O, ec, er, want_frac, st, &launches);
             CK(cudaGetLastError());
             if ((rc = refill()) != BLP_OK) return rc;
         }
+        if (active > 0) refreeze(refills > refills_before ? 1 : 0);
         if (o.verbose >= 2) {
             double t[8 * 4];
             const int kshow = std::min(4, S.B);
@@ -1092,6 +1142,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         stats->primal_kernel_ms = primal_ms;
         stats->dual_kernel_ms = dual_ms;
         stats->refills = refills;
+        stats->skipped_col_updates = skipped_cols;
+        stats->skipped_row_updates = skipped_rows;
     }
     return BLP_OK;
 }

@@ -91,7 +91,16 @@ struct DevState {
     // the primal step reads the dense l,u of a row only for those nodes. Layout [block][row].
     double *lref, *uref;
     uint32_t* lumask;
-    int32_t* counters;                             // see k_tick
+    int32_t* counters;                             // see k_tick; [8..11] = two 64-bit counts of k_freeze_count
+    // Frozen coordinates (k_freeze_cols / k_freeze_rows): one byte per (32-node block, row), layout
+    // [block][row] like lref; 1 = every running node of the block agrees that the coordinate rests.
+    uint8_t *cfrz, *rfrz;
+};
+
+// Margins of the freezing rule in the scaled problem's units (blp.cu: solve set-up).
+struct FreezeArgs {
+    double c_lo, c_hi;      // reduced-cost margin below which a frozen column is released / above which it freezes
+    double r_lo, r_hi;      // the same for the slack of a row with zero multiplier
 };
 
 // caller-side output arrays (node-fastest, leading dimension ld; entries indexed by ORIGINAL node)
@@ -621,6 +630,33 @@ __device__ __forceinline__ void dot2_entries_pair(const int4* __restrict__ E, in
     }
 }
 
+// Frozen coordinates of a CTA's chunk (rows [r0, r1) of the node tile whose 32-node blocks are h0, h0 + 1): one
+// byte per row in shared memory, 1 = both blocks agree (a block without a running node agrees to everything).
+// `live` is the warp's ballot of running lanes: lanes 0-15 hold the nodes of block h0, lanes 16-31 those of h0 + 1.
+constexpr int kMaxChunkRows = 512;
+__shared__ uint16_t s_rows[kMaxChunkRows];   // local rows of the chunk that are NOT frozen, in no particular order
+__shared__ int s_nrows;
+
+// The CTA's work list: the rows of its chunk that are not frozen for this tile, compacted so that the warps share
+// them evenly whatever the pattern (rows are independent, so their order is free). Call with all threads; the list
+// is published by the next __syncthreads (the slab's). s_nrows must have been zeroed before a barrier.
+__device__ __forceinline__ void stage_unfrozen(const uint8_t* __restrict__ flags, const int rows, const int h0,
+                                               const int r0, const int r1, const unsigned live) {
+    const bool live0 = (live & 0x0000ffffu) != 0, live1 = (live & 0xffff0000u) != 0;
+    const uint8_t* __restrict__ f0 = flags + (size_t)h0 * rows + r0;
+    const uint8_t* __restrict__ f1 = f0 + rows;
+    const int lane = threadIdx.x & 31, nrows = r1 - r0;
+    for (int t0 = threadIdx.x - lane; t0 < nrows; t0 += kCtaThreads) {
+        const int t = t0 + lane;
+        const bool keep = t < nrows && !((!live0 || f0[t] != 0) && (!live1 || f1[t] != 0));
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        int pos = 0;
+        if (lane == 0 && bal) pos = atomicAdd(&s_nrows, __popc(bal));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (keep) s_rows[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)t;
+    }
+}
+
 #ifndef BLP_PAIR_ROWS
 #define BLP_PAIR_ROWS 0       // 1: a warp of the primal step keeps two rows in flight (measured slower, see below)
 #endif
@@ -639,7 +675,8 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
     const int node = (tile0 + blockIdx.y) * kBlk + lane * 2;   // this lane: nodes node, node + 1
     const bool k0 = node < S.B && S.fin[node] == 0;
     const bool k1 = node + 1 < S.B && S.fin[node + 1] == 0;
-    if (__ballot_sync(0xffffffffu, k0 || k1) == 0) return;     // whole block retired
+    const unsigned live = __ballot_sync(0xffffffffu, k0 || k1);
+    if (live == 0) return;                                     // whole block retired
     double w0 = 0, w1 = 0, tau0 = 0, tau1 = 0;
     if (k0) {
         const int s = S.sbase[node] + it;
@@ -653,6 +690,12 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
     }
     const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
     const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
+    const bool frz = !MAJOR && S.cfrz != nullptr;
+    if (frz) {
+        if (threadIdx.x == 0) s_nrows = 0;
+        __syncthreads();
+        stage_unfrozen(S.cfrz, P.n, (tile0 + blockIdx.y) * 2, r0, r1, live);   // published by the slab's barrier
+    }
     const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.n);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
@@ -661,6 +704,7 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
     const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
     double cg0 = 0.0, cg1 = 0.0;
     if (coop) {
+        if (frz && s_nrows == 0) return;
         coop_dot2(sl, P.cent, yn, warp, lane, cg0, cg1);
         if (warp != 0) return;
     }
@@ -725,7 +769,9 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
         return;
     }
 #endif
-    for (int j = r0 + warp; j < r1; j += kWarps) {
+    const int ntrips = frz ? s_nrows : r1 - r0;                // frozen columns rest at their bound for the whole tile
+    for (int k = warp; k < ntrips; k += kWarps) {
+        const int j = r0 + (frz ? (int)s_rows[k] : k);
         const size_t e = base + (size_t)j * kBlk;
         const double2 xb = ld2(S.xbar + e);
         const double2 a = ldcs2(S.xa + e);
@@ -760,7 +806,8 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
     const int node = (tile0 + blockIdx.y) * kBlk + lane * 2;
     const bool k0 = node < S.B && S.fin[node] == 0;
     const bool k1 = node + 1 < S.B && S.fin[node + 1] == 0;
-    if (__ballot_sync(0xffffffffu, k0 || k1) == 0) return;
+    const unsigned live = __ballot_sync(0xffffffffu, k0 || k1);
+    if (live == 0) return;
     double w0 = 0, w1 = 0, sig0 = 0, sig1 = 0;
     if (k0) {
         const int s = S.sbase[node] + it;
@@ -774,12 +821,19 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
     }
     const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
     const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
+    const bool frz = !MAJOR && S.rfrz != nullptr;
+    if (frz) {
+        if (threadIdx.x == 0) s_nrows = 0;
+        __syncthreads();
+        stage_unfrozen(S.rfrz, P.m, (tile0 + blockIdx.y) * 2, r0, r1, live);
+    }
     const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.m);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
     const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
     double cg0 = 0.0, cg1 = 0.0;
     if (coop) {
+        if (frz && s_nrows == 0) return;
         coop_dot2(sl, P.ent, xn, warp, lane, cg0, cg1);
         if (warp != 0) return;
     }
@@ -838,7 +892,9 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
         return;
     }
 #endif
-    for (int i = r0 + warp; i < r1; i += kWarps) {
+    const int ntrips = frz ? s_nrows : r1 - r0;                // a frozen row's multiplier rests at zero for the whole tile
+    for (int k = warp; k < ntrips; k += kWarps) {
+        const int i = r0 + (frz ? (int)s_rows[k] : k);
         const size_t e = base + (size_t)i * kBlk;
         const double2 yc = ld2(S.y + e);
         const double2 a = ldcs2(S.ya + e);
@@ -1166,6 +1222,120 @@ k_apply_restart(const DevProb P, const DevState S) {
         S.ya[e] = (anc_t)v;
         S.y[e] = v;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Freezing of settled coordinates. Most columns of a node LP rest on a bound with a reduced cost of the right
+// sign, and the rows with slack keep a zero multiplier, from the warm start to the end of the solve (C5 frontier:
+// 60 % of the columns, 24 % of the rows); the iteration recomputes the same values for them, 20 bytes of HBM
+// stream per coordinate, node and iteration. A coordinate is FROZEN for a 64-node tile when, for every running
+// node of the tile,
+//   column:  x' = x_iterate = anchor = the bound (lower with r_j >= margin, upper with r_j <= -margin; or l == u),
+//   row:     y' = y_iterate = anchor = 0 and (A x' - b)_i >= margin (or the row is masked off for the node),
+// i.e. exactly when the full iteration would reproduce the coordinate. The step kernels skip frozen coordinates
+// (k_primal2 / k_dual2, all iterations of a period but the last); the last iteration of a period updates
+// everything, so the evaluation — KKT test on the FULL problem, certificates, restart rule — sees exact x', y',
+// A'y, and whatever the frozen set was, a status is only ever assigned by the full test. The flags are recomputed
+// after every evaluation with hysteresis (freeze above *_hi, release below *_lo; a node loaded by the last refill
+// is held to *_hi), per 32-node block; a tile's two blocks must agree. Screened on the host first
+// (tests/tools/cpu_freeze_lab.py: same iteration counts, half the coordinate updates skipped on C4 and C5).
+//   mode 0: after an evaluation; 1: after a refill (S.fresh marks the new nodes); 2: ignore the stored flags
+__device__ __forceinline__ bool rests_on(const double v, const double bound, const double width) {
+    return fabs(v - bound) <= 1e-6 * width;      // fp32 anchors and the Halpern average leave ~1e-8 relative
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_freeze_cols(const DevProb P, const DevState S, const FreezeArgs F, const int rows_per_cta, const int mode) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = blockIdx.y * 32 + lane;
+    const bool live = node < S.B && S.fin[node] == 0;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) S.counters[8 + threadIdx.x] = 0;   // k_freeze_count follows
+    if (__ballot_sync(0xffffffffu, live) == 0) return;        // uniform over the CTA
+    const bool strict = mode == 2 || (mode == 1 && live && S.fresh[node] != 0);
+    uint8_t* __restrict__ flags = S.cfrz + (size_t)blockIdx.y * P.n;
+    const double* __restrict__ yn = S.Y1 + tix(0, node, P.m);
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(P.n, r0 + rows_per_cta);
+    for (int j = r0 + warp; j < r1; j += kWarps) {
+        const uint8_t stored = flags[j], prev = mode == 2 ? 0 : stored;
+        const double gp = row_dot<32>(P.cptr, P.cent, j, true, yn, live);
+        bool ok = true;
+        if (live) {
+            const size_t e = tix(j, node, P.n);
+            const double xp = S.X1[e], lo = S.l[e], hi = S.u[e];
+            ok = false;
+            if (xp == lo || xp == hi) {
+                const double r = __ldg(P.c + j) - gp;
+                const double th = (prev && !strict) ? F.c_lo : F.c_hi;
+                const double width = is_inf(hi - lo) ? fabs(xp) : fmax(hi - lo, fabs(xp));
+                const bool settled = lo >= hi || (xp == lo ? r >= th : -r >= th);
+                ok = settled && rests_on(S.xbar[e], xp, width) && (anc_t)xp == S.xa[e];
+            }
+        }
+        const bool all = __all_sync(0xffffffffu, ok);
+        if (lane == 0 && (uint8_t)all != stored) flags[j] = all;
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_freeze_rows(const DevProb P, const DevState S, const FreezeArgs F, const int rows_per_cta, const int mode) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int node = blockIdx.y * 32 + lane;
+    const bool live = node < S.B && S.fin[node] == 0;
+    if (__ballot_sync(0xffffffffu, live) == 0) return;
+    const bool strict = mode == 2 || (mode == 1 && live && S.fresh[node] != 0);
+    uint8_t* __restrict__ flags = S.rfrz + (size_t)blockIdx.y * P.m;
+    const double* __restrict__ xn = S.X1 + tix(0, node, P.n);
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(P.m, r0 + rows_per_cta);
+    for (int i = r0 + warp; i < r1; i += kWarps) {
+        const uint8_t stored = flags[i], prev = mode == 2 ? 0 : stored;
+        const double ax = row_dot<32>(P.rowptr, P.ent, i, true, xn, live);
+        bool ok = true;
+        if (live) {
+            const size_t e = tix(i, node, P.m);
+            const bool zero = S.Y1[e] == 0.0 && S.y[e] == 0.0 && S.ya[e] == (anc_t)0;
+            const bool off = i >= P.m_base && S.rowmask && S.rowmask[(size_t)(i - P.m_base) * S.ld + node] == 0;
+            const double th = (prev && !strict) ? F.r_lo : F.r_hi;
+            ok = zero && (off || ax - __ldg(P.b + i) >= th);
+        }
+        const bool all = __all_sync(0xffffffffu, ok);
+        if (lane == 0 && (uint8_t)all != stored) flags[i] = all;
+    }
+}
+
+// Frozen (coordinate, running node) pairs of the whole batch, as the step kernels will see them (both 32-node
+// blocks of a tile agree): counters[8..9] = columns, counters[10..11] = rows, as two 64-bit counts. One CTA per tile.
+__global__ void __launch_bounds__(kCtaThreads)
+k_freeze_count(const DevProb P, const DevState S) {
+    __shared__ int s_live[2];
+    __shared__ unsigned long long s_cnt[2];
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0ull;
+    if (warp < 2) {
+        const int node = tile * kBlk + warp * 32 + lane;
+        const unsigned bal = __ballot_sync(0xffffffffu, node < S.B && S.fin[node] == 0);
+        if (lane == 0) s_live[warp] = __popc(bal);
+    }
+    __syncthreads();
+    const int l0 = s_live[0], l1 = s_live[1];
+    if (l0 + l1 == 0) return;
+    unsigned long long cnt[2] = {0ull, 0ull};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int rows = a == 0 ? P.n : P.m;
+        const uint8_t* __restrict__ f0 = (a == 0 ? S.cfrz : S.rfrz) + (size_t)(2 * tile) * rows;
+        const uint8_t* __restrict__ f1 = f0 + rows;
+        int c = 0;
+        for (int r = threadIdx.x; r < rows; r += kCtaThreads)
+            c += ((l0 == 0 || f0[r] != 0) && (l1 == 0 || f1[r] != 0)) ? 1 : 0;
+        cnt[a] = (unsigned long long)c * (unsigned long long)(l0 + l1);
+    }
+    atomicAdd(&s_cnt[0], cnt[0]);
+    atomicAdd(&s_cnt[1], cnt[1]);
+    __syncthreads();
+    if (threadIdx.x < 2)
+        atomicAdd(reinterpret_cast<unsigned long long*>(S.counters + 8) + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -228,3 +228,84 @@ def test_branch_and_bound_with_lp_cutoff_builds_the_same_tree(blp_lib, monkeypat
     a, b = run(False), run(True)
     assert a[0] == b[0] == 'optimal' and abs(a[1] - b[1]) <= 1e-6 * abs(a[1]) and a[2] == b[2]
     print('nodes stopped by the objective limit:', b[3], 'of', len(b[2]))
+
+
+def _c4_frontier(B):
+    z = np.load(os.path.join(ROOT, 'bench_data', 'c4_root.npz'))
+    d = numpy_random_mip(int(z['n']), int(z['m']), density=float(z['density']), seed=int(z['seed']))
+    lbs, ubs, _ = frontier_nodes(d, z['x'], 0, B, 16, seed=0)
+    return d, lbs, ubs, z['x'], np.maximum(z['y'], 0.0)
+
+
+def test_frozen_coordinates_do_not_change_answers(blp_lib):
+    """blp_opts.freeze: the wide-batch step kernels skip coordinates that rest for a whole 64-node tile (columns on a
+    bound with a safe reduced cost, rows with zero multiplier and safe slack). The evaluation is always the full
+    problem's, so statuses are equal and objectives agree within the solve tolerance; the iteration counts stay
+    within a few percent (the frozen iteration IS the full iteration while the margins hold), and the statistics
+    say how much stream was saved. Resident batch and continuous batching (refills re-derive the flags)."""
+    from simple_mip_solver_b200 import engine as eng
+    d, lbs, ubs, x0, y0 = _c4_frontier(160)
+    B = lbs.shape[0]
+    lbs, ubs = lbs.copy(), ubs.copy()
+    lbs[150, 3], ubs[150, 3] = 1.0, 0.0                 # an empty box among the pending nodes
+    X0, Y0 = np.tile(x0, (B, 1)), np.tile(y0, (B, 1))
+    lp = eng.BatchLP(d.A, d.b, d.c)
+    res = {}
+    for name, kw in (('off', dict(freeze=0)), ('on', {}), ('on_refill', dict(max_active=128)),
+                     ('off_refill', dict(freeze=0, max_active=128)), ('loose', dict(freeze_margin=0.005))):
+        res[name] = lp.solve_batch(lbs, ubs, x0=X0, y0=Y0, integer_indices=d.integer_indices, opts=eng.default_opts(**kw))
+    lp.close()
+    off = res['off']
+    ok = off.status == 0
+    assert ok.sum() == B - 1 and off.status[150] == 1
+    assert off.stats['skipped_col_updates'] == 0 and off.stats['skipped_row_updates'] == 0
+    total_c, total_r = off.stats['node_iterations'] * d.n, off.stats['node_iterations'] * d.m
+    for name in ('on', 'on_refill', 'loose'):
+        r = res[name]
+        assert np.array_equal(r.status, off.status), name
+        assert np.allclose(r.objective[ok], off.objective[ok], rtol=2e-7, atol=0), name
+        # the most fractional index: equal, except where two candidates tie within the solve tolerance
+        for k in np.nonzero(ok & (r.frac_idx != off.frac_idx))[0]:
+            dist = np.minimum(off.x[k] - np.floor(off.x[k]), np.ceil(off.x[k]) - off.x[k])
+            assert r.frac_idx[k] >= 0 and off.frac_idx[k] >= 0, (name, k)
+            assert abs(dist[r.frac_idx[k]] - dist[off.frac_idx[k]]) < 1e-5, (name, k)
+        assert (r.frac_idx[ok] == off.frac_idx[ok]).mean() > 0.9, name
+        assert abs(r.iterations[ok].mean() / off.iterations[ok].mean() - 1.0) < 0.05, name
+        assert r.stats['skipped_col_updates'] > 0.3 * total_c, (name, r.stats['skipped_col_updates'] / total_c)
+        assert r.stats['skipped_row_updates'] > 0.1 * total_r, (name, r.stats['skipped_row_updates'] / total_r)
+        # x is the point the objective was computed at, and it is feasible to the solve tolerance
+        assert np.allclose((r.x[ok] * d.c).sum(1), r.objective[ok], rtol=1e-9, atol=1e-9)
+        viol = np.maximum(d.b[None, :] - (d.A @ r.x[ok].T).T, 0.0)
+        assert (np.linalg.norm(viol, axis=1) <= 1.01e-7 * (1.0 + np.linalg.norm(d.b))).all(), name
+    assert np.array_equal(res['off_refill'].status, off.status)
+    assert res['loose'].stats['skipped_col_updates'] >= res['on'].stats['skipped_col_updates']
+
+
+def test_frozen_coordinates_with_cut_rows_masked_per_node(blp_lib):
+    """A pool row that is switched off for every node of a tile counts as frozen (its multiplier is held at zero);
+    rows that are on for some nodes keep iterating. Same answers as without freezing."""
+    from simple_mip_solver_b200 import engine as eng
+    d, lbs, ubs, x0, y0 = _c4_frontier(128)
+    B = lbs.shape[0]
+    rng = np.random.default_rng(5)
+    k = 6
+    rows = np.zeros((k, d.n))
+    for i in range(k):
+        idx = rng.choice(d.n, 300, replace=False)
+        rows[i, idx] = rng.integers(1, 10, 300)
+    rhs = rows @ x0 + np.array([0.5, 1.0, 0.25, 2.0, 0.1, 0.75])      # violated by the root optimum
+    lp = eng.BatchLP(d.A, d.b, d.c)
+    lp.append_rows(rows, rhs)
+    mask = np.zeros((B, k), dtype=np.uint8)
+    mask[:64, 0] = 1                      # on for the first tile only
+    mask[::2, 1] = 1                      # on for every other node
+    mask[:, 2] = 1                        # on everywhere; rows 3..5 off everywhere
+    X0, Y0 = np.tile(x0, (B, 1)), np.tile(np.concatenate([y0, np.zeros(k)]), (B, 1))
+    a = lp.solve_batch(lbs, ubs, row_mask=mask, x0=X0, y0=Y0, opts=eng.default_opts(freeze=0))
+    b = lp.solve_batch(lbs, ubs, row_mask=mask, x0=X0, y0=Y0, opts=eng.default_opts())
+    lp.close()
+    assert np.array_equal(a.status, b.status) and (a.status == 0).all()
+    assert np.allclose(a.objective, b.objective, rtol=2e-7, atol=0)
+    assert b.stats['skipped_row_updates'] > 0
+    # the cuts bind: nodes that carry row 2 (all) are more expensive than the root
+    assert (b.objective > float(np.load(os.path.join(ROOT, 'bench_data', 'c4_root.npz'))['objective'])).all()

@@ -360,6 +360,7 @@ int prepare(blp_handle h) {
     P.m = m;
     P.m_base = h->m_base;
     P.n = n;
+    P.nnz = (int)As.ptr.back();
     P.rowptr = h->rowptr.as<int32_t>();
     P.ent = h->ent.as<Ent>();
     P.cptr = h->cptr.as<int32_t>();
@@ -443,6 +444,17 @@ size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
     s.counters = cv.take<int32_t>(16);
     s.cfrz = cv.take<uint8_t>(n * (size_t)(ld / 32));
     s.rfrz = cv.take<uint8_t>(m * (size_t)(ld / 32));
+    {   // folded matrices of every 64-node tile (k_fold_*): 32 bytes per stored entry and tile
+        const size_t tiles = ld / kBlk, nnz = h->A0.ptr.empty() ? 0 : (size_t)h->A0.ptr.back();
+        s.cval = cv.take<double>(n * (size_t)(ld / 32));
+        s.fcol = cv.take<uint8_t>(n * tiles);
+        s.fval = cv.take<double>(n * tiles);
+        s.fentA = cv.take<Ent>(nnz * tiles);
+        s.fentAT = cv.take<Ent>(nnz * tiles);
+        s.fendA = cv.take<int32_t>(m * tiles);
+        s.fendAT = cv.take<int32_t>(n * tiles);
+        s.rconst = cv.take<double>(m * tiles);
+    }
     if (S) *S = s;
     return align_up(cv.off, 256);
 }
@@ -496,7 +508,7 @@ void launch_eval_nt(const DevProb& P, const DevState& S, const Plan& ec, const P
 }
 
 // Recompute the frozen-coordinate flags of every 32-node block (mode: see k_freeze_cols) and their count.
-constexpr int kFreezeLaunches = 3;
+constexpr int kFreezeLaunches = 6;
 void launch_freeze(const DevProb& P, const DevState& S, const FreezeArgs& F, int mode, cudaStream_t st) {
     const int halves = (S.B + 31) / 32;
     auto rows_per_cta = [&](int rows) {
@@ -505,9 +517,17 @@ void launch_freeze(const DevProb& P, const DevState& S, const FreezeArgs& F, int
         return std::max(kWarps, (r + kWarps - 1) / kWarps * kWarps);
     };
     const int rc = rows_per_cta(P.n), rr = rows_per_cta(P.m);
-    k_freeze_cols<<<dim3((P.n + rc - 1) / rc, halves), kCtaThreads, 0, st>>>(P, S, F, rc, mode);
-    k_freeze_rows<<<dim3((P.m + rr - 1) / rr, halves), kCtaThreads, 0, st>>>(P, S, F, rr, mode);
-    k_freeze_count<<<(S.B + kBlk - 1) / kBlk, kCtaThreads, 0, st>>>(P, S);
+    if (mode >= 0) {
+        k_freeze_cols<<<dim3((P.n + rc - 1) / rc, halves), kCtaThreads, 0, st>>>(P, S, F, rc, mode);
+        k_freeze_rows<<<dim3((P.m + rr - 1) / rr, halves), kCtaThreads, 0, st>>>(P, S, F, rr, mode);
+    }
+    // mode < 0: the flags were just cleared (compaction) — only rebuild the tiles' matrices from them
+    const int tiles = (S.B + kBlk - 1) / kBlk;
+    auto per_tile = [&](int rows) { return dim3(std::max(1, std::min((rows + kCtaThreads - 1) / kCtaThreads, 148 * 4 / tiles + 1)), tiles); };
+    k_fold_cols<<<per_tile(P.n), kCtaThreads, 0, st>>>(P, S);
+    k_fold_A<<<per_tile(P.m), kCtaThreads, 0, st>>>(P, S);
+    k_fold_AT<<<per_tile(P.n), kCtaThreads, 0, st>>>(P, S);
+    k_freeze_count<<<tiles, kCtaThreads, 0, st>>>(P, S);
 }
 
 void launch_eval(const DevProb& P, const DevState& S, const Plan& ec, const Plan& er,
@@ -1025,6 +1045,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 if (freeze) {      // the slots moved and x', y' are stale until the next evaluation: release everything
                     CK(cudaMemsetAsync(cfrz_ws, 0, frz_bytes, st));
                     CK(cudaMemsetAsync(S.counters + 8, 0, 4 * sizeof(int32_t), st));
+                    launch_freeze(P, S, F, -1, st);
+                    launches += 4;
                 }
                 launches += 3;
                 ++compactions;

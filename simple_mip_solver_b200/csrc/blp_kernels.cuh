@@ -61,7 +61,7 @@ struct __align__(16) Ent {
 };
 
 struct DevProb {
-    int m, m_base, n;
+    int m, m_base, n, nnz;
     const int32_t* rowptr; const Ent* ent;       // scaled A   (m x n), CSR
     const int32_t* cptr;   const Ent* cent;      // scaled A^T (n x m), CSR
     const double* c; const double* b;            // scaled objective / row lower bounds
@@ -95,6 +95,14 @@ struct DevState {
     // Frozen coordinates (k_freeze_cols / k_freeze_rows): one byte per (32-node block, row), layout
     // [block][row] like lref; 1 = every running node of the block agrees that the coordinate rests.
     uint8_t *cfrz, *rfrz;
+    // Folded matrices of a 64-node tile (k_fold_*): the entries the step kernels still have to gather once the
+    // frozen coordinates are taken out. Row i of tile t keeps its slots [ptr[i], ptr[i+1]) in a per-tile copy of the
+    // entry array, the kept entries packed to the front; fendA / fendAT hold the end of the kept part.
+    double* cval;                                  // [block][n] x' of a frozen column if the block's nodes agree on it
+    uint8_t* fcol; double* fval;                   // [tile][n] column folded into rconst, with the value it rests at
+    Ent *fentA, *fentAT;                           // [tile][nnz]
+    int32_t *fendA, *fendAT;                       // [tile][m], [tile][n]
+    double* rconst;                                // [tile][m] sum of a_ij x_j over the folded columns of row i
 };
 
 // Margins of the freezing rule in the scaled problem's units (blp.cu: solve set-up).
@@ -207,6 +215,7 @@ struct Slab {
     const int* sp;       // shared: absolute row pointers of rows r0 .. r1
     const int4* se;      // shared: entries [sp[0], sp[nrows]) or nullptr if they did not fit
     int base;
+    const int* ends = nullptr;   // shared: end of row lr's entries if it is not sp[lr + 1] (folded matrices)
 };
 
 extern __shared__ int4 dyn_smem[];
@@ -545,7 +554,7 @@ __device__ __forceinline__ void dot2_entries(const int4* __restrict__ E, const i
 __device__ __forceinline__ void slab_dot2(const Slab& sl, const Ent* __restrict__ ent, const int lr,
                                           const double* __restrict__ Vn, double& g0, double& g1,
                                           const int ld = kBlk) {
-    const int p0 = sl.sp[lr], p1 = sl.sp[lr + 1];
+    const int p0 = sl.sp[lr], p1 = sl.ends ? sl.ends[lr] : sl.sp[lr + 1];
     if (sl.se) dot2_entries<true>(sl.se - sl.base, p0, p1, Vn, g0, g1, ld);
     else dot2_entries<false>(reinterpret_cast<const int4*>(ent), p0, p1, Vn, g0, g1, ld);
 }
@@ -557,7 +566,7 @@ __device__ __forceinline__ void coop_dot2(const Slab& sl, const Ent* __restrict_
                                           const double* __restrict__ Vn, const int warp, const int lane,
                                           double& g0, double& g1) {
     __shared__ double2 red[kWarps][32];
-    const int p0 = sl.sp[0], p1 = sl.sp[1];
+    const int p0 = sl.sp[0], p1 = sl.ends ? sl.ends[0] : sl.sp[1];
     const int seg = ((p1 - p0 + kWarps - 1) / kWarps + BLP_U - 1) / BLP_U * BLP_U;
     const int a = min(p1, p0 + warp * seg), b = min(p1, a + seg);
     double s0 = 0.0, s1 = 0.0;
@@ -634,27 +643,73 @@ __device__ __forceinline__ void dot2_entries_pair(const int4* __restrict__ E, in
 // byte per row in shared memory, 1 = both blocks agree (a block without a running node agrees to everything).
 // `live` is the warp's ballot of running lanes: lanes 0-15 hold the nodes of block h0, lanes 16-31 those of h0 + 1.
 constexpr int kMaxChunkRows = 512;
-__shared__ uint16_t s_rows[kMaxChunkRows];   // local rows of the chunk that are NOT frozen, in no particular order
+__shared__ uint16_t s_rows[kMaxChunkRows];   // local rows of the chunk that are NOT frozen, ascending
+__shared__ int s_ends[kMaxChunkRows];        // end of the kept entries of each local row (folded matrix)
+__shared__ int s_group[kMaxChunkRows / 32 + 1];
 __shared__ int s_nrows;
 
-// The CTA's work list: the rows of its chunk that are not frozen for this tile, compacted so that the warps share
-// them evenly whatever the pattern (rows are independent, so their order is free). Call with all threads; the list
-// is published by the next __syncthreads (the slab's). s_nrows must have been zeroed before a barrier.
-__device__ __forceinline__ void stage_unfrozen(const uint8_t* __restrict__ flags, const int rows, const int h0,
-                                               const int r0, const int r1, const unsigned live) {
+// Slab of a CTA whose tile has frozen coordinates: as stage_slab, plus the CTA's WORK LIST — the rows of its chunk
+// that are not frozen for this tile (both 32-node blocks h0, h0 + 1 agree, a block without a running node agrees to
+// everything), compacted so the warps share them evenly — and the ends of the rows' kept entries in the tile's
+// folded matrix `ent`. Everything global is loaded in the two phases stage_slab has anyway (pointers, ends and
+// flags together, then the entries), so a CTA pays no extra round trip. `live`: the warp's ballot of running lanes,
+// lanes 0-15 hold the nodes of block h0, lanes 16-31 those of h0 + 1.
+__device__ __forceinline__ Slab stage_slab_frozen(const int32_t* __restrict__ ptr, const Ent* __restrict__ ent,
+                                                  const int32_t* __restrict__ ends, const uint8_t* __restrict__ flags,
+                                                  const int rows, const int h0, const unsigned live, const int r0,
+                                                  const int r1, const int rows_per_cta, const int cap) {
+    int* sp = reinterpret_cast<int*>(dyn_smem);
+    int4* se = dyn_smem + (rows_per_cta + 4) / 4;
+    const int nrows = r1 - r0, lane = threadIdx.x & 31;
     const bool live0 = (live & 0x0000ffffu) != 0, live1 = (live & 0xffff0000u) != 0;
     const uint8_t* __restrict__ f0 = flags + (size_t)h0 * rows + r0;
     const uint8_t* __restrict__ f1 = f0 + rows;
-    const int lane = threadIdx.x & 31, nrows = r1 - r0;
-    for (int t0 = threadIdx.x - lane; t0 < nrows; t0 += kCtaThreads) {
-        const int t = t0 + lane;
-        const bool keep = t < nrows && !((!live0 || f0[t] != 0) && (!live1 || f1[t] != 0));
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        int pos = 0;
-        if (lane == 0 && bal) pos = atomicAdd(&s_nrows, __popc(bal));
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        if (keep) s_rows[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)t;
+    // phase 1: row pointers, row ends, flags; a thread owns local rows t and t + 256
+    bool keep[2];
+    int rank[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int t = threadIdx.x + q * kCtaThreads;
+        keep[q] = false;
+        if (t <= nrows) sp[t] = __ldg(ptr + r0 + t);
+        if (t < nrows) {
+            s_ends[t] = __ldg(ends + r0 + t);
+            keep[q] = !((!live0 || f0[t] != 0) && (!live1 || f1[t] != 0));
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep[q]);
+        rank[q] = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) s_group[t >> 5] = __popc(bal);
     }
+    __syncthreads();
+    Slab s;
+    s.sp = sp;
+    s.base = sp[0];
+    s.se = nullptr;
+    s.ends = s_ends;
+    const int cnt = sp[nrows] - s.base;
+    // phase 2: the entries (their loads fly while the work list is written)
+    if (cnt <= cap) {
+        const int4* __restrict__ src = reinterpret_cast<const int4*>(ent) + s.base;
+        for (int t = threadIdx.x; t < cnt; t += kCtaThreads) se[t] = __ldg(src + t);
+        s.se = se;
+    }
+    const int groups = (nrows + 31) >> 5;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int t = threadIdx.x + q * kCtaThreads;
+        if (keep[q]) {
+            int before = 0;
+            for (int g = 0; g < (t >> 5); ++g) before += s_group[g];
+            s_rows[before + rank[q]] = (uint16_t)t;
+        }
+    }
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int g = 0; g < groups; ++g) total += s_group[g];
+        s_nrows = total;
+    }
+    __syncthreads();
+    return s;
 }
 
 #ifndef BLP_PAIR_ROWS
@@ -691,12 +746,12 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
     const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
     const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
     const bool frz = !MAJOR && S.cfrz != nullptr;
-    if (frz) {
-        if (threadIdx.x == 0) s_nrows = 0;
-        __syncthreads();
-        stage_unfrozen(S.cfrz, P.n, (tile0 + blockIdx.y) * 2, r0, r1, live);   // published by the slab's barrier
-    }
-    const Slab sl = stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
+    const int tile = tile0 + blockIdx.y;
+    // with frozen coordinates: the tile's folded A' (entries of frozen rows, whose multiplier is zero, taken out)
+    const Ent* __restrict__ cent = frz ? S.fentAT + (size_t)tile * P.nnz : P.cent;
+    const Slab sl = frz ? stage_slab_frozen(P.cptr, cent, S.fendAT + (size_t)tile * P.n, S.cfrz, P.n, tile * 2, live,
+                                            r0, r1, rows_per_cta, cap)
+                        : stage_slab(P.cptr, P.cent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.n);
     const double* __restrict__ yn = S.y + tix(0, node, P.m);
     const size_t fblk = (size_t)(node >> 5) * P.n;
@@ -705,11 +760,11 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
     double cg0 = 0.0, cg1 = 0.0;
     if (coop) {
         if (frz && s_nrows == 0) return;
-        coop_dot2(sl, P.cent, yn, warp, lane, cg0, cg1);
+        coop_dot2(sl, cent, yn, warp, lane, cg0, cg1);
         if (warp != 0) return;
     }
 #if BLP_PAIR_ROWS
-    if (!coop) {
+    if (!coop && !frz) {
         // two rows per trip: rows j and j + kWarps. All streaming loads and the gathers of both rows
         // are issued before the first result is needed.
         for (int j = r0 + warp; j < r1; j += 2 * kWarps) {
@@ -784,7 +839,7 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
             if (mk & 2u) { lo1 = l2.y; hi1 = u2.y; }
         }
         double g0 = cg0, g1 = cg1;
-        if (!coop) slab_dot2(sl, P.cent, j - r0, yn, g0, g1);
+        if (!coop) slab_dot2(sl, cent, j - r0, yn, g0, g1);
         const double cj = __ldg(P.c + j);
         const double xc0 = fma(w0, xb.x - a.x, a.x), xc1 = fma(w1, xb.y - a.y, a.y);
         const double xp0 = fmin(fmax(xc0 - tau0 * (cj - g0), lo0), hi0);
@@ -822,23 +877,30 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
     const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
     const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
     const bool frz = !MAJOR && S.rfrz != nullptr;
-    if (frz) {
-        if (threadIdx.x == 0) s_nrows = 0;
-        __syncthreads();
-        stage_unfrozen(S.rfrz, P.m, (tile0 + blockIdx.y) * 2, r0, r1, live);
-    }
-    const Slab sl = stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
+    const int tile = tile0 + blockIdx.y;
+    // with frozen coordinates: the tile's folded A (columns that rest at one value for the whole tile are summed
+    // into rconst once per evaluation period instead of being gathered every iteration)
+    const Ent* __restrict__ aent = frz ? S.fentA + (size_t)tile * P.nnz : P.ent;
+    const double* __restrict__ rconst = S.rconst + (size_t)tile * P.m;
+    const Slab sl = frz ? stage_slab_frozen(P.rowptr, aent, S.fendA + (size_t)tile * P.m, S.rfrz, P.m, tile * 2, live,
+                                            r0, r1, rows_per_cta, cap)
+                        : stage_slab(P.rowptr, P.ent, r0, r1, rows_per_cta, cap);
     const size_t base = tix(0, node, P.m);
     const double* __restrict__ xn = S.xbar + tix(0, node, P.n);
     const bool coop = (r1 - r0 == 1) && (sl.sp[1] - sl.sp[0] > kLongRow);
     double cg0 = 0.0, cg1 = 0.0;
     if (coop) {
         if (frz && s_nrows == 0) return;
-        coop_dot2(sl, P.ent, xn, warp, lane, cg0, cg1);
+        coop_dot2(sl, aent, xn, warp, lane, cg0, cg1);
         if (warp != 0) return;
+        if (frz) {
+            const double rc = __ldg(rconst + r0);
+            cg0 += rc;
+            cg1 += rc;
+        }
     }
 #if BLP_PAIR_ROWS_DUAL
-    if (!coop) {
+    if (!coop && !frz) {
         for (int i = r0 + warp; i < r1; i += 2 * kWarps) {
             const int ib = i + kWarps;
             const bool hb = ib < r1;
@@ -905,7 +967,10 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
             on1 = mrow[1] != 0;
         }
         double ax0 = cg0, ax1 = cg1;
-        if (!coop) slab_dot2(sl, P.ent, i - r0, xn, ax0, ax1);
+        if (!coop) {
+            if (frz) ax0 = ax1 = __ldg(rconst + i);
+            slab_dot2(sl, aent, i - r0, xn, ax0, ax1);
+        }
         const double bi = __ldg(P.b + i);
         const double yp0 = on0 ? fmax(0.0, yc.x + sig0 * (bi - ax0)) : 0.0;
         const double yp1 = on1 ? fmax(0.0, yc.y + sig1 * (bi - ax1)) : 0.0;
@@ -1250,9 +1315,11 @@ k_freeze_cols(const DevProb P, const DevState S, const FreezeArgs F, const int r
     const int node = blockIdx.y * 32 + lane;
     const bool live = node < S.B && S.fin[node] == 0;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) S.counters[8 + threadIdx.x] = 0;   // k_freeze_count follows
-    if (__ballot_sync(0xffffffffu, live) == 0) return;        // uniform over the CTA
+    const unsigned running = __ballot_sync(0xffffffffu, live);
+    if (running == 0) return;                                 // uniform over the CTA
     const bool strict = mode == 2 || (mode == 1 && live && S.fresh[node] != 0);
     uint8_t* __restrict__ flags = S.cfrz + (size_t)blockIdx.y * P.n;
+    double* __restrict__ cval = S.cval + (size_t)blockIdx.y * P.n;
     const double* __restrict__ yn = S.Y1 + tix(0, node, P.m);
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(P.n, r0 + rows_per_cta);
@@ -1260,9 +1327,11 @@ k_freeze_cols(const DevProb P, const DevState S, const FreezeArgs F, const int r
         const uint8_t stored = flags[j], prev = mode == 2 ? 0 : stored;
         const double gp = row_dot<32>(P.cptr, P.cent, j, true, yn, live);
         bool ok = true;
+        double xp = 0.0;
         if (live) {
             const size_t e = tix(j, node, P.n);
-            const double xp = S.X1[e], lo = S.l[e], hi = S.u[e];
+            const double lo = S.l[e], hi = S.u[e];
+            xp = S.X1[e];
             ok = false;
             if (xp == lo || xp == hi) {
                 const double r = __ldg(P.c + j) - gp;
@@ -1273,7 +1342,14 @@ k_freeze_cols(const DevProb P, const DevState S, const FreezeArgs F, const int r
             }
         }
         const bool all = __all_sync(0xffffffffu, ok);
-        if (lane == 0 && (uint8_t)all != stored) flags[j] = all;
+        // 3: frozen, and every running node of the block rests at the same value (the column can be folded)
+        const double ref = __shfl_sync(0xffffffffu, xp, __ffs(running) - 1);
+        const bool uniform = __all_sync(0xffffffffu, !live || xp == ref);
+        const uint8_t flag = all ? (uniform ? 3 : 1) : 0;
+        if (lane == 0) {
+            if (flag != stored) flags[j] = flag;
+            if (flag == 3) cval[j] = ref;
+        }
     }
 }
 
@@ -1301,6 +1377,85 @@ k_freeze_rows(const DevProb P, const DevState S, const FreezeArgs F, const int r
         }
         const bool all = __all_sync(0xffffffffu, ok);
         if (lane == 0 && (uint8_t)all != stored) flags[i] = all;
+    }
+}
+
+// Folded matrices of every tile with a running node, from the flags (see DevState). One thread per column / row.
+//   k_fold_cols: which columns rest at ONE value for the whole tile (both blocks flag 3 with equal values, a block
+//                without a running node agrees) — their contribution to A x is a per-row constant of the tile
+//   k_fold_A:    per row of A the entries of the other columns, packed; rconst = sum over the folded ones
+//   k_fold_AT:   per row of A' (column of A) the entries whose row is not frozen (a frozen row's multiplier is zero)
+// running nodes of the tile's two 32-node blocks -> s_l[0], s_l[1] (all threads of the CTA call; ends with a barrier)
+__device__ __forceinline__ void tile_running(const DevState& S, const int tile, int* s_l) {
+    if (threadIdx.x < kBlk) {
+        const int node = tile * kBlk + threadIdx.x;
+        const unsigned bal = __ballot_sync(0xffffffffu, node < S.B && S.fin[node] == 0);
+        if ((threadIdx.x & 31) == 0) s_l[threadIdx.x >> 5] = __popc(bal);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_fold_cols(const DevProb P, const DevState S) {
+    __shared__ int s_l[2];
+    const int tile = blockIdx.y;
+    tile_running(S, tile, s_l);
+    const int l0 = s_l[0], l1 = s_l[1];
+    if (l0 + l1 == 0) return;
+    const uint8_t* __restrict__ f0 = S.cfrz + (size_t)(2 * tile) * P.n;
+    const double* __restrict__ v0 = S.cval + (size_t)(2 * tile) * P.n;
+    for (int j = blockIdx.x * kCtaThreads + threadIdx.x; j < P.n; j += gridDim.x * kCtaThreads) {
+        const bool a = l0 == 0 || f0[j] == 3, b = l1 == 0 || f0[P.n + j] == 3;
+        const double va = l0 ? v0[j] : v0[P.n + j], vb = l1 ? v0[P.n + j] : va;
+        const bool fold = a && b && va == vb;
+        S.fcol[(size_t)tile * P.n + j] = fold;
+        S.fval[(size_t)tile * P.n + j] = fold ? va : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_fold_A(const DevProb P, const DevState S) {
+    __shared__ int s_l[2];
+    const int tile = blockIdx.y;
+    tile_running(S, tile, s_l);
+    if (s_l[0] + s_l[1] == 0) return;
+    const uint8_t* __restrict__ fcol = S.fcol + (size_t)tile * P.n;
+    const double* __restrict__ fval = S.fval + (size_t)tile * P.n;
+    int4* __restrict__ out = reinterpret_cast<int4*>(S.fentA + (size_t)tile * P.nnz);
+    const int4* __restrict__ in = reinterpret_cast<const int4*>(P.ent);
+    for (int i = blockIdx.x * kCtaThreads + threadIdx.x; i < P.m; i += gridDim.x * kCtaThreads) {
+        const int p0 = __ldg(P.rowptr + i), p1 = __ldg(P.rowptr + i + 1);
+        int w = p0;
+        double c = 0.0;
+        for (int p = p0; p < p1; ++p) {
+            const int4 e = __ldg(in + p);
+            if (fcol[e.x]) c = fma(__hiloint2double(e.w, e.z), fval[e.x], c);
+            else out[w++] = e;
+        }
+        S.fendA[(size_t)tile * P.m + i] = w;
+        S.rconst[(size_t)tile * P.m + i] = c;
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_fold_AT(const DevProb P, const DevState S) {
+    __shared__ int s_l[2];
+    const int tile = blockIdx.y;
+    tile_running(S, tile, s_l);
+    const int l0 = s_l[0], l1 = s_l[1];
+    if (l0 + l1 == 0) return;
+    const uint8_t* __restrict__ f0 = S.rfrz + (size_t)(2 * tile) * P.m;
+    int4* __restrict__ out = reinterpret_cast<int4*>(S.fentAT + (size_t)tile * P.nnz);
+    const int4* __restrict__ in = reinterpret_cast<const int4*>(P.cent);
+    for (int j = blockIdx.x * kCtaThreads + threadIdx.x; j < P.n; j += gridDim.x * kCtaThreads) {
+        const int p0 = __ldg(P.cptr + j), p1 = __ldg(P.cptr + j + 1);
+        int w = p0;
+        for (int p = p0; p < p1; ++p) {
+            const int4 e = __ldg(in + p);
+            const bool frozen = (l0 == 0 || f0[e.x] != 0) && (l1 == 0 || f0[P.m + e.x] != 0);
+            if (!frozen) out[w++] = e;
+        }
+        S.fendAT[(size_t)tile * P.n + j] = w;
     }
 }
 

@@ -294,7 +294,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='blp', choices=['blp', 'reference'])
     ap.add_argument('--workload', default='c5', choices=list(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=1024,
+    ap.add_argument('--batch', type=int, default=2048,
                     help='open nodes per step: per GPU with --scaling weak, in total with --scaling strong')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: every GPU solves --batch nodes per step; strong: --batch nodes per step are '
@@ -541,22 +541,25 @@ def main():
         bytes_AT = 12 * d.A.nnz + 4 * (n + 1)
         # iteration pair over the TIMED steps (CUDA events around each period's step graph)
         it_timed = max(agg['iters'], 1)
-        # coordinates the kernels skipped because they were frozen (blp_opts.freeze) cost no stream bytes
-        pair_bytes = ((pb + db) * agg['node_iters'] - 20 * (agg['skipped_cols'] + agg['skipped_rows'])
+        # a coordinate the kernels skipped as frozen (blp_opts.freeze) costs neither its 20 stream bytes nor, its entries
+        # being folded out of the tile's matrices, the 8 bytes of its gathered value: 28 bytes per ACTIVE coordinate
+        pair_bytes = ((pb + db) * agg['node_iters'] - 28 * (agg['skipped_cols'] + agg['skipped_rows'])
                       + (bytes_A + bytes_AT) * it_timed) / it_timed
         pair_s = agg['step_ms'] * 1e-3 / it_timed
         pair_gbs = pair_bytes / pair_s / 1e9
         # per-kernel split from the profile step (same slice as the last timed step)
         it_prof = max(prof['iterations'], 1)
-        primal_bytes = (pb * prof['node_iterations'] - 20 * prof['skipped_col_updates'] + bytes_AT * it_prof) / it_prof
-        dual_bytes = (db * prof['node_iterations'] - 20 * prof['skipped_row_updates'] + bytes_A * it_prof) / it_prof
+        primal_bytes = (pb * prof['node_iterations'] - 20 * prof['skipped_col_updates'] - 8 * prof['skipped_row_updates']
+                        + bytes_AT * it_prof) / it_prof
+        dual_bytes = (db * prof['node_iterations'] - 20 * prof['skipped_row_updates'] - 8 * prof['skipped_col_updates']
+                      + bytes_A * it_prof) / it_prof
         primal_s = prof['primal_kernel_ms'] * 1e-3 / it_prof
         dual_s = prof['dual_kernel_ms'] * 1e-3 / it_prof
         prim_gbs = primal_bytes / primal_s / 1e9 if primal_s > 0 else 0.0
         dual_gbs = dual_bytes / dual_s / 1e9 if dual_s > 0 else 0.0
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2n_traffic.json')))
             if tr['workload'] == args.workload and tr['batch'] == W:
                 # DRAM read+write bytes of one k_primal2 + one k_dual2 launch at full batch width (ncu)
                 traffic = tr['k_primal2_dram_bytes_per_launch'] + tr['k_dual2_dram_bytes_per_launch']
@@ -580,13 +583,15 @@ def main():
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': 'PDHG iteration = k_primal + k_dual (one launch each)',
                          'achieved': pair_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': pair_gbs / peak,
-                         'traffic': traffic, 'traffic_note': 'ncu dram read+write of one iteration at FULL batch width '
-                         '(profiles/r2_traffic.json); bytes_per_launch is the average over the timed steps, '
+                         'traffic': traffic, 'traffic_note': 'ncu dram read+write of one iteration at FULL batch width early in a solve '
+                         '(profiles/r2n_traffic.json: 66 % of the columns, 27 % of the rows frozen; algorithmic bytes of that '
+                         'launch pair: 450 MB); bytes_per_launch is the average over the timed steps, '
                          'where slots of finished nodes are refilled while nodes are pending and the tail of a step is compacted', 'full_width_bytes': (pb + db) * W + bytes_A + bytes_AT,
                          'peak_source': peak_src, 'bytes_per_launch': pair_bytes,
                          'ms_per_launch': pair_s * 1e3,
                          'measured': 'CUDA events around every period graph (64 iterations) of the timed steps; '
-                                     'bytes = 28(n+m) per running node and iteration, less 20 per coordinate update skipped as frozen, '
+                                     'bytes = 28 per ACTIVE (coordinate, node) and iteration — 20 streamed + 8 gathered; frozen coordinates '
+                                     '(nodes.frozen_*_share) are neither updated nor gathered — '
                                      '+ both matrices (bounds kept as block reference + mask, fp32 anchors)',
                          'k_primal': {'achieved': prim_gbs, 'frac': prim_gbs / peak, 'bytes_per_launch': primal_bytes,
                                       'ms_per_launch': primal_s * 1e3},

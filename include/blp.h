@@ -77,6 +77,11 @@ typedef struct blp_opts {
                               frozen set; what is saved is HBM stream (blp_stats.skipped_*). default 1 */
     double freeze_margin;  /* safety margin of that rule in units of the scaled problem's rms cost / right-hand
                               side: freeze above it, release below a third of it. default 0.05 */
+    double step_safety;    /* with frozen coordinates the iteration of a tile is PDHG on the rows and columns that
+                              still move, A_UU, and its step may be step_safety / ||A_UU||_2 (power iteration per
+                              tile, re-estimated after every evaluation) instead of 0.998 / ||A||_2; a node whose
+                              fixed-point error grows under the larger step returns to 0.998 / ||A||_2 for good.
+                              0 keeps 0.998 / ||A||_2. In [0, 1]; default 0.98 */
 } blp_opts;
 
 typedef struct blp_stats {
@@ -92,6 +97,7 @@ typedef struct blp_stats {
     int refills;               /* nodes that entered through a freed slot (max_active < B) */
     double skipped_col_updates;/* (column, node, iteration) updates skipped because the column was frozen */
     double skipped_row_updates;/* the same for rows; node_iterations * (n + m) is the total without freezing */
+    int step_resets;           /* nodes the watchdog sent back from step_safety / ||A_UU|| to 0.998 / ||A|| */
 } blp_stats;
 
 /* default options */

@@ -454,7 +454,15 @@ size_t carve_state(const blp_handle h, int B, void* ws, DevState* S) {
         s.fendA = cv.take<int32_t>(m * tiles);
         s.fendAT = cv.take<int32_t>(n * tiles);
         s.rconst = cv.take<double>(m * tiles);
+        s.ftc = cv.take<uint8_t>(n * tiles);
+        s.ftr = cv.take<uint8_t>(m * tiles);
+        s.pv = cv.take<double>(n * tiles);
+        s.pw = cv.take<double>(m * tiles);
+        s.ppart = cv.take<double>((size_t)kPowChunks * tiles);
+        s.eta_tile = cv.take<double>(tiles);
     }
+    s.eta = cv.take<double>(ld);
+    s.eta_lock = cv.take<int32_t>(ld);
     if (S) *S = s;
     return align_up(cv.off, 256);
 }
@@ -508,8 +516,11 @@ void launch_eval_nt(const DevProb& P, const DevState& S, const Plan& ec, const P
 }
 
 // Recompute the frozen-coordinate flags of every 32-node block (mode: see k_freeze_cols) and their count.
-constexpr int kFreezeLaunches = 6;
-void launch_freeze(const DevProb& P, const DevState& S, const FreezeArgs& F, int mode, cudaStream_t st) {
+struct StepArgs {
+    double safety, cap;      // step of a tile = min(cap / ||A||, safety / ||A_UU||); safety 0 = keep 0.998 / ||A||
+    int passes_first, passes;
+};
+int launch_freeze(const DevProb& P, const DevState& S, const FreezeArgs& F, const StepArgs& T, int mode, cudaStream_t st) {
     const int halves = (S.B + 31) / 32;
     auto rows_per_cta = [&](int rows) {
         const int want_chunks = std::max(1, 148 * 8 / halves);
@@ -517,17 +528,27 @@ void launch_freeze(const DevProb& P, const DevState& S, const FreezeArgs& F, int
         return std::max(kWarps, (r + kWarps - 1) / kWarps * kWarps);
     };
     const int rc = rows_per_cta(P.n), rr = rows_per_cta(P.m);
-    if (mode >= 0) {
-        k_freeze_cols<<<dim3((P.n + rc - 1) / rc, halves), kCtaThreads, 0, st>>>(P, S, F, rc, mode);
-        k_freeze_rows<<<dim3((P.m + rr - 1) / rr, halves), kCtaThreads, 0, st>>>(P, S, F, rr, mode);
-    }
-    // mode < 0: the flags were just cleared (compaction) — only rebuild the tiles' matrices from them
+    k_freeze_cols<<<dim3((P.n + rc - 1) / rc, halves), kCtaThreads, 0, st>>>(P, S, F, rc, mode);
+    k_freeze_rows<<<dim3((P.m + rr - 1) / rr, halves), kCtaThreads, 0, st>>>(P, S, F, rr, mode);
     const int tiles = (S.B + kBlk - 1) / kBlk;
     auto per_tile = [&](int rows) { return dim3(std::max(1, std::min((rows + kCtaThreads - 1) / kCtaThreads, 148 * 4 / tiles + 1)), tiles); };
     k_fold_cols<<<per_tile(P.n), kCtaThreads, 0, st>>>(P, S);
     k_fold_A<<<per_tile(P.m), kCtaThreads, 0, st>>>(P, S);
     k_fold_AT<<<per_tile(P.n), kCtaThreads, 0, st>>>(P, S);
+    int launched = 6;
+    if (T.safety > 0.0) {
+        const dim3 gp(std::min(kPowChunks, std::max(1, (std::max(P.n, P.m) + 4 * kCtaThreads - 1) / (4 * kCtaThreads))), tiles);
+        if (mode == 2) k_pow_init<<<gp, kCtaThreads, 0, st>>>(P, S);
+        const int passes = mode == 2 ? T.passes_first : T.passes;
+        for (int q = 0; q < passes; ++q) {
+            k_pow_A<<<gp, kCtaThreads, 0, st>>>(P, S);
+            k_pow_AT<<<gp, kCtaThreads, 0, st>>>(P, S);
+        }
+        k_pow_finish<<<tiles, kBlk, 0, st>>>(P, S, T.safety, T.cap, mode);
+        launched += 2 * passes + 1 + (mode == 2 ? 1 : 0);
+    }
     k_freeze_count<<<tiles, kCtaThreads, 0, st>>>(P, S);
+    return launched;
 }
 
 void launch_eval(const DevProb& P, const DevState& S, const Plan& ec, const Plan& er,
@@ -636,9 +657,10 @@ int check_opts(const blp_opts* in, blp_opts* o) {
     blp_default_opts(o);
     if (in) *o = *in;
     if (!(o->eps_rel > 0.0) || !(o->eps_infeas > 0.0) || o->max_iters < 1 || o->eval_every < 1 ||
-        o->max_active < 0 || std::isnan(o->obj_cutoff) || !(o->freeze_margin >= 0.0))
+        o->max_active < 0 || std::isnan(o->obj_cutoff) || !(o->freeze_margin >= 0.0) || !(o->step_safety >= 0.0) ||
+        o->step_safety > 1.0)
         return fail(BLP_ERR_ARG, "blp_opts: eps_rel/eps_infeas must be > 0, max_iters/eval_every >= 1, "
-                                 "max_active >= 0, freeze_margin >= 0");
+                                 "max_active >= 0, freeze_margin >= 0, 0 <= step_safety <= 1");
     return BLP_OK;
 }
 
@@ -661,6 +683,7 @@ void blp_default_opts(blp_opts* o) {
     o->obj_cutoff = INFINITY;
     o->freeze = 1;
     o->freeze_margin = 0.05;
+    o->step_safety = 0.98;
 }
 
 int blp_slots(int B, const blp_opts* o) {
@@ -822,6 +845,8 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     const double fm = env_dbl("BLP_FREEZE_MARGIN", o.freeze_margin), fl = env_dbl("BLP_FREEZE_RELEASE", 1.0 / 3.0);
     const FreezeArgs F{h->frz_c > 0.0 ? fl * fm * h->frz_c : INFINITY, h->frz_c > 0.0 ? fm * h->frz_c : INFINITY,
                        h->frz_r > 0.0 ? fl * fm * h->frz_r : INFINITY, h->frz_r > 0.0 ? fm * h->frz_r : INFINITY};
+    const StepArgs T{freeze ? env_dbl("BLP_STEP_SAFETY", o.step_safety) : 0.0, env_dbl("BLP_STEP_CAP", 4.0),
+                     env_int("BLP_POW_FIRST", 40), env_int("BLP_POW_PASSES", 3)};
     uint8_t* const cfrz_ws = S.cfrz;
     const size_t frz_bytes = (size_t)(S.rfrz - S.cfrz) + (size_t)P.m * (S.ld / 32);
     if (!freeze) S.cfrz = S.rfrz = nullptr;
@@ -871,7 +896,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     k_count_active<<<(W + 127) / 128, 128, 0, st>>>(S);
     launches += 6;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_counters, S.counters, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_counters, S.counters, 13 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     int active = h->h_counters[0];
 
@@ -949,7 +974,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
             k_count_active<<<(S.B + 127) / 128, 128, 0, st>>>(S);
             launches += 6;
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h->h_counters, S.counters, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h->h_counters, S.counters, 13 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             next += nnew;
             refills += nnew;
@@ -962,8 +987,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     // frozen coordinates exist for the two-nodes-per-lane step kernels only (wide batches)
     auto refreeze = [&](int mode) {
         if (!freeze || pc.V != 2) return;
-        launch_freeze(P, S, F, mode, st);
-        launches += kFreezeLaunches;
+        launches += launch_freeze(P, S, F, T, mode, st);
     };
     refreeze(2);
 
@@ -1038,22 +1062,23 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
                 pick_nt(active) < NT) {
                 const int oldB = S.B;
                 k_compact_plan<<<1, 1024, 0, st>>>(S);
-                k_compact_vecs<<<elementwise_grid((size_t)(4 * P.n + 2 * P.m) * 32), kCtaThreads, 0, st>>>(P, S, oldB);
+                k_compact_vecs<<<elementwise_grid((size_t)(5 * P.n + 3 * P.m) * 32), kCtaThreads, 0, st>>>(P, S, oldB);
                 CK(cudaGetLastError());
                 S.B = active;
                 k_build_lumask<<<elementwise_grid((size_t)P.n * ((S.B + 31) / 32) * 32), kCtaThreads, 0, st>>>(P, S);
-                if (freeze) {      // the slots moved and x', y' are stale until the next evaluation: release everything
-                    CK(cudaMemsetAsync(cfrz_ws, 0, frz_bytes, st));
-                    CK(cudaMemsetAsync(S.counters + 8, 0, 4 * sizeof(int32_t), st));
-                    launch_freeze(P, S, F, -1, st);
-                    launches += 4;
-                }
                 launches += 3;
                 ++compactions;
                 NT = pick_nt(S.B);
                 pc = step_plan(P.n, S.B, true);
                 pr = step_plan(P.m, S.B);
                 if ((rc = finish_step_plans()) != BLP_OK) return rc;
+                if (freeze) {
+                    // the slots moved: the tiles are new sets of nodes and their flags start afresh (x', y' travelled
+                    // with the nodes); a batch that has become too narrow for the freezing kernels updates every
+                    // coordinate again, so its nodes return to the step of the full matrix
+                    if (pc.V == 2) launches += launch_freeze(P, S, F, T, 2, st);
+                    else k_eta_reset<<<(S.ld + 127) / 128, 128, 0, st>>>(P, S), ++launches;
+                }
                 coop_rejected = false;
                 ec = make_plan(P.n, S.B, 1, kEvalChunks);
                 er = make_plan(P.m, S.B, 1, kEvalChunks);
@@ -1105,7 +1130,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
             launch_eval(P, S, ec, er, D, K, st);
         }
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->h_counters, S.counters, 12 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->h_counters, S.counters, 13 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
@@ -1166,6 +1191,7 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
         stats->refills = refills;
         stats->skipped_col_updates = skipped_cols;
         stats->skipped_row_updates = skipped_rows;
+        stats->step_resets = h->h_counters[12];
     }
     return BLP_OK;
 }

@@ -103,7 +103,14 @@ struct DevState {
     Ent *fentA, *fentAT;                           // [tile][nnz]
     int32_t *fendA, *fendAT;                       // [tile][m], [tile][n]
     double* rconst;                                // [tile][m] sum of a_ij x_j over the folded columns of row i
+    // Step size of a node (k_pow_*): eta = P.eta = 0.998 / ||A|| unless its tile has frozen coordinates, then up to
+    // safety / ||A_UU||, A_UU = the rows and columns of the tile that still move.
+    double* eta; int32_t* eta_lock;                // [ld] current step; 1 = the watchdog sent the node back to P.eta
+    uint8_t *ftc, *ftr;                            // [tile][n], [tile][m] 1 = frozen for the tile
+    double *pv, *pw;                               // [tile][n], [tile][m] power-iteration vectors
+    double *ppart, *eta_tile;                      // [tile][kPowChunks] partial ||v||^2; [tile] step the tile allows
 };
+constexpr int kPowChunks = 32;
 
 // Margins of the freezing rule in the scaled problem's units (blp.cu: solve set-up).
 struct FreezeArgs {
@@ -349,7 +356,7 @@ __device__ __forceinline__ void primal_chunk(const DevProb& P, const DevState& S
     if (node_ok) {
         const int s = S.sbase[node] + it;
         w = (double)s / (double)(s + 1);
-        tau = P.eta / S.omega[node];
+        tau = S.eta[node] / S.omega[node];
     }
     const int r0 = __ldg(chunk_ptr + 2 * cx);              // chunk cx = rows [r0, r1); heaviest chunks first
     const int r1 = __ldg(chunk_ptr + 2 * cx + 1);
@@ -416,7 +423,7 @@ __device__ __forceinline__ void dual_chunk(const DevProb& P, const DevState& S, 
     if (node_ok) {
         const int s = S.sbase[node] + it;
         w = (double)(s + 1) / (double)(s + 2);
-        sig = P.eta * S.omega[node];
+        sig = S.eta[node] * S.omega[node];
     }
     const int r0 = __ldg(chunk_ptr + 2 * cx);              // chunk cx = rows [r0, r1); heaviest chunks first
     const int r1 = __ldg(chunk_ptr + 2 * cx + 1);
@@ -736,12 +743,12 @@ k_primal2(const DevProb P, const DevState S, const int it, const int rows_per_ct
     if (k0) {
         const int s = S.sbase[node] + it;
         w0 = (double)s / (double)(s + 1);
-        tau0 = P.eta / S.omega[node];
+        tau0 = S.eta[node] / S.omega[node];
     }
     if (k1) {
         const int s = S.sbase[node + 1] + it;
         w1 = (double)s / (double)(s + 1);
-        tau1 = P.eta / S.omega[node + 1];
+        tau1 = S.eta[node + 1] / S.omega[node + 1];
     }
     const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
     const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
@@ -867,12 +874,12 @@ k_dual2(const DevProb P, const DevState S, const int it, const int rows_per_cta,
     if (k0) {
         const int s = S.sbase[node] + it;
         w0 = (double)(s + 1) / (double)(s + 2);
-        sig0 = P.eta * S.omega[node];
+        sig0 = S.eta[node] * S.omega[node];
     }
     if (k1) {
         const int s = S.sbase[node + 1] + it;
         w1 = (double)(s + 1) / (double)(s + 2);
-        sig1 = P.eta * S.omega[node + 1];
+        sig1 = S.eta[node + 1] * S.omega[node + 1];
     }
     const int r0 = __ldg(chunk_ptr + 2 * blockIdx.x);
     const int r1 = __ldg(chunk_ptr + 2 * blockIdx.x + 1);
@@ -1165,7 +1172,8 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
             r[a] = (a < R_NSUM) ? r[a] + v : fmax(r[a], v);
         }
     const double omega = S.omega[node];
-    const double tau = P.eta / omega, sig = P.eta * omega;
+    const double eta = S.eta[node];
+    const double tau = eta / omega, sig = eta * omega;
     const double fpe = sqrt(fmax(c[C_DX2] / tau + r[R_DY2] / sig + 2.0 * c[C_CROSS], 0.0));
     const double pobj = c[C_CX] * P.objscale;
     const double dobj = (r[R_BY] + c[C_BND]) * P.objscale;
@@ -1233,7 +1241,15 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
     const int s_now = S.sbase[node] + D.steps_in_period;
     const double f0 = S.fpe0[node], fprev = S.fpe_prev[node];
     const bool first = !(f0 < INFINITY);
-    const bool do_restart = first || fpe <= D.beta_suff * f0 || (fpe <= D.beta_nec * f0 && fpe > fprev) ||
+    // a step above 1 / ||A|| rests on the frozen set staying frozen and on a power-iteration estimate; if the
+    // fixed-point error grows by half within a phase the node goes back to 1 / ||A|| for good and restarts
+    const bool runaway = eta > P.eta && !first && fpe > 1.5 * fmin(f0, fprev);
+    if (runaway) {
+        S.eta[node] = P.eta;
+        S.eta_lock[node] = 1;
+        atomicAdd(S.counters + 12, 1);
+    }
+    const bool do_restart = first || runaway || fpe <= D.beta_suff * f0 || (fpe <= D.beta_nec * f0 && fpe > fprev) ||
                             (double)s_now >= D.beta_art * (double)total;
     if (do_restart) {
         const double ddx = sqrt(c[C_DXA2]), ddy = sqrt(r[R_DYA2]);
@@ -1252,7 +1268,7 @@ __global__ void k_decide(const DevProb P, const DevState S, const DecideArgs D) 
             if (fb <= 1e4 * P.omega0 && fb >= 1e-4 * P.omega0) om = fb;
         }
         S.omega[node] = om;
-        S.fpe0[node] = fpe;
+        S.fpe0[node] = runaway ? INFINITY : fpe;
         S.fpe_prev[node] = INFINITY;
         S.sbase[node] = 0;
         S.restart[node] = 1;
@@ -1410,7 +1426,11 @@ k_fold_cols(const DevProb P, const DevState S) {
         const bool fold = a && b && va == vb;
         S.fcol[(size_t)tile * P.n + j] = fold;
         S.fval[(size_t)tile * P.n + j] = fold ? va : 0.0;
+        S.ftc[(size_t)tile * P.n + j] = (l0 == 0 || f0[j] != 0) && (l1 == 0 || f0[P.n + j] != 0);
     }
+    const uint8_t* __restrict__ g0 = S.rfrz + (size_t)(2 * tile) * P.m;
+    for (int i = blockIdx.x * kCtaThreads + threadIdx.x; i < P.m; i += gridDim.x * kCtaThreads)
+        S.ftr[(size_t)tile * P.m + i] = (l0 == 0 || g0[i] != 0) && (l1 == 0 || g0[P.m + i] != 0);
 }
 
 __global__ void __launch_bounds__(kCtaThreads)
@@ -1457,6 +1477,108 @@ k_fold_AT(const DevProb P, const DevState S) {
         }
         S.fendAT[(size_t)tile * P.n + j] = w;
     }
+}
+
+// Step size of a tile with frozen coordinates. While the frozen coordinates rest, the iteration of the tile's
+// nodes is PDHG on the rows and columns that still move, A_UU, whose norm bounds the step: eta <= 1 / ||A_UU||_2.
+// (Round 1 looked for a larger step under the FULL matrix' norm and found none that converges on C5; the norm of
+// the active block is the rigorous version: C4 0.47 ||A||, C5 0.86 ||A||, tests/tools/cpu_freeze_lab.py.)
+// Power iteration on A_UU' A_UU per tile, warm-started from the tile's previous vector (the sets change slowly):
+//   k_pow_A:  w = M_r A M_c (v / ||v||)      one thread per row, ||v||^2 = sum of the previous pass' partials
+//   k_pow_AT: v = M_c A' w, partial ||v||^2  one thread per column, fixed-order reductions (deterministic)
+//   k_pow_finish: sigma = ||v||^(1/2); eta_tile = min(cap * P.eta, safety / sigma); a node takes a LARGER step only at
+//                 a restart or when it was just loaded, a smaller one at once; nodes the watchdog locked stay at P.eta
+__global__ void __launch_bounds__(kCtaThreads)
+k_pow_init(const DevProb P, const DevState S) {
+    const int tile = blockIdx.y;
+    for (int j = blockIdx.x * kCtaThreads + threadIdx.x; j < P.n; j += gridDim.x * kCtaThreads)
+        S.pv[(size_t)tile * P.n + j] = 1.0;
+    if (blockIdx.x == 0 && threadIdx.x < kPowChunks)
+        S.ppart[(size_t)tile * kPowChunks + threadIdx.x] = threadIdx.x == 0 ? (double)P.n : 0.0;
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_pow_A(const DevProb P, const DevState S) {
+    const int tile = blockIdx.y;
+    double tot = 0.0;
+    for (int q = 0; q < kPowChunks; ++q) tot += S.ppart[(size_t)tile * kPowChunks + q];
+    const double scale = tot > 0.0 ? rsqrt(tot) : 0.0;
+    const uint8_t* __restrict__ ftc = S.ftc + (size_t)tile * P.n;
+    const uint8_t* __restrict__ ftr = S.ftr + (size_t)tile * P.m;
+    const double* __restrict__ v = S.pv + (size_t)tile * P.n;
+    const int4* __restrict__ E = reinterpret_cast<const int4*>(P.ent);
+    for (int i = blockIdx.x * kCtaThreads + threadIdx.x; i < P.m; i += gridDim.x * kCtaThreads) {
+        double acc = 0.0;
+        if (!ftr[i])
+            for (int p = __ldg(P.rowptr + i); p < __ldg(P.rowptr + i + 1); ++p) {
+                const int4 e = __ldg(E + p);
+                if (!ftc[e.x]) acc = fma(__hiloint2double(e.w, e.z), v[e.x], acc);
+            }
+        S.pw[(size_t)tile * P.m + i] = acc * scale;
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads)
+k_pow_AT(const DevProb P, const DevState S) {
+    __shared__ double red[kCtaThreads];
+    const int tile = blockIdx.y;
+    const uint8_t* __restrict__ ftc = S.ftc + (size_t)tile * P.n;
+    const double* __restrict__ w = S.pw + (size_t)tile * P.m;
+    const int4* __restrict__ E = reinterpret_cast<const int4*>(P.cent);
+    double sq = 0.0;
+    for (int j = blockIdx.x * kCtaThreads + threadIdx.x; j < P.n; j += gridDim.x * kCtaThreads) {
+        double acc = 0.0;
+        if (!ftc[j])
+            for (int p = __ldg(P.cptr + j); p < __ldg(P.cptr + j + 1); ++p) {
+                const int4 e = __ldg(E + p);
+                acc = fma(__hiloint2double(e.w, e.z), w[e.x], acc);     // w is zero on frozen rows
+            }
+        S.pv[(size_t)tile * P.n + j] = acc;
+        sq = fma(acc, acc, sq);
+    }
+    red[threadIdx.x] = sq;
+    __syncthreads();
+    for (int h = kCtaThreads / 2; h > 0; h >>= 1) {
+        if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) S.ppart[(size_t)tile * kPowChunks + blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(kBlk)
+k_pow_finish(const DevProb P, const DevState S, const double safety, const double cap, const int mode) {
+    const int tile = blockIdx.x, node = tile * kBlk + threadIdx.x;
+    double tot = 0.0;
+    for (int q = 0; q < kPowChunks; ++q) tot += S.ppart[(size_t)tile * kPowChunks + q];
+    const double sigma = sqrt(sqrt(tot));          // ||A_UU' A_UU v|| for a unit v: the largest singular value, squared
+    double et = cap * P.eta;
+    if (sigma > 0.0) et = fmin(et, safety / sigma);
+    et = fmax(et, P.eta);
+    if (threadIdx.x == 0) S.eta_tile[tile] = et;
+    if (node >= S.B || S.fin[node] != 0) return;
+    const bool may_raise = S.restart[node] != 0 || mode == 2 || (mode == 1 && S.fresh[node] != 0);
+    const double cur = S.eta[node];
+    const double nxt = (may_raise && !S.eta_lock[node]) ? et : fmin(cur, et);
+    if (nxt != cur) {
+        // the fixed-point error is measured in the step's own metric, ~ sqrt(eta) for the same move: keep the
+        // restart rule's and the watchdog's references comparable across the change
+        const double f = sqrt(nxt / cur);
+        S.eta[node] = nxt;
+        S.fpe0[node] *= f;
+        S.fpe_prev[node] *= f;
+    }
+}
+
+__global__ void k_eta_reset(const DevProb P, const DevState S) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= S.ld) return;
+    const double cur = S.eta[node];
+    if (cur != P.eta) {
+        const double f = sqrt(P.eta / cur);
+        S.fpe0[node] *= f;
+        S.fpe_prev[node] *= f;
+    }
+    S.eta[node] = P.eta;
 }
 
 // Frozen (coordinate, running node) pairs of the whole batch, as the step kernels will see them (both 32-node
@@ -1621,6 +1743,8 @@ __global__ void k_init_nodes(const DevProb P, const DevState S) {
     S.origin[node] = node;
     S.start[node] = 0;
     S.fresh[node] = 0;
+    S.eta[node] = P.eta;
+    S.eta_lock[node] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1667,6 +1791,8 @@ __global__ void __launch_bounds__(1024) k_refill_plan(const DevProb P, const Dev
             S.status[k] = 3;
             S.iters[k] = 0;
             S.restart[k] = 0;
+            S.eta[k] = P.eta;
+            S.eta_lock[k] = 0;
         }
         if (tid == 0) base_s += total;
         __syncthreads();
@@ -1843,11 +1969,12 @@ __global__ void __launch_bounds__(1024) k_compact_plan(const DevState S) {
     for (int c0 = 0; c0 < S.B; c0 += 1024) {
         const int k = c0 + tid;
         const bool keep = k < S.B && S.fin[k] == 0;
-        double om = 0, f0 = 0, fp = 0, po = 0, dq = 0;
-        int sb = 0, stt = 0, itr = 0, org = 0, beg = 0;
+        double om = 0, f0 = 0, fp = 0, po = 0, dq = 0, et = 0;
+        int sb = 0, stt = 0, itr = 0, org = 0, beg = 0, lck = 0;
         if (keep) {
             om = S.omega[k]; f0 = S.fpe0[k]; fp = S.fpe_prev[k]; po = S.pobj[k]; dq = S.dobj[k];
             sb = S.sbase[k]; stt = S.status[k]; itr = S.iters[k]; org = S.origin[k]; beg = S.start[k];
+            et = S.eta[k]; lck = S.eta_lock[k];
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) wsum[warp] = __popc(bal);
@@ -1863,6 +1990,7 @@ __global__ void __launch_bounds__(1024) k_compact_plan(const DevState S) {
             S.omega[pos] = om; S.fpe0[pos] = f0; S.fpe_prev[pos] = fp; S.pobj[pos] = po; S.dobj[pos] = dq;
             S.sbase[pos] = sb; S.status[pos] = stt; S.iters[pos] = itr; S.origin[pos] = org;
             S.start[pos] = beg;
+            S.eta[pos] = et; S.eta_lock[pos] = lck;
         }
         if (tid == 0) base_s += total;
         __syncthreads();
@@ -1881,7 +2009,8 @@ k_compact_vecs(const DevProb P, const DevState S, const int oldB) {
     const int gwarp = (blockIdx.x * kCtaThreads + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * kCtaThreads) >> 5;
     const int mc = S.rowmask ? P.m - P.m_base : 0;
-    const int total = 4 * P.n + 2 * P.m + mc;
+    const int ncol = 5 * P.n, nrow = 3 * P.m;         // xbar, xa, l, u, X1; y, ya, Y1 (x', y' feed the freezing rule)
+    const int total = ncol + nrow + mc;
     // one state row (512-byte segments of all node blocks) per warp and pass
     auto move_row = [&](auto* arr, const int row, const int rows) {
         for (int c0 = 0; c0 < oldB; c0 += 32) {
@@ -1893,18 +2022,18 @@ k_compact_vecs(const DevProb P, const DevState S, const int oldB) {
         }
     };
     for (int r = gwarp; r < total; r += nwarps) {
-        if (r < 4 * P.n + 2 * P.m) {
-            if (r < 4 * P.n) {
+        if (r < ncol + nrow) {
+            if (r < ncol) {
                 const int a = r / P.n, row = r % P.n;
                 if (a == 1) move_row(S.xa, row, P.n);
-                else move_row(a == 0 ? S.xbar : a == 2 ? S.l : S.u, row, P.n);
+                else move_row(a == 0 ? S.xbar : a == 2 ? S.l : a == 3 ? S.u : S.X1, row, P.n);
             } else {
-                const int q = r - 4 * P.n, row = q % P.m;
-                if (q < P.m) move_row(S.y, row, P.m);
-                else move_row(S.ya, row, P.m);
+                const int q = r - ncol, a = q / P.m, row = q % P.m;
+                if (a == 1) move_row(S.ya, row, P.m);
+                else move_row(a == 0 ? S.y : S.Y1, row, P.m);
             }
         } else {
-            uint8_t* base = S.rowmask + (size_t)(r - 4 * P.n - 2 * P.m) * S.ld;
+            uint8_t* base = S.rowmask + (size_t)(r - ncol - nrow) * S.ld;
             for (int c0 = 0; c0 < oldB; c0 += 32) {
                 const int k = c0 + lane;
                 const int p = k < oldB ? S.newpos[k] : -1;

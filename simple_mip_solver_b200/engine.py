@@ -34,7 +34,7 @@ class BlpOpts(C.Structure):
     _fields_ = [('eps_rel', C.c_double), ('eps_infeas', C.c_double), ('max_iters', C.c_int),
                 ('eval_every', C.c_int), ('use_graph', C.c_int), ('compact', C.c_int),
                 ('verbose', C.c_int), ('profile', C.c_int), ('max_active', C.c_int), ('obj_cutoff', C.c_double),
-                ('freeze', C.c_int), ('freeze_margin', C.c_double)]
+                ('freeze', C.c_int), ('freeze_margin', C.c_double), ('step_safety', C.c_double)]
 
 
 class BlpStats(C.Structure):
@@ -42,7 +42,7 @@ class BlpStats(C.Structure):
                 ('compactions', C.c_int), ('step_kernel_ms', C.c_double), ('total_ms', C.c_double),
                 ('node_iterations', C.c_double), ('primal_kernel_ms', C.c_double),
                 ('dual_kernel_ms', C.c_double), ('refills', C.c_int),
-                ('skipped_col_updates', C.c_double), ('skipped_row_updates', C.c_double)]
+                ('skipped_col_updates', C.c_double), ('skipped_row_updates', C.c_double), ('step_resets', C.c_int)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -640,7 +640,7 @@ class MultiGpuBatchLP:
     def _merge_stats(self, parts, pairs):
         st = dict(parts[0].stats)
         for k in ('kernel_launches', 'node_iterations', 'refills', 'compactions', 'evaluations',
-                  'skipped_col_updates', 'skipped_row_updates'):
+                  'skipped_col_updates', 'skipped_row_updates', 'step_resets'):
             st[k] = sum(p.stats.get(k, 0) for p in parts)
         for k in ('iterations', 'total_ms', 'step_kernel_ms'):
             st[k] = max(p.stats.get(k, 0) for p in parts)

@@ -51,6 +51,7 @@ def solve_tile(P, lb, ub, x0, y0, eps=1e-7, max_iters=150000, K=64, theta=0.05, 
     fc = np.zeros(n, dtype=bool)        # tile-wide frozen columns / rows
     fr = np.zeros(m, dtype=bool)
     work = skipped = 0.0
+    runaway = np.zeros(B, dtype=np.int64)
     freeze = m_lo is not None
     cabs = np.abs(P.c)[:, None] + 1e-300
 
@@ -140,6 +141,8 @@ def solve_tile(P, lb, ub, x0, y0, eps=1e-7, max_iters=150000, K=64, theta=0.05, 
                 obj[fin] = pobj[fin]
                 done |= fin
                 for k in np.nonzero(~done)[0]:
+                    if np.isfinite(fpe0[k]) and fpe[k] > 1.5 * min(fpe0[k], fpe_prev[k]):
+                        runaway[k] += 1            # the device's watchdog would send the node back to 1 / ||A|| here
                     why = fpe[k] <= suff * fpe0[k] or (fpe[k] <= nec * fpe0[k] and fpe[k] > fpe_prev[k]) \
                         or t[k] + 1 >= art * tot_it or not np.isfinite(fpe0[k])
                     if why:
@@ -169,7 +172,7 @@ def solve_tile(P, lb, ub, x0, y0, eps=1e-7, max_iters=150000, K=64, theta=0.05, 
         total += Kp
         periods += 1
     iters[~done] = total
-    return dict(iters=iters, obj=obj, skipped=skipped / max(work, 1.0), done=done)
+    return dict(iters=iters, obj=obj, skipped=skipped / max(work, 1.0), done=done, runaway=runaway)
 
 
 def main():
@@ -184,7 +187,7 @@ def main():
     t0 = time.time()
     r = solve_tile(P, lb, ub, root['x'], root['y'], m_lo=m_lo, m_hi=m_hi, sub_step=sub_step, log=lambda s: print(s, flush=True))
     print('margins', m_lo, m_hi, 'sub_step', sub_step, 'iters', r['iters'].tolist(), 'mean %.0f' % r['iters'].mean(), 'skipped %.3f' % r['skipped'],
-          'obj', np.round(r['obj'], 6).tolist(), 'time %.0f' % (time.time() - t0))
+          'runaway', r['runaway'].tolist(), 'obj', np.round(r['obj'], 6).tolist(), 'time %.0f' % (time.time() - t0))
 
 
 if __name__ == '__main__':

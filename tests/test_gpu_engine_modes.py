@@ -251,8 +251,9 @@ def test_frozen_coordinates_do_not_change_answers(blp_lib):
     X0, Y0 = np.tile(x0, (B, 1)), np.tile(y0, (B, 1))
     lp = eng.BatchLP(d.A, d.b, d.c)
     res = {}
-    for name, kw in (('off', dict(freeze=0)), ('on', {}), ('on_refill', dict(max_active=128)),
-                     ('off_refill', dict(freeze=0, max_active=128)), ('loose', dict(freeze_margin=0.005))):
+    for name, kw in (('off', dict(freeze=0)), ('on', dict(step_safety=0.0)), ('on_refill', dict(max_active=128, step_safety=0.0)),
+                     ('off_refill', dict(freeze=0, max_active=128)), ('loose', dict(freeze_margin=0.005, step_safety=0.0)),
+                     ('step', {}), ('step_refill', dict(max_active=128))):
         res[name] = lp.solve_batch(lbs, ubs, x0=X0, y0=Y0, integer_indices=d.integer_indices, opts=eng.default_opts(**kw))
     lp.close()
     off = res['off']
@@ -277,6 +278,17 @@ def test_frozen_coordinates_do_not_change_answers(blp_lib):
         assert (np.linalg.norm(viol, axis=1) <= 1.01e-7 * (1.0 + np.linalg.norm(d.b))).all(), name
     assert np.array_equal(res['off_refill'].status, off.status)
     assert res['loose'].stats['skipped_col_updates'] >= res['on'].stats['skipped_col_updates']
+    # blp_opts.step_safety (default on): the step of a tile follows the norm of the rows and columns that still move
+    # (0.47 ||A|| on this matrix), which nearly halves the iterations; same statuses, same objectives
+    for name in ('step', 'step_refill'):
+        r = res[name]
+        assert np.array_equal(r.status, off.status), name
+        assert np.allclose(r.objective[ok], off.objective[ok], rtol=2e-7, atol=0), name
+        assert r.iterations[ok].mean() < 0.75 * off.iterations[ok].mean(), (name, r.iterations[ok].mean())
+        assert r.stats['step_resets'] <= 0.1 * B, (name, r.stats['step_resets'])
+        viol = np.maximum(d.b[None, :] - (d.A @ r.x[ok].T).T, 0.0)
+        assert (np.linalg.norm(viol, axis=1) <= 1.01e-7 * (1.0 + np.linalg.norm(d.b))).all(), name
+    assert off.stats['step_resets'] == 0 and res['on'].stats['step_resets'] == 0
 
 
 def test_frozen_coordinates_with_cut_rows_masked_per_node(blp_lib):

@@ -740,6 +740,11 @@ int blp_create(int device, int m, int n, int64_t nnz, const int32_t* rowptr, con
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->coop_ok, cudaDevAttrCooperativeLaunch, device);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    // the wide step kernels carry ~8 KB of static shared memory next to a slab of up to 44 KB: opt in above 48 KB
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_primal2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_primal2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dual2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dual2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_counters, 16 * sizeof(int32_t));
     for (int q = 0; q < 4 && e == cudaSuccess; ++q) e = cudaEventCreate(&h->ev[q]);
     for (int q = 0; q < blp_handle_s::kLanes - 1 && e == cudaSuccess; ++q) {

@@ -319,3 +319,24 @@ def test_frozen_coordinates_with_cut_rows_masked_per_node(blp_lib):
     assert b.stats['skipped_row_updates'] > 0
     # the cuts bind: nodes that carry row 2 (all) are more expensive than the root
     assert (b.objective > float(np.load(os.path.join(ROOT, 'bench_data', 'c4_root.npz'))['objective'])).all()
+
+
+def test_wide_batch_with_rows_too_heavy_for_the_shared_memory_slab(blp_lib):
+    """Rows of ~50 entries: a CTA's chunk of A (128 rows) does not fit the shared-memory slab, so the dual step reads
+    the entries of its rows from global memory — with frozen coordinates, from the tile's folded matrix with the row
+    ends — and the slab is at its 44 KB cap next to the kernels' static shared memory (a launch that needs the
+    opt-in above 48 KB; the C5 stress variant of SURVEY 8d failed to launch before it was requested)."""
+    from simple_mip_solver_b200 import engine as eng
+    d = numpy_random_mip(20000, 2000, density=0.0025, seed=9)
+    lp = eng.BatchLP(d.A, d.b, d.c)
+    root = lp.solve_batch(d.l[None], d.u[None], want_y=True)
+    assert root.status[0] == 0
+    lbs, ubs, _ = frontier_nodes(d, root.x[0], 0, 64, 12, seed=1)
+    X0, Y0 = np.tile(root.x[0], (64, 1)), np.tile(root.y[0], (64, 1))
+    off = lp.solve_batch(lbs, ubs, x0=X0, y0=Y0, opts=eng.default_opts(freeze=0))
+    on = lp.solve_batch(lbs, ubs, x0=X0, y0=Y0, opts=eng.default_opts())
+    lp.close()
+    assert np.array_equal(on.status, off.status) and (off.status == 0).sum() >= 60
+    ok = off.status == 0
+    assert np.allclose(on.objective[ok], off.objective[ok], rtol=2e-7, atol=0)
+    assert on.stats['skipped_col_updates'] > 0 and off.stats['skipped_col_updates'] == 0

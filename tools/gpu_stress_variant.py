@@ -42,18 +42,21 @@ print(out['frontier'], flush=True)
 p = lp.solve_children(d.l, d.u, deltas, x0=root.x[0], y0=root.y[0], want_x=False, want_y=False,
                       opts=engine.default_opts(max_iters=512, profile=1)).stats
 it = p['iterations']
-pb, db = 20 * n + 8 * m, 8 * n + 20 * m
 bytes_A = 12 * d.A.nnz + 4 * (m + 1)
 bytes_AT = 12 * d.A.nnz + 4 * (n + 1)
 primal_ms, dual_ms = p['primal_kernel_ms'] / it, p['dual_kernel_ms'] / it
 width = p['node_iterations'] / it
+# active (coordinate, node) pairs per iteration: frozen coordinates are neither updated (20 bytes) nor gathered (8)
+act_c = (p['node_iterations'] * n - p['skipped_col_updates']) / it
+act_r = (p['node_iterations'] * m - p['skipped_row_updates']) / it
+pbytes, dbytes = 20 * act_c + 8 * act_r + bytes_AT, 20 * act_r + 8 * act_c + bytes_A
 peak = 6547.5
 out['kernels'] = dict(width=width, k_primal_ms=primal_ms, k_dual_ms=dual_ms,
-                      k_primal_gbs=(pb * width + bytes_AT) / primal_ms / 1e6, k_dual_gbs=(db * width + bytes_A) / dual_ms / 1e6,
-                      k_primal_frac=(pb * width + bytes_AT) / primal_ms / 1e6 / peak,
-                      k_dual_frac=(db * width + bytes_A) / dual_ms / 1e6 / peak,
-                      gather_l2_bytes_per_iteration=16.0 * d.A.nnz * width * 2,
-                      hbm_bytes_per_iteration=(pb + db) * width + bytes_A + bytes_AT, peak_gbs=peak)
+                      frozen_col_share=1 - act_c / (width * n), frozen_row_share=1 - act_r / (width * m),
+                      k_primal_gbs=pbytes / primal_ms / 1e6, k_dual_gbs=dbytes / dual_ms / 1e6,
+                      k_primal_frac=pbytes / primal_ms / 1e6 / peak, k_dual_frac=dbytes / dual_ms / 1e6 / peak,
+                      hbm_bytes_per_iteration=pbytes + dbytes,
+                      hbm_bytes_per_iteration_without_freezing=28 * (n + m) * width + bytes_A + bytes_AT, peak_gbs=peak)
 print(out['kernels'], flush=True)
 os.makedirs('gpurun_out', exist_ok=True)
 json.dump(out, open('gpurun_out/stress_variant.json', 'w'), indent=1)

@@ -927,7 +927,9 @@ int blp_solve_batch(blp_handle h, int B, const double* lb, const double* ub,
     const bool allow_v2 = env_int("BLP_V2", 1) != 0;
     const int graph_lanes = env_int("BLP_GRAPH_LANES", 2);
     const int rpw2 = std::min(env_int("BLP_ROWS_PER_WARP2", 16), kMaxChunkRows / kWarps);   // two-nodes-per-lane kernels: 128 rows per CTA
-    const int rpw2p = std::min(env_int("BLP_ROWS_PER_WARP2P", rpw2), kMaxChunkRows / kWarps);
+    // primal step with frozen coordinates: a third of a chunk's rows are left, 192-row chunks amortise the slab better
+    // (profiles/r2v_variant_sweep.log: -2.7 %; 5 or 4 CTAs per SM, 8 gathers in flight, 4 graph lanes all lose)
+    const int rpw2p = std::min(env_int("BLP_ROWS_PER_WARP2P", freeze ? 24 : rpw2), kMaxChunkRows / kWarps);
     auto step_plan = [&](int rows, int width, bool primal = false) {
         // two nodes per lane pay off when a launch has real work; tiny LPs stay on the
         // one-node-per-lane kernels, which can run a whole period as one cooperative launch

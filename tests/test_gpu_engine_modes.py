@@ -340,3 +340,35 @@ def test_wide_batch_with_rows_too_heavy_for_the_shared_memory_slab(blp_lib):
     ok = off.status == 0
     assert np.allclose(on.objective[ok], off.objective[ok], rtol=2e-7, atol=0)
     assert on.stats['skipped_col_updates'] > 0 and off.stats['skipped_col_updates'] == 0
+
+
+def test_infeasible_nodes_inside_a_frozen_wide_batch(blp_lib):
+    """Nodes of a wide batch that are infeasible only through TWO rows together (sum_S x >= K and sum_S x <= K - 1, pool
+    rows switched on per node; each row alone passes the row-activity screen) must get status 1 from the Farkas test
+    with freezing and the larger step on, exactly as without, while their neighbours in the same tiles solve to the
+    same objectives. The certificate needs multipliers on rows that start frozen at zero: they have to be released."""
+    from simple_mip_solver_b200 import engine as eng
+    d = numpy_random_mip(20000, 2000, density=0.0025, seed=9)
+    lp = eng.BatchLP(d.A, d.b, d.c)
+    root = lp.solve_batch(d.l[None], d.u[None], want_y=True)
+    B, k = 64, 2
+    lbs, ubs, _ = frontier_nodes(d, root.x[0], 0, B, 12, seed=1)
+    S = np.arange(0, 400)
+    K = float(np.floor(root.x[0][S].sum()))
+    rows = np.zeros((k, d.n))
+    rows[0, S], rows[1, S] = 1.0, -1.0
+    lp.append_rows(rows, np.array([K, -(K - 1.0)]))
+    mask = np.zeros((B, k), dtype=np.uint8)
+    bad = np.arange(B) % 5 == 2
+    mask[bad] = 1                       # both rows on: infeasible
+    mask[np.arange(B) % 5 == 3, 0] = 1  # only the first row: feasible
+    X0, Y0 = np.tile(root.x[0], (B, 1)), np.tile(np.concatenate([root.y[0], np.zeros(k)]), (B, 1))
+    res = [lp.solve_batch(lbs, ubs, row_mask=mask, x0=X0, y0=Y0, opts=eng.default_opts(**kw))
+           for kw in (dict(freeze=0), dict(step_safety=0.0), dict())]
+    lp.close()
+    off = res[0]
+    assert (off.status[bad] == 1).all() and (off.status[~bad] == 0).all(), off.status
+    for r in res[1:]:
+        assert np.array_equal(r.status, off.status)
+        assert np.allclose(r.objective[~bad], off.objective[~bad], rtol=2e-7, atol=0)
+        assert r.stats['skipped_col_updates'] > 0

@@ -25,7 +25,7 @@ INF = float('inf')
 
 
 def solve_tile(P, lb, ub, x0, y0, eps=1e-7, max_iters=150000, K=64, theta=0.05, art=0.36, suff=0.2, nec=0.8,
-               long_after=32, balance=0.3, bal_dead=0.25, m_lo=None, m_hi=None, log=None, sub_step=0.0):
+               long_after=32, balance=0.3, bal_dead=0.25, m_lo=None, m_hi=None, log=None, sub_step=0.0, imb=0.0, imb_min=0.1):
     """lb, ub: [B, n]. Returns per-node iteration counts and the skipped share. m_lo/m_hi None: no freezing.
     sub_step > 0: the step is sub_step / ||A_UU||, A_UU = the rows and columns that are not frozen (power iteration,
     re-estimated at every change of the sets), instead of 0.998 / ||A||."""
@@ -145,6 +145,10 @@ def solve_tile(P, lb, ub, x0, y0, eps=1e-7, max_iters=150000, K=64, theta=0.05, 
                         runaway[k] += 1            # the device's watchdog would send the node back to 1 / ||A|| here
                     why = fpe[k] <= suff * fpe0[k] or (fpe[k] <= nec * fpe0[k] and fpe[k] > fpe_prev[k]) \
                         or t[k] + 1 >= art * tot_it or not np.isfinite(fpe0[k])
+                    # experiment: restart early when one criterion lags the other by more than a factor exp(imb)
+                    if not why and imb > 0 and rp[k] > 0 and rg[k] > 0 and t[k] + 1 >= imb_min * tot_it \
+                            and abs(np.log(rp[k] / rg[k])) > imb and max(rp[k], rg[k]) > eps:
+                        why = True
                     if why:
                         ddx, ddy = np.linalg.norm(xp[:, k] - xa[:, k]), np.linalg.norm(yp[:, k] - ya[:, k])
                         if np.isfinite(fpe0[k]):
@@ -181,12 +185,14 @@ def main():
     m_lo = float(sys.argv[3]) if len(sys.argv) > 3 else None
     m_hi = float(sys.argv[4]) if len(sys.argv) > 4 else None
     sub_step = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
+    imb = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0
+    imb_min = float(sys.argv[7]) if len(sys.argv) > 7 else 0.1
     d, depth, root = bench.load_instance(wl)
     P = BatchPDHG(d.A, d.b, d.c)
     lb, ub, _ = frontier_nodes(d, root['x'], k0, k1 - k0, depth, seed=0)
     t0 = time.time()
-    r = solve_tile(P, lb, ub, root['x'], root['y'], m_lo=m_lo, m_hi=m_hi, sub_step=sub_step, log=lambda s: print(s, flush=True))
-    print('margins', m_lo, m_hi, 'sub_step', sub_step, 'iters', r['iters'].tolist(), 'mean %.0f' % r['iters'].mean(), 'skipped %.3f' % r['skipped'],
+    r = solve_tile(P, lb, ub, root['x'], root['y'], m_lo=m_lo, m_hi=m_hi, sub_step=sub_step, imb=imb, imb_min=imb_min, log=None)
+    print('margins', m_lo, m_hi, 'sub_step', sub_step, 'imb', imb, imb_min, 'max', int(r['iters'].max()), 'iters', r['iters'].tolist(), 'mean %.0f' % r['iters'].mean(), 'skipped %.3f' % r['skipped'],
           'runaway', r['runaway'].tolist(), 'obj', np.round(r['obj'], 6).tolist(), 'time %.0f' % (time.time() - t0))
 
 

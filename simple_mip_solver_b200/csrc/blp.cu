@@ -3,8 +3,11 @@
 // One handle = one GPU + one CUDA stream + the shared LP data (A, A', c, b, scaling, step size).
 // blp_solve_batch runs restarted Halpern PDHG for a whole batch of node LPs:
 //   set-up kernels -> [ period graph: K x (k_primal, k_dual) | evaluation graph: k_tick,
-//   k_eval_cols, k_eval_rows, k_decide, k_apply_restart ] repeated until every node has a
-//   status -> output kernels.  The host only reads one int per period (nodes still running).
+//   k_eval_cols, k_eval_rows, k_decide, k_apply_restart | harvest / refill of finished slots |
+//   wide batches: k_freeze_cols/rows (frozen flags per 32-node block), k_fold_cols/A/AT (the tiles'
+//   folded matrices), k_pow_A/AT/finish (step of the block that still moves), k_freeze_count ]
+//   repeated until every node has a status -> output kernels.  The host reads 13 ints per period
+//   (nodes running / finished / restarting, frozen counts, watchdog resets).
 #include "../../include/blp.h"
 
 #include <cuda_runtime.h>

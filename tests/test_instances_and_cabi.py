@@ -66,6 +66,24 @@ def test_library_exports_every_declared_symbol():
     assert engine.load_library().blp_version().decode().endswith('sm_100a')
 
 
+def test_ctypes_structs_mirror_the_header():
+    """blp_opts / blp_stats cross the C ABI by value layout: the ctypes mirrors in engine.py must list the same fields,
+    in the same order and with the same C types as include/blp.h, and blp_default_opts must fill every field."""
+    import ctypes as C
+    from simple_mip_solver_b200 import engine
+    header = open(os.path.join(ROOT, 'include', 'blp.h')).read()
+    ctype = {'double': C.c_double, 'int': C.c_int}
+    for name, mirror in (('blp_opts', engine.BlpOpts), ('blp_stats', engine.BlpStats)):
+        body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (name, name), header, re.S).group(1)
+        body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+        fields = re.findall(r'\b(double|int)\s+([a-z_0-9]+)\s*;', body)
+        assert [(f, ctype[t]) for t, f in fields] == list(mirror._fields_), name
+    o = engine.default_opts()
+    assert o.freeze == 1 and o.freeze_margin == 0.05 and o.step_safety == 0.98 and o.obj_cutoff == float('inf')
+    with pytest.raises(TypeError):
+        engine.default_opts(no_such_option=1)
+
+
 def test_product_fails_loudly_without_gpu_or_library(monkeypatch, tmp_path):
     import scipy.sparse as sp
     import torch

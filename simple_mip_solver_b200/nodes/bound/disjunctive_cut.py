@@ -8,7 +8,7 @@ step: every re-solve after a cut is the batched GPU LP solve, the cut itself com
 from __future__ import annotations
 
 import re
-from typing import Any, Dict, List, Tuple, Union
+from typing import Any, Dict, Iterable, List, Tuple, Union
 
 import numpy as np
 
@@ -16,7 +16,7 @@ from simple_mip_solver_b200.compat.cylp_like import CyLPArray
 from simple_mip_solver_b200.nodes.base_node import BaseNode
 from simple_mip_solver_b200.utils.cut_generating_lp import CutGeneratingLP
 from simple_mip_solver_b200.utils.floating_point import numerically_safe_cut
-from simple_mip_solver_b200.utils.tolerance import min_cglp_norm
+from simple_mip_solver_b200.utils.tolerance import min_cglp_norm, variable_epsilon
 
 
 class DisjunctiveCutBoundNode(BaseNode):
@@ -42,6 +42,41 @@ class DisjunctiveCutBoundNode(BaseNode):
         self.number_cglp_created = 0
         self.number_cglp_added = 0
         self.number_cglp_removed = 0
+
+    @staticmethod
+    def prefetch(nodes: Iterable[BaseNode]) -> int:
+        """BaseNode.prefetch, then the FIRST disjunctive cut of every node of the batch that is going
+        to ask for one: nodes that share a CGLP differ only in the point they want cut off, so their
+        CGLPs are one batched device call (``CutGeneratingLP.prefetch``; the reference solves one
+        CGLP per node and round, :122). A node's first cut round then finds its answer cached."""
+        nodes = list(nodes)
+        sent = BaseNode.prefetch(nodes)
+        groups: Dict[int, Tuple[CutGeneratingLP, list, list]] = {}
+        for node in nodes:
+            point = node._first_cglp_point() if isinstance(node, DisjunctiveCutBoundNode) else None
+            if point is not None:
+                _, points, bases = groups.setdefault(id(node.cglp), (node.cglp, [], []))
+                points.append(point)
+                bases.append(node.prev_cglp_basis)
+        for cglp, points, bases in groups.values():
+            if len(points) > 1:
+                cglp.prefetch(points, bases)
+        return sent
+
+    def _first_cglp_point(self) -> Union[None, np.ndarray]:
+        """The point this node's first cut round will hand to its CGLP (``_cut_generation_iteration``
+        clips the LP solution at zero first), or None if the node will not get that far: no CGLP, LP not
+        solved to optimality, or an integral solution."""
+        if self.cglp is None or not self.previous_cglp_added or self.cut_generation_iterations:
+            return None
+        lp = self.lp
+        if getattr(lp, '_solved_key', None) is None or lp.getStatusCode() != 0:
+            return None
+        x = np.maximum(np.asarray(lp.primalVariableSolution['x'], dtype=float), 0)
+        ints = x[self._integer_indices]
+        if not len(ints) or np.max(np.abs(np.round(ints) - ints)) <= variable_epsilon:
+            return None
+        return x
 
     def bound(self, total_number_cglp_created: int = 0, total_number_cglp_added: int = 0,
               total_number_cglp_removed: int = 0, **kwargs: Any) -> Dict[str, Any]:

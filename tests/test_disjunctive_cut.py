@@ -122,3 +122,114 @@ def test_children_inherit_cglp_only_after_a_useful_cut(monkeypatch):
         for d in ('left', 'right'):
             assert isinstance(kids[d], DisjunctiveCutBoundNode)
             assert (kids[d].cglp is cglp) == node.current_node_added_cglp
+
+
+# ---------------------------------------------------------------- batched CGLP
+def cold(cglp):
+    return (np.full(cglp.lp.nVariables, 3, dtype=np.int32), np.full(cglp.lp.nConstraints, 1, dtype=np.int32))
+
+
+def test_cglp_known_answers_of_the_reference(monkeypatch):
+    """test_cut_generating_lp.py:371-415 of the reference: the cuts its CGLP finds on `square` and on
+    small_branch, and the one that cuts off a point from above."""
+    use_oracle_engine(monkeypatch)
+    bb = BranchAndBound(model_from(EXAMPLES['square']), BaseNode, gomory_cuts=False)
+    bb.solve()
+    pi, pi0 = CutGeneratingLP(bb, bb.root_node.idx).solve()
+    want = [0, 1] if abs(pi[1]) > abs(pi[0]) else [1, 0]
+    np.testing.assert_allclose(pi / pi0, want, atol=.01)
+    assert (pi - .01 < 0).all() and pi0 - .01 < 0
+
+    bb = partial_tree(EXAMPLES['small_branch'], node_limit=10)
+    pi, pi0 = CutGeneratingLP(bb, bb.root_node.idx).solve()
+    np.testing.assert_allclose(pi / pi0, [0, 0, 1], atol=.01)
+
+    bb = partial_tree(EXAMPLES['square'], node_limit=1)
+    cglp = CutGeneratingLP(bb, bb.root_node.idx)
+    pi, pi0 = cglp.solve(x_star=CyLPArray([1.5, 2]))
+    assert pi0 == pytest.approx(-.75, abs=.01)
+    np.testing.assert_allclose(pi, [0, -.5], atol=.01)
+    assert cglp.lp.objectiveValue == pytest.approx(float(np.dot(pi, [1.5, 2])) - pi0, abs=1e-9)
+    pi, pi0 = cglp.solve(x_star=CyLPArray([.5, .5]))        # a point that cannot be separated: still an answer
+    assert pi is not None and pi0 is not None and cglp.lp.objectiveValue >= -1e-9
+
+
+@pytest.mark.parametrize('name', ['cut1', 'cut2', 'lift_project', 'square', 'small_branch', 'random'])
+def test_cglp_batch_is_the_single_solves(monkeypatch, name):
+    """K points through ONE device call give, point for point, what K single solves give, and the
+    optimum of every LP is the optimum of the reference's primal model (HiGHS on `cglp._M`)."""
+    from oracle.highs_lp import HIGHS_INF, HighsLP
+    oracle = use_oracle_engine(monkeypatch)
+    bb = partial_tree(EXAMPLES[name])
+    root = bb.root_node
+    cglp = CutGeneratingLP(bb, root.idx)
+    x = np.asarray(root.solution, dtype=float)
+    rng = np.random.default_rng(5)
+    points = [CyLPArray(x)] + [CyLPArray(np.maximum(x * rng.uniform(.7, 1.2, len(x)), 0)) for _ in range(6)]
+    before = list(oracle.batch_sizes)
+    cuts = cglp.solve_batch(points, starting_bases=[cold(cglp)] * len(points))
+    assert oracle.batch_sizes[len(before):] == [len(points)] and cglp.batch_calls == 1
+    fin = lambda v, big: np.where(np.isinf(v), big, v)
+    for p, (pi, pi0) in zip(points, cuts):
+        one = CutGeneratingLP(bb, root.idx)
+        pi1, pi01 = one.solve(x_star=p, starting_basis=cold(one))
+        assert np.array_equal(pi, pi1) and pi0 == pi01
+        c = np.zeros(cglp.lp.nVariables)
+        c[:cglp.n], c[cglp.n] = p, -1.0
+        r = HighsLP(cglp._M, c, cglp._r, np.full(cglp._M.shape[0], HIGHS_INF),
+                    fin(cglp._lo, -HIGHS_INF), fin(cglp._hi, HIGHS_INF)).solve()
+        assert r.status == 0
+        assert float(np.dot(pi, p)) - pi0 == pytest.approx(r.objective, abs=1e-8)
+        # valid for every integer point (small boxes) / for the LP optimum of every disjunctive term
+        for q in integer_points(EXAMPLES[name]) if len(x) <= 4 else []:
+            assert float(np.dot(pi, q)) >= pi0 - 1e-7
+        for leaf in bb.tree.get_leaves(root.idx):
+            if leaf.lp_feasible and leaf.solution is not None:
+                lo = np.maximum(np.asarray(leaf.lp.variablesLower), 0)
+                assert float(np.dot(pi, np.maximum(leaf.solution, lo))) >= pi0 - 1e-6
+
+
+def test_cglp_basis_round_trip(monkeypatch):
+    """test_cut_generating_lp.py:417-428: a solve started from the basis of an earlier one needs no
+    iteration; the arrays have the reference model's shapes and survive a plain-array copy."""
+    use_oracle_engine(monkeypatch)
+    bb = partial_tree(EXAMPLES['small_branch'], node_limit=10)
+    cglp = CutGeneratingLP(bb, bb.root_node.idx)
+    pi, pi0 = cglp.solve()
+    assert cglp.lp.iteration > 0
+    cols, rows = cglp.lp.getBasisStatus()
+    assert cols.shape == (cglp.lp.nVariables,) and rows.shape == (cglp.lp.nConstraints,)
+    assert set(np.unique(cols)) <= {1, 3} and set(np.unique(rows)) <= {1, 3}
+    again = CutGeneratingLP(bb, bb.root_node.idx)
+    pi2, pi02 = again.solve(starting_basis=(cols, rows))
+    assert again.lp.iteration == 0 and np.allclose(pi, pi2) and pi0 == pytest.approx(pi02)
+    plain = CutGeneratingLP(bb, bb.root_node.idx)            # CLP-coded arrays without the device basis
+    pi3, pi03 = plain.solve(starting_basis=(np.array(cols), np.array(rows)))
+    assert plain.lp.iteration < cglp.lp.iteration and np.allclose(pi, pi3)
+    with pytest.raises(AssertionError, match='first starting_basis element'):
+        cglp.solve(starting_basis=(np.append(cols, 1), rows))
+    with pytest.raises(AssertionError, match='second starting_basis element'):
+        cglp.solve(starting_basis=(cols, np.append(rows, 1)))
+
+
+def test_frontier_prefetch_batches_the_first_disjunctive_cut(monkeypatch):
+    """With a frontier batch the nodes that share a CGLP get their first cut from one batched call
+    (DisjunctiveCutBoundNode.prefetch); the optimum is the one-node-at-a-time optimum."""
+    use_oracle_engine(monkeypatch)
+    hits = batched = 0
+    for name, rec in list(SCALE1.items())[::9] + [('cut2', EXAMPLES['cut2']), ('random', EXAMPLES['random'])]:
+        tree = partial_tree(rec)
+        want = rec.get('mip_optimum', rec['reference']['BaseNode']['objective'])
+        for fb in (1, 8):
+            cglp = CutGeneratingLP(tree, tree.root_node.idx)
+            bb = BranchAndBound(model_from(rec), DisjunctiveCutBoundNode, cglp=cglp,
+                                gomory_cuts=False, frontier_batch=fb)
+            bb.solve()
+            assert bb.status == 'optimal' and bb.objective_value == pytest.approx(want, abs=1e-6), (name, fb)
+            assert cglp.points_solved >= cglp.batch_calls
+            if fb == 1:
+                assert cglp.prefetch_hits == 0
+            else:
+                hits += cglp.prefetch_hits
+                batched += cglp.points_solved - cglp.batch_calls
+    assert hits > 0 and batched > 0

@@ -96,6 +96,9 @@ class _CglpLP:
 
 
 class CutGeneratingLP:
+    # which device path solves the CGLP: 'auto' = the batched dual simplex while the device LP has at
+    # most blp_simplex_batch_rows() rows, PDHG beyond; 'pdhg' forces the first-order path
+    method = 'auto'
 
     def __init__(self, bb, root_id: int, A=None, b: CyLPArray = None, var_lb: CyLPArray = None,
                  var_ub: CyLPArray = None, depth: int = None):
@@ -320,7 +323,7 @@ class CutGeneratingLP:
         nrow = self._dM.shape[0]
         self.points_solved += K
         answers: List[CglpAnswer] = []
-        if getattr(lp, 'simplex_batched', False):
+        if self.method != 'pdhg' and getattr(lp, 'simplex_batched', False):
             coded = [self._device_coded(st) for st in starts]
             chunk = max(1, min(K, SIMPLEX_CHUNK_BYTES // (8 * nrow * nrow)))
             for a in range(0, K, chunk):

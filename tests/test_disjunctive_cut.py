@@ -233,3 +233,23 @@ def test_frontier_prefetch_batches_the_first_disjunctive_cut(monkeypatch):
                 hits += cglp.prefetch_hits
                 batched += cglp.points_solved - cglp.batch_calls
     assert hits > 0 and batched > 0
+
+
+def test_cglp_first_order_path_gives_the_same_optimum(monkeypatch):
+    """CGLPs too large for the simplex kernel go to the engine's first-order path (here: HiGHS behind the
+    same call); the cut is read from the row duals in the same way."""
+    use_oracle_engine(monkeypatch)
+    bb = partial_tree(EXAMPLES['random'])
+    exact = CutGeneratingLP(bb, bb.root_node.idx)
+    pi, pi0 = exact.solve()
+    first_order = CutGeneratingLP(bb, bb.root_node.idx)
+    first_order.method = 'pdhg'
+    x = np.asarray(bb.root_node.solution, dtype=float)
+    (pi1, pi01), (pi2, pi02) = first_order.solve_batch([CyLPArray(x), CyLPArray(x * .9)])
+    assert first_order.batch_calls == 1 and first_order.lp._basis is None
+    assert float(np.dot(pi1, x)) - pi01 == pytest.approx(exact.lp.objectiveValue, abs=1e-8)
+    assert float(np.dot(pi1, x)) - pi01 == pytest.approx(float(np.dot(pi, x)) - pi0, abs=1e-8)
+    for leaf in bb.tree.get_leaves(bb.root_node.idx):
+        if leaf.lp_feasible and leaf.solution is not None:
+            for p, p0 in ((pi1, pi01), (pi2, pi02)):
+                assert float(np.dot(p, np.maximum(leaf.solution, 0))) >= p0 - 1e-6

@@ -106,3 +106,27 @@ def test_frontier_prefetch_batches_the_first_disjunctive_cut_on_the_device(blp_l
         bb.model.lp._shared.close()
         tree.model.lp._shared.close()
     assert hits > 0 and batched > 0
+
+
+def test_cglp_through_the_first_order_kernels(blp_lib):
+    """A CGLP above blp_simplex_batch_rows() rows is solved by PDHG; forced here on a small one and
+    compared with the exact path: same optimum, valid cuts."""
+    bb = partial_tree(EXAMPLES['random'])
+    root = bb.root_node
+    x = np.asarray(root.solution, dtype=float)
+    points = [CyLPArray(x), CyLPArray(x * .9), CyLPArray(np.maximum(x - .05, 0))]
+    exact = CutGeneratingLP(bb, root.idx)
+    want = exact.solve_batch(points)
+    first_order = CutGeneratingLP(bb, root.idx)
+    first_order.method = 'pdhg'
+    got = first_order.solve_batch(points)
+    assert first_order.batch_calls == 1
+    for p, (pi, pi0), (qi, qi0) in zip(points, want, got):
+        assert qi is not None
+        assert abs((float(np.dot(qi, p)) - qi0) - (float(np.dot(pi, p)) - pi0)) <= 1e-6
+        for leaf in bb.tree.get_leaves(root.idx):
+            if leaf.lp_feasible and leaf.solution is not None:
+                assert float(np.dot(qi, np.maximum(leaf.solution, 0))) >= qi0 - 1e-5
+    exact.close()
+    first_order.close()
+    bb.model.lp._shared.close()

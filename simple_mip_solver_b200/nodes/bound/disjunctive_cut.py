@@ -48,7 +48,7 @@ class DisjunctiveCutBoundNode(BaseNode):
         """BaseNode.prefetch, then the FIRST disjunctive cut of every node of the batch that is going
         to ask for one: nodes that share a CGLP differ only in the point they want cut off, so their
         CGLPs are one batched device call (``CutGeneratingLP.prefetch``; the reference solves one
-        CGLP per node and round, :122). A node's first cut round then finds its answer cached."""
+        CGLP per node and round, :133). A node's first cut round then finds its answer cached."""
         nodes = list(nodes)
         sent = BaseNode.prefetch(nodes)
         groups: Dict[int, Tuple[CutGeneratingLP, list, list]] = {}

@@ -155,48 +155,54 @@ class CutGeneratingLP:
         self.n = n
         self._x_root = np.asarray(root.solution, dtype=float).copy()
 
-        # variable vector z = [pi (n) | pi0 | u_1 w_1 v_1 | u_2 w_2 v_2 | ...]
+        # the reference's model: z = [pi (n) | pi0 | u_1 w_1 v_1 | u_2 w_2 v_2 | ...], per term n + 1 rows, then the
+        # normalisation as two rows. Only its SIZES are needed to answer (cglp.lp); the model itself is
+        # assembled on demand (`primal_model`, read by the parity tests)
+        self._blocks = blocks
         ncol = n + 1 + sum(At.shape[0] + 2 * n for At, *_ in blocks)
-        rows, rhs = [], []
-        lo_z = np.full(ncol, 0.0)
-        hi_z = np.full(ncol, _INF)
-        lo_z[:n + 1] = -_INF                                   # pi, pi0 free
-        ones = np.zeros(ncol)
-        eye = sp.identity(n, format='csr')
-        off = n + 1
-        for At, bt, lt, ut, has_l, has_u in blocks:
-            m = At.shape[0]
-            iu, iw, iv = off, off + m, off + m + n
-            # pi - A_t' u - w + v >= 0
-            blk = sp.lil_matrix((n, ncol))
-            blk[:, :n] = eye
-            blk[:, iu:iu + m] = -At.T
-            blk[:, iw:iw + n] = -eye
-            blk[:, iv:iv + n] = eye
-            rows.append(blk.tocsr())
-            rhs.append(np.zeros(n))
-            # -pi0 + b.u + l.w - u.v >= 0
-            r = sp.lil_matrix((1, ncol))
-            r[0, n] = -1.0
-            r[0, iu:iu + m] = bt
-            r[0, iw:iw + n] = lt
-            r[0, iv:iv + n] = -ut
-            rows.append(r.tocsr())
-            rhs.append(np.zeros(1))
-            hi_z[iw:iw + n] = np.where(has_l, _INF, 0.0)
-            hi_z[iv:iv + n] = np.where(has_u, _INF, 0.0)
-            ones[iu:iv + n] = 1.0
-            off = iv + n
-        # normalisation  sum(u, w, v) = 1  as two >= rows
-        rows.append(sp.csr_matrix(ones[None, :]))
-        rhs.append(np.ones(1))
-        rows.append(sp.csr_matrix(-ones[None, :]))
-        rhs.append(-np.ones(1))
-        self._M = sp.vstack(rows, format='csr') if blocks else sp.csr_matrix((0, ncol))
-        self._r = np.concatenate(rhs)
-        self._lo, self._hi = lo_z, hi_z
-        self.lp = _CglpLP(ncol, self._M.shape[0])
+        self.lp = _CglpLP(ncol, len(blocks) * (n + 1) + 2 if blocks else 0)
+        self._primal = None
         self._create_dual_form(blocks)
+
+    def primal_model(self):
+        """``(M, r, lo, hi)`` of the reference's CGLP in the engine's canonical form ``min c.z, M z >= r,
+        lo <= z <= hi`` with ``c = [x_star, -1, 0...]`` (reference :52-177). The device never sees it."""
+        if self._primal is None:
+            n, blocks = self.n, self._blocks
+            ncol = self.lp.nVariables
+            lo_z = np.zeros(ncol)
+            hi_z = np.full(ncol, _INF)
+            lo_z[:n + 1] = -_INF                                   # pi, pi0 free
+            ones = np.zeros(ncol)
+            eye = sp.identity(n, format='csr')
+            rows, off = [], n + 1
+            for At, bt, lt, ut, has_l, has_u in blocks:
+                m = At.shape[0]
+                pad_l, pad_r = off - (n + 1), ncol - (off + m + 2 * n)
+                z = lambda k, w: sp.csr_matrix((k, w))
+                row = lambda v: sp.csr_matrix(np.asarray(v, dtype=float)[None, :])
+                # pi - A_t' u - w + v >= 0
+                rows.append(sp.hstack([eye, z(n, 1 + pad_l), -At.T, -eye, eye, z(n, pad_r)], format='csr'))
+                # -pi0 + b.u + l.w - u.v >= 0
+                rows.append(sp.hstack([z(1, n), row([-1.0]), z(1, pad_l), row(bt), row(lt), row(-ut), z(1, pad_r)],
+                                      format='csr'))
+                hi_z[off + m:off + m + n] = np.where(has_l, _INF, 0.0)
+                hi_z[off + m + n:off + m + 2 * n] = np.where(has_u, _INF, 0.0)
+                ones[off:off + m + 2 * n] = 1.0
+                off += m + 2 * n
+            # normalisation  sum(u, w, v) = 1  as two >= rows
+            rows += [sp.csr_matrix(ones[None, :]), sp.csr_matrix(-ones[None, :])]
+            M = sp.vstack(rows, format='csr') if blocks else sp.csr_matrix((0, ncol))
+            r = np.zeros(M.shape[0])
+            if blocks:
+                r[-2], r[-1] = 1.0, -1.0
+            self._primal = (M, r, lo_z, hi_z)
+        return self._primal
+
+    _M = property(lambda self: self.primal_model()[0])
+    _r = property(lambda self: self.primal_model()[1])
+    _lo = property(lambda self: self.primal_model()[2])
+    _hi = property(lambda self: self.primal_model()[3])
 
     def _create_dual_form(self, blocks) -> None:
         """The LP the device solves (module docstring): columns ``[xi_1 .. xi_T | lambda | gamma | s]``,

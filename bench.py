@@ -559,7 +559,7 @@ def main():
         dual_gbs = dual_bytes / dual_s / 1e9 if dual_s > 0 else 0.0
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2n_traffic.json')))
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r2z_traffic.json')))
             if tr['workload'] == args.workload and tr['batch'] == W:
                 # DRAM read+write bytes of one k_primal2 + one k_dual2 launch at full batch width (ncu)
                 traffic = tr['k_primal2_dram_bytes_per_launch'] + tr['k_dual2_dram_bytes_per_launch']
@@ -584,7 +584,7 @@ def main():
             'roofline': {'bound': 'hbm', 'kernel': 'PDHG iteration = k_primal + k_dual (one launch each)',
                          'achieved': pair_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': pair_gbs / peak,
                          'traffic': traffic, 'traffic_note': 'ncu dram read+write of one iteration at FULL batch width early in a solve '
-                         '(profiles/r2n_traffic.json: 66 % of the columns, 27 % of the rows frozen; algorithmic bytes of that '
+                         '(profiles/r2z_traffic.json: 66 % of the columns, 27 % of the rows frozen; algorithmic bytes of that '
                          'launch pair: 450 MB); bytes_per_launch is the average over the timed steps, '
                          'where slots of finished nodes are refilled while nodes are pending and the tail of a step is compacted', 'full_width_bytes': (pb + db) * W + bytes_A + bytes_AT,
                          'peak_source': peak_src, 'bytes_per_launch': pair_bytes,

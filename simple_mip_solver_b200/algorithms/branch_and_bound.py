@@ -229,9 +229,10 @@ class BranchAndBound(BaseAlgorithm):
         assert parent_id in self.tree, 'parent must already exist in tree'
         for direction in ['left', 'right']:
             assert direction in rtn, f'{direction} must be in the returned dict'
-            child = rtn.pop(direction)
+            child = rtn[direction]
             assert isinstance(child, self._Node), f'{direction} value must be type {type(self._Node)}'
             assert child.idx not in self.tree, 'please give unique node ID'
+            del rtn[direction]          # only a child that was accepted leaves the caller's dict
             self._node_queue.put(child)
             getattr(self.tree, f'add_{direction}_child')(child.idx, parent_id, node=child)
         self._process_rtn(rtn)

@@ -20,6 +20,8 @@ from __future__ import annotations
 
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
+import types
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -108,6 +110,14 @@ class CyLPExpr:
             raise ValueError(f'coefficients have {M.shape[1]} columns, variable has {var.dim}')
         self.coefs = M
         self._pending_lower = None
+
+    def __sub__(self, constant):
+        """``pi * x - pi0``: an expression keeps only its linear part (a constant moves no optimum;
+        the reference writes objectives this way, test_floating_point.py)."""
+        assert np.isscalar(constant) or np.asarray(constant).size == 1, 'only a constant can be subtracted'
+        return self
+
+    __add__ = __sub__
 
     def __ge__(self, lower):
         k = self.coefs.shape[0]
@@ -261,6 +271,13 @@ class CyClpSimplex:
         self._cuts: Dict[str, Tuple[np.ndarray, float]] = {}      # cut rows present in this LP
         self._cut_keys: Dict[str, Tuple[str, int]] = {}            # their pool identities
         self._pending_rows = []                                    # rows added before `shared` exists
+        # Modelling-only state. The device solves `A x >= b` over ONE variable vector; CyLP models can hold
+        # more (rows with an upper bound, further variables, no base rows). Such a model is kept so
+        # that the Node layer can inspect and REJECT it exactly as the reference does (`_sense`,
+        # `_x_only_variable`, base_node.py:111-112, 683-710); it cannot be solved.
+        self._foreign_rows: Dict[str, Tuple[np.ndarray, float, float]] = {}   # name -> (pi, lower, upper)
+        self._base_off = False                                     # the base rows were removed by name
+        self._foreign_base = None                                  # (A csr, lower, upper): base rows of a "<=" model
         self._objective = None
         self.logLevel = 0
         self.maxNumIteration = 2147483647
@@ -276,6 +293,7 @@ class CyClpSimplex:
         self._basis = None              # (cols, rows) handed over by setBasisStatus, rows in this LP's order
         self._basis_out = None          # (cols, base rows, {cut name: status}) of the last simplex solve
         self._basis_exact = False       # _basis_out is a basis of the LP as it is now
+        self._basis_kept = None         # the last exact basis minus slack cuts removed since (see removeConstraint)
         self._factor_ref = None         # (simplex call id, slot, cut names) of the last simplex solve
         self._parent_ref = None         # the parent's _factor_ref (copy_for_child)
         self._parent_bounds = (None, None)   # the parent's bound arrays (children of one parent share them)
@@ -292,11 +310,13 @@ class CyClpSimplex:
 
     # ---- model building (the subset the reference exercises) -------------------------------
     def addVariable(self, name: str, dim: int, isInt: bool = False):
-        assert not self._vars, 'this LP look-alike holds a single variable vector'
         v = CyLPVar(name, dim)
         self._vars.append(v)
-        self._l = CyLPArray(np.zeros(dim))
-        self._u = CyLPArray(np.full(dim, COIN_INFINITY))
+        if len(self._vars) == 1:
+            self._l = CyLPArray(np.zeros(dim))
+            self._u = CyLPArray(np.full(dim, COIN_INFINITY))
+        else:
+            self._solved_key = None         # a second variable vector: modelling-only from here on
         return v
 
     def getVarByName(self, name: str):
@@ -307,12 +327,19 @@ class CyClpSimplex:
 
     def __iadd__(self, stmt):
         if isinstance(stmt, CyLPBounds):
+            if self._vars and stmt.var.name != self._vars[0].name:
+                if stmt.lower is not None:
+                    stmt.var.lower = CyLPArray(stmt.lower)
+                if stmt.upper is not None:
+                    stmt.var.upper = CyLPArray(stmt.upper)
+                return self
             if stmt.lower is not None:
                 self._l = CyLPArray(stmt.lower)
             if stmt.upper is not None:
                 self._u = CyLPArray(stmt.upper)
             self._solved_key = None
             self._basis_exact = False
+            self._basis_kept = None
         elif isinstance(stmt, CyLPConstraint):
             self.addConstraint(stmt)
         else:
@@ -328,22 +355,47 @@ class CyClpSimplex:
             assert (np.asarray(cons.upper) >= 1e300).all(), 'rows must be one sided: a.x >= b'
             self._pending_rows.append(cons)
             return
-        assert (np.asarray(cons.upper) >= 1e300).all(), 'rows must be one sided: a.x >= b'
+        one_sided = (np.asarray(cons.upper) >= 1e300).all() and cons.variables[0].name == self._vars[0].name
         for r in range(M.shape[0]):
             nm = cons.name if M.shape[0] == 1 else f'{cons.name}_{r}'
             pi, pi0 = np.asarray(M.getrow(r).todense()).ravel(), float(cons.lower[r])
-            self._cuts[nm] = (pi, pi0)
-            self._cut_keys[nm] = (nm, hash((pi.tobytes(), pi0)))
+            if one_sided:
+                self._cuts[nm] = (pi, pi0)
+                self._cut_keys[nm] = (nm, hash((pi.tobytes(), pi0)))
+            else:
+                self._foreign_rows[nm] = (pi, pi0, float(cons.upper[r]))
+        self._solved_key = None
+        self._basis_exact = False
+        self._basis_kept = None
+
+    def removeConstraint(self, name: str):
+        if name in self._foreign_rows:
+            del self._foreign_rows[name]
+        elif name == 'R_base' and self._foreign_base is not None:
+            self._foreign_base = None
+        elif name == 'R_base' and not self._base_off and self._shared is not None:
+            self._base_off = True
+        elif name in self._cuts:
+            del self._cuts[name]
+            del self._cut_keys[name]
+            kept = self._basis_out if self._basis_exact else self._basis_kept
+            if kept is not None and kept[2].get(name) == BASIC:
+                # the row's slack was basic: without the row the same x is the basic solution of the same
+                # basis minus that slack (CLP keeps its statuses across the removal of a slack cut too,
+                # base_node.py:326-341 followed by the tableau of :513-530). Kept as a second opinion for
+                # `kept_basis_status`; getBasisStatus() itself answers from the solution as before
+                self._basis_kept = (kept[0], kept[1], {nm: st for nm, st in kept[2].items() if nm != name})
+            else:
+                self._basis_kept = None
+        else:
+            raise KeyError(f'Constraint "{name}" does not exist')       # CyLP's wording
         self._solved_key = None
         self._basis_exact = False
 
-    def removeConstraint(self, name: str):
-        if name not in self._cuts:
-            raise KeyError(f'no removable constraint named {name!r}')
-        del self._cuts[name]
-        del self._cut_keys[name]
-        self._solved_key = None
-        self._basis_exact = False
+    @property
+    def solvable(self) -> bool:
+        """False for a model the device form cannot express (see ``_foreign_rows``)."""
+        return len(self._vars) == 1 and not self._foreign_rows and not self._base_off and self._foreign_base is None
 
     def _finalize(self, device: int = 0):
         """Turn a model built with addVariable/addConstraint/objective into a shared LP."""
@@ -369,26 +421,51 @@ class CyClpSimplex:
     def constraints(self):
         sh = self._need_shared()
         x = self._vars[0]
-        base = CyLPConstraint(CyLPExpr(x, sh.A), sh.b, np.full(sh.m, COIN_INFINITY), name='R_base')
-        out = [base]
+        out = []
+        if not self._base_off:
+            out.append(CyLPConstraint(CyLPExpr(x, sh.A), sh.b, np.full(sh.m, COIN_INFINITY), name='R_base'))
         for nm, (pi, pi0) in self._cuts.items():
             out.append(CyLPConstraint(CyLPExpr(x, pi), [pi0], [COIN_INFINITY], name=nm))
+        if self._foreign_base is not None:
+            A, lo, up = self._foreign_base
+            out.append(CyLPConstraint(CyLPExpr(x, A), lo, up, name='R_base'))
+        for nm, (pi, lo, up) in self._foreign_rows.items():
+            out.append(CyLPConstraint(CyLPExpr(x, pi[:x.dim]), [lo], [up], name=nm))
         return out
+
+    def _foreign(self):
+        """(rows as csr, lower, upper) of everything the device form does not hold."""
+        n = self._vars[0].dim
+        mats, los, ups = [], [], []
+        if self._foreign_base is not None:
+            A, lo, up = self._foreign_base
+            mats.append(A), los.append(lo), ups.append(up)
+        for pi, lo, up in self._foreign_rows.values():
+            mats.append(sp.csr_matrix(pi[None, :n])), los.append([lo]), ups.append([up])
+        if not mats:
+            return sp.csr_matrix((0, n)), np.zeros(0), np.zeros(0)
+        return sp.vstack(mats, format='csr'), np.concatenate(los), np.concatenate(ups)
 
     @property
     def nVariables(self):
-        return self._vars[0].dim
+        return sum(v.dim for v in self._vars)
 
     nCols = nVariables
 
     @property
+    def _base_rows(self) -> int:
+        return 0 if self._base_off else self._need_shared().m
+
+    @property
     def nConstraints(self):
-        return self._need_shared().m + len(self._cuts)
+        return self._base_rows + len(self._cuts) + self._foreign()[0].shape[0]
 
     nRows = nConstraints
 
     @property
     def variablesLower(self):
+        if len(self._vars) > 1:
+            return CyLPArray(np.concatenate([self._l] + [v.lower for v in self._vars[1:]]))
         return self._l
 
     @variablesLower.setter
@@ -396,9 +473,12 @@ class CyClpSimplex:
         self._l = CyLPArray(v)
         self._solved_key = None
         self._basis_exact = False
+        self._basis_kept = None
 
     @property
     def variablesUpper(self):
+        if len(self._vars) > 1:
+            return CyLPArray(np.concatenate([self._u] + [v.upper for v in self._vars[1:]]))
         return self._u
 
     @variablesUpper.setter
@@ -406,22 +486,26 @@ class CyClpSimplex:
         self._u = CyLPArray(v)
         self._solved_key = None
         self._basis_exact = False
+        self._basis_kept = None
 
     @property
     def constraintsLower(self):
         sh = self._need_shared()
-        return CyLPArray(np.concatenate([sh.b, [p0 for _, p0 in self._cuts.values()]]))
+        return CyLPArray(np.concatenate([sh.b[:self._base_rows], [p0 for _, p0 in self._cuts.values()],
+                                         self._foreign()[1]]))
 
     @property
     def constraintsUpper(self):
-        return CyLPArray(np.full(self.nConstraints, COIN_INFINITY))
+        return CyLPArray(np.concatenate([np.full(self._base_rows + len(self._cuts), COIN_INFINITY),
+                                         self._foreign()[2]]))
 
     @property
     def coefMatrix(self):
         sh = self._need_shared()
-        if not self._cuts:
+        if not self._cuts and self.solvable:
             return sh.A.tocsc()
-        return sp.vstack([sh.A] + [sp.csr_matrix(p[None, :]) for p, _ in self._cuts.values()]).tocsc()
+        return sp.vstack([sh.A[:self._base_rows]] + [sp.csr_matrix(p[None, :]) for p, _ in self._cuts.values()] +
+                         [self._foreign()[0]]).tocsc()
 
     @property
     def objective(self):
@@ -440,6 +524,13 @@ class CyClpSimplex:
         self._objective = value
 
     objectiveCoefficients = objective
+
+    @property
+    def matrix(self):
+        """CLP's packed column-major matrix; the reference's tests read ``lp.matrix.elements``."""
+        A = self.coefMatrix.tocsc()
+        A.sort_indices()
+        return types.SimpleNamespace(elements=A.data.copy(), indices=A.indices.copy(), vectorStarts=A.indptr.copy())
 
     @staticmethod
     def getCoinInfinity():
@@ -491,8 +582,13 @@ class CyClpSimplex:
             cols, base, cuts = self._basis_out
             rows = np.concatenate([base, [cuts.get(nm, BASIC) for nm in self._cuts]]).astype(np.int32)
             return cols.astype(np.int32), rows
+        n, m = self.nVariables, self.nConstraints
+        unsolved = self._solved_key is None or self._solved_key != self._state_key()
+        if unsolved and self._basis is not None and len(self._basis[0]) == n and len(self._basis[1]) == m:
+            # not solved since setBasisStatus: CLP hands back what it was given (a child right after
+            # _base_branch carries its parent's basis, base_node.py:608)
+            return self._basis[0].astype(np.int32), self._basis[1].astype(np.int32)
         if self._x is None:
-            n, m = self.nVariables, self.nConstraints
             return np.full(n, 3, dtype=np.int32), np.full(m, 1, dtype=np.int32)
         tol = 1e-6
         x = self._x
@@ -503,6 +599,15 @@ class CyClpSimplex:
         slack = self.coefMatrix @ x - self.constraintsLower
         rows = np.where(slack > tol * (1.0 + np.abs(self.constraintsLower)), 1, 3).astype(np.int32)
         return cols, rows
+
+    def kept_basis_status(self):
+        """(cols, rows) of the last simplex basis with the slack cuts removed since taken out, or None
+        if anything else changed the LP after that solve."""
+        kept = self._basis_kept
+        if kept is None or self._x is None or set(kept[2]) != set(self._cuts):
+            return None
+        rows = np.concatenate([kept[1], [kept[2][nm] for nm in self._cuts]]).astype(np.int32)
+        return kept[0].astype(np.int32), rows
 
     @property
     def has_exact_basis(self) -> bool:
@@ -588,6 +693,8 @@ def solve_lps(lps: Iterable[CyClpSimplex], force: bool = False) -> int:
     groups: Dict[int, List[CyClpSimplex]] = {}
     for lp in lps:
         sh = lp._need_shared()
+        assert lp.solvable, 'the device solves A x >= b over one variable vector: this model has rows with an ' \
+                            'upper bound, further variables or no base rows (BaseAlgorithm converts "<=" models)'
         if force or lp._solved_key is None or lp._solved_key != lp._state_key():
             groups.setdefault(id(sh), []).append(lp)
     sent = 0
@@ -735,6 +842,7 @@ def _solve_group_simplex(sh: SharedLP, batch: List[CyClpSimplex], budget: int, d
                          {nm: int(res.row_status[k, r]) for nm, r in zip(lp._cuts, rows)})
         lp._factor_ref = (sh.simplex_calls, k, tuple(lp._cut_keys.values()))
         lp._basis_exact = True
+        lp._basis_kept = None
         if st == 1:
             lp._obj, lp._x, lp._y, lp._rc, lp._lower_bound = float('inf'), None, None, None, float('inf')
             continue
@@ -837,6 +945,7 @@ def _solve_group_pdhg(sh: SharedLP, batch: List[CyClpSimplex], budget: int, defa
         lp._lower_bound = float(res.lower_bound[k])
         lp._basis_out = None
         lp._basis_exact = False
+        lp._basis_kept = None
         lp._factor_ref = None
         rows = [sh.pool_row(lp, nm) + m for nm in lp._cuts]
         if st == 1:

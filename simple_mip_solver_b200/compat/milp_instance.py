@@ -46,10 +46,22 @@ class MILPInstance:
         # the LP object keeps rows in ">=" form; a "<=" model is flipped by BaseAlgorithm
         # (base_algorithm.py:47-61) before any node sees it
         if self.sense == '>=':
-            shared = SharedLP(Am, np.asarray(self.b), np.asarray(obj), device=device)
+            # CyLP broadcasts a one-element right-hand side over the rows of `A * x >= b` (the reference's
+            # `unbounded` example model passes one, example_models.py:155-163)
+            rhs = np.asarray(self.b, dtype=float)
+            rhs = np.full(Am.shape[0], rhs[0]) if rhs.size == 1 and Am.shape[0] > 1 else rhs
+            shared = SharedLP(Am, rhs, np.asarray(obj), device=device)
             self.lp = CyClpSimplex(shared, self.l.copy(), self.u.copy())
         else:
-            self.lp = _UnflippedLP(np.asarray(obj))
+            # a "<=" model, as cuppy builds it: the same CyClpSimplex protocol with rows bounded from above.
+            # It is modelling-only (BaseNode rejects it with 'must have Ax >= b', base_node.py:111) until
+            # BaseAlgorithm rebuilds the instance in ">=" form
+            shared = SharedLP(sp.csr_matrix((0, Am.shape[1])), np.zeros(0), np.asarray(obj), device=device)
+            self.lp = CyClpSimplex(shared, self.l.copy(), self.u.copy())
+            rhs = np.asarray(self.b, dtype=float)
+            rhs = np.full(Am.shape[0], rhs[0]) if rhs.size == 1 and Am.shape[0] > 1 else rhs
+            self.lp._base_off = True
+            self.lp._foreign_base = (Am, np.full(Am.shape[0], -COIN_INFINITY), rhs)
         self.lp._objective = CyLPArray(obj)
 
     def _from_mps(self, file_name, device):
@@ -67,12 +79,3 @@ class MILPInstance:
         self.u = CyLPArray(np.where(np.isinf(mdl.u), COIN_INFINITY, mdl.u))
         self.integerIndices = list(mdl.integer_indices)
         self._build_lp(mdl.A, self.c, device)
-
-
-class _UnflippedLP:
-    """Placeholder ``.lp`` of a '<=' model: only carries the (minimisation) objective until
-    BaseAlgorithm rebuilds the instance in '>=' form."""
-
-    def __init__(self, obj):
-        self.objective = CyLPArray(obj)
-        self._objective = self.objective

@@ -88,6 +88,7 @@ class BaseNode:
         self.cut_name_pattern = re.compile('^cut_')
         self.gmic_name_pattern = re.compile('^cut_gomory_')
         self._cut_pool = {}
+        self._status_override = None    # (cols, rows) to read the basis from instead of lp.getBasisStatus()
         self.cut_generation_iterations = 0
         self.cut_generation_stalled = False
         self.cut_generation_terminator = None
@@ -97,7 +98,8 @@ class BaseNode:
             setattr(self, f'iterations_gmic_{op}', 0)
             setattr(self, f'number_gmic_{op}', 0)
         base_rows = self.lp.constraints[0].varCoefs[self.lp.getVarByName('x')]
-        self.max_term = float(np.max(np.abs(base_rows.data))) if base_rows.nnz else 0.0
+        # a 0-d CyLPArray, as CyLP's coefficient matrices make it (the reference's tests check the type)
+        self.max_term = CyLPArray(float(np.max(np.abs(base_rows.data))) if base_rows.nnz else 0.0)
 
         assert self._sense == '>=', 'must have Ax >= b'
         assert self._variables_nonnegative, 'must have x >= 0 for all variables'
@@ -369,6 +371,24 @@ class BaseNode:
         return added
 
     def _find_gomory_cuts(self: T, max_rows: int = None) -> Dict[int, Tuple[CyLPArray, float]]:
+        """GMI cuts of the current solution (reference :468-511). The basis is what ``getBasisStatus``
+        reports; when that is not a basis of this solution (after slack cuts were removed the LP has no
+        solve of its own yet, and the active set of a degenerate vertex need not be one), the basis of the
+        last solve minus the removed slack rows is tried — what CLP keeps across ``removeConstraint``."""
+        cuts = self._gomory_cuts_of_basis(max_rows)
+        kept = getattr(self.lp, 'kept_basis_status', lambda: None)() if cuts is None else None
+        if kept is not None:
+            self._status_override = kept
+            try:
+                cuts = self._gomory_cuts_of_basis(max_rows)
+            finally:
+                self._status_override = None
+        return cuts if cuts is not None else {}
+
+    def _basis_status(self):
+        return self._status_override if self._status_override is not None else self.lp.getBasisStatus()
+
+    def _gomory_cuts_of_basis(self: T, max_rows: int = None) -> Union[None, Dict[int, Tuple[CyLPArray, float]]]:
         """Gomory mixed integer cuts from the rows of the LP tableau that belong to fractional
         basic integer variables (reference :468-511; Conforti et al. 5.31), vectorised.
 
@@ -380,13 +400,14 @@ class BaseNode:
         the special case without shifts (its pinned ``cut3`` example, test_base_node.py:654-684,
         gives the same cut). When the LP was solved by the first-order path (LPs too large for the
         simplex kernels) the basis is the active set of the solution and is used only if the basic
-        solution it defines reproduces the solver's x."""
+        solution it defines reproduces the solver's x. Returns None when the status at hand
+        (``_basis_status``) is not a basis of this solution."""
         cuts = {}
         n, m = self.lp.nVariables, self.lp.nConstraints
-        col_stat, row_stat = self.lp.getBasisStatus()
+        col_stat, row_stat = self._basis_status()
         basic = self.basic_variable_indices
         if len(basic) != m:
-            return cuts
+            return None
         is_basic = np.zeros(n + m, dtype=bool)
         is_basic[basic] = True
         is_int = np.zeros(n + m, dtype=bool)
@@ -400,28 +421,28 @@ class BaseNode:
         offset = np.concatenate([np.where(col_stat == 2, u, l), np.zeros(m)])
         offset[is_basic] = 0.0
         if not np.isfinite(offset).all():
-            return cuts
+            return None
         sign = np.where(at_upper, -1.0, 1.0)
         x = np.asarray(self.solution, dtype=float)
-        if self.lp.has_exact_basis:
+        if self._status_override is None and self.lp.has_exact_basis:
             x_basic = np.concatenate([x, A @ x - b])[basic]
         elif m <= 512:
             full = np.concatenate((A.toarray(), -np.identity(m)), axis=1)
             try:
                 x_basic = np.linalg.solve(full[:, basic], b - full @ offset)
             except np.linalg.LinAlgError:
-                return cuts
+                return None
         else:
             lu = self._sparse_basis_factor(basic)
             if lu is None:
-                return cuts
+                return None
             A_full = sp.hstack([sp.csr_matrix(A), -sp.identity(m, format='csr')], format='csr')
             x_basic = lu.solve(b - A_full @ offset)
-        if not self.lp.has_exact_basis:
+        if self._status_override is not None or not self.lp.has_exact_basis:
             z = offset.copy()
             z[basic] = x_basic
             if np.max(np.abs(z[:n] - x) / (1.0 + np.abs(x))) > 1e-5:
-                return cuts                      # the active set is not the basis of this solution
+                return None                      # the active set is not the basis of this solution
         is_int &= np.abs(offset - np.round(offset)) <= 1e-9          # shifted variable stays integer
         eps = good_coefficient_approximation_epsilon
         wanted = []
@@ -439,7 +460,7 @@ class BaseNode:
             wanted = sorted(keep)
         rows = self._tableau_rows([int(basic[r]) for r, _ in wanted])
         if rows is None:
-            return cuts
+            return None
         for (row_idx, f0), trow in zip(wanted, rows):
             row = np.where(is_basic, 0.0, trow * sign)               # coefficients of the shifted nonbasics
             f = row - np.floor(row)
@@ -458,7 +479,7 @@ class BaseNode:
         """Rows of inv([A, -I]_B) [A, -I] for the given basic variables: from the device when the
         factorised basis of this LP's solve is still in the engine's store, else from a dense solve on
         the host (what the reference does for every row, :513-526)."""
-        rows = self.lp.tableau_rows(variables)
+        rows = self.lp.tableau_rows(variables) if self._status_override is None else None
         if rows is not None:
             return rows
         basic = self.basic_variable_indices
@@ -513,7 +534,7 @@ class BaseNode:
 
     @property
     def basic_variable_indices(self):
-        return np.where(np.concatenate(self.lp.getBasisStatus()) == 1)[0]
+        return np.where(np.concatenate(self._basis_status()) == 1)[0]
 
     # ---------------------------------------------------------------- branching
     def branch(self: T, **kwargs: Any) -> Dict[str, T]:

@@ -42,17 +42,28 @@ class PseudoCostBranchNode(BaseNode):
         batch), then update the cost of the variable this node was branched on (reference :46-66)."""
         sb_indices = [idx for idx in self._integer_indices
                       if self._is_fractional(float(self.solution[idx])) and idx not in self.pseudo_costs]
-        # up to 256 candidates (512 child LPs) per GPU call: wide enough for the kernels, and the child
-        # LP objects of a chunk (each holds its own bound vectors, as in the reference :592-608) are
-        # dropped before the next chunk is built, so a root with thousands of candidates stays small
+        if getattr(self._strong_branch, '__func__', None) is not BaseNode._strong_branch:
+            # `_strong_branch` is the reference's plugin point for one variable (base_node.py:629-647):
+            # a subclass or instance that replaces it is served by it, variable by variable (:60-62)
+            pairs = ((idx, self._strong_branch(idx, self.strong_branch_iters)) for idx in sb_indices)
+        else:
+            pairs = self._strong_branch_chunks(sb_indices)
+        for _, children in pairs:
+            for child in children.values():
+                self._calculate_costs(child)
+        if self._b_idx is not None and self._b_idx not in sb_indices:
+            self._calculate_costs(self)
+
+    def _strong_branch_chunks(self: T, sb_indices: List[int]):
+        """(variable, its two solved children) for all ``sb_indices``, one GPU call per chunk: up to 256
+        candidates (512 child LPs) per call — wide enough for the kernels, and the child LP objects of a
+        chunk (each holds its own bound vectors, as in the reference :592-608) are dropped before the next
+        chunk is built, so a root with thousands of candidates stays small."""
         for first in range(0, len(sb_indices), self.strong_branch_chunk):
             chunk = sb_indices[first:first + self.strong_branch_chunk]
             children = self._strong_branch_batch(chunk, self.strong_branch_iters)
             for idx in chunk:
-                for child in children[idx].values():
-                    self._calculate_costs(child)
-        if self._b_idx is not None and self._b_idx not in sb_indices:
-            self._calculate_costs(self)
+                yield idx, children[idx]
 
     def _calculate_costs(self: T, node: T) -> None:
         """Running mean of (objective change) / (variable change) for node's branching variable

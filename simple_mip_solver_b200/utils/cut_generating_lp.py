@@ -160,13 +160,15 @@ class CutGeneratingLP:
         # assembled on demand (`primal_model`, read by the parity tests)
         self._blocks = blocks
         ncol = n + 1 + sum(At.shape[0] + 2 * n for At, *_ in blocks)
-        self.lp = _CglpLP(ncol, len(blocks) * (n + 1) + 2 if blocks else 0)
+        self.lp = _CglpLP(ncol, len(blocks) * (n + 1) + 1 if blocks else 0)     # one normalisation row (:169-171)
         self._primal = None
         self._create_dual_form(blocks)
 
     def primal_model(self):
         """``(M, r, lo, hi)`` of the reference's CGLP in the engine's canonical form ``min c.z, M z >= r,
-        lo <= z <= hi`` with ``c = [x_star, -1, 0...]`` (reference :52-177). The device never sees it."""
+        lo <= z <= hi`` with ``c = [x_star, -1, 0...]`` (reference :52-177); the normalisation, one equality
+        row in the reference, is two ``>=`` rows here, so ``M`` has ``cglp.lp.nConstraints + 1`` rows. The device
+        never sees it."""
         if self._primal is None:
             n, blocks = self.n, self._blocks
             ncol = self.lp.nVariables
@@ -271,7 +273,7 @@ class CutGeneratingLP:
         rows = np.full(self.lp.nConstraints, 1, dtype=np.int32)
         rows[self._d_primal_row_of_xi] = np.where(cs[:T * n] == 1, 3, 1)
         rows[self._d_primal_row_of_lam] = np.where(cs[c_lam:c_lam + T] == 1, 3, 1)
-        rows[-2] = 3 if cs[c_gam] == 1 else 1
+        rows[-1] = 3 if cs[c_gam] == 1 else 1
         basis = (np.array(cs, dtype=np.int8), np.array(rs, dtype=np.int8))
         return BasisArray(cols, basis), BasisArray(rows, basis)
 
@@ -293,7 +295,7 @@ class CutGeneratingLP:
         cols, rows = np.asarray(start[0]), np.asarray(start[1])
         cs[:T * n] = np.where(rows[self._d_primal_row_of_xi] == 1, 3, 1)
         cs[c_lam:c_lam + T] = np.where(rows[self._d_primal_row_of_lam] == 1, 3, 1)
-        cs[c_gam] = 1 if (rows[-2] != 1 or rows[-1] != 1) else 3
+        cs[c_gam] = 1 if rows[-1] != 1 else 3
         rs[:n] = np.where(cols[:n] == 1, 3, 1)
         rs[2 * n] = 3 if cols[n] == 1 else 1
         rs[2 * n + 2:] = np.where(cols[self._d_primal_col] == 1, 3, 1)

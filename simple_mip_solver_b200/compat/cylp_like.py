@@ -670,6 +670,8 @@ class CyClpSimplex:
         child = CyClpSimplex(self._need_shared(), self._l.copy(), self._u.copy())
         child._cuts = dict(self._cuts)
         child._cut_keys = dict(self._cut_keys)
+        child._foreign_rows, child._foreign_base, child._base_off = dict(self._foreign_rows), self._foreign_base, self._base_off
+        child._vars += self._vars[1:]
         child._objective = self._objective
         child.integer_indices_hint = self.integer_indices_hint
         child.solver_opts = self.solver_opts

@@ -175,3 +175,87 @@ def test_cut_generation_dual_bound_dict_messages(monkeypatch):
     assert good({1: {0: 1.0, 2: 2.0}}) == (False, 'index 1 should have dictionary keyed by range of ints')
     with pytest.raises(AssertionError, match='index 4 has already been processed'):
         node._base_bound(cut_generation_dual_bound_dict={4: {0: 1.0}})
+
+
+def test_models_the_device_cannot_hold_are_kept_for_inspection_and_rejected(monkeypatch):
+    """CyLP models may hold rows with an upper bound, further variable vectors and '<=' rows; the look-alike
+    keeps them so that the Node layer rejects them with the reference's own messages
+    (base_node.py:111-112, 683-710; test_base_node.py:123-125, 383-386, 867-905), and refuses to solve them."""
+    from helpers import use_oracle_engine
+    from simple_mip_solver_b200 import BaseNode, CyLPArray, MILPInstance
+    from simple_mip_solver_b200.compat import solve_lps
+    use_oracle_engine(monkeypatch)
+
+    def small(sense='>='):
+        A = np.array([[1.0, 0.0, 1.0], [0.0, 1.0, 0.0]])
+        sgn = -1.0 if sense == '>=' else 1.0
+        return MILPInstance(A=sgn * A, b=sgn * CyLPArray([1.5, 1.25]), c=-CyLPArray([1, 1, 1]), l=CyLPArray([0, 0, 0]),
+                            u=CyLPArray([10, 10, 10]), sense=['Min', sense], integerIndices=[0, 1, 2], numVars=3)
+
+    # a '<=' model: a real LP object with rows bounded from above; the node refuses it by its sense
+    m = small('<=')
+    assert m.lp.nConstraints == 2 and (m.lp.constraintsUpper == [1.5, 1.25]).all() and not m.lp.solvable
+    assert (np.asarray(m.lp.constraintsLower) <= -1e300).all()
+    with pytest.raises(AssertionError, match='must have Ax >= b'):
+        BaseNode(lp=m.lp, integer_indices=m.integerIndices)
+    with pytest.raises(AssertionError, match='the device solves A x >= b'):
+        solve_lps([m.lp])
+
+    # a row with an upper bound on a '>=' model: mixed senses
+    m = small()
+    node = BaseNode(m.lp, m.integerIndices, 0)
+    x = node.lp.getVarByName('x')
+    node.lp.addConstraint(CyLPArray([1, 0, 0]) * x <= 1, 'upper')
+    assert node.lp.nConstraints == 3
+    with pytest.raises(AssertionError, match='all constraints should be bounded same way'):
+        node._sense
+    node.lp.removeConstraint('upper')
+    assert node._sense == '>=' and node.lp.solvable
+
+    # all rows replaced by '<=' rows (test_base_node.py:873-884)
+    A, b = -node.lp.constraints[0].varCoefs[x], -node.lp.constraints[0].lower
+    for constr in node.lp.constraints:
+        node.lp.removeConstraint(constr.name)
+    assert node.lp.nConstraints == 0
+    node.lp.addConstraint(A * x <= b)
+    assert node._sense == '<=' and node.lp.nConstraints == 2
+    with pytest.raises(Exception, match='Constraint "nope" does not exist'):
+        node.lp.removeConstraint('nope')
+
+    # a second variable vector
+    m = small()
+    s = m.lp.addVariable('s', 1)
+    m.lp += s >= CyLPArray([0])
+    node = BaseNode(m.lp, m.integerIndices, 0)
+    assert not node._x_only_variable and node.lp.nVariables == 4 and len(node.lp.variablesLower) == 4
+    with pytest.raises(AssertionError, match='x must be our only variable'):
+        node._bound_lp()
+    with pytest.raises(AssertionError, match='x must be our only variable'):
+        node._base_branch(branch_idx=1)
+
+
+def test_basis_round_trip_and_strong_branch_override(monkeypatch):
+    """A child right after _base_branch reports its parent's basis (base_node.py:608, test_base_node.py:748-751);
+    an overridden _strong_branch is the one _update_pseudo_costs calls (test_pseudo_cost.py:72-87)."""
+    from unittest.mock import patch
+    from helpers import use_oracle_engine
+    from simple_mip_solver_b200 import BaseNode, CyLPArray, MILPInstance, PseudoCostBranchNode
+    use_oracle_engine(monkeypatch)
+    A = np.array([[1.0, 0.0, 1.0], [0.0, 1.0, 0.0]])
+    mk = lambda: MILPInstance(A=-A, b=-CyLPArray([1.5, 1.25]), c=-CyLPArray([1, 1, 1]), l=CyLPArray([0, 0, 0]),
+                              u=CyLPArray([10, 10, 10]), sense=['Min', '>='], integerIndices=[0, 1, 2], numVars=3)
+    m = mk()
+    node = BaseNode(m.lp, m.integerIndices, 0)
+    node.bound(gomory_cuts=False)
+    kids = node._base_branch(2, 1)
+    for d in ('left', 'right'):
+        for i in (0, 1):
+            assert (node.lp.getBasisStatus()[i] == kids[d].lp.getBasisStatus()[i]).all()
+    m = mk()
+    node = PseudoCostBranchNode(m.lp, m.integerIndices)
+    node.pseudo_costs = {}
+    node._base_bound(gomory_cuts=False)
+    with patch.object(node, '_strong_branch') as sb, patch.object(node, '_calculate_costs') as cc:
+        sb.return_value = {'right': PseudoCostBranchNode(mk().lp, [0, 1, 2]), 'left': PseudoCostBranchNode(mk().lp, [0, 1, 2])}
+        node._update_pseudo_costs()
+        assert sb.call_count == 2 and cc.call_count == 4

@@ -20,6 +20,11 @@ and the only collective is the 16-byte all-reduce(min) of [incumbent, dual bound
   cpu_baseline  the HiGHS dual-simplex stand-in for the reference's CLP path (oracle/highs_lp.py),
           warm-started from the root basis, one LP per task on all host cores, bounded sample.
 
+  named_config  BASELINE.json config 5 AS NAMED, timed in the same run after the steps above: ``--named-batch``
+          (4096) concurrent node LPs per step split over the N GPUs (strong scaling: 4096/N per GPU), device
+          resident, CUDA events, max over ranks, golden nodes validated — so that the driver's 1/2/4/8-GPU
+          runs carry the weak-scaling curve (`value`) and the strong-scaling curve of the named frontier.
+
 ``--impl reference`` times only that CPU path (rank 0).
 """
 from __future__ import annotations
@@ -307,6 +312,11 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--cpu-nodes', type=int, default=0, help='CPU arm: nodes per step (default: one per core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--named-batch', type=int, default=4096,
+                    help='weak-scaling runs also time BASELINE.json config 5 AS NAMED in the same process: this many '
+                         'concurrent node LPs per step split over the GPUs (strong scaling); 0 = skip')
+    ap.add_argument('--named-steps', type=int, default=2)
+    ap.add_argument('--named-warmup', type=int, default=1)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -399,13 +409,13 @@ def main():
     x0 = torch.from_numpy(root['x']).to(dev)[:, None].expand(n, ld).contiguous()
     y0 = torch.from_numpy(root['y']).to(dev)[:, None].expand(m, ld).contiguous()
 
-    def exchange(res_obj, res_lower, res_status, res_frac):
+    def exchange(res_obj, res_lower, res_status, res_frac, count=B):
         """16-byte all-reduce(min) of [best integral objective in slice, min open lower bound]."""
-        st = res_status[:B]
-        integral = (st == 0) & (res_frac[:B] < 0)
-        inc = float(res_obj[:B][integral].min().item()) if bool(integral.any()) else float('inf')
+        st = res_status[:count]
+        integral = (st == 0) & (res_frac[:count] < 0)
+        inc = float(res_obj[:count][integral].min().item()) if bool(integral.any()) else float('inf')
         open_ = (st == 0) & ~integral
-        lowb = float(res_lower[:B][open_].min().item()) if bool(open_.any()) else float('inf')
+        lowb = float(res_lower[:count][open_].min().item()) if bool(open_.any()) else float('inf')
         return parallel.allreduce_bounds(inc, lowb, device=dev, lp=lp if use_comm else None)
 
     total_steps = args.warmup + args.steps
@@ -528,6 +538,60 @@ def main():
     e2e_s = parallel.allreduce_max(time.perf_counter() - t0, device=dev)
     e2e_total = parallel.allreduce_sum([e2e_solved], device=dev)[0]
 
+    # ---- BASELINE.json config 5 as named, in the same run: --named-batch concurrent node LPs per step split
+    # over the GPUs (strong scaling), device-resident and timed like `value`. Only next to a weak-scaling run of the
+    # named workload; every rank takes the same branches, so the collectives inside line up.
+    named = None
+    Bn = args.named_batch // world if args.named_batch > 0 else 0
+    if args.scaling == 'weak' and args.workload == 'c5' and args.named_steps > 0 and Bn >= 64 and \
+            Bn * world == args.named_batch and Bn % 64 == 0:
+        del x0, y0
+        ldn = engine.leading_dim(Bn)
+        Wn = min(args.slots, Bn) if args.slots > 0 else Bn
+        xn = torch.from_numpy(root['x']).to(dev)[:, None].expand(n, ldn).contiguous()
+        yn = torch.from_numpy(root['y']).to(dev)[:, None].expand(m, ldn).contiguous()
+        opts_n = engine.default_opts(eps_rel=args.eps, max_iters=args.max_iters, max_active=Wn)
+        checker_n = Validator(gold)
+        n_steps = args.named_warmup + args.named_steps
+        # slices of the same frontier generator, far from the ones timed above
+        n_slices = [step_nodes(d, root, depth, args.seed, 100_000 + s * world + rank, Bn, gold) for s in range(n_steps)]
+        n_packed = [pack(sl[0]) for sl in n_slices]
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_solved = n_iters = 0
+        n_node_iters = 0.0
+        if args.named_warmup == 0:
+            barrier()
+            n0.record(ext)
+        for s in range(n_steps):
+            lb, ub = to_device(n_packed[s], Bn)
+            if s == args.named_warmup and s > 0:
+                barrier()
+                n0.record(ext)
+            r = lp.solve_batch_device(lb, ub, x0=xn, y0=yn, int_idx=int_idx, opts=opts_n, want_x=True, want_y=True)
+            exchange(r['obj'], r['lower'], r['status'], r['frac'], count=Bn)
+            if s >= args.named_warmup:
+                st = r['status'][:Bn]
+                n_solved += int(((st == 0) | (st == 1) | (st == 2)).sum().item())
+                n_iters += r['stats']['iterations']
+                n_node_iters += r['stats']['node_iterations']
+                g = len(n_slices[s][1])
+                if g:
+                    checker_n.add(n_slices[s][1], st[Bn - g:Bn].cpu().numpy(), r['obj'][Bn - g:Bn].cpu().numpy())
+            log(f'[rank {rank}] named step {s} iters {r["stats"]["iterations"]} total_ms {r["stats"]["total_ms"]:.0f}')
+            del lb, ub
+        n1.record(ext)
+        barrier()
+        n_ms = parallel.allreduce_max(n0.elapsed_time(n1), device=dev)
+        n_total = parallel.allreduce_sum([n_solved], device=dev)[0]
+        named = {'value': n_total / (n_ms * 1e-3), 'unit': UNIT, 'scaling': 'strong',
+                 'nodes_per_step': args.named_batch, 'nodes_per_gpu': Bn, 'resident_slots': Wn,
+                 'steps': args.named_steps, 'warmup': args.named_warmup, 'ms_per_step': n_ms / args.named_steps,
+                 'slot_utilisation': n_node_iters / max(n_iters * Wn, 1), 'validated': checker_n.report(),
+                 'note': 'BASELINE.json config 5 as named (this many concurrent node LPs, sharded by node over the GPUs), '
+                         'timed in the same run after the steps behind `value`: CUDA events on the library stream, '
+                         'barrier + synchronize on both sides, max over ranks; slot_utilisation is rank 0\'s'}
+        del xn, yn
+
     if rank == 0:
         peaks = {}
         try:
@@ -605,6 +669,7 @@ def main():
                      'AT': {'ms': spmv['AT'], 'achieved': (bytes_AT + 8 * W * (n + m)) / spmv['AT'] / 1e6,
                             'frac': (bytes_AT + 8 * W * (n + m)) / spmv['AT'] / 1e6 / peak}},
             'cpu_baseline': cpu,
+            'named_config': named,
             'nodes': {'solved': int(sums[0]), 'iteration_limit': int(sums[1]), 'infeasible': int(sums[3]),
                       'pdhg_iterations_per_step': agg['iters'] / max(args.steps, 1),
                       'refills_per_step': agg['refills'] / max(args.steps, 1),

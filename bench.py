@@ -315,8 +315,9 @@ def main():
     ap.add_argument('--named-batch', type=int, default=4096,
                     help='weak-scaling runs also time BASELINE.json config 5 AS NAMED in the same process: this many '
                          'concurrent node LPs per step split over the GPUs (strong scaling); 0 = skip')
-    ap.add_argument('--named-steps', type=int, default=2)
-    ap.add_argument('--named-warmup', type=int, default=1)
+    ap.add_argument('--named-steps', type=int, default=1)
+    ap.add_argument('--named-warmup', type=int, default=0,
+                    help='extra warm-up steps of the named leg (it runs warm: after the W + K steps behind `value`)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -588,7 +589,7 @@ def main():
                  'steps': args.named_steps, 'warmup': args.named_warmup, 'ms_per_step': n_ms / args.named_steps,
                  'slot_utilisation': n_node_iters / max(n_iters * Wn, 1), 'validated': checker_n.report(),
                  'note': 'BASELINE.json config 5 as named (this many concurrent node LPs, sharded by node over the GPUs), '
-                         'timed in the same run after the steps behind `value`: CUDA events on the library stream, '
+                         'timed in the same run, warm, after the W + K steps behind `value`: CUDA events on the library stream, '
                          'barrier + synchronize on both sides, max over ranks; slot_utilisation is rank 0\'s'}
         del xn, yn
 

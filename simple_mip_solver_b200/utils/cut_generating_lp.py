@@ -43,6 +43,7 @@ from simple_mip_solver_b200.compat.cylp_like import CyLPArray
 _INF = float('inf')
 SIMPLEX_CHUNK_BYTES = 4 << 30       # dense basis inverses one simplex call may hold (8 m^2 bytes per point)
 PREFETCH_CACHE_POINTS = 4096        # answers kept for nodes that have not asked yet
+ROUND_OFF_BELOW_ZERO = 1e-9
 
 
 class BasisArray(np.ndarray):
@@ -327,6 +328,9 @@ class CutGeneratingLP:
         from simple_mip_solver_b200 import engine
         lp = self._device_lp()
         K = points.shape[0]
+        # round-off below zero (an LP solution read back from the device) is zero: a negative component
+        # makes the CGLP unbounded — its dual has no point sum xi_t = x_star with xi_t >= 0
+        points = np.where((points < 0) & (points > -ROUND_OFF_BELOW_ZERO), 0.0, points)
         lo, hi = self._point_bounds(points)
         nrow = self._dM.shape[0]
         self.points_solved += K

@@ -253,3 +253,20 @@ def test_cglp_first_order_path_gives_the_same_optimum(monkeypatch):
         if leaf.lp_feasible and leaf.solution is not None:
             for p, p0 in ((pi1, pi01), (pi2, pi02)):
                 assert float(np.dot(p, np.maximum(leaf.solution, 0))) >= p0 - 1e-6
+
+
+def test_cglp_points_with_round_off_below_zero_and_outside_the_orthant(monkeypatch):
+    use_oracle_engine(monkeypatch)
+    bb = partial_tree(EXAMPLES['small_branch'], node_limit=10)
+    cglp = CutGeneratingLP(bb, bb.root_node.idx)
+    x = np.asarray(bb.root_node.solution, dtype=float)
+    pi, pi0 = cglp.solve()
+    noisy = x.copy()
+    noisy[0] = -3e-13                                   # x_0 = 0 at the root, read back with round-off
+    pi1, pi01 = cglp.solve(x_star=CyLPArray(noisy), starting_basis=cold(cglp))
+    assert pi1 is not None and np.allclose(pi1, pi) and pi01 == pytest.approx(pi0)
+    # a point outside x >= 0 makes the CGLP unbounded (reference: CLP status 2): reported as a failure
+    far = x.copy()
+    far[0] = -1.0
+    assert cglp.solve(x_star=CyLPArray(far)) == (None, None)
+    assert cglp.cylp_failure and cglp.lp.getStatusCode() == 2

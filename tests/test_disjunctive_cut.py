@@ -270,3 +270,35 @@ def test_cglp_points_with_round_off_below_zero_and_outside_the_orthant(monkeypat
     far[0] = -1.0
     assert cglp.solve(x_star=CyLPArray(far)) == (None, None)
     assert cglp.cylp_failure and cglp.lp.getStatusCode() == 2
+
+
+def test_cglp_dual_form_optimum_on_every_fixture(monkeypatch):
+    """All 64 scale_1 fixtures: the cut read from the device LP's multipliers attains the optimum of the
+    reference's primal CGLP model (HiGHS), is valid for every integer point, and never fails."""
+    from oracle.highs_lp import HIGHS_INF, HighsLP
+    use_oracle_engine(monkeypatch)
+    fin = lambda v, big: np.where(np.isinf(v), big, v)
+    solved = separated = 0
+    for name, rec in SCALE1.items():
+        bb = partial_tree(rec, node_limit=6)
+        root = bb.root_node
+        if root.solution is None:
+            continue
+        cglp = CutGeneratingLP(bb, root.idx)
+        if not cglp.term_ids:
+            continue
+        x = np.asarray(root.solution, dtype=float)
+        pts = [CyLPArray(x), CyLPArray(np.maximum(x * 0.8, 0)), CyLPArray(np.maximum(x + 0.3, 0))]
+        pool = integer_points(rec) if len(x) <= 4 else []
+        for p, (pi, pi0) in zip(pts, cglp.solve_batch(pts)):
+            assert pi is not None, name
+            c = np.zeros(cglp.lp.nVariables)
+            c[:cglp.n], c[cglp.n] = p, -1.0
+            M, r, lo, hi = cglp.primal_model()
+            h = HighsLP(M, c, r, np.full(M.shape[0], HIGHS_INF), fin(lo, -HIGHS_INF), fin(hi, HIGHS_INF)).solve()
+            assert h.status == 0 and float(np.dot(pi, p)) - pi0 == pytest.approx(h.objective, abs=1e-7), name
+            for q in pool:
+                assert float(np.dot(pi, q)) >= pi0 - 1e-6 * max(1.0, abs(pi0)), (name, q)
+            solved += 1
+            separated += float(np.dot(pi, p)) - pi0 < -1e-9
+    assert solved >= 150 and separated >= 40

@@ -299,6 +299,7 @@ class CyClpSimplex:
         self._parent_bounds = (None, None)   # the parent's bound arrays (children of one parent share them)
         self._basis_start = None        # setBasisStatus by row NAME: (cols, base rows, {cut name: status})
         self.integer_indices_hint: Optional[Sequence[int]] = None
+        self.integer_index_set = None           # frozenset of the hint once a node has checked it
         self.solver_opts: Dict[str, float] = {}
         if shared is not None:
             v = CyLPVar('x', shared.n)
@@ -596,7 +597,11 @@ class CyClpSimplex:
         at_l = x - self._l <= tol * scale
         at_u = self._u - x <= tol * scale
         cols = np.where(at_l, 3, np.where(at_u, 2, 1)).astype(np.int32)
-        slack = self.coefMatrix @ x - self.constraintsLower
+        # row activities without the CSC copy `coefMatrix` makes for its callers: base rows, then this LP's cuts
+        sh = self._need_shared()
+        act = [(sh.A if self._base_rows == sh.m else sh.A[:self._base_rows]) @ x] + [[float(np.dot(p, x))] for p, _ in self._cuts.values()]
+        act.append(self._foreign()[0] @ x)
+        slack = np.concatenate(act) - self.constraintsLower
         rows = np.where(slack > tol * (1.0 + np.abs(self.constraintsLower)), 1, 3).astype(np.int32)
         return cols, rows
 
@@ -674,6 +679,7 @@ class CyClpSimplex:
         child._vars += self._vars[1:]
         child._objective = self._objective
         child.integer_indices_hint = self.integer_indices_hint
+        child.integer_index_set = self.integer_index_set
         child.solver_opts = self.solver_opts
         if self._factor_ref is not None and self._solved_key == self._state_key():
             child._parent_ref = self._factor_ref

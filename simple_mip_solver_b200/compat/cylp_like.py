@@ -187,6 +187,7 @@ class SharedLP:
         # base_node.py:595-600) and, once solved, its primal/dual pair (the common warm start of a frontier)
         self.root_bounds = None
         self.root_xy = None
+        self.max_abs_coef = None        # max |A_ij| (BaseNode.max_term), computed on first use
 
     @property
     def engine(self):
@@ -260,6 +261,16 @@ class SharedLP:
             self._on_device = 0
 
 
+_EMPTY_ROWS: Dict[int, Tuple[sp.csr_matrix, np.ndarray, np.ndarray]] = {}
+
+
+def _empty_rows(n: int):
+    """(0 x n matrix, no lower bounds, no upper bounds), one shared instance per width."""
+    if n not in _EMPTY_ROWS:
+        _EMPTY_ROWS[n] = (sp.csr_matrix((0, n)), np.zeros(0), np.zeros(0))
+    return _EMPTY_ROWS[n]
+
+
 class CyClpSimplex:
     """Per-node LP with the attribute/method names of cylp.cy.CyClpSimplex that the reference uses."""
 
@@ -294,6 +305,7 @@ class CyClpSimplex:
         self._basis_out = None          # (cols, base rows, {cut name: status}) of the last simplex solve
         self._basis_exact = False       # _basis_out is a basis of the LP as it is now
         self._basis_kept = None         # the last exact basis minus slack cuts removed since (see removeConstraint)
+        self._basis_guess = None        # (solved key, cols, rows): active-set status of the last first-order solve
         self._factor_ref = None         # (simplex call id, slot, cut names) of the last simplex solve
         self._parent_ref = None         # the parent's _factor_ref (copy_for_child)
         self._parent_bounds = (None, None)   # the parent's bound arrays (children of one parent share them)
@@ -437,15 +449,30 @@ class CyClpSimplex:
     def _foreign(self):
         """(rows as csr, lower, upper) of everything the device form does not hold."""
         n = self._vars[0].dim
+        if self._foreign_base is None and not self._foreign_rows:
+            return _empty_rows(n)
         mats, los, ups = [], [], []
         if self._foreign_base is not None:
             A, lo, up = self._foreign_base
             mats.append(A), los.append(lo), ups.append(up)
         for pi, lo, up in self._foreign_rows.values():
             mats.append(sp.csr_matrix(pi[None, :n])), los.append([lo]), ups.append([up])
-        if not mats:
-            return sp.csr_matrix((0, n)), np.zeros(0), np.zeros(0)
         return sp.vstack(mats, format='csr'), np.concatenate(los), np.concatenate(ups)
+
+    def first_constraint_max_term(self) -> float:
+        """max |coefficient| of the first constraint object (what BaseNode keeps as ``max_term``,
+        base_node.py:104), without building the constraint list: for the base rows it is a property of the
+        shared matrix, computed once per model."""
+        sh = self._need_shared()
+        if not self._base_off and sh.m:
+            if sh.max_abs_coef is None:
+                sh.max_abs_coef = float(np.max(np.abs(sh.A.data))) if sh.A.nnz else 0.0
+            return sh.max_abs_coef
+        cons = self.constraints
+        if not cons:
+            return 0.0
+        M = cons[0].varCoefs[cons[0].variables[0]]
+        return float(np.max(np.abs(M.data))) if M.nnz else 0.0
 
     @property
     def nVariables(self):
@@ -591,6 +618,9 @@ class CyClpSimplex:
             return self._basis[0].astype(np.int32), self._basis[1].astype(np.int32)
         if self._x is None:
             return np.full(n, 3, dtype=np.int32), np.full(m, 1, dtype=np.int32)
+        key = self._solved_key
+        if self._basis_guess is not None and self._basis_guess[0] == key and key is not None and not unsolved:
+            return self._basis_guess[1].copy(), self._basis_guess[2].copy()      # asked once per strong-branching child
         tol = 1e-6
         x = self._x
         scale = 1.0 + np.abs(x)
@@ -599,10 +629,13 @@ class CyClpSimplex:
         cols = np.where(at_l, 3, np.where(at_u, 2, 1)).astype(np.int32)
         # row activities without the CSC copy `coefMatrix` makes for its callers: base rows, then this LP's cuts
         sh = self._need_shared()
-        act = [(sh.A if self._base_rows == sh.m else sh.A[:self._base_rows]) @ x] + [[float(np.dot(p, x))] for p, _ in self._cuts.values()]
+        act = [(sh.A if self._base_rows == sh.m else sh.A[:self._base_rows]) @ x]
+        act += [[float(np.dot(p, x))] for p, _ in self._cuts.values()]
         act.append(self._foreign()[0] @ x)
-        slack = np.concatenate(act) - self.constraintsLower
-        rows = np.where(slack > tol * (1.0 + np.abs(self.constraintsLower)), 1, 3).astype(np.int32)
+        lower = np.asarray(self.constraintsLower)
+        rows = np.where(np.concatenate(act) - lower > tol * (1.0 + np.abs(lower)), 1, 3).astype(np.int32)
+        if not unsolved:
+            self._basis_guess = (key, cols.copy(), rows.copy())
         return cols, rows
 
     def kept_basis_status(self):

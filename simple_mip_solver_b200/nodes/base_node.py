@@ -105,9 +105,9 @@ class BaseNode:
         for op in ('created', 'added', 'removed'):
             setattr(self, f'iterations_gmic_{op}', 0)
             setattr(self, f'number_gmic_{op}', 0)
-        base_rows = self.lp.constraints[0].varCoefs[self.lp.getVarByName('x')]
-        # a 0-d CyLPArray, as CyLP's coefficient matrices make it (the reference's tests check the type)
-        self.max_term = CyLPArray(float(np.max(np.abs(base_rows.data))) if base_rows.nnz else 0.0)
+        # largest |coefficient| of the first constraint object (reference :104); a 0-d CyLPArray, as CyLP's
+        # coefficient matrices make it (the reference's tests check the type)
+        self.max_term = CyLPArray(self.lp.first_constraint_max_term())
 
         assert self._sense == '>=', 'must have Ax >= b'
         assert self._variables_nonnegative, 'must have x >= 0 for all variables'

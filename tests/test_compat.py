@@ -259,3 +259,27 @@ def test_basis_round_trip_and_strong_branch_override(monkeypatch):
         sb.return_value = {'right': PseudoCostBranchNode(mk().lp, [0, 1, 2]), 'left': PseudoCostBranchNode(mk().lp, [0, 1, 2])}
         node._update_pseudo_costs()
         assert sb.call_count == 2 and cc.call_count == 4
+
+
+def test_integer_index_checks_run_once_per_model_but_still_catch_a_new_list(monkeypatch):
+    """Children carry the list their parent was checked with, so the O(|I|) checks are skipped for them;
+    any other list is checked as before (test_base_node.py:80-92)."""
+    from helpers import use_oracle_engine
+    from simple_mip_solver_b200 import BaseNode, CyLPArray, MILPInstance
+    use_oracle_engine(monkeypatch)
+    A = np.array([[1.0, 0.0, 1.0], [0.0, 1.0, 0.0]])
+    m = MILPInstance(A=-A, b=-CyLPArray([1.5, 1.25]), c=-CyLPArray([1, 1, 1]), l=CyLPArray([0, 0, 0]),
+                     u=CyLPArray([10, 10, 10]), sense=['Min', '>='], integerIndices=[0, 1, 2], numVars=3)
+    node = BaseNode(m.lp, m.integerIndices, 0)
+    assert m.lp.integer_index_set == frozenset({0, 1, 2})
+    node.bound(gomory_cuts=False)
+    kids = node._base_branch(2, 1)
+    assert kids['left'].lp.integer_index_set is m.lp.integer_index_set
+    assert kids['left']._integer_indices is m.integerIndices
+    with pytest.raises(AssertionError, match='indices must match variables'):
+        BaseNode(kids['left'].lp, [0, 1, 5])
+    with pytest.raises(AssertionError, match='indices must be distinct'):
+        BaseNode(kids['left'].lp, [0, 1, 1])
+    with pytest.raises(AssertionError, match='branch index corresponds to integer variable'):
+        BaseNode(kids['right'].lp, m.integerIndices, b_idx=4, b_dir='right', b_val=.5)
+    assert node.max_term == 1.0 and node.max_term.shape == ()

@@ -532,7 +532,8 @@ class CyClpSimplex:
         sh = self._need_shared()
         if not self._cuts and self.solvable:
             return sh.A.tocsc()
-        return sp.vstack([sh.A[:self._base_rows]] + [sp.csr_matrix(p[None, :]) for p, _ in self._cuts.values()] +
+        base = sh.A if self._base_rows == sh.m else sh.A[:self._base_rows]
+        return sp.vstack([base] + [sp.csr_matrix(p[None, :]) for p, _ in self._cuts.values()] +
                          [self._foreign()[0]]).tocsc()
 
     @property

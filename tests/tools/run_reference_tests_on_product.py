@@ -8,7 +8,10 @@ dual simplex, HiGHS for the first-order path) unless --device is given on a box 
 branch and cut (oracle/gurobi_like.py). The reference's tests live in /root/reference, which exists only in the authoring container, so this
 is a tool, not part of the suites.
 
-    python tests/tools/run_reference_tests_on_product.py [--device] [module ...]
+    python tests/tools/run_reference_tests_on_product.py [--device] [--pdhg] [module ...]
+
+--pdhg routes every node LP through the host code of the first-order path (`SharedLP.default_method = 'pdhg'`;
+with the CPU stand-in that is HiGHS behind `solve_batch` / `solve_children`).
 """
 import importlib
 import os
@@ -77,8 +80,11 @@ def install(reference_root='/root/reference', device=False):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if a != '--device']
+    args = [a for a in sys.argv[1:] if a not in ('--device', '--pdhg')]
     install(device='--device' in sys.argv)
+    if '--pdhg' in sys.argv:
+        from simple_mip_solver_b200.compat.cylp_like import SharedLP
+        SharedLP.default_method = 'pdhg'
     import numpy as np
     np.random.seed(0)        # the reference's helpers sample 10 % of (model, option set) pairs with the global RNG
     if not hasattr(unittest.TestCase, 'assertRegexpMatches'):

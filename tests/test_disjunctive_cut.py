@@ -302,3 +302,41 @@ def test_cglp_dual_form_optimum_on_every_fixture(monkeypatch):
             solved += 1
             separated += float(np.dot(pi, p)) - pi0 < -1e-9
     assert solved >= 150 and separated >= 40
+
+
+# ---------------------------------------------------------------- goldens made by the unmodified reference
+CGLP_GOLD = json.load(open(os.path.join(GOLD, 'cglp.json')))
+
+
+def check_against_reference_cglp(name, gold, rec):
+    """The product's disjunction, LP size and optima against what the UNMODIFIED reference's
+    CutGeneratingLP produced on the same model (tests/golden/make_cglp_goldens.py)."""
+    bb = partial_tree(rec, node_limit=gold['node_limit'])
+    root = bb.root_node
+    terms = {str(n.idx): n for n in bb.tree.get_leaves(root.idx) if n.lp_feasible is not False}
+    assert set(terms) == set(gold['terms']), name                              # the same disjunction ...
+    for idx, n in terms.items():
+        assert np.array_equal(np.asarray(n.lp.variablesLower), gold['terms'][idx]['lower']), (name, idx)
+        assert np.array_equal(np.minimum(np.asarray(n.lp.variablesUpper), 1e308), gold['terms'][idx]['upper'])
+    cglp = CutGeneratingLP(bb, root.idx)
+    assert cglp.lp.nVariables == gold['n_variables'] and cglp.lp.nConstraints == gold['n_constraints'], name
+    points = [CyLPArray(q['x_star']) for q in gold['points']]
+    assert np.allclose(points[0], np.asarray(root.solution), rtol=1e-12, atol=1e-12)    # ... and the same root vertex
+    cuts = cglp.solve_batch(points)
+    for q, p, (pi, pi0) in zip(gold['points'], points, cuts):
+        assert q['status'] == 0 and pi is not None, name
+        mine = float(np.dot(pi, p)) - pi0
+        assert mine == pytest.approx(q['optimum'], abs=1e-8 * (1 + abs(q['optimum']))), (name, mine, q['optimum'])
+        # the reference's own cut and ours are both valid for every term's LP optimum
+        for n in terms.values():
+            if n.lp_feasible and n.solution is not None:
+                z = np.maximum(np.asarray(n.solution, dtype=float), 0)
+                assert float(np.dot(pi, z)) >= pi0 - 1e-6 and float(np.dot(q['pi'], z)) >= q['pi0'] - 1e-6
+    return cglp, bb
+
+
+@pytest.mark.parametrize('name', sorted(CGLP_GOLD))
+def test_cglp_against_the_unmodified_reference(monkeypatch, name):
+    use_oracle_engine(monkeypatch)
+    rec = EXAMPLES[name] if name in EXAMPLES else SCALE1[name]
+    check_against_reference_cglp(name, CGLP_GOLD[name], rec)

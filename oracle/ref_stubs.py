@@ -326,3 +326,14 @@ def install(reference_root: str = '/root/reference'):
     if reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     return this
+
+
+def enable_cglp():
+    """Give the reference's cut generating LP (simple_mip_solver/utils/cut_generating_lp.py) the multi-variable
+    modelling algebra it builds its LP with (oracle/cylp_multivar.py). Call after ``install()``; returns the
+    reference module. Every other reference module keeps the single-variable look-alike above."""
+    import simple_mip_solver.utils.cut_generating_lp as ref_cglp
+    from oracle.cylp_multivar import MultiVarSimplex
+    ref_cglp.CyClpSimplex = MultiVarSimplex
+    return ref_cglp
+

@@ -24,12 +24,10 @@ from oracle import ref_stubs  # noqa: E402
 
 ref_stubs.install()
 import simple_mip_solver as ref  # noqa: E402
-import simple_mip_solver.utils.cut_generating_lp as ref_cglp  # noqa: E402
 from coinor.cuppy.milpInstance import MILPInstance  # noqa: E402  (the stand-in)
-from oracle.cylp_multivar import MultiVarSimplex  # noqa: E402
 from oracle.ref_lookalikes import CyLPArray  # noqa: E402
 
-ref_cglp.CyClpSimplex = MultiVarSimplex      # the one name the reference's CGLP module binds from cylp
+ref_cglp = ref_stubs.enable_cglp()           # rebinds the one name the reference's CGLP module takes from cylp
 
 NODE_LIMIT = 8
 

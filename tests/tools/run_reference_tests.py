@@ -4,6 +4,7 @@ import os, sys, unittest
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import ref_stubs
 ref_stubs.install()
+ref_stubs.enable_cglp()
 if not hasattr(unittest.TestCase, 'assertRegexpMatches'):
     unittest.TestCase.assertRegexpMatches = unittest.TestCase.assertRegex
 mods = sys.argv[1:] or ['test_simple_mip_solver.test_nodes.test_base_node',

@@ -72,6 +72,28 @@ def main():
                             pi=[float(v) for v in pi] if ok else None, pi0=float(pi0) if ok else None))
         out[name] = dict(node_limit=NODE_LIMIT, evaluated_nodes=bb.evaluated_nodes, terms=leaves,
                          n_variables=int(cglp.lp.nVariables), n_constraints=int(cglp.lp.nConstraints), points=pts)
+        # the constructor's options (reference :13-50): a depth limit on the disjunction, other constraints for
+        # every term, extra variable bounds (terms they empty are dropped, :113-121)
+        x = np.asarray(root.solution, dtype=float)
+        lo_x, hi_x = np.floor(x), np.floor(x) + 1
+        options = dict(
+            depth_1=dict(depth=1),
+            root_rows=dict(A=root.lp.coefMatrix.copy(), b=CyLPArray(np.asarray(root.lp.constraintsLower).copy())),
+            unit_box=dict(var_lb=CyLPArray(lo_x), var_ub=CyLPArray(hi_x)),
+        )
+        variants = {}
+        for key, kw in options.items():
+            try:
+                other = ref_cglp.CutGeneratingLP(bb, root.idx, **kw)
+                pi, pi0 = other.solve(x_star=CyLPArray(x))
+            except Exception as exc:          # e.g. every term emptied by the box: recorded, the product must agree
+                variants[key] = dict(error=type(exc).__name__)
+                continue
+            ok = pi is not None
+            variants[key] = dict(n_variables=int(other.lp.nVariables), n_constraints=int(other.lp.nConstraints),
+                                 status=int(other.lp.getStatusCode()),
+                                 optimum=float(np.dot(pi, x) - pi0) if ok else None)
+        out[name]['variants'] = variants
         print(name, 'terms', len(leaves), 'lp', cglp.lp.nVariables, 'x', cglp.lp.nConstraints,
               'optima', [None if q['optimum'] is None else round(q['optimum'], 6) for q in pts])
     ref_stubs.LP_BACKEND = 'highs'

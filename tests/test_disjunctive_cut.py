@@ -339,4 +339,25 @@ def check_against_reference_cglp(name, gold, rec):
 def test_cglp_against_the_unmodified_reference(monkeypatch, name):
     use_oracle_engine(monkeypatch)
     rec = EXAMPLES[name] if name in EXAMPLES else SCALE1[name]
-    check_against_reference_cglp(name, CGLP_GOLD[name], rec)
+    gold = CGLP_GOLD[name]
+    _, bb = check_against_reference_cglp(name, gold, rec)
+    # the constructor's options (reference :13-50), as the generator applied them
+    root = bb.root_node
+    x = np.asarray(root.solution, dtype=float)
+    options = dict(
+        depth_1=dict(depth=1),
+        root_rows=dict(A=root.lp.coefMatrix.copy(), b=CyLPArray(np.asarray(root.lp.constraintsLower).copy())),
+        unit_box=dict(var_lb=CyLPArray(np.floor(x)), var_ub=CyLPArray(np.floor(x) + 1)),
+    )
+    for key, kw in options.items():
+        want = gold['variants'][key]
+        other = CutGeneratingLP(bb, root.idx, **kw)
+        if 'error' in want:
+            # no term survives (the reference trips over its empty term list there): nothing to separate with
+            assert not other.term_ids and other.solve(x_star=CyLPArray(x)) == (None, None) and other.cylp_failure
+            continue
+        assert (other.lp.nVariables, other.lp.nConstraints) == (want['n_variables'], want['n_constraints']), (name, key)
+        pi, pi0 = other.solve(x_star=CyLPArray(x))
+        assert want['status'] == 0 and pi is not None
+        assert float(np.dot(pi, x)) - pi0 == pytest.approx(want['optimum'], abs=1e-8 * (1 + abs(want['optimum']))), \
+            (name, key)

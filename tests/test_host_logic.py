@@ -277,3 +277,90 @@ def test_pdhg_path_sends_nodes_as_deltas(monkeypatch):
     bb.solve()
     check_against_reference(bb, rec['reference']['BaseNode'])
     assert eng.children_calls > 0
+
+
+FUZZ = json.load(open(os.path.join(GOLD, 'fuzz_models.json')))
+
+
+def first_divergence_is_a_tie(bb, gold_tree, tol=1e-9):
+    """The trees differ: walk the nodes in creation order to the first one whose parent / branching variable is
+    not the reference's, and check that at its parent the two candidates are an exact tie of the branching rule
+    that only the last ulp of the LP solution decides. (The reference solves every node LP twice — its cut loop
+    re-solves once even without cuts, base_node.py:213-216 — so its x comes from a fresh factorisation of the
+    optimal basis, the product's from the inverse the pivots left: same vertex, last bits may differ.)"""
+    for idx in sorted(gold_tree, key=int):
+        parent, b_idx, b_dir = gold_tree[idx][:3]
+        if parent is None:
+            continue
+        if int(idx) in bb.tree.nodes:
+            n = bb.tree.get_node_instances(int(idx))
+            if (bb.tree.get_parent(int(idx)), n._b_idx, n._b_dir) == (parent, b_idx, b_dir):
+                continue
+            mine_parent, mine_idx = bb.tree.get_parent(int(idx)), n._b_idx
+        else:
+            return False
+        if mine_parent != parent:
+            return False                                   # a different node was expanded: not a tie of the rule
+        x = np.asarray(bb.tree.get_node_instances(parent).solution, dtype=float)
+        dist = np.minimum(x - np.floor(x), np.ceil(x) - x)
+        return abs(dist[mine_idx] - dist[b_idx]) <= tol and dist[b_idx] >= dist.max() - tol
+    return False
+
+
+@pytest.mark.parametrize('label', ['BaseNode', 'DepthFirstSearchNode'])
+@pytest.mark.parametrize('frontier', [1, 8])
+def test_fuzz_models_same_tree_as_reference(monkeypatch, label, frontier):
+    """15 GrUMPy-style random MILPs of 6-14 variables (trees of up to 759 nodes, tests/golden/
+    make_fuzz_goldens.py): node for node the tree the UNMODIFIED reference built on the same simplex; where
+    it is not, the first difference must be a last-ulp tie of the most-fractional rule."""
+    use_oracle_engine(monkeypatch)
+    Node, kw = CASES[label]
+    same = 0
+    for name, rec in FUZZ.items():
+        gold = rec['reference_ds'][label]
+        bb = BranchAndBound(model_from(rec), Node, frontier_batch=frontier, **dict(kw))
+        bb.solve()
+        assert bb.status == gold['status'] and bb.objective_value == pytest.approx(unfl(rec['mip_optimum']), abs=1e-6)
+        try:
+            check_against_reference(bb, gold)
+            same += 1
+        except AssertionError:
+            assert first_divergence_is_a_tie(bb, gold['tree']), name
+    assert same >= len(FUZZ) - 2
+
+
+@pytest.mark.parametrize('label', ['PseudoCostBranchNode', 'PseudoCostBranchDepthFirstSearchNode'])
+def test_fuzz_models_pseudo_cost_trees_and_costs(monkeypatch, label):
+    """The same 15 models with strong branching (5 dual simplex pivots per child, as the reference's default)
+    and pseudo-cost branching: identical trees (up to 625 nodes) and identical pseudo costs."""
+    use_oracle_engine(monkeypatch)
+    Node, kw = CASES[label]
+    for name, rec in FUZZ.items():
+        gold = rec['reference_ds'][label]
+        bb = BranchAndBound(model_from(rec), Node, **{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()})
+        bb.solve()
+        check_against_reference(bb, gold)
+        pc = bb._kwargs['pseudo_costs']
+        assert set(map(str, pc)) == set(gold['pseudo_costs']), name
+        for i, v in gold['pseudo_costs'].items():
+            for d, e in v.items():
+                assert pc[int(i)][d]['times'] == e['times'], name
+                assert pc[int(i)][d]['cost'] == pytest.approx(e['cost'], rel=1e-7, abs=1e-9), name
+
+
+def test_fuzz_models_default_bound_loop_reaches_the_optimum(monkeypatch):
+    """Default options (Gomory rounds on). The trees are NOT the reference's here: the product's GMI cuts
+    shift / complement nonbasic variables that sit at a nonzero bound (branching bounds, upper bounds) before
+    the rounding formula, which the reference's formula assumes away (base_node.py:468-511), so the rounds are
+    not the same cuts (on random_14x8_seed3 the product evaluates 3 nodes where the reference evaluates 29).
+    Status and optimum must agree."""
+    use_oracle_engine(monkeypatch)
+    fewer = 0
+    for name, rec in FUZZ.items():
+        gold = rec['reference_ds']['BaseNode_gomory']
+        bb = BranchAndBound(model_from(rec), BaseNode)
+        bb.solve()
+        assert bb.status == gold['status'] == 'optimal', name
+        assert bb.objective_value == pytest.approx(unfl(rec['mip_optimum']), abs=1e-6), name
+        fewer += bb.evaluated_nodes <= gold['evaluated_nodes']
+    assert fewer >= 12

@@ -364,3 +364,26 @@ def test_fuzz_models_default_bound_loop_reaches_the_optimum(monkeypatch):
         assert bb.objective_value == pytest.approx(unfl(rec['mip_optimum']), abs=1e-6), name
         fewer += bb.evaluated_nodes <= gold['evaluated_nodes']
     assert fewer >= 12
+
+
+@pytest.mark.parametrize('label', list(CASES))
+def test_fuzz_models_first_order_host_path(monkeypatch, label):
+    """The same 15 models through the host code of the first-order path (SharedLP.method = 'pdhg'; HiGHS
+    behind solve_batch / solve_children) against the unmodified reference run on HiGHS: identical trees for the
+    most-fractional classes. With pseudo costs one model differs: on that path a strong-branching budget is not a
+    pivot count (here the stand-in converges every child, the reference stops HiGHS after 5 iterations), which
+    changes a pseudo cost where 5 iterations are not enough; optimum and status agree everywhere."""
+    use_oracle_engine(monkeypatch, 'pdhg')
+    Node, kw = CASES[label]
+    same = 0
+    for name, rec in FUZZ.items():
+        gold = rec['reference'][label]
+        bb = BranchAndBound(model_from(rec), Node, **{k: (dict(v) if isinstance(v, dict) else v) for k, v in kw.items()})
+        bb.solve()
+        assert bb.status == gold['status'] and bb.objective_value == pytest.approx(unfl(rec['mip_optimum']), abs=1e-6)
+        try:
+            check_against_reference(bb, gold)
+            same += 1
+        except AssertionError:
+            assert 'PseudoCost' in label, name
+    assert same >= len(FUZZ) - ('PseudoCost' in label)

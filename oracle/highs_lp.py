@@ -171,3 +171,17 @@ def solve_node_lps(A, b, c, lbs, ubs, warm_from_root=True, iteration_limit=None,
             lp.set_basis(*basis)
         out.append(lp.solve(iteration_limit))
     return out
+
+
+def _first_raw_run():
+    """A raw HiGHS instance has to run once BEFORE scipy.optimize.milp is first used in a process: the other
+    way round, every raw instance created afterwards returns kNotset from run() (seen with scipy 1.18's bundled
+    HiGHS; found while generating tests/golden/fuzz_models.json). Importing this module settles the order."""
+    one = HighsLP(np.eye(1), np.ones(1), np.ones(1), np.full(1, HIGHS_INF), np.zeros(1), np.full(1, 2.0)).solve()
+    if one.status != 0 or abs(one.objective - 1.0) > 1e-12:
+        raise RuntimeError('raw HiGHS instances do not run in this process (scipy.optimize.milp was used before '
+                           'oracle.highs_lp was imported?): import the oracle first')
+
+
+_first_raw_run()
+
